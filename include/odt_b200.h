@@ -1,0 +1,205 @@
+/*
+ * odt_b200.h -- C ABI of the B200-native detection hot path.
+ *
+ * This is the drop-in boundary underneath the reference's Python surface
+ * (SSD300.SSD300 / RetinaNet.RetinaNet / YOLOv3.YOLOv3 / FCOS.FCOS /
+ * SSD512.SSD512 .test_one_image()).  The reference has no FFI of its own: all
+ * of its arithmetic is executed by TensorFlow 1.13 ops called from Python.
+ * Each entry point below replaces one class of TF op *call sites* on the
+ * inference path; the call site it stands in for is cited as
+ * "ref: <file>:<line>" (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / C++ types.
+ *   - every pointer is a DEVICE pointer unless its name ends in _host.
+ *   - every function is asynchronous on `stream` (a cudaStream_t passed as
+ *     void*), never allocates, never synchronises, and returns ODT_OK (0) or a
+ *     negative error code; odt_last_error() returns a thread-local message.
+ *   - tensors are NHWC.  Boxes are (y1, x1, y2, x2) in input pixels
+ *     (ref: SSD300.py:169-171).
+ *   - dtype codes: ODT_F16 = 0 (IEEE half), ODT_F32 = 1.
+ *   - thread-compatible: no mutable globals (the only global state is the
+ *     lazily resolved driver entry points for cuTensorMapEncode*).
+ */
+#ifndef ODT_B200_H_
+#define ODT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ODT_OK 0
+#define ODT_ERR_INVALID (-1)   /* bad argument                                 */
+#define ODT_ERR_CUDA (-2)      /* a CUDA runtime / driver call failed          */
+#define ODT_ERR_UNSUPPORTED (-3)
+#define ODT_ERR_OVERFLOW (-4)  /* candidate list capacity exceeded (reported by
+                                  odt_nms_status)                              */
+
+#define ODT_F16 0
+#define ODT_F32 1
+
+#define ODT_ACT_NONE 0
+#define ODT_ACT_RELU 1
+#define ODT_ACT_LEAKY 2 /* max(x, 0.1 x)  ref: YOLOv3.py:506 */
+
+#define ODT_MAX_LEVELS 8
+#define ODT_MAX_PRIORS 9
+
+/* ---------------------------------------------------------------- misc --- */
+int odt_abi_version(void);
+const char* odt_last_error(void);
+/* TF "SAME" geometry: out = ceil(in/stride); pad_before = pad_total/2.
+ * ref: every tf.layers.conv2d/max_pooling2d(padding='same'), e.g. SSD300.py:524,540 */
+int odt_same_pad(int in, int k, int stride, int dil, int* out, int* pad_before, int* pad_after);
+
+/* --------------------------------------------------------------- input --- */
+/* images - mean (RGB 123.68,116.779,103.979), fp32 [B,H,W,3] -> dtype [B,H,W,ld]
+ * (channels >= 3 are zero).  ref: SSD300.py:52-66, RetinaNet.py:101-115,
+ * YOLOv3.py:62-76, FCOS.py:51-65 */
+int odt_normalize_input(const float* images, void* out, int out_dtype, int B, int H, int W,
+                        int out_ld, const float* mean3_host, void* stream);
+
+/* ---------------------------------------------------------------- conv --- */
+typedef struct {
+  /* input  [B,H,W,in_ld] (Cin real channels, in_ld >= Cin channel stride)    */
+  int B, H, W, Cin, in_ld;
+  /* output geometry (TF SAME) and filter                                      */
+  int OH, OW, Cout;
+  int R, S, stride, dil, pad_t, pad_l;
+  /* weights: KRSC [Cout_pad][R][S][w_ld] in the activation dtype; rows
+   * >= Cout and channels >= Cin must be zero.  (TF stores HWIO; the host
+   * transposes at load -- ref: SSD300.py:519,524.)                            */
+  int w_ld;      /* channel stride inside one filter tap (>= Cin)             */
+  int Cout_pad;  /* number of filter rows present in memory                   */
+  /* epilogue 1:  v = act(acc*scale[c] + shift[c]) (+ residual)  -> out0      */
+  const float* scale; /* [Cout] or NULL (=1)  folded BN gamma*rsqrt(var+eps)  */
+  const float* shift; /* [Cout] or NULL (=0)  bias / folded BN beta           */
+  int act;
+  const void* residual; /* activation dtype, same addressing as out0, or NULL */
+  void* out0;           /* may be NULL when only out1 is wanted               */
+  int out0_dtype;       /* ODT_F16 / ODT_F32                                  */
+  long long out0_img_stride; /* elements between images                       */
+  int out0_pix_stride;       /* elements between pixels                       */
+  int out0_group;            /* channel regrouping: channel n is stored at    */
+  int out0_group_stride;     /* (n/group)*group_stride + n%group; 0 = off     */
+  /* epilogue 2 (pre-activation of the consumer):
+   *   out1 = act2(v*scale2[c] + shift2[c]),  activation dtype                */
+  const float* scale2;
+  const float* shift2;
+  int act2;
+  void* out1; /* or NULL */
+  long long out1_img_stride;
+  int out1_pix_stride;
+} odt_conv_params;
+
+/* tcgen05 / TMA implicit-GEMM forward convolution, fp16 in, fp32 accumulate.
+ * Requires in_ld % 64 == 0, w_ld == in_ld, Cout_pad % 32 == 0.
+ * ref: tf.nn.conv2d SSD300.py:519; tf.layers.conv2d SSD300.py:524,
+ * RetinaNet.py:579,599,609, YOLOv3.py:495, FCOS.py:449,469,479; the fused
+ * epilogue is bias_add/BN/ReLU SSD300.py:520-521,534-537 */
+int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_conv_params* p, void* stream);
+/* generic direct convolution on CUDA cores: any Cin/Cout/filter; `dtype` is
+ * the activation dtype (ODT_F32: reference-precision path, ODT_F16: stems and
+ * shapes the tensor-core kernel does not take).  Same call sites as above. */
+int odt_conv2d_direct(const void* in, const void* weights, int dtype, const odt_conv_params* p,
+                      void* stream);
+/* stem variant: fp32 image minus mean is read directly (a1 fused), output dtype `dtype` */
+int odt_conv2d_stem(const float* images, const float* mean3_host, const void* weights, int dtype,
+                    const odt_conv_params* p, void* stream);
+
+/* --------------------------------------------------------------- glue ---- */
+/* max pooling, TF SAME (pads ignored).  ref: SSD300.py:539-547, RetinaNet.py:645-653 */
+int odt_maxpool(const void* in, void* out, int dtype, int B, int H, int W, int C, int ld, int k,
+                int stride, void* stream);
+/* x * rsqrt(max(sum_c x^2, 1e-12)) * gamma.  ref: SSD300.py:74-83 */
+int odt_l2norm_scale(const void* in, void* out, int dtype, long long pixels, int C, int ld,
+                     float gamma, void* stream);
+/* y = act(x*scale[c] + shift[c])  (stand-alone BN/affine + activation).
+ * ref: RetinaNet.py:594-597, SSD300.py:506-512 */
+int odt_affine_act(const void* in, void* out, int dtype, long long pixels, int C, int ld,
+                   const float* scale, const float* shift, int act, void* stream);
+/* out = a + legacy_bilinear_resize(top) (TF1 align_corners=False, no half pixel).
+ * ref: RetinaNet.py:309-310, FCOS.py:372-373.  Optional second output
+ * out1 = act(out*scale2+shift2). */
+int odt_upsample_bilinear_add(const void* top, const void* a, void* out, int dtype, int B, int TH,
+                              int TW, int H, int W, int C, int ld, const float* scale2,
+                              const float* shift2, int act2, void* out1, void* stream);
+/* out[..., :Ca] = a ; out[..., Ca:Ca+Cb] = nearest_resize(b).  ref: YOLOv3.py:406-407 */
+int odt_upsample_nearest_concat(const void* a, const void* b, void* out, int dtype, int B, int H,
+                                int W, int Ca, int lda, int BH, int BW, int Cb, int ldb, int ldo,
+                                void* stream);
+/* GroupNorm(groups) statistics: stats[b][g] = (mean, rstd), eps inside.  ref: FCOS.py:438-446 */
+int odt_groupnorm_stats(const void* in, float* stats, int dtype, int B, long long hw, int C,
+                        int ld, int groups, float eps, void* stream);
+/* y = act((x-mean)*rstd*gamma[c] + beta[c]) */
+int odt_groupnorm_apply(const void* in, void* out, const float* stats, int dtype, int B,
+                        long long hw, int C, int ld, int groups, const float* gamma,
+                        const float* beta, int act, void* stream);
+
+/* ------------------------------------------------- decode + NMS tail ----- */
+#define ODT_DECODE_SSD 0    /* SSD300/SSD512/RetinaNet: softmax+argmax+bg filter */
+#define ODT_DECODE_YOLO3 1  /* sigmoid cls * sigmoid obj, additive exp           */
+#define ODT_DECODE_FCOS 2   /* sigmoid cls * sigmoid ctr, exp(l,r,t,b)           */
+
+typedef struct {
+  int H, W, A;  /* feature grid and priors per cell                            */
+  int offset;   /* first candidate row of this level                          */
+  /* centre: cy = ((i+0.5)*cmul_y)/cdiv_y   (SSD: cmul=input, cdiv=H;
+   *         RetinaNet: cmul = W_in/H_feat, cdiv = 1).  YOLO: cy = i+0.5.
+   *         FCOS: cy = i.                                                     */
+  float cmul_y, cdiv_y, cmul_x, cdiv_x;
+  float out_mul; /* YOLO: 32,32,16 ; FCOS: stride                              */
+  float prior_h[ODT_MAX_PRIORS], prior_w[ODT_MAX_PRIORS];
+} odt_level;
+
+typedef struct {
+  int kind;       /* ODT_DECODE_*                                              */
+  int num_levels;
+  int N;          /* candidates (rows) per image                               */
+  int num_fg;     /* classes thresholded (SSD/RetinaNet: 20 of 21; YOLO 20;
+                     FCOS 20)                                                  */
+  int nms_classes;/* classes the NMS loop visits (FCOS: 19, ref FCOS.py:252)   */
+  float score_thr, iou_thr;
+  int max_boxes;
+  int cap;        /* candidate capacity per (image, class)                     */
+  odt_level level[ODT_MAX_LEVELS];
+} odt_tail_params;
+
+/* fused: score activation + anchor/prior generation + threshold + candidate
+ * compaction.  head: fp32 [B,N,25] rows (layout per kind).
+ * cand_keys: u64 [B,num_fg,cap]; cand_count: i32 [B,num_fg] (zeroed here).
+ * ref: SSD300.py:157-172,323-343; RetinaNet.py:224-239,328-355;
+ *      YOLOv3.py:320-351,419-433; FCOS.py:130-150,197-248 */
+int odt_decode_candidates(const float* head, const odt_tail_params* p, int B,
+                          unsigned long long* cand_keys, int* cand_count, void* stream);
+/* per-(image,class) exact TF NonMaxSuppressionV3 + class-major compaction.
+ * dets: f32 [B, nms_classes*max_boxes, 6] rows (score,y1,x1,y2,x2,class);
+ * det_anchor: i32 same rows (candidate row index = the keep index);
+ * det_count: i32 [B]; status: i32 [1] (0 ok, ODT_ERR_OVERFLOW if any list
+ * overflowed `cap`).  work: i32 [B] zero-initialised scratch (reset by the kernel).
+ * ref: SSD300.py:173-190; RetinaNet.py:240-256; YOLOv3.py:352-368; FCOS.py:249-264 */
+int odt_nms_per_class(const float* head, const odt_tail_params* p, int B,
+                      unsigned long long* cand_keys, const int* cand_count, float* dets,
+                      int* det_anchor, int* det_count, int* sel_scratch, int* work, int* status,
+                      void* stream);
+/* bytes of sel_scratch needed by odt_nms_per_class */
+long long odt_nms_scratch_bytes(const odt_tail_params* p, int B);
+
+/* RetinaNet softmax focal loss + smooth-L1 (anchor/GT matching included),
+ * forward only.  cls/reg come from the same [B,N,25] head buffer; gt: f32
+ * [B,G,5] rows (y,x,h,w,id) padded with -1 (G <= 128).  loss_out: f32 [B]
+ * per-image loss (the reference averages them over the batch and adds weight
+ * decay on the host side of the graph).  partial_scratch: f32
+ * [odt_retina_loss_scratch_floats(B)]; match_scratch: i32 [B*G].
+ * ref: RetinaNet.py:357-474 */
+int odt_retina_loss_fwd(const float* head, const odt_tail_params* p, int B, const float* gt, int G,
+                        float alpha, float gamma, float* partial_scratch, int* match_scratch,
+                        float* loss_out, void* stream);
+long long odt_retina_loss_scratch_floats(int B);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ODT_B200_H_ */

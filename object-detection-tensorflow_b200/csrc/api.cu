@@ -1,0 +1,32 @@
+// Error reporting and small host-side helpers of the C ABI.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace odt {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace odt
+
+extern "C" int odt_abi_version(void) { return 1; }
+extern "C" const char* odt_last_error(void) { return odt::g_err; }
+
+// TF SAME padding: out = ceil(in/stride),
+// pad_total = max((out-1)*stride + (k-1)*dil + 1 - in, 0), before = total/2.
+extern "C" int odt_same_pad(int in, int k, int stride, int dil, int* out, int* pad_before,
+                            int* pad_after) {
+  ODT_CHECK_ARG(in > 0 && k > 0 && stride > 0 && dil > 0, "non-positive geometry");
+  int o = (in + stride - 1) / stride;
+  int total = (o - 1) * stride + (k - 1) * dil + 1 - in;
+  if (total < 0) total = 0;
+  if (out) *out = o;
+  if (pad_before) *pad_before = total / 2;
+  if (pad_after) *pad_after = total - total / 2;
+  return ODT_OK;
+}

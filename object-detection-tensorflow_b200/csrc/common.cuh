@@ -1,0 +1,63 @@
+// Shared helpers for the sm_100a kernels behind include/odt_b200.h.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/odt_b200.h"
+
+namespace odt {
+
+void set_error(const char* fmt, ...);
+
+#define ODT_CHECK_ARG(cond, msg)                                   \
+  do {                                                             \
+    if (!(cond)) {                                                 \
+      odt::set_error("%s: invalid argument: %s", __func__, msg);   \
+      return ODT_ERR_INVALID;                                      \
+    }                                                              \
+  } while (0)
+
+#define ODT_CUDA_OK(expr)                                                        \
+  do {                                                                           \
+    cudaError_t e__ = (expr);                                                    \
+    if (e__ != cudaSuccess) {                                                    \
+      odt::set_error("%s: %s -> %s", __func__, #expr, cudaGetErrorString(e__));  \
+      return ODT_ERR_CUDA;                                                       \
+    }                                                                            \
+  } while (0)
+
+#define ODT_LAUNCH_OK()                                                          \
+  do {                                                                           \
+    cudaError_t e__ = cudaGetLastError();                                        \
+    if (e__ != cudaSuccess) {                                                    \
+      odt::set_error("%s: launch failed: %s", __func__, cudaGetErrorString(e__)); \
+      return ODT_ERR_CUDA;                                                       \
+    }                                                                            \
+  } while (0)
+
+constexpr int kNumSMs = 148;
+
+template <typename T>
+struct Elem;
+template <>
+struct Elem<float> {
+  static __device__ __forceinline__ float ld(const float* p) { return *p; }
+  static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
+};
+template <>
+struct Elem<__half> {
+  static __device__ __forceinline__ float ld(const __half* p) { return __half2float(*p); }
+  static __device__ __forceinline__ void st(__half* p, float v) { *p = __float2half_rn(v); }
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == ODT_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == ODT_ACT_LEAKY) return fmaxf(v, 0.1f * v);
+  return v;
+}
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace odt

@@ -1,0 +1,148 @@
+// CUDA-core implicit-GEMM convolution: any filter / stride / dilation / channel
+// count, fp32 accumulate.  Used for (i) the reference-precision fp32 path that
+// backs the 1e-4 box parity claim, (ii) the Cin=3 stems (mean subtraction fused
+// into the operand load) and (iii) as the on-device cross-check of the tcgen05
+// kernel.  ref: tf.nn.conv2d SSD300.py:519, tf.layers.conv2d SSD300.py:524.
+#include "epilogue.cuh"
+
+namespace odt {
+
+constexpr int DM = 64, DN = 64, DK = 16, DTHREADS = 256;
+
+struct DirectGeom {
+  int B, H, W, Cin, in_ld, OH, OW, Cout, R, S, stride, dil, pad_t, pad_l, w_ld;
+  float mean[3];
+};
+
+template <typename T, bool STEM>
+__global__ void __launch_bounds__(DTHREADS)
+    conv_direct_kernel(const void* __restrict__ in_, const T* __restrict__ wgt,
+                       const __grid_constant__ DirectGeom g, const __grid_constant__ Epi e) {
+  __shared__ float As[DK][DM + 4];
+  __shared__ float Bs[DK][DN + 4];
+  const int tid = threadIdx.x;
+  const long long M = (long long)g.B * g.OH * g.OW;
+  const int K = g.R * g.S * g.Cin;
+  const long long m0 = (long long)blockIdx.x * DM;
+  const int n0 = blockIdx.y * DN;
+
+  // loader mapping: row = tid/4 (0..63), k sub-block = (tid%4)*4 .. +3
+  const int lrow = tid >> 2, lk = (tid & 3) * 4;
+  const long long lm = m0 + lrow;
+  const bool lm_ok = lm < M;
+  int lb = 0, loy = 0, lox = 0;
+  if (lm_ok) {
+    lox = (int)(lm % g.OW);
+    loy = (int)((lm / g.OW) % g.OH);
+    lb = (int)(lm / ((long long)g.OW * g.OH));
+  }
+  const int ln = n0 + lrow;
+  const bool ln_ok = ln < g.Cout;
+
+  // compute mapping: 16x16 threads, 4x4 micro tile
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += DK) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + lk + j;
+      float av = 0.f, bv = 0.f;
+      if (k < K) {
+        const int tap = k / g.Cin, c = k - tap * g.Cin;
+        if (lm_ok) {
+          const int r = tap / g.S, s = tap - r * g.S;
+          const int iy = loy * g.stride - g.pad_t + r * g.dil;
+          const int ix = lox * g.stride - g.pad_l + s * g.dil;
+          if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W) {
+            const long long off = (((long long)lb * g.H + iy) * g.W + ix) * g.in_ld + c;
+            if (STEM)
+              av = __fsub_rn(reinterpret_cast<const float*>(in_)[off], g.mean[c]);
+            else
+              av = Elem<T>::ld(reinterpret_cast<const T*>(in_) + off);
+          }
+        }
+        if (ln_ok) bv = Elem<T>::ld(wgt + ((long long)ln * g.R * g.S + tap) * g.w_ld + c);
+      }
+      As[lk + j][lrow] = av;
+      Bs[lk + j][lrow] = bv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < DK; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  const int ohw = g.OH * g.OW;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    const int b = (int)(m / ohw), pix = (int)(m - (long long)b * ohw);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < g.Cout) epi_store_one<T>(e, b, pix, n, acc[i][j]);
+    }
+  }
+}
+
+template <bool STEM>
+static int launch_direct(const void* in, const void* w, int dtype, const odt_conv_params* p,
+                         const float* mean, cudaStream_t st) {
+  DirectGeom g;
+  g.B = p->B; g.H = p->H; g.W = p->W; g.Cin = p->Cin; g.in_ld = p->in_ld;
+  g.OH = p->OH; g.OW = p->OW; g.Cout = p->Cout; g.R = p->R; g.S = p->S;
+  g.stride = p->stride; g.dil = p->dil; g.pad_t = p->pad_t; g.pad_l = p->pad_l; g.w_ld = p->w_ld;
+  g.mean[0] = mean ? mean[0] : 0.f;
+  g.mean[1] = mean ? mean[1] : 0.f;
+  g.mean[2] = mean ? mean[2] : 0.f;
+  Epi e = make_epi(*p);
+  long long M = (long long)p->B * p->OH * p->OW;
+  dim3 grid((unsigned)((M + DM - 1) / DM), (unsigned)((p->Cout + DN - 1) / DN));
+  if (dtype == ODT_F16)
+    conv_direct_kernel<__half, STEM><<<grid, DTHREADS, 0, st>>>(in, (const __half*)w, g, e);
+  else
+    conv_direct_kernel<float, STEM><<<grid, DTHREADS, 0, st>>>(in, (const float*)w, g, e);
+  return ODT_OK;
+}
+
+}  // namespace odt
+
+using namespace odt;
+
+extern "C" int odt_conv2d_direct(const void* in, const void* weights, int dtype,
+                                 const odt_conv_params* p, void* stream) {
+  int rc = check_conv_params(p);
+  if (rc) return rc;
+  ODT_CHECK_ARG(in && weights, "null tensor");
+  ODT_CHECK_ARG(dtype == ODT_F16 || dtype == ODT_F32, "dtype");
+  launch_direct<false>(in, weights, dtype, p, nullptr, (cudaStream_t)stream);
+  ODT_LAUNCH_OK();
+  return ODT_OK;
+}
+
+extern "C" int odt_conv2d_stem(const float* images, const float* mean3_host, const void* weights,
+                               int dtype, const odt_conv_params* p, void* stream) {
+  int rc = check_conv_params(p);
+  if (rc) return rc;
+  ODT_CHECK_ARG(images && weights && mean3_host, "null tensor");
+  ODT_CHECK_ARG(p->Cin == 3, "stem expects Cin == 3");
+  ODT_CHECK_ARG(dtype == ODT_F16 || dtype == ODT_F32, "dtype");
+  launch_direct<true>(images, weights, dtype, p, mean3_host, (cudaStream_t)stream);
+  ODT_LAUNCH_OK();
+  return ODT_OK;
+}

@@ -1,0 +1,525 @@
+// tcgen05 / TMA implicit-GEMM forward convolution for sm_100a.
+//
+//   D[m, n] = sum_{r,s,c} X[b, p*stride - pad + r*dil, q*stride - pad + s*dil, c] * W[n, r, s, c]
+//   m = (b, p, q) linearised over B*OH*OW, fp16 operands, fp32 accumulation in TMEM.
+//
+// * A operand (activations, NHWC): one im2col-mode TMA load per (filter tap,
+//   64-channel chunk) brings a [128 pixels x 64 channels] slab -- 128 consecutive
+//   output pixels in B*OH*OW order, wrapping across rows and images, zero-filled
+//   where the tap falls into the SAME padding -- into 128B-swizzled shared memory.
+// * B operand (weights, KRSC = K-major): one tiled TMA load [BN x 64].
+// * MMA: tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN(<=256), K=16, issued by
+//   one thread; accumulators double-buffered in TMEM (2 x 256 columns) so the
+//   epilogue of tile i overlaps the MMAs of tile i+1.
+// * Epilogue: tcgen05.ld -> folded bias/BN scale+shift, activation, residual,
+//   optional second (pre-activated) output -> 128-bit global stores.
+// * Persistent: one CTA per SM, static round-robin tile schedule, warp roles:
+//   w0 = TMA producer, w1 = TMEM allocator + MMA issuer, w2..5 = epilogue.
+//
+// ref call sites: tf.nn.conv2d SSD300.py:519; tf.layers.conv2d SSD300.py:524,
+// RetinaNet.py:579,599,609, YOLOv3.py:495, FCOS.py:449,469,479.
+#include <cuda.h>
+
+#include "epilogue.cuh"
+
+namespace odt {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;
+constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KiB
+constexpr int TC_SMEM_LIMIT = 232448;          // 227 KiB
+
+struct TcGeom {
+  long long M;  // B*OH*OW
+  int OH, OW, ohw;
+  int R, S, stride, dil;
+  int lower_w, lower_h;
+  int cchunks;     // in_ld / 64
+  int num_m_tiles, num_n_tiles, BN;
+  int stages;
+  int fast_store;  // 1: fp16 out0, no regroup, 16-byte aligned rows
+};
+
+// ------------------------------------------------------------ PTX wrappers --
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  long long t0 = 0;
+  int spins = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && (++spins & 0x3FF) == 0) {
+      // watchdog: a lost arrival must fail the launch, never hang the GPU
+      long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) __trap();
+    }
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_im2col(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                                int c, int w, int h, int n, uint16_t off_w,
+                                                uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      :
+      : "r"(dst), "l"(map), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                           uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (sm_100 version 1)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);  // start address
+  d |= (uint64_t)1 << 16;                  // LBO (ignored for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;        // SBO: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
+  return d;
+}
+
+// --------------------------------------------------------------- kernel ----
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const __grid_constant__ TcGeom g, const __grid_constant__ Epi e) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve (base rounded up to 1024 for the 128B swizzle atoms)
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const int stages = g.stages;
+  const uint32_t b_bytes = (uint32_t)g.BN * 128u;
+  const uint32_t a_base = base;
+  const uint32_t b_base = base + (uint32_t)stages * TC_A_BYTES;
+  const uint32_t bar_base = b_base + (uint32_t)stages * b_bytes;  // 8-byte aligned
+  // barriers: full[stages], empty[stages], tfull[2], tempty[2], then tmem ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (TC_MAX_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * TC_MAX_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * TC_MAX_STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * TC_MAX_STAGES + 4);
+  uint32_t* tmem_slot_ptr =
+      reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int num_tiles = g.num_m_tiles * g.num_n_tiles;
+  const int kblocks = g.R * g.S * g.cchunks;
+
+  if (warp == 0) {
+    // ===================== TMA producer ======================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % g.num_n_tiles, m_tile = tile / g.num_n_tiles;
+        const long long m0 = (long long)m_tile * TC_BM;
+        const int img = (int)(m0 / g.ohw);
+        const int rem = (int)(m0 - (long long)img * g.ohw);
+        const int p = rem / g.OW, q = rem - p * g.OW;
+        const int cw = q * g.stride + g.lower_w, ch = p * g.stride + g.lower_h;
+        const int n0 = n_tile * g.BN;
+        int kcol = 0;
+        for (int r = 0; r < g.R; ++r) {
+          for (int s = 0; s < g.S; ++s) {
+            for (int cc = 0; cc < g.cchunks; ++cc) {
+              mbar_wait(empty_bar(stage), phase ^ 1u);
+              mbar_expect_tx(full_bar(stage), TC_A_BYTES + b_bytes);
+              tma_load_im2col(a_base + (uint32_t)stage * TC_A_BYTES, &tmA, full_bar(stage),
+                              cc * TC_BK, cw, ch, img, (uint16_t)(s * g.dil),
+                              (uint16_t)(r * g.dil));
+              tma_load_2d(b_base + (uint32_t)stage * b_bytes, &tmB, full_bar(stage), kcol, n0);
+              kcol += TC_BK;
+              if (++stage == stages) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =========================================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=f16, K-major both, N, M=128
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(g.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase[2] = {0u, 0u};
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase[acc] ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint64_t adesc = make_desc_sw128(a_base + (uint32_t)stage * TC_A_BYTES);
+          const uint64_t bdesc = make_desc_sw128(b_base + (uint32_t)stage * b_bytes);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            // advance 16 elements (32 bytes) along K inside the swizzle atom
+            tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                       (uint32_t)((kb | k) != 0));
+          }
+          tc_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        acc_phase[acc] ^= 1u;
+        acc ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase[2] = {0u, 0u};
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_tile = tile % g.num_n_tiles, m_tile = tile / g.num_n_tiles;
+      const long long m = (long long)m_tile * TC_BM + quarter * 32 + lane;
+      const bool row_ok = m < g.M;
+      const int img = row_ok ? (int)(m / g.ohw) : 0;
+      const int pix = row_ok ? (int)(m - (long long)img * g.ohw) : 0;
+      const int n0 = n_tile * g.BN;
+      mbar_wait(tfull_bar(acc), acc_phase[acc]);
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(quarter * 32) << 16);
+      for (int j = 0; j < g.BN / 32; ++j) {
+        uint32_t r[32];
+        tc_ld32(taddr0 + (uint32_t)(j * 32), r);
+        tc_wait_ld();
+        const int nb = n0 + j * 32;
+        if (nb >= e.Cout) continue;  // fully padded chunk (uniform)
+        if (g.fast_store && nb + 32 <= e.Cout) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float sc = e.scale ? __ldg(e.scale + nb + i) : 1.f;
+            float sh = e.shift ? __ldg(e.shift + nb + i) : 0.f;
+            v[i] = apply_act(fmaf(__uint_as_float(r[i]), sc, sh), e.act);
+          }
+          if (row_ok) {
+            const long long o0 =
+                (long long)img * e.out0_img_stride + (long long)pix * e.out0_pix_stride + nb;
+            if (e.residual) {
+              const uint4* rp =
+                  reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(e.residual) + o0);
+#pragma unroll
+              for (int qd = 0; qd < 4; ++qd) {
+                uint4 t = __ldg(rp + qd);
+                const __half2* h = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  float2 f = __half22float2(h[i]);
+                  v[qd * 8 + 2 * i] += f.x;
+                  v[qd * 8 + 2 * i + 1] += f.y;
+                }
+              }
+            }
+            uint4 packed[4];
+            __half2* ph = reinterpret_cast<__half2*>(packed);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) ph[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+            if (e.out0) {
+              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out0) + o0);
+#pragma unroll
+              for (int qd = 0; qd < 4; ++qd) op[qd] = packed[qd];
+            }
+            if (e.out1) {
+              uint4 packed1[4];
+              __half2* p1 = reinterpret_cast<__half2*>(packed1);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                float2 f = __half22float2(ph[i]);  // consumer sees the rounded value
+                float s0 = e.scale2 ? __ldg(e.scale2 + nb + 2 * i) : 1.f;
+                float s1 = e.scale2 ? __ldg(e.scale2 + nb + 2 * i + 1) : 1.f;
+                float h0 = e.shift2 ? __ldg(e.shift2 + nb + 2 * i) : 0.f;
+                float h1 = e.shift2 ? __ldg(e.shift2 + nb + 2 * i + 1) : 0.f;
+                p1[i] = __floats2half2_rn(apply_act(fmaf(f.x, s0, h0), e.act2),
+                                          apply_act(fmaf(f.y, s1, h1), e.act2));
+              }
+              const long long o1 =
+                  (long long)img * e.out1_img_stride + (long long)pix * e.out1_pix_stride + nb;
+              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out1) + o1);
+#pragma unroll
+              for (int qd = 0; qd < 4; ++qd) op[qd] = packed1[qd];
+            }
+          }
+        } else if (row_ok) {
+          // generic path: fp32 head outputs, channel regrouping, ragged Cout
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int n = nb + i;
+            if (n < e.Cout) epi_store_one<__half>(e, img, pix, n, __uint_as_float(r[i]));
+          }
+        }
+      }
+      // release the accumulator buffer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      acc_phase[acc] ^= 1u;
+      acc ^= 1;
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ----------------------------------------------------- host: tensor maps ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                   const cuuint64_t*, const cuuint64_t*, const int*, const int*,
+                                   cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn g_encode_tiled = nullptr;
+static EncodeIm2colFn g_encode_im2col = nullptr;
+
+static int resolve_driver() {
+  if (g_encode_tiled && g_encode_im2col) return ODT_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  ODT_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  if (!fn || q != cudaDriverEntryPointSuccess) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return ODT_ERR_CUDA;
+  }
+  g_encode_tiled = (EncodeTiledFn)fn;
+  fn = nullptr;
+  ODT_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q));
+  if (!fn || q != cudaDriverEntryPointSuccess) {
+    set_error("cuTensorMapEncodeIm2col not available from the driver");
+    return ODT_ERR_CUDA;
+  }
+  g_encode_im2col = (EncodeIm2colFn)fn;
+  return ODT_OK;
+}
+
+int check_conv_params(const odt_conv_params* p) {
+  ODT_CHECK_ARG(p != nullptr, "params null");
+  ODT_CHECK_ARG(p->B > 0 && p->H > 0 && p->W > 0 && p->Cin > 0 && p->in_ld >= p->Cin,
+                "input geometry");
+  ODT_CHECK_ARG(p->OH > 0 && p->OW > 0 && p->Cout > 0, "output geometry");
+  ODT_CHECK_ARG(p->R > 0 && p->S > 0 && p->stride > 0 && p->dil > 0, "filter geometry");
+  ODT_CHECK_ARG(p->w_ld >= p->Cin && p->Cout_pad >= p->Cout, "weight geometry");
+  ODT_CHECK_ARG(p->out0 || p->out1, "no output");
+  ODT_CHECK_ARG(p->act >= 0 && p->act <= 2 && p->act2 >= 0 && p->act2 <= 2, "activation code");
+  ODT_CHECK_ARG(p->out0_dtype == ODT_F16 || p->out0_dtype == ODT_F32, "out0 dtype");
+  return ODT_OK;
+}
+
+}  // namespace odt
+
+using namespace odt;
+
+static int pick_bn(int cout_pad) {
+  // largest N tile <= 256 that divides the padded Cout into equal 32-multiples
+  if (cout_pad <= 256) return cout_pad;
+  for (int bn = 256; bn >= 32; bn -= 32)
+    if (cout_pad % bn == 0) return bn;
+  return 256;
+}
+
+extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_conv_params* p,
+                                 void* stream) {
+  int rc = check_conv_params(p);
+  if (rc) return rc;
+  ODT_CHECK_ARG(in && weights, "null tensor");
+  ODT_CHECK_ARG(p->in_ld % 64 == 0, "in_ld must be a multiple of 64 for the tensor-core path");
+  ODT_CHECK_ARG(p->w_ld == p->in_ld, "w_ld must equal in_ld");
+  ODT_CHECK_ARG(p->Cout_pad % 32 == 0, "Cout_pad must be a multiple of 32");
+  ODT_CHECK_ARG(((uintptr_t)in & 15) == 0 && ((uintptr_t)weights & 15) == 0, "16-byte alignment");
+  ODT_CHECK_ARG(p->stride <= 8, "stride > 8 unsupported by TMA traversal stride");
+  rc = resolve_driver();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+
+  // TF SAME upper pads
+  const int pad_b = max((p->OH - 1) * p->stride + (p->R - 1) * p->dil + 1 - p->H, 0) - p->pad_t;
+  const int pad_r = max((p->OW - 1) * p->stride + (p->S - 1) * p->dil + 1 - p->W, 0) - p->pad_l;
+  ODT_CHECK_ARG(pad_b >= 0 && pad_r >= 0, "pad_t/pad_l exceed the SAME total");
+
+  TcGeom g;
+  g.M = (long long)p->B * p->OH * p->OW;
+  g.OH = p->OH;
+  g.OW = p->OW;
+  g.ohw = p->OH * p->OW;
+  g.R = p->R;
+  g.S = p->S;
+  g.stride = p->stride;
+  g.dil = p->dil;
+  g.lower_w = -p->pad_l;
+  g.lower_h = -p->pad_t;
+  g.cchunks = p->in_ld / 64;
+  g.BN = pick_bn(p->Cout_pad);
+  g.num_m_tiles = (int)((g.M + TC_BM - 1) / TC_BM);
+  g.num_n_tiles = (p->Cout_pad + g.BN - 1) / g.BN;
+  const int stage_bytes = TC_A_BYTES + g.BN * 128;
+  int stages = (TC_SMEM_LIMIT - 2048) / stage_bytes;
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  ODT_CHECK_ARG(stages >= 2, "tile too large for shared memory");
+  g.stages = stages;
+  g.fast_store = (p->out0_dtype == ODT_F16 || !p->out0) && p->out0_group == 0 &&
+                 (p->out0_pix_stride % 8 == 0) && (p->out0_img_stride % 8 == 0) &&
+                 (!p->out0 || ((uintptr_t)p->out0 & 15) == 0) &&
+                 (!p->residual || ((uintptr_t)p->residual & 15) == 0) &&
+                 (!p->out1 || (((uintptr_t)p->out1 & 15) == 0 && p->out1_pix_stride % 8 == 0 &&
+                               p->out1_img_stride % 8 == 0));
+  if (!p->out0 && p->out1) {
+    // out1-only: address math of the fast path still uses out0 strides for the residual
+    ODT_CHECK_ARG(!p->residual, "residual requires out0 addressing");
+  }
+
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)p->in_ld, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->B};
+    cuuint64_t strides[3] = {(cuuint64_t)p->in_ld * 2, (cuuint64_t)p->W * p->in_ld * 2,
+                             (cuuint64_t)p->H * p->W * p->in_ld * 2};
+    int lower[2] = {-p->pad_l, -p->pad_t};
+    int upper[2] = {pad_r - (p->S - 1) * p->dil, pad_b - (p->R - 1) * p->dil};
+    cuuint32_t estr[4] = {1, (cuuint32_t)p->stride, (cuuint32_t)p->stride, 1};
+    CUresult cr = g_encode_im2col(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(in),
+                                  dims, strides, lower, upper, TC_BK, TC_BM, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeIm2col failed (%d): dims %d %d %d %d lower %d %d upper %d %d stride %d",
+                (int)cr, p->in_ld, p->W, p->H, p->B, lower[0], lower[1], upper[0], upper[1], p->stride);
+      return ODT_ERR_CUDA;
+    }
+  }
+  {
+    const cuuint64_t ktot = (cuuint64_t)p->R * p->S * p->w_ld;
+    cuuint64_t dims[2] = {ktot, (cuuint64_t)p->Cout_pad};
+    cuuint64_t strides[1] = {ktot * 2};
+    cuuint32_t box[2] = {TC_BK, (cuuint32_t)g.BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult cr = g_encode_tiled(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                                 const_cast<void*>(weights), dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(weights) failed (%d)", (int)cr);
+      return ODT_ERR_CUDA;
+    }
+  }
+
+  const int smem = stages * stage_bytes + 2048;
+  static int smem_set = 0;
+  if (smem_set < smem) {
+    ODT_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     TC_SMEM_LIMIT));
+    smem_set = TC_SMEM_LIMIT;
+  }
+  Epi e = make_epi(*p);
+  const int num_tiles = g.num_m_tiles * g.num_n_tiles;
+  const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
+  conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, g, e);
+  ODT_LAUNCH_OK();
+  return ODT_OK;
+}

@@ -1,0 +1,485 @@
+// HBM-bound glue kernels between the convolutions (NHWC, fp16 or fp32 storage,
+// fp32 math): input normalisation, SAME max-pool, channel L2-norm, per-channel
+// affine+activation, legacy bilinear / nearest up-sampling, GroupNorm.
+// 128-bit vectorised along C whenever C and the channel stride allow it.
+#include "common.cuh"
+
+namespace odt {
+
+// ---- 16-byte vector access helpers ---------------------------------------
+template <typename T, int V>
+struct VecIO;
+template <>
+struct VecIO<float, 1> {
+  static __device__ __forceinline__ void ld(const float* p, float* v) { v[0] = *p; }
+  static __device__ __forceinline__ void st(float* p, const float* v) { *p = v[0]; }
+};
+template <>
+struct VecIO<__half, 1> {
+  static __device__ __forceinline__ void ld(const __half* p, float* v) { v[0] = __half2float(*p); }
+  static __device__ __forceinline__ void st(__half* p, const float* v) { *p = __float2half_rn(v[0]); }
+};
+template <>
+struct VecIO<float, 4> {
+  static __device__ __forceinline__ void ld(const float* p, float* v) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void st(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <>
+struct VecIO<__half, 8> {
+  static __device__ __forceinline__ void ld(const __half* p, float* v) {
+    uint4 t = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = __half22float2(h[i]);
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ void st(__half* p, const float* v) {
+    uint4 t;
+    __half2* h = reinterpret_cast<__half2*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = t;
+  }
+};
+template <typename T>
+struct FullVec;
+template <>
+struct FullVec<float> {
+  static constexpr int V = 4;
+};
+template <>
+struct FullVec<__half> {
+  static constexpr int V = 8;
+};
+
+static inline bool can_vec(const void* a, const void* b, int C, int ld, int V, int esize) {
+  return C % V == 0 && ld % V == 0 && ((uintptr_t)a % 16) == 0 && ((uintptr_t)b % 16) == 0 &&
+         V * esize == 16;
+}
+
+static inline int grid_for(long long work, int threads) {
+  long long b = (work + threads - 1) / threads;
+  long long cap = (long long)kNumSMs * 16;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+// ---- input normalisation (a1) ---------------------------------------------
+template <typename T>
+__global__ void normalize_kernel(const float* __restrict__ img, T* __restrict__ out,
+                                 long long pixels, int ld, float m0, float m1, float m2) {
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < pixels;
+       p += (long long)gridDim.x * blockDim.x) {
+    const float* s = img + p * 3;
+    T* d = out + p * ld;
+    Elem<T>::st(d + 0, __fsub_rn(s[0], m0));
+    Elem<T>::st(d + 1, __fsub_rn(s[1], m1));
+    Elem<T>::st(d + 2, __fsub_rn(s[2], m2));
+    for (int c = 3; c < ld; ++c) Elem<T>::st(d + c, 0.f);
+  }
+}
+
+// ---- max pool, TF SAME (a4) -------------------------------------------------
+template <typename T, int V>
+__global__ void maxpool_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int H, int W,
+                               int OH, int OW, int C, int ld, int k, int stride, int pt, int pl) {
+  const int cv = C / V;
+  const long long total = (long long)B * OH * OW * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % cv) * V;
+    long long pix = i / cv;
+    int ox = (int)(pix % OW);
+    int oy = (int)((pix / OW) % OH);
+    int b = (int)(pix / ((long long)OW * OH));
+    float m[V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) m[q] = -INFINITY;
+    for (int r = 0; r < k; ++r) {
+      int iy = oy * stride - pt + r;
+      if (iy < 0 || iy >= H) continue;
+      for (int s = 0; s < k; ++s) {
+        int ix = ox * stride - pl + s;
+        if (ix < 0 || ix >= W) continue;
+        float v[V];
+        VecIO<T, V>::ld(in + (((long long)b * H + iy) * W + ix) * ld + c, v);
+#pragma unroll
+        for (int q = 0; q < V; ++q) m[q] = fmaxf(m[q], v[q]);
+      }
+    }
+    VecIO<T, V>::st(out + pix * ld + c, m);
+  }
+}
+
+// ---- conv4_3 L2 normalisation x learned scale (a5) -------------------------
+template <typename T>
+__global__ void l2norm_kernel(const T* __restrict__ in, T* __restrict__ out, long long pixels,
+                              int C, int ld, float gamma) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long p = warp; p < pixels; p += nwarps) {
+    const T* s = in + p * ld;
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      float v = Elem<T>::ld(s + c);
+      acc = fmaf(v, v, acc);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    float rs = __frsqrt_rn(fmaxf(acc, 1e-12f));
+    T* d = out + p * ld;
+    for (int c = lane; c < C; c += 32)
+      Elem<T>::st(d + c, __fmul_rn(gamma, __fmul_rn(Elem<T>::ld(s + c), rs)));
+  }
+}
+
+// ---- y = act(x*scale[c]+shift[c]) ------------------------------------------
+template <typename T, int V>
+__global__ void affine_act_kernel(const T* __restrict__ in, T* __restrict__ out, long long pixels,
+                                  int C, int ld, const float* __restrict__ scale,
+                                  const float* __restrict__ shift, int act) {
+  const int cv = C / V;
+  const long long total = pixels * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % cv) * V;
+    long long p = i / cv;
+    float v[V];
+    VecIO<T, V>::ld(in + p * ld + c, v);
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+      float sc = scale ? __ldg(scale + c + q) : 1.f;
+      float sh = shift ? __ldg(shift + c + q) : 0.f;
+      v[q] = apply_act(fmaf(v[q], sc, sh), act);
+    }
+    VecIO<T, V>::st(out + p * ld + c, v);
+  }
+}
+
+// ---- FPN: out = a + legacy bilinear(top) (a16) ------------------------------
+template <typename T, int V>
+__global__ void upsample_bilinear_add_kernel(const T* __restrict__ top, const T* __restrict__ a,
+                                             T* __restrict__ out, int B, int TH, int TW, int H,
+                                             int W, int C, int ld, float hs, float ws,
+                                             const float* __restrict__ scale2,
+                                             const float* __restrict__ shift2, int act2,
+                                             T* __restrict__ out1) {
+  const int cv = C / V;
+  const long long total = (long long)B * H * W * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % cv) * V;
+    long long pix = i / cv;
+    int x = (int)(pix % W);
+    int y = (int)((pix / W) % H);
+    int b = (int)(pix / ((long long)W * H));
+    // TF1 resize_bilinear, align_corners=False: src = dst*scale (App. A.6)
+    float sy = __fmul_rn((float)y, hs), sx = __fmul_rn((float)x, ws);
+    int y0 = (int)floorf(sy), x0 = (int)floorf(sx);
+    int y1 = min((int)ceilf(sy), TH - 1), x1 = min((int)ceilf(sx), TW - 1);
+    float ly = __fsub_rn(sy, (float)y0), lx = __fsub_rn(sx, (float)x0);
+    float tl[V], tr[V], bl[V], br[V], av[V], o[V];
+    const T* tb = top + (long long)b * TH * TW * ld + c;
+    VecIO<T, V>::ld(tb + ((long long)y0 * TW + x0) * ld, tl);
+    VecIO<T, V>::ld(tb + ((long long)y0 * TW + x1) * ld, tr);
+    VecIO<T, V>::ld(tb + ((long long)y1 * TW + x0) * ld, bl);
+    VecIO<T, V>::ld(tb + ((long long)y1 * TW + x1) * ld, br);
+    VecIO<T, V>::ld(a + pix * ld + c, av);
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+      float t = __fadd_rn(tl[q], __fmul_rn(__fsub_rn(tr[q], tl[q]), lx));
+      float bt = __fadd_rn(bl[q], __fmul_rn(__fsub_rn(br[q], bl[q]), lx));
+      float r = __fadd_rn(t, __fmul_rn(__fsub_rn(bt, t), ly));
+      o[q] = __fadd_rn(av[q], r);
+    }
+    VecIO<T, V>::st(out + pix * ld + c, o);
+    if (out1) {
+#pragma unroll
+      for (int q = 0; q < V; ++q) {
+        float sc = scale2 ? __ldg(scale2 + c + q) : 1.f;
+        float sh = shift2 ? __ldg(shift2 + c + q) : 0.f;
+        // the consumer sees the stored (rounded) sum
+        float stored = Elem<T>::ld(out + pix * ld + c + q);
+        o[q] = apply_act(fmaf(stored, sc, sh), act2);
+      }
+      VecIO<T, V>::st(out1 + pix * ld + c, o);
+    }
+  }
+}
+
+// ---- YOLOv3: concat([a, nearest(b)]) (a18) ----------------------------------
+template <typename T>
+__global__ void upsample_nearest_concat_kernel(const T* __restrict__ a, const T* __restrict__ bsrc,
+                                               T* __restrict__ out, int B, int H, int W, int Ca,
+                                               int lda, int BH, int BW, int Cb, int ldb, int ldo,
+                                               float hs, float ws) {
+  const int CT = Ca + Cb;
+  const long long total = (long long)B * H * W * CT;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % CT);
+    long long pix = i / CT;
+    int x = (int)(pix % W);
+    int y = (int)((pix / W) % H);
+    int b = (int)(pix / ((long long)W * H));
+    T v;
+    if (c < Ca) {
+      v = a[pix * lda + c];
+    } else {
+      int sy = min((int)floorf(__fmul_rn((float)y, hs)), BH - 1);
+      int sx = min((int)floorf(__fmul_rn((float)x, ws)), BW - 1);
+      v = bsrc[(((long long)b * BH + sy) * BW + sx) * ldb + (c - Ca)];
+    }
+    out[pix * ldo + c] = v;
+  }
+}
+
+// ---- GroupNorm (a19) --------------------------------------------------------
+// stats[b][g] = (mean, rsqrt(var+eps)); two-pass like tf.nn.moments.
+template <typename T>
+__global__ void groupnorm_stats_kernel(const T* __restrict__ in, float* __restrict__ stats,
+                                       long long hw, int C, int ld, int groups, float eps) {
+  const int g = blockIdx.x, b = blockIdx.y;
+  const int cpg = C / groups;
+  const T* base = in + (long long)b * hw * ld + g * cpg;
+  const long long n = hw * cpg;
+  __shared__ float red[32];
+  __shared__ float s_mean;
+  float acc = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x)
+    acc += Elem<T>::ld(base + (i / cpg) * ld + (i % cpg));
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) s_mean = v / (float)n;
+  }
+  __syncthreads();
+  const float mean = s_mean;
+  acc = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    float d = Elem<T>::ld(base + (i / cpg) * ld + (i % cpg)) - mean;
+    acc = fmaf(d, d, acc);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) {
+      float var = v / (float)n;
+      stats[((long long)b * groups + g) * 2 + 0] = mean;
+      stats[((long long)b * groups + g) * 2 + 1] = __frsqrt_rn(var + eps);
+    }
+  }
+}
+
+template <typename T, int V>
+__global__ void groupnorm_apply_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                       const float* __restrict__ stats, int B, long long hw, int C,
+                                       int ld, int groups, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, int act) {
+  const int cv = C / V;
+  const int cpg = C / groups;
+  const long long total = (long long)B * hw * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % cv) * V;
+    long long pix = i / cv;
+    int b = (int)(pix / hw);
+    float v[V];
+    VecIO<T, V>::ld(in + pix * ld + c, v);
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+      int g = (c + q) / cpg;
+      float mean = __ldg(stats + ((long long)b * groups + g) * 2);
+      float rstd = __ldg(stats + ((long long)b * groups + g) * 2 + 1);
+      // tf.contrib group_norm: gain = rstd*gamma; offset = -mean*gain + beta
+      float gm = gamma ? __ldg(gamma + c + q) : 1.f;
+      float bt = beta ? __ldg(beta + c + q) : 0.f;
+      float gain = __fmul_rn(rstd, gm);
+      float off = __fadd_rn(__fmul_rn(-mean, gain), bt);
+      v[q] = apply_act(__fadd_rn(__fmul_rn(v[q], gain), off), act);
+    }
+    VecIO<T, V>::st(out + pix * ld + c, v);
+  }
+}
+
+}  // namespace odt
+
+using namespace odt;
+
+#define DISPATCH_DTYPE(dtype, ...)              \
+  if ((dtype) == ODT_F16) {                     \
+    using T = __half;                           \
+    __VA_ARGS__                                 \
+  } else if ((dtype) == ODT_F32) {              \
+    using T = float;                            \
+    __VA_ARGS__                                 \
+  } else {                                      \
+    odt::set_error("%s: bad dtype", __func__);  \
+    return ODT_ERR_INVALID;                     \
+  }
+
+extern "C" int odt_normalize_input(const float* images, void* out, int out_dtype, int B, int H,
+                                   int W, int out_ld, const float* mean3_host, void* stream) {
+  ODT_CHECK_ARG(images && out && mean3_host && B > 0 && H > 0 && W > 0 && out_ld >= 3, "args");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long pixels = (long long)B * H * W;
+  DISPATCH_DTYPE(out_dtype, {
+    normalize_kernel<T><<<grid_for(pixels, 256), 256, 0, st>>>(
+        images, (T*)out, pixels, out_ld, mean3_host[0], mean3_host[1], mean3_host[2]);
+  })
+  ODT_LAUNCH_OK();
+  return ODT_OK;
+}
+
+extern "C" int odt_maxpool(const void* in, void* out, int dtype, int B, int H, int W, int C,
+                           int ld, int k, int stride, void* stream) {
+  ODT_CHECK_ARG(in && out && B > 0 && H > 0 && W > 0 && C > 0 && ld >= C && k > 0 && stride > 0,
+                "args");
+  int OH, OW, pt, pl, pa;
+  odt_same_pad(H, k, stride, 1, &OH, &pt, &pa);
+  odt_same_pad(W, k, stride, 1, &OW, &pl, &pa);
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_DTYPE(dtype, {
+    constexpr int V = FullVec<T>::V;
+    if (can_vec(in, out, C, ld, V, sizeof(T))) {
+      long long work = (long long)B * OH * OW * (C / V);
+      maxpool_kernel<T, V><<<grid_for(work, 256), 256, 0, st>>>((const T*)in, (T*)out, B, H, W, OH,
+                                                               OW, C, ld, k, stride, pt, pl);
+    } else {
+      long long work = (long long)B * OH * OW * C;
+      maxpool_kernel<T, 1><<<grid_for(work, 256), 256, 0, st>>>((const T*)in, (T*)out, B, H, W, OH,
+                                                               OW, C, ld, k, stride, pt, pl);
+    }
+  })
+  ODT_LAUNCH_OK();
+  return ODT_OK;
+}
+
+extern "C" int odt_l2norm_scale(const void* in, void* out, int dtype, long long pixels, int C,
+                                int ld, float gamma, void* stream) {
+  ODT_CHECK_ARG(in && out && pixels > 0 && C > 0 && ld >= C, "args");
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_DTYPE(dtype, {
+    l2norm_kernel<T><<<grid_for(pixels * 32, 256), 256, 0, st>>>((const T*)in, (T*)out, pixels, C,
+                                                               ld, gamma);
+  })
+  ODT_LAUNCH_OK();
+  return ODT_OK;
+}
+
+extern "C" int odt_affine_act(const void* in, void* out, int dtype, long long pixels, int C, int ld,
+                              const float* scale, const float* shift, int act, void* stream) {
+  ODT_CHECK_ARG(in && out && pixels > 0 && C > 0 && ld >= C, "args");
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_DTYPE(dtype, {
+    constexpr int V = FullVec<T>::V;
+    if (can_vec(in, out, C, ld, V, sizeof(T))) {
+      affine_act_kernel<T, V><<<grid_for(pixels * (C / V), 256), 256, 0, st>>>(
+          (const T*)in, (T*)out, pixels, C, ld, scale, shift, act);
+    } else {
+      affine_act_kernel<T, 1><<<grid_for(pixels * C, 256), 256, 0, st>>>(
+          (const T*)in, (T*)out, pixels, C, ld, scale, shift, act);
+    }
+  })
+  ODT_LAUNCH_OK();
+  return ODT_OK;
+}
+
+extern "C" int odt_upsample_bilinear_add(const void* top, const void* a, void* out, int dtype,
+                                         int B, int TH, int TW, int H, int W, int C, int ld,
+                                         const float* scale2, const float* shift2, int act2,
+                                         void* out1, void* stream) {
+  ODT_CHECK_ARG(top && a && out && B > 0 && TH > 0 && TW > 0 && H > 0 && W > 0 && C > 0 && ld >= C,
+                "args");
+  cudaStream_t st = (cudaStream_t)stream;
+  float hs = (float)TH / (float)H, ws = (float)TW / (float)W;
+  DISPATCH_DTYPE(dtype, {
+    constexpr int V = FullVec<T>::V;
+    bool vec = can_vec(top, a, C, ld, V, sizeof(T)) && can_vec(out, out1 ? out1 : out, C, ld, V, sizeof(T));
+    if (vec) {
+      long long work = (long long)B * H * W * (C / V);
+      upsample_bilinear_add_kernel<T, V><<<grid_for(work, 256), 256, 0, st>>>(
+          (const T*)top, (const T*)a, (T*)out, B, TH, TW, H, W, C, ld, hs, ws, scale2, shift2, act2,
+          (T*)out1);
+    } else {
+      long long work = (long long)B * H * W * C;
+      upsample_bilinear_add_kernel<T, 1><<<grid_for(work, 256), 256, 0, st>>>(
+          (const T*)top, (const T*)a, (T*)out, B, TH, TW, H, W, C, ld, hs, ws, scale2, shift2, act2,
+          (T*)out1);
+    }
+  })
+  ODT_LAUNCH_OK();
+  return ODT_OK;
+}
+
+extern "C" int odt_upsample_nearest_concat(const void* a, const void* b, void* out, int dtype,
+                                           int B, int H, int W, int Ca, int lda, int BH, int BW,
+                                           int Cb, int ldb, int ldo, void* stream) {
+  ODT_CHECK_ARG(a && b && out && B > 0 && H > 0 && W > 0 && Ca > 0 && Cb > 0 && lda >= Ca &&
+                    ldb >= Cb && ldo >= Ca + Cb,
+                "args");
+  cudaStream_t st = (cudaStream_t)stream;
+  float hs = (float)BH / (float)H, ws = (float)BW / (float)W;
+  long long work = (long long)B * H * W * (Ca + Cb);
+  DISPATCH_DTYPE(dtype, {
+    upsample_nearest_concat_kernel<T><<<grid_for(work, 256), 256, 0, st>>>(
+        (const T*)a, (const T*)b, (T*)out, B, H, W, Ca, lda, BH, BW, Cb, ldb, ldo, hs, ws);
+  })
+  ODT_LAUNCH_OK();
+  return ODT_OK;
+}
+
+extern "C" int odt_groupnorm_stats(const void* in, float* stats, int dtype, int B, long long hw,
+                                   int C, int ld, int groups, float eps, void* stream) {
+  ODT_CHECK_ARG(in && stats && B > 0 && hw > 0 && C > 0 && ld >= C && groups > 0 && C % groups == 0,
+                "args");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(groups, B);
+  DISPATCH_DTYPE(dtype, {
+    groupnorm_stats_kernel<T><<<grid, 1024, 0, st>>>((const T*)in, stats, hw, C, ld, groups, eps);
+  })
+  ODT_LAUNCH_OK();
+  return ODT_OK;
+}
+
+extern "C" int odt_groupnorm_apply(const void* in, void* out, const float* stats, int dtype, int B,
+                                   long long hw, int C, int ld, int groups, const float* gamma,
+                                   const float* beta, int act, void* stream) {
+  ODT_CHECK_ARG(in && out && stats && B > 0 && hw > 0 && C > 0 && ld >= C && groups > 0 &&
+                    C % groups == 0,
+                "args");
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_DTYPE(dtype, {
+    constexpr int V = FullVec<T>::V;
+    if (can_vec(in, out, C, ld, V, sizeof(T))) {
+      long long work = (long long)B * hw * (C / V);
+      groupnorm_apply_kernel<T, V><<<grid_for(work, 256), 256, 0, st>>>(
+          (const T*)in, (T*)out, stats, B, hw, C, ld, groups, gamma, beta, act);
+    } else {
+      long long work = (long long)B * hw * C;
+      groupnorm_apply_kernel<T, 1><<<grid_for(work, 256), 256, 0, st>>>(
+          (const T*)in, (T*)out, stats, B, hw, C, ld, groups, gamma, beta, act);
+    }
+  })
+  ODT_LAUNCH_OK();
+  return ODT_OK;
+}

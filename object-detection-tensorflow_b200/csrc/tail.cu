@@ -1,0 +1,373 @@
+// Inference tail of the five detectors on sm_100a: score activation, analytic
+// anchor/prior generation, box decode, thresholding, candidate compaction and
+// exact per-class TF NonMaxSuppressionV3.
+//
+// All arithmetic that feeds a discrete decision (class id, keep index) is done
+// with explicitly rounded fp32 intrinsics (__fmul_rn/__fadd_rn/__fdiv_rn), in
+// the operation order of the reference graphs, so no FMA contraction can change
+// a result relative to the TF1.13 CPU kernels.
+//
+// Reference call sites restated here (never copied): SSD300.py:157-190,323-343;
+// RetinaNet.py:224-256,328-355; YOLOv3.py:320-368,419-433; FCOS.py:130-150,197-264.
+#include "tail_common.cuh"
+
+namespace odt {
+
+constexpr int kDecodeWarps = 8;
+
+// One warp = 32 consecutive candidate rows (3200 contiguous bytes), staged
+// through shared memory with 128-bit loads, then one lane per row.
+__global__ void __launch_bounds__(kDecodeWarps * 32)
+    decode_candidates_kernel(const float* __restrict__ head, const __grid_constant__ TailP tp,
+                             long long total_rows, unsigned long long* __restrict__ cand_keys,
+                             int* __restrict__ cand_count) {
+  const odt_tail_params& p = tp.p;
+  __shared__ __align__(16) float srow[kDecodeWarps][32 * kRow];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* my = srow[warp];
+  const long long warps_total = (long long)gridDim.x * kDecodeWarps;
+  const long long groups = (total_rows + 31) / 32;
+  for (long long g = (long long)blockIdx.x * kDecodeWarps + warp; g < groups; g += warps_total) {
+    const long long row0 = g * 32;
+    const int nrows = (int)min((long long)32, total_rows - row0);
+    const float* src = head + row0 * kRow;
+    // row0*25 floats: 32-row groups start at a multiple of 800 floats = 3200 B -> 16 B aligned
+    const int nvec = nrows * kRow / 4;
+    const float4* src4 = reinterpret_cast<const float4*>(src);
+    float4* dst4 = reinterpret_cast<float4*>(my);
+    for (int i = lane; i < nvec; i += 32) dst4[i] = __ldg(src4 + i);
+    for (int i = nvec * 4 + lane; i < nrows * kRow; i += 32) my[i] = __ldg(src + i);
+    __syncwarp();
+
+    const bool active = lane < nrows;
+    const long long row = row0 + lane;
+    const int b = active ? (int)(row / p.N) : 0;
+    const int n = active ? (int)(row % p.N) : 0;
+    const float* r = my + lane * kRow;
+    float conf[20];
+    bool keep_row = active;
+    if (p.kind == ODT_DECODE_SSD) {
+      // softmax over 21 logits, TF form exp(x-max) * (1/sum); argmax first-max; drop
+      // rows whose argmax is background (last index).  ref SSD300.py:159-164
+      float m = r[0];
+#pragma unroll
+      for (int i = 1; i < 21; ++i) m = fmaxf(m, r[i]);
+      float e[21];
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 21; ++i) {
+        e[i] = expf(__fsub_rn(r[i], m));
+        s = __fadd_rn(s, e[i]);
+      }
+      float inv = __fdiv_rn(1.f, s);
+      float best = -1.f;
+      int arg = 0;
+#pragma unroll
+      for (int i = 0; i < 21; ++i) {
+        float pi = __fmul_rn(e[i], inv);
+        if (pi > best) {
+          best = pi;
+          arg = i;
+        }
+        if (i < 20) conf[i] = pi;
+      }
+      keep_row = keep_row && (arg < 20);
+    } else if (p.kind == ODT_DECODE_YOLO3) {
+      float so = sigmoid_rn(r[24]);  // ref YOLOv3.py:338-339,349
+#pragma unroll
+      for (int i = 0; i < 20; ++i) conf[i] = __fmul_rn(sigmoid_rn(r[i]), so);
+    } else {
+      float sc = sigmoid_rn(r[20]);  // ref FCOS.py:197-201
+#pragma unroll
+      for (int i = 0; i < 20; ++i) conf[i] = __fmul_rn(sigmoid_rn(r[i]), sc);
+    }
+#pragma unroll
+    for (int c = 0; c < 20; ++c) {
+      if (c >= p.num_fg) break;
+      const bool pass = keep_row && (conf[c] >= p.score_thr);
+      const unsigned mask = __ballot_sync(0xffffffffu, pass);
+      if (mask == 0) continue;
+      // rows of one warp may straddle several images: aggregate the counter
+      // update per image (warp-uniform loop)
+      unsigned rem = mask;
+      int slot = -1;
+      while (rem) {
+        const int leader = __ffs(rem) - 1;
+        const int bl = __shfl_sync(0xffffffffu, b, leader);
+        const unsigned grp = __ballot_sync(0xffffffffu, pass && b == bl);
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&cand_count[bl * p.num_fg + c], __popc(grp));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (pass && b == bl) slot = base + __popc(grp & ((1u << lane) - 1));
+        rem &= ~grp;
+      }
+      if (pass && slot < p.cap) {
+        const unsigned long long key =
+            ((unsigned long long)__float_as_uint(conf[c]) << 32) | (0xFFFFFFFFu - (unsigned)n);
+        cand_keys[((long long)b * p.num_fg + c) * p.cap + slot] = key;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ----------------------------------------------------------------- NMS ----
+// TF NonMaxSuppressionV3 IoU, float32, no contraction.
+__device__ __forceinline__ float iou_tf(const float4& a, const float4& b) {
+  float ymin_i = fminf(a.x, a.z), xmin_i = fminf(a.y, a.w);
+  float ymax_i = fmaxf(a.x, a.z), xmax_i = fmaxf(a.y, a.w);
+  float ymin_j = fminf(b.x, b.z), xmin_j = fminf(b.y, b.w);
+  float ymax_j = fmaxf(b.x, b.z), xmax_j = fmaxf(b.y, b.w);
+  float area_i = __fmul_rn(__fsub_rn(ymax_i, ymin_i), __fsub_rn(xmax_i, xmin_i));
+  float area_j = __fmul_rn(__fsub_rn(ymax_j, ymin_j), __fsub_rn(xmax_j, xmin_j));
+  if (area_i <= 0.f || area_j <= 0.f) return 0.f;
+  float iy1 = fmaxf(ymin_i, ymin_j), ix1 = fmaxf(xmin_i, xmin_j);
+  float iy2 = fminf(ymax_i, ymax_j), ix2 = fminf(xmax_i, xmax_j);
+  float inter = __fmul_rn(fmaxf(__fsub_rn(iy2, iy1), 0.f), fmaxf(__fsub_rn(ix2, ix1), 0.f));
+  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_i, area_j), inter));
+}
+
+constexpr int kNmsThreads = 256;
+constexpr int kNmsSmemKeys = 4096;  // per-class candidates sorted in shared memory
+
+// Normalised bitonic sort (descending): every compare-exchange puts the larger
+// key at the lower index, so virtual zero padding beyond `n` never moves.
+__device__ void bitonic_desc(unsigned long long* k, int n) {
+  int np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  for (int size = 2; size <= np2; size <<= 1) {
+    // flip stage
+    for (int i = threadIdx.x; i < np2 / 2; i += blockDim.x) {
+      int blk = i / (size / 2), off = i % (size / 2);
+      int lo = blk * size + off, hi = blk * size + size - 1 - off;
+      if (hi < n) {
+        unsigned long long a = k[lo], b = k[hi];
+        if (a < b) {
+          k[lo] = b;
+          k[hi] = a;
+        }
+      }
+    }
+    __syncthreads();
+    for (int j = size / 4; j >= 1; j >>= 1) {
+      for (int i = threadIdx.x; i < np2 / 2; i += blockDim.x) {
+        int lo = (i / j) * 2 * j + (i % j), hi = lo + j;
+        if (hi < n) {
+          unsigned long long a = k[lo], b = k[hi];
+          if (a < b) {
+            k[lo] = b;
+            k[hi] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+struct NmsSmem {
+  unsigned long long keys[kNmsSmemKeys];
+  float4 box[kNmsSmemKeys];
+};
+
+__global__ void __launch_bounds__(kNmsThreads)
+    nms_per_class_kernel(const float* __restrict__ head, const __grid_constant__ TailP tp, int B,
+                         unsigned long long* __restrict__ cand_keys,
+                         const int* __restrict__ cand_count, float* __restrict__ dets,
+                         int* __restrict__ det_anchor, int* __restrict__ det_count,
+                         int* __restrict__ scratch, int* __restrict__ work,
+                         int* __restrict__ status) {
+  const odt_tail_params& p = tp.p;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  NmsSmem& sm = *reinterpret_cast<NmsSmem*>(smem_raw);
+  __shared__ int s_head;
+  __shared__ int s_last;
+  const int c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const int C = p.nms_classes, MB = p.max_boxes;
+  // staging: per (b,c): nsel + MB * (6 floats + anchor)
+  int* nsel_all = scratch;                                   // [B*C]
+  float* st_det = reinterpret_cast<float*>(scratch + B * C); // [B*C*MB*6]
+  int* st_anchor = scratch + B * C + (long long)B * C * MB * 6;  // [B*C*MB]
+  const long long bc = (long long)b * C + c;
+
+  int cnt = cand_count[b * p.num_fg + c];
+  if (cnt > p.cap) {
+    if (tid == 0) atomicExch(status, ODT_ERR_OVERFLOW);
+    cnt = p.cap;
+  }
+  unsigned long long* gkeys = cand_keys + ((long long)b * p.num_fg + c) * p.cap;
+  const bool in_smem = cnt <= kNmsSmemKeys;
+  unsigned long long* keys = in_smem ? sm.keys : gkeys;
+  if (in_smem) {
+    for (int i = tid; i < cnt; i += blockDim.x) sm.keys[i] = gkeys[i];
+  }
+  __syncthreads();
+  if (cnt > 1) bitonic_desc(keys, cnt);
+  const float* hb = head + (long long)b * p.N * kRow;
+  if (in_smem) {
+    for (int i = tid; i < cnt; i += blockDim.x) {
+      int n = (int)(0xFFFFFFFFu - (unsigned)(sm.keys[i] & 0xFFFFFFFFull));
+      Cell cell = locate(p, n);
+      sm.box[i] = decode_box(p, cell, hb + (long long)n * kRow);
+    }
+  }
+  __syncthreads();
+
+  // greedy selection: identical decisions to the sequential TF loop -- a
+  // candidate is kept iff no previously kept box has IoU > thr with it.
+  int head_pos = 0, nsel = 0;
+  while (nsel < MB) {
+    if (tid == 0) {
+      int h = head_pos;
+      while (h < cnt && keys[h] == 0ull) ++h;
+      s_head = h;
+    }
+    __syncthreads();
+    const int h = s_head;
+    if (h >= cnt) break;
+    const unsigned long long hk = keys[h];
+    const int hn = (int)(0xFFFFFFFFu - (unsigned)(hk & 0xFFFFFFFFull));
+    float4 cur;
+    if (in_smem) {
+      cur = sm.box[h];
+    } else {
+      Cell cell = locate(p, hn);
+      cur = decode_box(p, cell, hb + (long long)hn * kRow);
+    }
+    if (tid == 0) {
+      float* d = st_det + (bc * MB + nsel) * 6;
+      d[0] = __uint_as_float((unsigned)(hk >> 32));
+      d[1] = cur.x;
+      d[2] = cur.y;
+      d[3] = cur.z;
+      d[4] = cur.w;
+      d[5] = (float)c;
+      st_anchor[bc * MB + nsel] = hn;
+    }
+    ++nsel;
+    if (nsel < MB) {
+      for (int j = h + 1 + tid; j < cnt; j += blockDim.x) {
+        const unsigned long long kj = keys[j];
+        if (kj == 0ull) continue;
+        float4 bj;
+        if (in_smem) {
+          bj = sm.box[j];
+        } else {
+          int n = (int)(0xFFFFFFFFu - (unsigned)(kj & 0xFFFFFFFFull));
+          Cell cell = locate(p, n);
+          bj = decode_box(p, cell, hb + (long long)n * kRow);
+        }
+        if (iou_tf(bj, cur) > p.iou_thr) keys[j] = 0ull;
+      }
+    }
+    __syncthreads();
+    head_pos = h + 1;
+  }
+  if (tid == 0) nsel_all[bc] = nsel;
+
+  // class-major compaction by the last block of this image
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    int done = atomicAdd(&work[b], 1);
+    s_last = (done == C - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  __shared__ int s_off[33];
+  if (tid == 0) {
+    int acc = 0;
+    for (int i = 0; i < C; ++i) {
+      s_off[i] = acc;
+      acc += ((volatile int*)nsel_all)[(long long)b * C + i];
+    }
+    s_off[C] = acc;
+    det_count[b] = acc;
+    work[b] = 0;
+  }
+  __syncthreads();
+  const long long D = (long long)C * MB;
+  for (int i = tid; i < C * MB; i += blockDim.x) {
+    int ci = i / MB, k = i % MB;
+    int ns = s_off[ci + 1] - s_off[ci];
+    if (k < ns) {
+      long long dst = (long long)b * D + s_off[ci] + k;
+      const float* s = st_det + (((long long)b * C + ci) * MB + k) * 6;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) dets[dst * 6 + q] = __ldcg(s + q);
+      det_anchor[dst] = __ldcg(st_anchor + ((long long)b * C + ci) * MB + k);
+    }
+  }
+}
+
+}  // namespace odt
+
+using namespace odt;
+
+static int check_tail(const odt_tail_params* p) {
+  ODT_CHECK_ARG(p != nullptr, "params null");
+  ODT_CHECK_ARG(p->kind >= 0 && p->kind <= 2, "kind");
+  ODT_CHECK_ARG(p->num_levels >= 1 && p->num_levels <= ODT_MAX_LEVELS, "num_levels");
+  ODT_CHECK_ARG(p->num_fg >= 1 && p->num_fg <= 20, "num_fg must be 1..20");
+  ODT_CHECK_ARG(p->nms_classes >= 1 && p->nms_classes <= p->num_fg && p->nms_classes <= 32,
+                "nms_classes");
+  ODT_CHECK_ARG(p->N > 0 && p->cap > 0 && p->max_boxes > 0, "N/cap/max_boxes");
+  for (int i = 0; i < p->num_levels; ++i)
+    ODT_CHECK_ARG(p->level[i].A >= 1 && p->level[i].A <= ODT_MAX_PRIORS, "level.A");
+  return ODT_OK;
+}
+
+extern "C" int odt_decode_candidates(const float* head, const odt_tail_params* p, int B,
+                                     unsigned long long* cand_keys, int* cand_count,
+                                     void* stream) {
+  int rc = check_tail(p);
+  if (rc) return rc;
+  ODT_CHECK_ARG(head && cand_keys && cand_count && B > 0, "null pointer / B");
+  ODT_CHECK_ARG(((uintptr_t)head & 15) == 0, "head must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  ODT_CUDA_OK(cudaMemsetAsync(cand_count, 0, sizeof(int) * (size_t)B * p->num_fg, st));
+  TailP tp;
+  tp.p = *p;
+  long long rows = (long long)B * p->N;
+  long long groups = (rows + 31) / 32;
+  int blocks = (int)((groups + kDecodeWarps - 1) / kDecodeWarps);
+  int maxb = kNumSMs * 8;
+  if (blocks > maxb) blocks = maxb;
+  decode_candidates_kernel<<<blocks, kDecodeWarps * 32, 0, st>>>(head, tp, rows, cand_keys,
+                                                                 cand_count);
+  ODT_LAUNCH_OK();
+  return ODT_OK;
+}
+
+extern "C" long long odt_nms_scratch_bytes(const odt_tail_params* p, int B) {
+  if (!p || B <= 0) return -1;
+  long long bc = (long long)B * p->nms_classes;
+  return bc * 4 + bc * p->max_boxes * 6 * 4 + bc * p->max_boxes * 4;
+}
+
+extern "C" int odt_nms_per_class(const float* head, const odt_tail_params* p, int B,
+                                 unsigned long long* cand_keys, const int* cand_count, float* dets,
+                                 int* det_anchor, int* det_count, int* sel_scratch, int* work,
+                                 int* status, void* stream) {
+  int rc = check_tail(p);
+  if (rc) return rc;
+  ODT_CHECK_ARG(head && cand_keys && cand_count && dets && det_anchor && det_count &&
+                    sel_scratch && work && status && B > 0,
+                "null pointer / B");
+  cudaStream_t st = (cudaStream_t)stream;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ODT_CUDA_OK(cudaFuncSetAttribute(nms_per_class_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(NmsSmem)));
+    attr_set = true;
+  }
+  TailP tp;
+  tp.p = *p;
+  dim3 grid(p->nms_classes, B);
+  nms_per_class_kernel<<<grid, kNmsThreads, sizeof(NmsSmem), st>>>(
+      head, tp, B, cand_keys, cand_count, dets, det_anchor, det_count, sel_scratch, work, status);
+  ODT_LAUNCH_OK();
+  return ODT_OK;
+}
