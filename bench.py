@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""Benchmark of the detection hot path (BASELINE.json metric: images/sec).
+
+Workload at every N: SSD300 VGG-16 fp16 inference, per-GPU batch 64 of 300x300
+synthetic VOC-shaped images (BASELINE.json configs[1]) -- backbone + heads
+(tcgen05 convs) + anchors + decode + per-class NMS; weak scaling (images shard
+batch-parallel, one NCCL all-gather of the detection records per step).
+
+  python bench.py --gpus N --steps K --warmup W          # this framework
+  python bench.py --impl reference --gpus N ...          # the reference's CPU path
+                                                         # (oracle port: TF1.13 cannot run here)
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "object-detection-tensorflow_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+BATCH = 64
+SIZE = 300
+CFG = {"mode": "test", "data_format": "channels_last", "num_classes": 20, "weight_decay": 1e-4,
+       "keep_prob": 0.5, "batch_size": BATCH, "nms_score_threshold": 0.5, "nms_max_boxes": 20,
+       "nms_iou_threshold": 0.5, "pretraining_weight": None, "precision": "fp16"}
+WORKLOAD = "SSD300 VGG-16 fp16 inference, batch 64/GPU, 300x300 synthetic VOC (BASELINE configs[1])"
+CONV_GFLOP_PER_IMG = 62.773  # SURVEY.md App. B, real (unpadded) channels
+
+
+def synthetic_images(b, seed=0):
+    return np.random.default_rng(seed).integers(0, 256, (b, SIZE, SIZE, 3)).astype(np.float32)
+
+
+def measured_peaks():
+    f = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(f):
+        d = json.load(open(f))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.lines, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_oracle_images_per_sec(n_images, repeats=1, threads=None):
+    """The reference's CPU path as restated by the oracle (torch-CPU fp32 + C NMS):
+    full test_one_image semantics, batch-1 graph semantics looped over images."""
+    import torch
+    from odt_b200.engine import init_weights
+    import SSD300
+    from oracle import nets as ON
+    from oracle import tails as OT
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    OT.build_nms_lib()
+    model = SSD300.SSD300(dict(CFG), None)
+    w = init_weights(model.variables(), seed=1)
+    img = synthetic_images(n_images, seed=0)
+    ON.ssd_heads(w, img[:1], SIZE)  # warm-up (thread pools, oneDNN primitives)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        for i in range(n_images):
+            preds = ON.ssd_heads(w, img[i:i + 1], SIZE)
+            OT.ssd_detect(preds, SIZE, CFG["nms_score_threshold"], CFG["nms_max_boxes"],
+                          CFG["nms_iou_threshold"])
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return n_images / best, threads
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path.  TF 1.13
+    is not installable here and SSD300.py does not parse, so this times the oracle
+    port (kind 'port') on all host cores; each step is a bounded sample of the workload."""
+    if rank != 0:
+        return
+    sample = 4
+    vals = []
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_oracle_images_per_sec(1)
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        v, threads = cpu_oracle_images_per_sec(sample)
+        vals.append(v)
+        if time.perf_counter() - t_all > 240:
+            break
+    v = float(np.mean(vals))
+    line = {"impl": "reference", "metric": "images/sec", "value": v, "unit": "images/sec",
+            "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
+            "ms_per_step": 1e3 * sample / v, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": BATCH * args.gpus},
+            "cpu_baseline": {"value": v, "unit": "images/sec", "cores": threads, "kind": "port",
+                             "sample": "%d images per step, batch-1 graph semantics, torch-CPU fp32 "
+                                       "convs + C NMS" % sample},
+            "e2e": {"value": v, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    assert args.warmup >= 0 and args.steps >= 1
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as tdist
+    from odt_b200 import dist as od
+    import __graft_entry__ as ge
+    rank, world, local = od.init_from_env()
+    if not os.path.exists(os.path.join(ROOT, "object-detection-tensorflow_b200", "odt_b200",
+                                       "libodt_b200.so")):
+        if rank == 0:
+            ge.build()
+        if world > 1:
+            tdist.barrier()
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    assert world == args.gpus, "launch with torchrun --nproc-per-node %d" % args.gpus
+    W = max(args.warmup, 3)
+    K = args.steps
+
+    import SSD300
+    model = SSD300.SSD300(dict(CFG), None)
+    net = model.engine(BATCH)  # builds, uploads seeded weights (identical on every rank), captures the graph
+    images = torch.from_numpy(synthetic_images(BATCH, seed=rank)).pin_memory()
+    net.image_buf.copy_(images)
+    torch.cuda.synchronize()
+
+    def step_resident():
+        net.run()
+        if world > 1:
+            od.gather_records(od.pack_records(net.tail.dets, net.tail.det_count))
+
+    def barrier():
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident throughput (value) ----------------------
+    for _ in range(W):
+        step_resident()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        step_resident()
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop()
+    ms_step = ms_total / K
+    value = world * BATCH * K / (ms_total / 1e3)
+
+    # ---------------- end to end through the public API ------------------------
+    def step_e2e():
+        if world > 1:
+            return model.detect_batch_sharded(images)
+        return model.detect_batch(images)
+
+    for _ in range(W):
+        step_e2e()
+    barrier()
+    e0.record()
+    for _ in range(K):
+        out = step_e2e()
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = world * BATCH * K / (ms_e2e / 1e3)
+    h2d = int(images.numel() * 4)
+    d2h = int(net.tail.dets.numel() * 4 + net.tail.det_count.numel() * 4 + 4) * world
+
+    # ---------------- roofline of the dominant kernel (tcgen05 conv) -----------
+    from odt_b200.engine import ConvOp
+    st = torch.cuda.current_stream().cuda_stream
+    tc_ops = [op for op in net.ops if isinstance(op, ConvOp) and getattr(op, "use_tc", False)]
+    evs = []
+    torch.cuda.synchronize()
+    reps = 3
+    for _ in range(reps):
+        for op in net.ops:
+            if op in tc_ops:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                op.launch(net, st)
+                b.record()
+                evs.append((op, a, b))
+            else:
+                op.launch(net, st)
+        net.tail.launch(net, st)
+    torch.cuda.synchronize()
+    tc_ms = sum(a.elapsed_time(b) for _, a, b in evs) / reps
+    tc_flops = sum(op.flops for op in tc_ops)
+    peaks, peak_src = measured_peaks()
+    peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+    achieved_tf = tc_flops / (tc_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM)",
+                "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": achieved_tf / peak_tf, "traffic": None,
+                "peak_source": peak_src + " cuBLAS bf16 sustained (kernel timed inside a long step)",
+                "launches_per_step": len(tc_ops), "tc_ms_per_step": tc_ms,
+                "algorithmic_gflop_per_step": tc_flops / 1e9,
+                "share_of_step": tc_ms / ms_step}
+
+    line = {"metric": "images/sec", "value": value, "unit": "images/sec", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "per_gpu_batch": BATCH,
+                       "parallelism": "dp%d (image shards, 1 all-gather of detections)" % world,
+                       "l2": "per-step activation working set ~2.9 GB >> 126 MB L2 (no reuse between steps)",
+                       "cuda_graph": True, "conv_gflop_per_img": CONV_GFLOP_PER_IMG,
+                       "conv_roofline_frac_whole_step":
+                           (BATCH * CONV_GFLOP_PER_IMG * 1e9 / (ms_step * 1e-3)) / (peak_tf * 1e12)},
+            "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K},
+            "gpu_launches": net.num_launches() * K,
+            "roofline": roofline, "clocks": clocks}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, threads = cpu_oracle_images_per_sec(8)
+        line["cpu_baseline"] = {"value": v, "unit": "images/sec", "cores": threads, "kind": "port",
+                                "sample": "8 of the 64 images, oracle port (torch-CPU fp32 + C NMS), "
+                                          "batch-1 graph semantics like the reference"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        tdist.barrier()
+        tdist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

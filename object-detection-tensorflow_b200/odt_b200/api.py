@@ -1,0 +1,273 @@
+"""The reference's public model surface on the B200 engine.
+
+Same class names, constructor signature `(config, data_provider)`, config keys,
+asserts and method names as the reference model scripts, so its test*.py
+drivers run unchanged:
+    SSD300.py:11-50,473-504   SSD512.py   RetinaNet.py:11-79,505-539
+    YOLOv3.py:11-60,444-483   FCOS.py:11-49,401-436
+Inference (`test_one_image`) runs entirely on the GPU kernels; there is no CPU
+fallback.  Extensions: `test_one_image` accepts [B,H,W,3] (returns a list per
+image for B > 1) and `detect_batch` / `detect_batch_sharded` expose the batched,
+multi-GPU path.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+from . import nets
+from .engine import init_weights
+
+
+def _as_host_tensor(images):
+    """numpy / array-like / torch CPU tensor -> contiguous float32 torch tensor (no copy if possible)."""
+    if isinstance(images, torch.Tensor):
+        return images.to(torch.float32).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(images, dtype=np.float32))
+
+
+def _precision(config):
+    return config.get("precision", os.environ.get("ODT_PRECISION", "fp16"))
+
+
+class _Detector:
+    name = "detector"
+    seed = 1
+
+    def _common_init(self, config, data_provider):
+        assert config["mode"] in ["train", "test"]
+        assert config["data_format"] in ["channels_first", "channels_last"]
+        self.config = config
+        self.data_provider = data_provider
+        self.mode = config["mode"]
+        self.data_format = config["data_format"]
+        self.weight_decay = config["weight_decay"]
+        self.prob = 1.0 - config["keep_prob"]
+        self.batch_size = config["batch_size"] if config["mode"] == "train" else 1
+        self.nms_score_threshold = config["nms_score_threshold"]
+        self.nms_max_boxes = config["nms_max_boxes"]
+        self.nms_iou_threshold = config["nms_iou_threshold"]
+        if self.mode == "train":
+            self.num_train = data_provider["num_train"]
+            self.num_val = data_provider["num_val"]
+            self.train_generator = data_provider["train_generator"]
+            self.train_initializer, self.train_iterator = self.train_generator
+            if data_provider["val_generator"] is not None:
+                self.val_generator = data_provider["val_generator"]
+                self.val_initializer, self.val_iterator = self.val_generator
+        self.precision = _precision(config)
+        self.global_step = 0
+        self._engines = {}
+        self._weights = None
+        self._bn_mode = config.get("bn_init", "tf_init")
+        self.device = config.get("device", "cuda")
+
+    # ---- engine management -------------------------------------------------
+    def _build(self, batch, precision, allow_tc=True):
+        raise NotImplementedError
+
+    def engine(self, batch=1, precision=None, graph=True, allow_tc=True):
+        """Build (once) the network for a fixed batch size: buffers, weights on
+        the device, kernel parameter blocks, CUDA graph."""
+        precision = precision or self.precision
+        key = (batch, precision, allow_tc)
+        if key in self._engines:
+            return self._engines[key]
+        net, tail = self._build(batch, precision, allow_tc)
+        if self._weights is None:
+            self._weights = self._initial_weights(net.vars)
+        net.finalize(self._weights, tail)
+        if graph:
+            net.capture()
+        self._engines[key] = net
+        return net
+
+    def variables(self):
+        """name -> (shape, init kind) without touching the GPU."""
+        return self._build_spec().vars
+
+    def _build_spec(self):
+        from .engine import Net
+        Net.spec_only = True
+        try:
+            net, _ = self._build(1, "fp32", False)
+        finally:
+            Net.spec_only = False
+        return net
+
+    def _initial_weights(self, variables):
+        w = init_weights(variables, seed=self.seed, bn_mode=self._bn_mode)
+        path = self.config.get("pretraining_weight")
+        if path and os.path.exists(path) and path.endswith(".npz"):
+            self._load_npz_into(w, path)
+        elif path:
+            sys.stderr.write("[odt_b200] pretraining weight %r not readable here (TF checkpoint "
+                             "reader is a follow-on); using seeded random init\n" % (path,))
+        return w
+
+    @staticmethod
+    def _load_npz_into(w, path):
+        data = np.load(path)
+        for k in data.files:
+            if k in w:
+                assert w[k].shape == data[k].shape, (k, w[k].shape, data[k].shape)
+                w[k] = data[k].astype(np.float32)
+
+    def set_weights(self, weights):
+        """Replace all variables (dict name -> array in TF layout); rebuilds engines."""
+        self._weights = {k: np.asarray(v, np.float32) for k, v in weights.items()}
+        self._engines = {}
+
+    def get_weights(self):
+        if self._weights is None:
+            self._weights = self._initial_weights(self.variables())
+        return self._weights
+
+    # ---- inference -----------------------------------------------------------
+    def detect_batch(self, images, precision=None):
+        """images: array-like [B,H,W,3] float (RGB, 0..255).  Returns a list of
+        [scores, bbox(y1,x1,y2,x2), class_id] per image."""
+        images = _as_host_tensor(images)
+        assert images.dim() == 4 and images.shape[3] == 3, "expected [B,H,W,3]"
+        net = self.engine(images.shape[0], precision)
+        assert tuple(images.shape[1:3]) == (net.in_h, net.in_w), (images.shape, net.in_h, net.in_w)
+        net.image_buf.copy_(images, non_blocking=True)  # H2D (async when the source is pinned)
+        net.run()
+        return net.tail.results()
+
+    def test_one_image(self, images):
+        """ref SSD300.py:486-488: returns [scores, bbox, class_id]."""
+        if self.data_format == "channels_first":
+            images = np.transpose(np.asarray(images), (0, 2, 3, 1))
+        res = self.detect_batch(images)
+        return res[0] if len(res) == 1 else res
+
+    def detect_batch_sharded(self, images_local):
+        """Batch-parallel multi-GPU inference: each rank runs its image shard,
+        one NCCL all-gather of the fixed-size detection records follows."""
+        from . import dist
+        return dist.detect_sharded(self, images_local)
+
+    # ---- training / checkpoints (API surface) --------------------
+    def train_one_epoch(self, lr):
+        raise NotImplementedError(
+            "%s.train_one_epoch: the training step (loss backward + momentum update) is outside "
+            "the accelerated hot path in this round (SURVEY.md 8f); inference and the RetinaNet "
+            "loss forward are available" % self.name)
+
+    def save_weight(self, mode, path):
+        assert mode in ["latest", "best"]
+        d = os.path.dirname(path)
+        if d and not os.path.exists(d):
+            os.makedirs(d)
+            print(d, "does not exist, create it done")
+        out = "%s-%d.npz" % (path, self.global_step)
+        np.savez(out, **self.get_weights())
+        print("save", mode, "model in", out, "successfully")
+        return out
+
+    def load_weight(self, path):
+        if not path.endswith(".npz"):
+            path = path + ".npz"
+        w = dict(self.get_weights())
+        self._load_npz_into(w, path)
+        self.set_weights(w)
+        print("load weight", path, "successfully")
+
+    def load_pretraining_weight(self, path):
+        self.load_weight(path)
+        print("load pretraining weight", path, "successfully")
+
+    load_pretrained_weight = load_pretraining_weight  # FCOS spelling (FCOS.py:434)
+
+
+class SSD300(_Detector):
+    name, input_size = "SSD300", 300
+
+    def __init__(self, config, data_provider):
+        self._common_init(config, data_provider)
+        self.num_classes = config["num_classes"] + 1
+        s = self.input_size
+        self.data_shape = [s, s, 3] if config["data_format"] == "channels_last" else [3, s, s]
+
+    def _build(self, batch, precision, allow_tc=True):
+        return nets.build_ssd(self.input_size, batch, self.config, precision, self.device, allow_tc)
+
+
+class SSD512(SSD300):
+    name, input_size = "SSD512", 512
+
+
+class RetinaNet(_Detector):
+    name = "RetinaNet"
+
+    def __init__(self, config, data_provider):
+        assert len(config["data_shape"]) == 3
+        self._common_init(config, data_provider)
+        if config["is_pretraining"]:
+            raise NotImplementedError("RetinaNet ImageNet-pretraining mode is classification, "
+                                      "outside the detection hot path (SURVEY.md section 2 #3)")
+        self.is_bottleneck = config["is_bottleneck"]
+        self.block_list = config["residual_block_list"]
+        self.data_shape = config["data_shape"]
+        self.num_classes = config["num_classes"] + 1
+        self.gamma, self.alpha = config["gamma"], config["alpha"]
+
+    def _build(self, batch, precision, allow_tc=True):
+        return nets.build_retinanet(batch, self.config, precision, self.device, allow_tc)
+
+    def loss_forward(self, images, ground_truth, precision=None):
+        """Forward of the training loss (matching + softmax focal + smooth-L1),
+        per image, on the same head rows the inference tail reads.
+        ground_truth: [B,G,5] (y,x,h,w,id) padded with -1.  ref RetinaNet.py:357-474."""
+        import ctypes as C
+        images = np.ascontiguousarray(images, dtype=np.float32)
+        gt = np.ascontiguousarray(ground_truth, dtype=np.float32)
+        net = self.engine(images.shape[0], precision)
+        B, G = gt.shape[0], gt.shape[1]
+        net.image_buf.copy_(torch.from_numpy(images))
+        net.run()
+        dev = net.device
+        gtd = torch.from_numpy(gt).to(dev)
+        nf = net.lib.odt_retina_loss_scratch_floats(B)
+        partial = torch.zeros(nf, dtype=torch.float32, device=dev)
+        match = torch.zeros(B * G, dtype=torch.int32, device=dev)
+        out = torch.zeros(B, dtype=torch.float32, device=dev)
+        from . import lib as L
+        L.check(net.lib.odt_retina_loss_fwd(net.head_buf.data_ptr(), C.byref(net.tail.p), B,
+                                            gtd.data_ptr(), G, float(self.alpha), float(self.gamma),
+                                            partial.data_ptr(), match.data_ptr(), out.data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream), "retina_loss")
+        return out.cpu().numpy()
+
+
+class YOLOv3(_Detector):
+    name = "YOLOv3"
+
+    def __init__(self, config, data_provider):
+        assert len(config["data_shape"]) == 3
+        self._common_init(config, data_provider)
+        self.data_shape = config["data_shape"]
+        self.num_classes = config["num_classes"]
+        self.coord_sacle = config["coord_scale"]
+        self.noobj_scale = config["noobj_scale"]
+        self.obj_scale = config["obj_scale"]
+        self.class_scale = config["class_scale"]
+        self.num_priors = config["num_priors"]
+
+    def _build(self, batch, precision, allow_tc=True):
+        return nets.build_yolov3(batch, self.config, precision, self.device, allow_tc)
+
+
+class FCOS(_Detector):
+    name = "FCOS"
+
+    def __init__(self, config, data_provider):
+        self._common_init(config, data_provider)
+        self.data_shape = config["data_shape"]
+        self.num_classes = config["num_classes"]
+
+    def _build(self, batch, precision, allow_tc=True):
+        return nets.build_fcos(batch, self.config, precision, self.device, allow_tc,
+                               share_heads=self.config.get("share_heads", True))

@@ -1,0 +1,638 @@
+"""Host runtime of the B200 detection path: a tiny static-graph builder whose
+ops are launches of the C-ABI kernels (include/odt_b200.h) on torch-owned
+device buffers.  PyTorch is plumbing only (allocation, streams, CUDA graphs).
+
+A model file (nets.py) describes its layers once through `Builder`; the builder
+  * names variables the way TF1 variable scopes do so the
+    same weight dict drives this path and the CPU oracle,
+  * pads fp16 activations to 64-channel multiples (TMA / UMMA K-chunk),
+  * fuses what the reference expresses as separate TF ops into conv epilogues:
+    bias / folded inference BN / ReLU / LeakyReLU / residual add / the
+    consumer's pre-activation BN+ReLU (second output) / direct scatter of the
+    head convolutions into the [B, N, 25] candidate-row buffer.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import lib as L
+
+BN_EPS = 1e-3   # tf.layers.batch_normalization default
+GN_EPS = 1e-6   # tf.contrib.layers.group_norm default (App. A.5)
+ACT = {None: L.ACT_NONE, "relu": L.ACT_RELU, "leaky": L.ACT_LEAKY}
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+def same_pad(size, k, stride, dil=1):
+    """TF SAME geometry; host twin of odt_same_pad."""
+    out = -(-size // stride)
+    total = max((out - 1) * stride + (k - 1) * dil + 1 - size, 0)
+    return out, total // 2, total - total // 2
+
+
+class Namer:
+    """TF1-style variable scopes: default layer names are uniquified per scope."""
+
+    def __init__(self):
+        self.stack, self.counts = [], {}
+
+    def push(self, name):
+        self.stack.append(name)
+
+    def pop(self):
+        self.stack.pop()
+
+    def prefix(self):
+        return "/".join(self.stack)
+
+    def unique(self, base):
+        key = (self.prefix(), base)
+        k = self.counts.get(key, 0)
+        self.counts[key] = k + 1
+        name = base if k == 0 else "%s_%d" % (base, k)
+        return (self.prefix() + "/" + name) if self.stack else name
+
+    def named(self, name):
+        return (self.prefix() + "/" + name) if self.stack else name
+
+    def reset_under(self, prefix):
+        self.counts = {k: v for k, v in self.counts.items() if not k[0].startswith(prefix)}
+
+
+class Act:
+    """An activation tensor [B,H,W,C] with channel stride ld."""
+
+    def __init__(self, name, B, H, W, C, ld, dtype):
+        self.name, self.B, self.H, self.W, self.C, self.ld, self.dtype = name, B, H, W, C, ld, dtype
+        self.buf = None
+        self.needed = True  # False when only a fused second output is consumed
+
+    @property
+    def pixels(self):
+        return self.B * self.H * self.W
+
+    def ptr(self):
+        return self.buf.data_ptr() if self.buf is not None else None
+
+
+class Op:
+    reads = ()
+    writes = ()
+
+    def prepare(self, net):
+        pass
+
+    def launch(self, net, stream):
+        raise NotImplementedError
+
+
+class ConvOp(Op):
+    def __init__(self, x, y, k, stride, dil, kernel, bias, bn, act, residual, head, is_image):
+        self.x, self.y = x, y
+        self.k, self.stride, self.dil = k, stride, dil
+        self.kernel, self.bias, self.bn, self.act = kernel, bias, bn, act
+        self.residual, self.head, self.is_image = residual, head, is_image
+        self.pre = None     # fused consumer pre-activation: (bn_scope, act, Act)
+        self.reads = tuple(t for t in (x, residual) if t is not None)
+        self.writes = (y,) if y is not None else ()
+        self.flops = 0
+
+    def prepare(self, net):
+        x, W = self.x, net.weights
+        dev = net.device
+        kern = np.asarray(W[self.kernel], dtype=np.float32)  # HWIO
+        R, S, cin, cout = kern.shape
+        assert cin == (3 if self.is_image else x.C), (self.kernel, cin, x.C)
+        self.cout = cout
+        f16 = net.precision == "fp16"
+        adt = torch.float16 if f16 else torch.float32
+        self.use_tc = f16 and (not self.is_image) and x.ld % 64 == 0 and net.allow_tc
+        ohwi = np.transpose(kern, (3, 0, 1, 2))  # [Cout,R,S,Cin]
+        if self.use_tc:
+            cpad = _round_up(cout, 32)
+            wp = np.zeros((cpad, R, S, x.ld), dtype=np.float32)
+            wp[:cout, :, :, :cin] = ohwi
+            self.w_ld, self.cout_pad = x.ld, cpad
+        else:
+            wp = np.ascontiguousarray(ohwi)
+            self.w_ld, self.cout_pad = cin, cout
+        self.wdev = torch.from_numpy(wp).to(dev).to(adt).contiguous()
+        bias = np.asarray(W[self.bias], dtype=np.float32) if self.bias else np.zeros(cout, np.float32)
+        if self.bn:
+            sc, sh = net.bn_fold(self.bn)
+            shift = sh + bias * sc
+            scale = sc
+        else:
+            scale, shift = None, bias
+        self.scale = torch.from_numpy(scale).to(dev) if scale is not None else None
+        self.shift = torch.from_numpy(np.ascontiguousarray(shift)).to(dev)
+        H, Wd = (net.in_h, net.in_w) if self.is_image else (x.H, x.W)
+        B = net.batch
+        OH, pt, _ = same_pad(H, R, self.stride, self.dil)
+        OW, pl, _ = same_pad(Wd, S, self.stride, self.dil)
+        p = L.ConvParams()
+        p.B, p.H, p.W, p.Cin = B, H, Wd, cin
+        p.in_ld = 3 if self.is_image else x.ld
+        p.OH, p.OW, p.Cout = OH, OW, cout
+        p.R, p.S, p.stride, p.dil, p.pad_t, p.pad_l = R, S, self.stride, self.dil, pt, pl
+        p.w_ld, p.Cout_pad = self.w_ld, self.cout_pad
+        p.scale = self.scale.data_ptr() if self.scale is not None else None
+        p.shift = self.shift.data_ptr()
+        p.act = ACT[self.act]
+        p.residual = self.residual.ptr() if self.residual is not None else None
+        if self.head is not None:
+            hb = net.head_buf
+            lvl_off, col, group, gstride, A = self.head
+            p.out0 = hb.data_ptr() + 4 * (lvl_off * 25 + col)
+            p.out0_dtype = L.ODT_F32
+            p.out0_img_stride = net.N * 25
+            p.out0_pix_stride = A * 25
+            p.out0_group, p.out0_group_stride = group, gstride
+        else:
+            y = self.y
+            assert (y.H, y.W, y.C) == (OH, OW, cout)
+            p.out0 = y.ptr() if y.needed else None
+            p.out0_dtype = L.ODT_F16 if f16 else L.ODT_F32
+            p.out0_img_stride = y.H * y.W * y.ld
+            p.out0_pix_stride = y.ld
+            p.out0_group = p.out0_group_stride = 0
+        if self.pre is not None:
+            scope, act2, t = self.pre
+            if scope is not None:
+                s2, h2 = net.bn_fold(scope)
+                self.scale2 = torch.from_numpy(s2).to(dev)
+                self.shift2 = torch.from_numpy(h2).to(dev)
+                p.scale2, p.shift2 = self.scale2.data_ptr(), self.shift2.data_ptr()
+            p.act2 = ACT[act2]
+            p.out1 = t.ptr()
+            p.out1_img_stride = t.H * t.W * t.ld
+            p.out1_pix_stride = t.ld
+        self.p = p
+        self.flops = 2 * B * OH * OW * cout * R * S * cin
+
+    def launch(self, net, stream):
+        lib = net.lib
+        if self.is_image:
+            rc = lib.odt_conv2d_stem(net.image_buf.data_ptr(), net.mean3, self.wdev.data_ptr(),
+                                     L.ODT_F16 if net.precision == "fp16" else L.ODT_F32,
+                                     C.byref(self.p), stream)
+        elif self.use_tc:
+            rc = lib.odt_conv2d_f16_tc(self.x.ptr(), self.wdev.data_ptr(), C.byref(self.p), stream)
+        else:
+            rc = lib.odt_conv2d_direct(self.x.ptr(), self.wdev.data_ptr(),
+                                       L.ODT_F16 if net.precision == "fp16" else L.ODT_F32,
+                                       C.byref(self.p), stream)
+        L.check(rc, "conv %s" % self.kernel)
+
+
+class PoolOp(Op):
+    def __init__(self, x, y, k, stride):
+        self.x, self.y, self.k, self.stride = x, y, k, stride
+        self.reads, self.writes = (x,), (y,)
+
+    def launch(self, net, stream):
+        x = self.x
+        # pooled over the padded channel range so pad lanes stay zero
+        L.check(net.lib.odt_maxpool(x.ptr(), self.y.ptr(), net.dt, x.B, x.H, x.W, x.ld, x.ld,
+                                    self.k, self.stride, stream), "maxpool")
+
+
+class L2NormOp(Op):
+    def __init__(self, x, y, var):
+        self.x, self.y, self.var = x, y, var
+        self.reads, self.writes = (x,), (y,)
+
+    def prepare(self, net):
+        self.gamma = float(np.asarray(net.weights[self.var], dtype=np.float32).reshape(-1)[0])
+
+    def launch(self, net, stream):
+        x = self.x
+        L.check(net.lib.odt_l2norm_scale(x.ptr(), self.y.ptr(), net.dt, x.pixels, x.C, x.ld,
+                                         self.gamma, stream), "l2norm")
+
+
+class AffineActOp(Op):
+    """Stand-alone inference BN (+activation): the pre-activation of RetinaNet's
+    _bn_activation_conv when it cannot be fused into the producer."""
+
+    def __init__(self, x, y, bn, act):
+        self.x, self.y, self.bn, self.act = x, y, bn, act
+        self.reads, self.writes = (x,), (y,)
+
+    def prepare(self, net):
+        s, h = net.bn_fold(self.bn)
+        x = self.x
+        sp = np.zeros(x.ld, np.float32)
+        hp = np.zeros(x.ld, np.float32)
+        sp[:x.C], hp[:x.C] = s, h
+        self.scale = torch.from_numpy(sp).to(net.device)
+        self.shift = torch.from_numpy(hp).to(net.device)
+
+    def launch(self, net, stream):
+        x = self.x
+        L.check(net.lib.odt_affine_act(x.ptr(), self.y.ptr(), net.dt, x.pixels, x.ld, x.ld,
+                                       self.scale.data_ptr(), self.shift.data_ptr(), ACT[self.act],
+                                       stream), "affine_act")
+
+
+class GroupNormActOp(Op):
+    def __init__(self, x, y, gn, act, groups=8):
+        self.x, self.y, self.gn, self.act, self.groups = x, y, gn, act, groups
+        self.reads, self.writes = (x,), (y,)
+
+    def prepare(self, net):
+        dev = net.device
+        self.gamma = torch.from_numpy(np.asarray(net.weights[self.gn + "/gamma"], np.float32)).to(dev)
+        self.beta = torch.from_numpy(np.asarray(net.weights[self.gn + "/beta"], np.float32)).to(dev)
+        self.stats = torch.empty(self.x.B * self.groups * 2, dtype=torch.float32, device=dev)
+
+    def launch(self, net, stream):
+        x = self.x
+        hw = x.H * x.W
+        L.check(net.lib.odt_groupnorm_stats(x.ptr(), self.stats.data_ptr(), net.dt, x.B, hw, x.C,
+                                            x.ld, self.groups, GN_EPS, stream), "gn_stats")
+        L.check(net.lib.odt_groupnorm_apply(x.ptr(), self.y.ptr(), self.stats.data_ptr(), net.dt,
+                                            x.B, hw, x.C, x.ld, self.groups, self.gamma.data_ptr(),
+                                            self.beta.data_ptr(), ACT[self.act], stream), "gn_apply")
+
+
+class UpsampleAddOp(Op):
+    def __init__(self, top, a, y):
+        self.top, self.a, self.y = top, a, y
+        self.pre = None
+        self.reads, self.writes = (top, a), (y,)
+
+    def prepare(self, net):
+        self.s2 = self.h2 = None
+        if self.pre is not None and self.pre[0] is not None:
+            s, h = net.bn_fold(self.pre[0])
+            sp = np.zeros(self.y.ld, np.float32)
+            hp = np.zeros(self.y.ld, np.float32)
+            sp[:self.y.C], hp[:self.y.C] = s, h
+            self.s2 = torch.from_numpy(sp).to(net.device)
+            self.h2 = torch.from_numpy(hp).to(net.device)
+
+    def launch(self, net, stream):
+        t, a, y = self.top, self.a, self.y
+        out1 = self.pre[2].ptr() if self.pre is not None else None
+        act2 = ACT[self.pre[1]] if self.pre is not None else 0
+        L.check(net.lib.odt_upsample_bilinear_add(
+            t.ptr(), a.ptr(), y.ptr(), net.dt, y.B, t.H, t.W, y.H, y.W, y.ld, y.ld,
+            self.s2.data_ptr() if self.s2 is not None else None,
+            self.h2.data_ptr() if self.h2 is not None else None, act2, out1, stream), "upsample_add")
+
+
+class NearestConcatOp(Op):
+    def __init__(self, a, b, y):
+        self.a, self.b, self.y = a, b, y
+        self.reads, self.writes = (a, b), (y,)
+
+    def launch(self, net, stream):
+        a, b, y = self.a, self.b, self.y
+        L.check(net.lib.odt_upsample_nearest_concat(a.ptr(), b.ptr(), y.ptr(), net.dt, y.B, y.H, y.W,
+                                                    a.C, a.ld, b.H, b.W, b.C, b.ld, y.ld, stream),
+                "nearest_concat")
+
+
+class Net:
+    """A built network: buffers + op list + the decode/NMS tail."""
+
+    spec_only = False  # class-level switch: describe the graph without touching CUDA
+
+    def __init__(self, batch, in_h, in_w, precision="fp16", device="cuda", allow_tc=True):
+        assert precision in ("fp16", "fp32")
+        self.lib = None if Net.spec_only else L.load()
+        self.batch, self.in_h, self.in_w = batch, in_h, in_w
+        self.precision, self.device, self.allow_tc = precision, torch.device(device), allow_tc
+        self.dt = L.ODT_F16 if precision == "fp16" else L.ODT_F32
+        self.tdtype = torch.float16 if precision == "fp16" else torch.float32
+        self.namer = Namer()
+        self.vars = {}      # name -> (shape, init kind), creation order
+        self.ops = []
+        self.acts = []
+        self.levels = []    # (H, W, A) per head level, in candidate order
+        self.tail = None
+        self.mean3 = (C.c_float * 3)(123.68, 116.779, 103.979)  # ref SSD300.py:55
+        self.weights = None
+        self.graph = None
+
+    # ---------------------------------------------------------- variables ---
+    def var(self, name, shape, kind):
+        if name not in self.vars:
+            self.vars[name] = (tuple(int(s) for s in shape), kind)
+        return name
+
+    def bn_fold(self, scope):
+        W = self.weights
+        g = np.asarray(W[scope + "/gamma"], np.float32)
+        b = np.asarray(W[scope + "/beta"], np.float32)
+        m = np.asarray(W[scope + "/moving_mean"], np.float32)
+        v = np.asarray(W[scope + "/moving_variance"], np.float32)
+        sc = (g / np.sqrt(v + np.float32(BN_EPS))).astype(np.float32)
+        return sc, (b - m * sc).astype(np.float32)
+
+    # -------------------------------------------------------------- build ---
+    def new_act(self, name, H, W, Cc):
+        ld = _round_up(Cc, 64) if self.precision == "fp16" else Cc
+        t = Act(name, self.batch, H, W, Cc, ld, self.precision)
+        self.acts.append(t)
+        return t
+
+    def scope(self, name):
+        net = self
+
+        class _S:
+            def __enter__(self_):
+                net.namer.push(name)
+
+            def __exit__(self_, *a):
+                net.namer.pop()
+
+        return _S()
+
+    def conv(self, x, cout, k, stride=1, dil=1, name=None, kernel_var=None, bias_var=None,
+             bn=False, act=None, residual=None, head=None, bias_init="zeros"):
+        """tf.layers.conv2d (+ BN + activation + residual).  x=None means the image."""
+        is_image = x is None
+        cin = 3 if is_image else x.C
+        if kernel_var is None:
+            vs = self.namer.named(name) if name else self.namer.unique("conv2d")
+            kernel_var, bias_var = vs + "/kernel", vs + "/bias"
+        self.var(kernel_var, (k, k, cin, cout), "he")
+        if bias_var:
+            self.var(bias_var, (cout,), bias_init)
+        bn_scope = self.bn_vars(cout) if bn else None
+        H, W = (self.in_h, self.in_w) if is_image else (x.H, x.W)
+        OH, _, _ = same_pad(H, k, stride, dil)
+        OW, _, _ = same_pad(W, k, stride, dil)
+        y = None if head is not None else self.new_act(kernel_var, OH, OW, cout)
+        op = ConvOp(x, y, k, stride, dil, kernel_var, bias_var, bn_scope, act, residual, head,
+                    is_image)
+        op.out_hw = (OH, OW)
+        self.ops.append(op)
+        return y if head is None else op
+
+    def bn_vars(self, c):
+        scope = self.namer.unique("batch_normalization")
+        self.var(scope + "/gamma", (c,), "bn_gamma")
+        self.var(scope + "/beta", (c,), "bn_beta")
+        self.var(scope + "/moving_mean", (c,), "bn_mean")
+        self.var(scope + "/moving_variance", (c,), "bn_var")
+        return scope
+
+    def preact_bn(self, x, act="relu"):
+        """inference BN -> activation as its own tensor (fused into the producer later)."""
+        scope = self.bn_vars(x.C)
+        y = self.new_act(scope + "/out", x.H, x.W, x.C)
+        self.ops.append(AffineActOp(x, y, scope, act))
+        return y
+
+    def preact_gn(self, x, act="relu"):
+        scope = self.namer.unique("GroupNorm")
+        self.var(scope + "/beta", (x.C,), "gn_beta")
+        self.var(scope + "/gamma", (x.C,), "gn_gamma")
+        y = self.new_act(scope + "/out", x.H, x.W, x.C)
+        self.ops.append(GroupNormActOp(x, y, scope, act))
+        return y
+
+    def maxpool(self, x, k, stride):
+        OH, _, _ = same_pad(x.H, k, stride)
+        OW, _, _ = same_pad(x.W, k, stride)
+        y = self.new_act(x.name + "/pool", OH, OW, x.C)
+        self.ops.append(PoolOp(x, y, k, stride))
+        return y
+
+    def l2norm(self, x, var):
+        self.var(var, (1,), "l2norm")
+        y = self.new_act(var + "/out", x.H, x.W, x.C)
+        self.ops.append(L2NormOp(x, y, var))
+        return y
+
+    def upsample_add(self, top, a):
+        y = self.new_act(a.name + "/topdown", a.H, a.W, a.C)
+        self.ops.append(UpsampleAddOp(top, a, y))
+        return y
+
+    def nearest_concat(self, a, b):
+        y = self.new_act(a.name + "/concat", a.H, a.W, a.C + b.C)
+        self.ops.append(NearestConcatOp(a, b, y))
+        return y
+
+    def add_level(self, H, W, A):
+        off = sum(h * w * a for h, w, a in self.levels)
+        self.levels.append((H, W, A))
+        return off
+
+    # ------------------------------------------------------------- fusion ---
+    def fuse(self):
+        """Fold stand-alone BN+ReLU pre-activations into the epilogue of the op
+        that produces their input; drop raw outputs nobody else reads."""
+        consumers = {}
+        for op in self.ops:
+            for t in op.reads:
+                consumers.setdefault(id(t), []).append(op)
+        producer = {}
+        for op in self.ops:
+            for t in op.writes:
+                producer[id(t)] = op
+        kept = []
+        for op in self.ops:
+            if isinstance(op, AffineActOp):
+                q = producer.get(id(op.x))
+                ok = isinstance(q, (ConvOp, UpsampleAddOp)) and q.pre is None
+                if ok and isinstance(q, ConvOp):
+                    ok = q.head is None
+                if ok:
+                    q.pre = (op.bn, op.act, op.y)
+                    producer[id(op.y)] = q
+                    consumers[id(op.x)].remove(op)
+                    if not consumers[id(op.x)] and isinstance(q, ConvOp):
+                        op.x.needed = False
+                    continue
+            kept.append(op)
+        self.ops = kept
+
+    # ------------------------------------------------------------ finalize --
+    def finalize(self, weights, tail, fuse=True):
+        """Allocate buffers, upload weights, build the kernel parameter blocks."""
+        self.weights = weights
+        missing = [k for k in self.vars if k not in weights]
+        if missing:
+            raise KeyError("weights missing %d variables, e.g. %s" % (len(missing), missing[:3]))
+        if fuse:
+            self.fuse()
+        dev = self.device
+        self.image_buf = torch.zeros((self.batch, self.in_h, self.in_w, 3), dtype=torch.float32,
+                                     device=dev)
+        for t in self.acts:
+            if t.needed or True:  # unneeded raws are tiny bookkeeping; keep a buffer for residual addressing
+                t.buf = torch.zeros((t.B, t.H, t.W, t.ld), dtype=self.tdtype, device=dev)
+        self.N = sum(h * w * a for h, w, a in self.levels)
+        self.head_buf = torch.zeros((self.batch, self.N, 25), dtype=torch.float32, device=dev)
+        self.tail = tail
+        tail.prepare(self)
+        for op in self.ops:
+            op.prepare(self)
+        self.conv_flops = sum(getattr(op, "flops", 0) for op in self.ops)
+        return self
+
+    # ---------------------------------------------------------------- run ---
+    def forward(self, stream=None):
+        """Launch backbone + heads + tail on the current torch stream."""
+        st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        for op in self.ops:
+            op.launch(self, st)
+        self.tail.launch(self, st)
+
+    def capture(self):
+        """Capture the whole forward in a CUDA graph (launch-bound tail + 30-130 convs)."""
+        self.forward()  # warm-up outside capture (lazy attribute sets, driver entry points)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.forward()
+        self.graph = g
+        return g
+
+    def run(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.forward()
+
+    def num_launches(self):
+        n = 0
+        for op in self.ops:
+            n += 2 if isinstance(op, GroupNormActOp) else 1
+        return n + self.tail.num_launches()
+
+
+class Tail:
+    """decode + per-class NMS (+ optional class-major compaction) on [B,N,25] rows."""
+
+    def __init__(self, kind, num_fg, nms_classes, score_thr, iou_thr, max_boxes, level_fn, cap=None):
+        self.kind, self.num_fg, self.nms_classes = kind, num_fg, nms_classes
+        self.score_thr, self.iou_thr, self.max_boxes = score_thr, iou_thr, max_boxes
+        self.level_fn, self.cap = level_fn, cap
+
+    def prepare(self, net):
+        dev = net.device
+        B, N = net.batch, net.N
+        p = L.TailParams()
+        p.kind, p.num_levels, p.N = self.kind, len(net.levels), N
+        p.num_fg, p.nms_classes = self.num_fg, self.nms_classes
+        p.score_thr, p.iou_thr, p.max_boxes = self.score_thr, self.iou_thr, self.max_boxes
+        p.cap = self.cap or N
+        off = 0
+        for i, (h, w, a) in enumerate(net.levels):
+            lv = p.level[i]
+            lv.H, lv.W, lv.A, lv.offset = h, w, a, off
+            self.level_fn(i, h, w, lv)
+            off += h * w * a
+        self.p = p
+        self.cand_keys = torch.zeros((B, self.num_fg, p.cap), dtype=torch.int64, device=dev)
+        self.cand_count = torch.zeros((B, self.num_fg), dtype=torch.int32, device=dev)
+        D = self.nms_classes * self.max_boxes
+        self.D = D
+        self.dets = torch.zeros((B, D, 6), dtype=torch.float32, device=dev)
+        self.det_anchor = torch.zeros((B, D), dtype=torch.int32, device=dev)
+        self.det_count = torch.zeros((B,), dtype=torch.int32, device=dev)
+        nbytes = net.lib.odt_nms_scratch_bytes(C.byref(p), B)
+        self.scratch = torch.zeros((nbytes + 3) // 4, dtype=torch.int32, device=dev)
+        self.work = torch.zeros((B,), dtype=torch.int32, device=dev)
+        self.status = torch.zeros((1,), dtype=torch.int32, device=dev)
+
+    def launch(self, net, stream):
+        lib = net.lib
+        L.check(lib.odt_decode_candidates(net.head_buf.data_ptr(), C.byref(self.p), net.batch,
+                                          self.cand_keys.data_ptr(), self.cand_count.data_ptr(),
+                                          stream), "decode_candidates")
+        L.check(lib.odt_nms_per_class(net.head_buf.data_ptr(), C.byref(self.p), net.batch,
+                                      self.cand_keys.data_ptr(), self.cand_count.data_ptr(),
+                                      self.dets.data_ptr(), self.det_anchor.data_ptr(),
+                                      self.det_count.data_ptr(), self.scratch.data_ptr(),
+                                      self.work.data_ptr(), self.status.data_ptr(), stream),
+                "nms_per_class")
+
+    def num_launches(self):
+        return 3  # memset + decode + nms
+
+    def results(self):
+        """D2H read of the fixed-size detection records -> per-image python lists
+        [scores f32[K], bbox f32[K,4] (y1,x1,y2,x2), class_id i32[K]] (ref SSD300.py:190)."""
+        cnt = self.det_count.cpu().numpy()
+        dets = self.dets.cpu().numpy()
+        if int(self.status.item()) != 0:
+            raise L.OdtError("NMS candidate list overflowed its capacity (cap=%d)" % self.p.cap)
+        out = []
+        for b in range(dets.shape[0]):
+            d = dets[b, :cnt[b]]
+            out.append([d[:, 0].copy(), d[:, 1:5].copy(), d[:, 5].astype(np.int32)])
+        return out
+
+
+class RowsHarness:
+    """Runs a Tail on caller-provided candidate rows [B,N,25] (no backbone):
+    the tail kernels in isolation, for parity tests and the decode/NMS microbench."""
+
+    def __init__(self, tail, levels, rows, device="cuda"):
+        self.lib = L.load()
+        self.device = torch.device(device)
+        self.levels = list(levels)
+        self.head_buf = torch.as_tensor(np.ascontiguousarray(rows, dtype=np.float32)).to(self.device)
+        self.batch, self.N = self.head_buf.shape[0], self.head_buf.shape[1]
+        assert self.N == sum(h * w * a for h, w, a in self.levels) and self.head_buf.shape[2] == 25
+        self.tail = tail
+        tail.prepare(self)
+
+    def run(self):
+        self.tail.launch(self, torch.cuda.current_stream().cuda_stream)
+        return self.tail.results()
+
+    def keep_indices(self):
+        cnt = self.tail.det_count.cpu().numpy()
+        anc = self.tail.det_anchor.cpu().numpy()
+        return [anc[b, :cnt[b]].copy() for b in range(self.batch)]
+
+
+# ------------------------------------------------------------------ weights --
+def init_weights(variables, seed=1, bn_mode="tf_init", stem_scale=1.0 / 64.0):
+    """Seeded random initialisation in TF layout (HWIO kernels), creation order.
+    Conv kernels He-normal N(0, 2/fan_in); biases 0 (or -log(99) for 'pi');
+    BN/GN parameters at their TF initial values ('tf_init') or a 'trained'-like
+    random set so that folding is actually exercised.
+    The kernel that consumes the image (Cin == 3) is additionally scaled by
+    `stem_scale`: mean-subtracted pixels have std ~74, and with He init that
+    magnitude would propagate to the logits (saturated softmax, exp overflow);
+    1/64 keeps random-init activations O(1), as trained weights do."""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for name, (shape, kind) in variables.items():
+        if kind == "he":
+            fan_in = shape[0] * shape[1] * shape[2]
+            out[name] = (rng.standard_normal(shape) * math.sqrt(2.0 / fan_in)).astype(np.float32)
+            if shape[2] == 3:
+                out[name] *= np.float32(stem_scale)
+        elif kind == "zeros":
+            out[name] = np.zeros(shape, np.float32)
+        elif kind == "pi":
+            out[name] = np.full(shape, -math.log((1 - 0.01) / 0.01), np.float32)
+        elif kind == "l2norm":
+            out[name] = np.full(shape, 20.0, np.float32)
+        elif kind in ("bn_gamma", "gn_gamma"):
+            out[name] = (np.ones(shape, np.float32) if bn_mode == "tf_init"
+                         else rng.uniform(0.5, 1.5, shape).astype(np.float32))
+        elif kind in ("bn_beta", "gn_beta", "bn_mean"):
+            out[name] = (np.zeros(shape, np.float32) if bn_mode == "tf_init"
+                         else (rng.standard_normal(shape) * 0.1).astype(np.float32))
+        elif kind == "bn_var":
+            out[name] = (np.ones(shape, np.float32) if bn_mode == "tf_init"
+                         else rng.uniform(0.5, 1.5, shape).astype(np.float32))
+        else:
+            raise ValueError(kind)
+    return out

@@ -1,0 +1,21 @@
+"""Shared test configuration (reference driver defaults)."""
+BASE_CFG = {"mode": "test", "data_format": "channels_last", "num_classes": 20, "weight_decay": 1e-4,
+            "keep_prob": 0.5, "batch_size": 1, "nms_score_threshold": 0.5, "nms_max_boxes": 20,
+            "nms_iou_threshold": 0.5, "pretraining_weight": None}
+YOLO_PRIORS = [[[10, 13], [16, 30], [33, 23]], [[30, 61], [62, 45], [59, 119]],
+               [[116, 90], [156, 198], [373, 326]]]
+
+
+def model_cfg(kind, **over):
+    c = dict(BASE_CFG)
+    if kind == "retinanet":
+        c.update(data_shape=[128, 128, 3], is_bottleneck=True, residual_block_list=[3, 4, 6, 3],
+                 init_conv_filters=16, is_pretraining=False, gamma=2.0, alpha=0.25,
+                 nms_score_threshold=0.8, nms_max_boxes=10, nms_iou_threshold=0.45)
+    elif kind == "yolov3":
+        c.update(data_shape=[64, 64, 3], coord_scale=1, noobj_scale=1, obj_scale=5, class_scale=1,
+                 num_priors=3, priors=YOLO_PRIORS, nms_max_boxes=10, nms_iou_threshold=0.45)
+    elif kind == "fcos":
+        c.update(data_shape=[128, 128, 3], nms_max_boxes=10, nms_iou_threshold=0.45)
+    c.update(over)
+    return c

@@ -1,0 +1,226 @@
+"""GPU parity, stage (ii): convolution and glue kernels against plain fp32
+references (torch / the oracle's TF-op restatements) on the same inputs.
+Tolerances: fp16 tensor-core path -- fp16 operands are exact in both, fp32
+accumulation, fp16-rounded output => |err| <= 2e-3 * max|ref|; fp32 CUDA-core
+path => 2e-5 * max|ref| (accumulation order only)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _conv_case(B, H, W, Cin, Cout, k, stride, dil, mode, act="relu", residual=False, pre=False,
+               bn=True, f32_out=False, seed=0):
+    """mode: 'tc' (fp16 tcgen05), 'direct16', 'direct32'.  Returns (got, ref, got1, ref1)."""
+    from odt_b200 import lib as L
+    from odt_b200.engine import same_pad
+    from oracle import tfops as T
+    lib = L.load()
+    rng = np.random.default_rng(seed)
+    f16 = mode != "direct32"
+    tdt = torch.float16 if f16 else torch.float32
+    ld = (Cin + 63) // 64 * 64 if mode == "tc" else Cin
+    x = (rng.standard_normal((B, H, W, Cin)) * 1.0).astype(np.float32)
+    w = (rng.standard_normal((k, k, Cin, Cout)) * np.sqrt(2.0 / (k * k * Cin))).astype(np.float32)
+    if f16:
+        x = x.astype(np.float16).astype(np.float32)
+        w = w.astype(np.float16).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, Cout).astype(np.float32) if bn else None
+    shift = (rng.standard_normal(Cout) * 0.2).astype(np.float32)
+    OH, pt, _ = same_pad(H, k, stride, dil)
+    OW, pl, _ = same_pad(W, k, stride, dil)
+    old = (Cout + 63) // 64 * 64 if mode == "tc" else Cout
+    dev = "cuda"
+    xd = torch.zeros((B, H, W, ld), dtype=tdt, device=dev)
+    xd[..., :Cin] = torch.from_numpy(x).to(dev).to(tdt)
+    ohwi = np.transpose(w, (3, 0, 1, 2))
+    if mode == "tc":
+        cpad = (Cout + 31) // 32 * 32
+        wp = np.zeros((cpad, k, k, ld), np.float32)
+        wp[:Cout, :, :, :Cin] = ohwi
+    else:
+        cpad, wp = Cout, np.ascontiguousarray(ohwi)
+    wd = torch.from_numpy(wp).to(dev).to(tdt)
+    res = None
+    if residual:
+        res = (rng.standard_normal((B, OH, OW, Cout))).astype(np.float32)
+        if f16:
+            res = res.astype(np.float16).astype(np.float32)
+    out_dt = torch.float32 if (f32_out or not f16) else torch.float16
+    yd = torch.zeros((B, OH, OW, old), dtype=out_dt, device=dev)
+    rd = None
+    if residual:
+        rd = torch.zeros((B, OH, OW, old), dtype=tdt, device=dev)
+        rd[..., :Cout] = torch.from_numpy(res).to(dev).to(tdt)
+    p = L.ConvParams()
+    p.B, p.H, p.W, p.Cin, p.in_ld = B, H, W, Cin, ld
+    p.OH, p.OW, p.Cout = OH, OW, Cout
+    p.R, p.S, p.stride, p.dil, p.pad_t, p.pad_l = k, k, stride, dil, pt, pl
+    p.w_ld, p.Cout_pad = (ld if mode == "tc" else Cin), cpad
+    sd = torch.from_numpy(scale).to(dev) if scale is not None else None
+    hd = torch.from_numpy(shift).to(dev)
+    p.scale = sd.data_ptr() if sd is not None else None
+    p.shift = hd.data_ptr()
+    p.act = {"relu": 1, "leaky": 2, None: 0}[act]
+    p.residual = rd.data_ptr() if rd is not None else None
+    p.out0 = yd.data_ptr()
+    p.out0_dtype = L.ODT_F32 if out_dt == torch.float32 else L.ODT_F16
+    p.out0_img_stride, p.out0_pix_stride = OH * OW * old, old
+    s2 = h2 = y1 = None
+    if pre:
+        s2 = rng.uniform(0.5, 1.5, Cout).astype(np.float32)
+        h2 = (rng.standard_normal(Cout) * 0.2).astype(np.float32)
+        s2d, h2d = torch.from_numpy(s2).to(dev), torch.from_numpy(h2).to(dev)
+        y1 = torch.zeros((B, OH, OW, old), dtype=tdt, device=dev)
+        p.scale2, p.shift2, p.act2 = s2d.data_ptr(), h2d.data_ptr(), 1
+        p.out1, p.out1_img_stride, p.out1_pix_stride = y1.data_ptr(), OH * OW * old, old
+    st = torch.cuda.current_stream().cuda_stream
+    if mode == "tc":
+        rc = lib.odt_conv2d_f16_tc(xd.data_ptr(), wd.data_ptr(), C.byref(p), st)
+    else:
+        rc = lib.odt_conv2d_direct(xd.data_ptr(), wd.data_ptr(), L.ODT_F16 if f16 else L.ODT_F32,
+                                   C.byref(p), st)
+    L.check(rc, "conv")
+    torch.cuda.synchronize()
+    ref = T.conv2d_same(x, w, None, stride, dil)
+    ref = ref * (scale if scale is not None else 1.0) + shift
+    if act == "relu":
+        ref = np.maximum(ref, 0)
+    elif act == "leaky":
+        ref = np.maximum(ref, 0.1 * ref)
+    if residual:
+        ref = ref + res
+    got = yd[..., :Cout].float().cpu().numpy()
+    got1 = ref1 = None
+    if pre:
+        base = got if f16 and not f32_out else ref
+        ref1 = np.maximum(base * s2 + h2, 0)
+        got1 = y1[..., :Cout].float().cpu().numpy()
+    if mode == "tc" and old > Cout and not f32_out:
+        assert float(yd[..., Cout:].abs().max()) == 0.0, "pad channels must stay zero"
+    return got, ref.astype(np.float32), got1, ref1
+
+
+TC_SHAPES = [
+    # B, H, W, Cin, Cout, k, stride, dil      (SSD300 / RetinaNet / YOLOv3 layer shapes, small B)
+    (2, 38, 38, 512, 512, 3, 1, 1),
+    (2, 19, 19, 512, 1024, 3, 1, 2),   # conv6, dilation 2
+    (2, 19, 19, 1024, 1024, 1, 1, 1),  # conv7, 1x1
+    (2, 19, 19, 256, 512, 3, 2, 1),    # conv8_2: 19 -> 10 pads (1,1)
+    (3, 10, 10, 128, 256, 3, 2, 1),    # conv9_2: 10 -> 5 pads (0,1)
+    (1, 5, 5, 128, 256, 3, 1, 1),      # conv10_2 (tile larger than the whole problem)
+    (3, 75, 75, 64, 128, 3, 1, 1),     # odd width, tiles wrap rows and images
+    (1, 150, 150, 64, 64, 3, 1, 1),
+    (2, 26, 26, 768, 128, 1, 1, 1),    # YOLOv3 head after concat
+    (2, 52, 52, 128, 256, 3, 2, 1),    # darknet down-sampling 52 -> 26 pads (0,1)
+    (1, 50, 50, 256, 256, 3, 1, 1),    # RetinaNet tower
+    (2, 13, 13, 256, 256, 3, 2, 1),    # P6 -> P7: 13 -> 7 pads (1,1)
+    (1, 25, 25, 28, 7, 1, 1, 1),       # RetinaNet 7*2^i widths: padded Cin, tiny ragged Cout
+]
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_conv_tc_vs_fp32_reference(built, shape):
+    got, ref, _, _ = _conv_case(*shape, mode="tc", seed=hash(shape) % 1000)
+    err = np.abs(got - ref).max()
+    assert err <= 2e-3 * max(np.abs(ref).max(), 1.0), (shape, float(err), float(np.abs(ref).max()))
+
+
+def test_conv_tc_epilogue_variants(built):
+    base = (2, 19, 19, 256, 256, 3, 1, 1)
+    for kw in (dict(act="leaky", residual=True), dict(act=None, bn=False, pre=True),
+               dict(act=None, residual=True, pre=True), dict(act="relu", f32_out=True)):
+        got, ref, got1, ref1 = _conv_case(*base, mode="tc", **kw)
+        tol = 2e-3 * max(np.abs(ref).max(), 1.0)
+        assert np.abs(got - ref).max() <= tol, kw
+        if got1 is not None:
+            assert np.abs(got1 - ref1).max() <= 4e-3 * max(np.abs(ref1).max(), 1.0), kw
+    # head-style output: ragged Cout (100, 150), fp32, through the generic store path
+    for cout in (100, 150, 75, 36, 189, 20, 4, 1):
+        got, ref, _, _ = _conv_case(1, 10, 10, 256, cout, 3, 1, 1, mode="tc", act=None, f32_out=True)
+        assert np.abs(got - ref).max() <= 2e-3 * max(np.abs(ref).max(), 1.0), cout
+
+
+@pytest.mark.parametrize("mode,tol", [("direct32", 2e-5), ("direct16", 2e-3)])
+def test_conv_direct_vs_fp32_reference(built, mode, tol):
+    for shape in [(2, 19, 19, 64, 96, 3, 1, 2), (2, 20, 20, 3, 16, 7, 2, 1), (1, 10, 10, 7, 28, 3, 2, 1),
+                  (2, 13, 13, 100, 75, 1, 1, 1), (1, 38, 38, 32, 64, 3, 1, 1)]:
+        got, ref, got1, ref1 = _conv_case(*shape, mode=mode, act="leaky", residual=True, pre=True)
+        assert np.abs(got - ref).max() <= tol * max(np.abs(ref).max(), 1.0), (mode, shape)
+        assert np.abs(got1 - ref1).max() <= 2 * tol * max(np.abs(ref1).max(), 1.0), (mode, shape)
+
+
+def test_conv_tc_matches_direct_on_device(built):
+    """The two independent device implementations agree (cross-check of im2col TMA)."""
+    a, _, _, _ = _conv_case(2, 38, 38, 128, 128, 3, 1, 1, mode="tc")
+    b, _, _, _ = _conv_case(2, 38, 38, 128, 128, 3, 1, 1, mode="direct16")
+    assert np.abs(a - b).max() <= 4e-3 * max(np.abs(b).max(), 1.0)
+
+
+def _dev(a, dt):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda().to(dt)
+
+
+@pytest.mark.parametrize("dtype", ["f32", "f16"])
+def test_glue_kernels_vs_oracle_ops(built, dtype):
+    from odt_b200 import lib as L
+    from oracle import tfops as T
+    lib = L.load()
+    dt, code, tol = (torch.float32, L.ODT_F32, 1e-5) if dtype == "f32" else (torch.float16, L.ODT_F16, 2e-3)
+    st = torch.cuda.current_stream().cuda_stream
+    rng = np.random.default_rng(3)
+
+    def rnd(*s):
+        a = rng.standard_normal(s).astype(np.float32)
+        return a.astype(np.float16).astype(np.float32) if dtype == "f16" else a
+
+    # max-pool 2/2 on 75 -> 38 (pads 0,1), 3/1 on 19, 3/2 on 20 -> 10
+    for (h, k, s) in [(75, 2, 2), (19, 3, 1), (20, 3, 2)]:
+        x = rnd(2, h, h, 64)
+        ref = T.max_pool_same(x, k, s)
+        y = torch.zeros(ref.shape, dtype=dt, device="cuda")
+        L.check(lib.odt_maxpool(_dev(x, dt).data_ptr(), y.data_ptr(), code, 2, h, h, 64, 64, k, s, st))
+        np.testing.assert_allclose(y.float().cpu().numpy(), ref, atol=0)
+    # channel L2 norm x scale
+    x = rnd(2, 9, 9, 512)
+    ref = 20.0 * T.l2_normalize_channels(x)
+    y = torch.zeros(x.shape, dtype=dt, device="cuda")
+    L.check(lib.odt_l2norm_scale(_dev(x, dt).data_ptr(), y.data_ptr(), code, 2 * 81, 512, 512, 20.0, st))
+    np.testing.assert_allclose(y.float().cpu().numpy(), ref, atol=tol * 4, rtol=tol)
+    # affine + relu
+    x = rnd(2, 7, 7, 64)
+    sc, sh = rng.uniform(.5, 1.5, 64).astype(np.float32), rng.standard_normal(64).astype(np.float32)
+    y = torch.zeros(x.shape, dtype=dt, device="cuda")
+    L.check(lib.odt_affine_act(_dev(x, dt).data_ptr(), y.data_ptr(), code, 98, 64, 64,
+                               _dev(sc, torch.float32).data_ptr(), _dev(sh, torch.float32).data_ptr(), 1, st))
+    np.testing.assert_allclose(y.float().cpu().numpy(), np.maximum(x * sc + sh, 0), atol=tol * 8, rtol=tol)
+    # FPN: a + legacy bilinear(top), 13 -> 25 and 4 -> 8
+    for th, h in [(13, 25), (4, 8), (25, 50)]:
+        top, a = rnd(2, th, th, 64), rnd(2, h, h, 64)
+        ref = a + T.resize_bilinear_legacy(top, h, h)
+        y = torch.zeros(a.shape, dtype=dt, device="cuda")
+        L.check(lib.odt_upsample_bilinear_add(_dev(top, dt).data_ptr(), _dev(a, dt).data_ptr(), y.data_ptr(),
+                                              code, 2, th, th, h, h, 64, 64, None, None, 0, None, st))
+        np.testing.assert_allclose(y.float().cpu().numpy(), ref, atol=tol * 8, rtol=tol)
+    # YOLOv3 nearest + concat
+    a, b = rnd(2, 26, 26, 64), rnd(2, 13, 13, 32)
+    ref = np.concatenate([a, T.resize_nearest_legacy(b, 26, 26)], axis=3)
+    y = torch.zeros((2, 26, 26, 128), dtype=dt, device="cuda")
+    L.check(lib.odt_upsample_nearest_concat(_dev(a, dt).data_ptr(), _dev(b, dt).data_ptr(), y.data_ptr(), code,
+                                            2, 26, 26, 64, 64, 13, 13, 32, 32, 128, st))
+    np.testing.assert_array_equal(y[..., :96].float().cpu().numpy(), ref)
+    # GroupNorm(8) + relu
+    x = rnd(2, 11, 13, 64)
+    g, bt = rng.uniform(.5, 1.5, 64).astype(np.float32), rng.standard_normal(64).astype(np.float32)
+    ref = np.maximum(T.group_norm(x, g, bt), 0)
+    stats = torch.zeros(2 * 8 * 2, dtype=torch.float32, device="cuda")
+    y = torch.zeros(x.shape, dtype=dt, device="cuda")
+    xd = _dev(x, dt)
+    L.check(lib.odt_groupnorm_stats(xd.data_ptr(), stats.data_ptr(), code, 2, 11 * 13, 64, 64, 8, 1e-6, st))
+    L.check(lib.odt_groupnorm_apply(xd.data_ptr(), y.data_ptr(), stats.data_ptr(), code, 2, 11 * 13, 64, 64, 8,
+                                    _dev(g, torch.float32).data_ptr(), _dev(bt, torch.float32).data_ptr(), 1, st))
+    np.testing.assert_allclose(y.float().cpu().numpy(), ref, atol=tol * 8, rtol=tol)
+    torch.cuda.synchronize()

@@ -1,0 +1,179 @@
+"""GPU parity, stage (iii): whole networks through the reference's model API
+against the CPU oracle on identical inputs and weights.
+  * fp32 CUDA-core path ("reference precision"): head rows within 2e-4 * max|ref|
+    (accumulation order), detections: class ids / keep indices exact and boxes
+    within 1e-4 whenever the oracle's own decision margins allow it (reported);
+  * fp16 tcgen05 path: head rows within 3e-2 * max|ref| (fp16 storage of 20-130
+    layers; SURVEY.md "hard part" 1 -- graded stage-wise, never by loosening the
+    tail tolerance: the tail is always exact on the rows the GPU produced)."""
+import numpy as np
+import pytest
+
+from helpers import model_cfg
+
+pytestmark = pytest.mark.gpu
+
+
+def _img(b, h, w, seed=0):
+    return np.random.default_rng(seed).integers(0, 256, (b, h, w, 3)).astype(np.float32)
+
+
+def _oracle_rows(kind, weights, img, cfg):
+    from oracle import nets as ON
+    from oracle import tails as OT
+    if kind in ("ssd300", "ssd512"):
+        return OT.ssd_rows(ON.ssd_heads(weights, img, int(kind[3:])))
+    if kind == "retinanet":
+        return OT.retina_rows(ON.retinanet_heads(weights, img))
+    if kind == "yolov3":
+        return OT.yolo_rows(ON.yolov3_heads(weights, img))
+    return OT.fcos_rows(ON.fcos_heads(weights, img))
+
+
+def _model(kind, **over):
+    import FCOS
+    import RetinaNet
+    import SSD300
+    import SSD512
+    import YOLOv3
+    if kind == "ssd300":
+        return SSD300.SSD300(model_cfg("ssd", **over), None)
+    if kind == "ssd512":
+        return SSD512.SSD512(model_cfg("ssd", **over), None)
+    if kind == "retinanet":
+        return RetinaNet.RetinaNet(model_cfg("retinanet", **over), None)
+    if kind == "yolov3":
+        return YOLOv3.YOLOv3(model_cfg("yolov3", **over), None)
+    return FCOS.FCOS(model_cfg("fcos", **over), None)
+
+
+def _tail_oracle_on_rows(kind, rows, cfg, image=0):
+    """Oracle tail fed the GPU's own head rows (stage-wise parity)."""
+    from oracle import tails as OT
+    r = rows[image]
+    thr, mb, iou = cfg["nms_score_threshold"], cfg["nms_max_boxes"], cfg["nms_iou_threshold"]
+    if kind in ("ssd300", "ssd512"):
+        size = int(kind[3:])
+        shapes = ([(38, 38), (19, 19), (10, 10), (5, 5), (5, 5), (3, 3)] if size == 300 else
+                  [(64, 64), (32, 32), (16, 16), (8, 8), (8, 8), (4, 4), (2, 2)])
+        _, _, ayx, ahw = OT.ssd_anchors(size, shapes)
+        return OT.softmax_tail(r[:, :21], r[:, 21:23], r[:, 23:], ayx, ahw, 20, thr, mb, iou)
+    raise NotImplementedError
+
+
+SHAPES = {"ssd300": (300, 300), "retinanet": (128, 128), "yolov3": (64, 64), "fcos": (128, 128)}
+
+
+@pytest.mark.parametrize("kind", ["ssd300", "retinanet", "yolov3", "fcos"])
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("fp16", 3e-2)])
+def test_head_rows_vs_oracle(built, kind, precision, tol):
+    m = _model(kind, bn_init="trained", precision=precision)
+    h, w = SHAPES[kind]
+    img = _img(2, h, w, seed=4)
+    m.detect_batch(img)
+    rows = m.engine(2).head_buf.cpu().numpy()
+    ref = _oracle_rows(kind, m.get_weights(), img, m.config)
+    assert rows.shape == ref.shape
+    scale = float(np.abs(ref).max())
+    err = float(np.abs(rows - ref).max())
+    print("%s %s: max|err| %.3g of max|ref| %.3g (%.2e rel)" % (kind, precision, err, scale, err / scale))
+    assert np.isfinite(rows).all()
+    assert err <= tol * scale, (kind, precision, err, scale)
+
+
+def test_ssd300_reference_plumbing_config_fp32(built):
+    """BASELINE config 0: random-init SSD300, ONE 300x300 image through
+    test_one_image, reference-precision path, against the end-to-end oracle."""
+    from oracle import nets as ON
+    from oracle import tails as OT
+    m = _model("ssd300", precision="fp32", nms_score_threshold=0.3)
+    img = _img(1, 300, 300, seed=0)
+    res = m.test_one_image(img)
+    assert len(res) == 3 and res[0].dtype == np.float32 and res[2].dtype == np.int32
+    assert res[1].shape == (len(res[0]), 4)
+    net = m.engine(1)
+    rows = net.head_buf.cpu().numpy()
+    # (a) tail exact on the GPU's rows
+    exp = _tail_oracle_on_rows("ssd300", rows, m.config)
+    np.testing.assert_array_equal(res[2], exp[2])
+    np.testing.assert_array_equal(net.tail.det_anchor.cpu().numpy()[0, :len(exp[3])], exp[3])
+    assert np.all(np.abs(res[1] - exp[1]) <= 1e-4 + 1e-6 * np.abs(exp[1]))
+    # (b) end to end against the oracle's own forward: identical decisions wherever the
+    #     oracle's margins exceed the measured row error
+    preds = ON.ssd_heads(m.get_weights(), img, 300)
+    full = OT.ssd_detect(preds, 300, 0.3, 20, 0.5)
+    same = len(full[2]) == len(res[2]) and np.array_equal(full[2], res[2]) and np.array_equal(
+        full[3], net.tail.det_anchor.cpu().numpy()[0, :len(full[3])])
+    rows_ref = OT.ssd_rows(preds)
+    print("end-to-end fp32: identical decisions =", same, " rows max|err| =",
+          float(np.abs(rows - rows_ref).max()))
+    if same:
+        d = np.abs(res[1] - full[1])
+        print("end-to-end fp32: max box |err| = %.3g px" % float(d.max()) if len(d) else "no boxes")
+        assert np.all(d <= 5e-3 + 1e-5 * np.abs(full[1]))
+    else:
+        frac = len(set(zip(full[2].tolist(), full[3].tolist())) &
+                   set(zip(res[2].tolist(), net.tail.det_anchor.cpu().numpy()[0, :len(res[2])].tolist())))
+        assert frac >= 0.9 * max(len(full[2]), 1), "more than 10% of decisions differ"
+
+
+def test_ssd300_fp16_batch_and_api(built):
+    m = _model("ssd300", precision="fp16", nms_score_threshold=0.3)
+    img = _img(4, 300, 300, seed=9)
+    res = m.test_one_image(img)
+    assert isinstance(res, list) and len(res) == 4
+    one = m.test_one_image(img[2:3])
+    # batch-invariance of the kernels: image 2 alone == image 2 inside the batch
+    for a, b in zip(one, res[2]):
+        np.testing.assert_array_equal(a, b)
+    rows = m.engine(4).head_buf.cpu().numpy()
+    for b in range(4):
+        exp = _tail_oracle_on_rows("ssd300", rows, m.config, image=b)
+        np.testing.assert_array_equal(res[b][2], exp[2])
+        assert np.all(np.abs(res[b][1] - exp[1]) <= 1e-4 + 1e-6 * np.abs(exp[1]))
+
+
+def test_ssd512_builds_and_runs(built):
+    m = _model("ssd512", precision="fp16", nms_score_threshold=0.3)
+    res = m.test_one_image(_img(1, 512, 512))
+    assert m.engine(1).N == 24912 and len(res) == 3
+
+
+def test_tc_and_direct_paths_agree_on_network(built):
+    m = _model("yolov3", precision="fp16", bn_init="trained")
+    img = _img(2, 64, 64, seed=2)
+    m.detect_batch(img)
+    a = m.engine(2).head_buf.cpu().numpy().copy()
+    net = m.engine(2, allow_tc=False, graph=False)
+    net.image_buf.copy_(__import__("torch").from_numpy(img))
+    net.run()
+    __import__("torch").cuda.synchronize()
+    b = net.head_buf.cpu().numpy()
+    assert np.abs(a - b).max() <= 2e-2 * np.abs(b).max()
+
+
+def test_retinanet_loss_forward_vs_oracle(built):
+    from oracle import loss as OL
+    from oracle import nets as ON
+    from oracle import tails as OT
+    m = _model("retinanet", precision="fp32", bn_init="trained")
+    B, G = 2, 12
+    img = _img(B, 128, 128, seed=6)
+    rng = np.random.default_rng(3)
+    gt = np.full((B, G, 5), -1.0, np.float32)
+    for b in range(B):
+        n = 3 + 4 * b
+        gt[b, :n, 0:2] = rng.uniform(10, 118, (n, 2))
+        gt[b, :n, 2:4] = rng.uniform(16, 64, (n, 2))
+        gt[b, :n, 4] = rng.integers(0, 20, n)
+    got = m.loss_forward(img, gt)
+    rows = m.engine(B).head_buf.cpu().numpy()
+    heads = ON.retinanet_heads(m.get_weights(), img)
+    shapes = [(c.shape[1], c.shape[2]) for c, _ in heads]
+    a1, a2, ayx, ahw = OT.retina_anchors([128, 128, 3], shapes)
+    for b in range(B):
+        ref, info = OL.retina_image_loss(rows[b, :, :21], rows[b, :, 21:23], rows[b, :, 23:], a1, a2, ayx,
+                                         ahw, gt[b])
+        print("image %d: loss gpu %.6f oracle %.6f (%d pos, %d neg)" % (b, got[b], ref, info["num_pos"],
+                                                                       info["num_neg"]))
+        assert abs(got[b] - ref) <= 2e-5 * max(abs(ref), 1.0)
