@@ -468,11 +468,6 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
                  (!p->residual || ((uintptr_t)p->residual & 15) == 0) &&
                  (!p->out1 || (((uintptr_t)p->out1 & 15) == 0 && p->out1_pix_stride % 8 == 0 &&
                                p->out1_img_stride % 8 == 0));
-  if (!p->out0 && p->out1) {
-    // out1-only: address math of the fast path still uses out0 strides for the residual
-    ODT_CHECK_ARG(!p->residual, "residual requires out0 addressing");
-  }
-
   CUtensorMap tmA, tmB;
   {
     cuuint64_t dims[4] = {(cuuint64_t)p->in_ld, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->B};

@@ -182,34 +182,38 @@ def test_glue_kernels_vs_oracle_ops(built, dtype):
         x = rnd(2, h, h, 64)
         ref = T.max_pool_same(x, k, s)
         y = torch.zeros(ref.shape, dtype=dt, device="cuda")
-        L.check(lib.odt_maxpool(_dev(x, dt).data_ptr(), y.data_ptr(), code, 2, h, h, 64, 64, k, s, st))
+        xd = _dev(x, dt)
+        L.check(lib.odt_maxpool(xd.data_ptr(), y.data_ptr(), code, 2, h, h, 64, 64, k, s, st))
         np.testing.assert_allclose(y.float().cpu().numpy(), ref, atol=0)
     # channel L2 norm x scale
     x = rnd(2, 9, 9, 512)
     ref = 20.0 * T.l2_normalize_channels(x)
     y = torch.zeros(x.shape, dtype=dt, device="cuda")
-    L.check(lib.odt_l2norm_scale(_dev(x, dt).data_ptr(), y.data_ptr(), code, 2 * 81, 512, 512, 20.0, st))
+    xd = _dev(x, dt)
+    L.check(lib.odt_l2norm_scale(xd.data_ptr(), y.data_ptr(), code, 2 * 81, 512, 512, 20.0, st))
     np.testing.assert_allclose(y.float().cpu().numpy(), ref, atol=tol * 4, rtol=tol)
     # affine + relu
     x = rnd(2, 7, 7, 64)
     sc, sh = rng.uniform(.5, 1.5, 64).astype(np.float32), rng.standard_normal(64).astype(np.float32)
     y = torch.zeros(x.shape, dtype=dt, device="cuda")
-    L.check(lib.odt_affine_act(_dev(x, dt).data_ptr(), y.data_ptr(), code, 98, 64, 64,
-                               _dev(sc, torch.float32).data_ptr(), _dev(sh, torch.float32).data_ptr(), 1, st))
+    xd, scd, shd = _dev(x, dt), _dev(sc, torch.float32), _dev(sh, torch.float32)
+    L.check(lib.odt_affine_act(xd.data_ptr(), y.data_ptr(), code, 98, 64, 64, scd.data_ptr(), shd.data_ptr(), 1, st))
     np.testing.assert_allclose(y.float().cpu().numpy(), np.maximum(x * sc + sh, 0), atol=tol * 8, rtol=tol)
     # FPN: a + legacy bilinear(top), 13 -> 25 and 4 -> 8
     for th, h in [(13, 25), (4, 8), (25, 50)]:
         top, a = rnd(2, th, th, 64), rnd(2, h, h, 64)
         ref = a + T.resize_bilinear_legacy(top, h, h)
         y = torch.zeros(a.shape, dtype=dt, device="cuda")
-        L.check(lib.odt_upsample_bilinear_add(_dev(top, dt).data_ptr(), _dev(a, dt).data_ptr(), y.data_ptr(),
+        topd, ad = _dev(top, dt), _dev(a, dt)
+        L.check(lib.odt_upsample_bilinear_add(topd.data_ptr(), ad.data_ptr(), y.data_ptr(),
                                               code, 2, th, th, h, h, 64, 64, None, None, 0, None, st))
         np.testing.assert_allclose(y.float().cpu().numpy(), ref, atol=tol * 8, rtol=tol)
     # YOLOv3 nearest + concat
     a, b = rnd(2, 26, 26, 64), rnd(2, 13, 13, 32)
     ref = np.concatenate([a, T.resize_nearest_legacy(b, 26, 26)], axis=3)
     y = torch.zeros((2, 26, 26, 128), dtype=dt, device="cuda")
-    L.check(lib.odt_upsample_nearest_concat(_dev(a, dt).data_ptr(), _dev(b, dt).data_ptr(), y.data_ptr(), code,
+    ad, bd = _dev(a, dt), _dev(b, dt)
+    L.check(lib.odt_upsample_nearest_concat(ad.data_ptr(), bd.data_ptr(), y.data_ptr(), code,
                                             2, 26, 26, 64, 64, 13, 13, 32, 32, 128, st))
     np.testing.assert_array_equal(y[..., :96].float().cpu().numpy(), ref)
     # GroupNorm(8) + relu
@@ -218,9 +222,9 @@ def test_glue_kernels_vs_oracle_ops(built, dtype):
     ref = np.maximum(T.group_norm(x, g, bt), 0)
     stats = torch.zeros(2 * 8 * 2, dtype=torch.float32, device="cuda")
     y = torch.zeros(x.shape, dtype=dt, device="cuda")
-    xd = _dev(x, dt)
+    xd, gd, btd = _dev(x, dt), _dev(g, torch.float32), _dev(bt, torch.float32)
     L.check(lib.odt_groupnorm_stats(xd.data_ptr(), stats.data_ptr(), code, 2, 11 * 13, 64, 64, 8, 1e-6, st))
     L.check(lib.odt_groupnorm_apply(xd.data_ptr(), y.data_ptr(), stats.data_ptr(), code, 2, 11 * 13, 64, 64, 8,
-                                    _dev(g, torch.float32).data_ptr(), _dev(bt, torch.float32).data_ptr(), 1, st))
+                                    gd.data_ptr(), btd.data_ptr(), 1, st))
     np.testing.assert_allclose(y.float().cpu().numpy(), ref, atol=tol * 8, rtol=tol)
     torch.cuda.synchronize()
