@@ -14,7 +14,7 @@
 // * Epilogue: tcgen05.ld -> folded bias/BN scale+shift, activation, residual,
 //   optional second (pre-activated) output -> 128-bit global stores.
 // * Persistent: one CTA per SM, static round-robin tile schedule, warp roles:
-//   w0 = TMA producer, w1 = TMEM allocator + MMA issuer, w2..5 = epilogue.
+//   w0 = TMA producer, w1 = TMEM allocator + MMA issuer, w2..9 = epilogue (2 warps per TMEM lane quarter).
 //
 // ref call sites: tf.nn.conv2d SSD300.py:519; tf.layers.conv2d SSD300.py:524,
 // RetinaNet.py:579,599,609, YOLOv3.py:495, FCOS.py:449,469,479.
@@ -26,7 +26,9 @@ namespace odt {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = 32 * (2 + TC_EPI_WARPS);  // TMA, MMA, 8 epilogue warps
+constexpr int TC_EPI_SMEM = 2 * 4 * 256 * 4;  // double-buffered scale/shift/scale2/shift2
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KiB
 constexpr int TC_SMEM_LIMIT = 232448;          // 227 KiB
@@ -164,6 +166,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const uint32_t tmem_slot = bar_base + 8u * (2 * TC_MAX_STAGES + 4);
   uint32_t* tmem_slot_ptr =
       reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+  // per-tile epilogue parameters staged in smem: [buf][scale|shift|scale2|shift2][256]
+  float* epi_par = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -176,7 +180,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), TC_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -263,36 +267,58 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
   } else {
     // ===================== epilogue warps =====================================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    int acc = 0;
+    // 8 warps: TMEM lane quarter = warp % 4 (hardware restriction), the two warps
+    // of a quarter split the 32-column chunks even/odd.
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int et = threadIdx.x - 64;  // 0..255 within the epilogue group
+    int acc = 0, local_tile = 0;
     uint32_t acc_phase[2] = {0u, 0u};
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
       const int n_tile = tile % g.num_n_tiles, m_tile = tile / g.num_n_tiles;
       const long long m = (long long)m_tile * TC_BM + quarter * 32 + lane;
       const bool row_ok = m < g.M;
       const int img = row_ok ? (int)(m / g.ohw) : 0;
       const int pix = row_ok ? (int)(m - (long long)img * g.ohw) : 0;
       const int n0 = n_tile * g.BN;
+      // stage this tile's per-channel parameters (broadcast reads later)
+      float* par = epi_par + (local_tile & 1) * 1024;
+      {
+        const int n = n0 + et;
+        const bool ok = et < g.BN && n < e.Cout;
+        par[et] = (ok && e.scale) ? __ldg(e.scale + n) : 1.f;
+        par[256 + et] = (ok && e.shift) ? __ldg(e.shift + n) : 0.f;
+        par[512 + et] = (ok && e.scale2) ? __ldg(e.scale2 + n) : 1.f;
+        par[768 + et] = (ok && e.shift2) ? __ldg(e.shift2 + n) : 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(tfull_bar(acc), acc_phase[acc]);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(quarter * 32) << 16);
-      for (int j = 0; j < g.BN / 32; ++j) {
+      const long long o0_row =
+          (long long)img * e.out0_img_stride + (long long)pix * e.out0_pix_stride;
+      const long long o1_row =
+          (long long)img * e.out1_img_stride + (long long)pix * e.out1_pix_stride;
+      for (int j = half; j < g.BN / 32; j += 2) {
+        const int nb = n0 + j * 32;
+        if (nb >= e.Cout) break;  // fully padded chunk (uniform)
         uint32_t r[32];
         tc_ld32(taddr0 + (uint32_t)(j * 32), r);
         tc_wait_ld();
-        const int nb = n0 + j * 32;
-        if (nb >= e.Cout) continue;  // fully padded chunk (uniform)
         if (g.fast_store && nb + 32 <= e.Cout) {
+          const float4* ps = reinterpret_cast<const float4*>(par + j * 32);
+          const float4* ph4 = reinterpret_cast<const float4*>(par + 256 + j * 32);
           float v[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float sc = e.scale ? __ldg(e.scale + nb + i) : 1.f;
-            float sh = e.shift ? __ldg(e.shift + nb + i) : 0.f;
-            v[i] = apply_act(fmaf(__uint_as_float(r[i]), sc, sh), e.act);
+          for (int i = 0; i < 8; ++i) {
+            const float4 sc = ps[i], sh = ph4[i];
+            v[4 * i + 0] = apply_act(fmaf(__uint_as_float(r[4 * i + 0]), sc.x, sh.x), e.act);
+            v[4 * i + 1] = apply_act(fmaf(__uint_as_float(r[4 * i + 1]), sc.y, sh.y), e.act);
+            v[4 * i + 2] = apply_act(fmaf(__uint_as_float(r[4 * i + 2]), sc.z, sh.z), e.act);
+            v[4 * i + 3] = apply_act(fmaf(__uint_as_float(r[4 * i + 3]), sc.w, sh.w), e.act);
           }
           if (row_ok) {
-            const long long o0 =
-                (long long)img * e.out0_img_stride + (long long)pix * e.out0_pix_stride + nb;
+            const long long o0 = o0_row + nb;
             if (e.residual) {
               const uint4* rp =
                   reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(e.residual) + o0);
@@ -318,21 +344,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               for (int qd = 0; qd < 4; ++qd) op[qd] = packed[qd];
             }
             if (e.out1) {
+              const float4* ps2 = reinterpret_cast<const float4*>(par + 512 + j * 32);
+              const float4* ph2 = reinterpret_cast<const float4*>(par + 768 + j * 32);
               uint4 packed1[4];
               __half2* p1 = reinterpret_cast<__half2*>(packed1);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                float2 f = __half22float2(ph[i]);  // consumer sees the rounded value
-                float s0 = e.scale2 ? __ldg(e.scale2 + nb + 2 * i) : 1.f;
-                float s1 = e.scale2 ? __ldg(e.scale2 + nb + 2 * i + 1) : 1.f;
-                float h0 = e.shift2 ? __ldg(e.shift2 + nb + 2 * i) : 0.f;
-                float h1 = e.shift2 ? __ldg(e.shift2 + nb + 2 * i + 1) : 0.f;
-                p1[i] = __floats2half2_rn(apply_act(fmaf(f.x, s0, h0), e.act2),
-                                          apply_act(fmaf(f.y, s1, h1), e.act2));
+              for (int i = 0; i < 8; ++i) {
+                const float4 sc = ps2[i], sh = ph2[i];
+                const float2 fa = __half22float2(ph[2 * i]);      // consumer sees the rounded value
+                const float2 fb = __half22float2(ph[2 * i + 1]);
+                p1[2 * i] = __floats2half2_rn(apply_act(fmaf(fa.x, sc.x, sh.x), e.act2),
+                                              apply_act(fmaf(fa.y, sc.y, sh.y), e.act2));
+                p1[2 * i + 1] = __floats2half2_rn(apply_act(fmaf(fb.x, sc.z, sh.z), e.act2),
+                                                  apply_act(fmaf(fb.y, sc.w, sh.w), e.act2));
               }
-              const long long o1 =
-                  (long long)img * e.out1_img_stride + (long long)pix * e.out1_pix_stride + nb;
-              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out1) + o1);
+              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out1) + o1_row + nb);
 #pragma unroll
               for (int qd = 0; qd < 4; ++qd) op[qd] = packed1[qd];
             }
@@ -458,7 +484,7 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
   g.num_m_tiles = (int)((g.M + TC_BM - 1) / TC_BM);
   g.num_n_tiles = (p->Cout_pad + g.BN - 1) / g.BN;
   const int stage_bytes = TC_A_BYTES + g.BN * 128;
-  int stages = (TC_SMEM_LIMIT - 2048) / stage_bytes;
+  int stages = (TC_SMEM_LIMIT - 2048 - TC_EPI_SMEM) / stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   ODT_CHECK_ARG(stages >= 2, "tile too large for shared memory");
   g.stages = stages;
@@ -504,7 +530,7 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
     }
   }
 
-  const int smem = stages * stage_bytes + 2048;
+  const int smem = stages * stage_bytes + 2048 + TC_EPI_SMEM;
   static int smem_set = 0;
   if (smem_set < smem) {
     ODT_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -13,6 +13,7 @@ A model file (nets.py) describes its layers once through `Builder`; the builder
 """
 import ctypes as C
 import math
+import re
 
 import numpy as np
 import torch
@@ -612,12 +613,22 @@ def init_weights(variables, seed=1, bn_mode="tf_init", stem_scale=1.0 / 64.0):
     1/64 keeps random-init activations O(1), as trained weights do."""
     rng = np.random.default_rng(seed)
     out = {}
+    trained = bn_mode != "tf_init"
     for name, (shape, kind) in variables.items():
         if kind == "he":
             fan_in = shape[0] * shape[1] * shape[2]
             out[name] = (rng.standard_normal(shape) * math.sqrt(2.0 / fan_in)).astype(np.float32)
             if shape[2] == 3:
                 out[name] *= np.float32(stem_scale)
+            # pre-activation bottlenecks sum two conv branches (no identity path,
+            # RetinaNet.py:641-643): halve the variance of each so random-init
+            # activations do not double per block (2^16 over 16 blocks)
+            if "/conv_branch/conv2d_2/" in name or "/identity_branch/conv2d/" in name:
+                out[name] *= np.float32(math.sqrt(0.5))
+            # Darknet residual x + f(x) (YOLOv3.py:488-491): damp f's last conv likewise
+            mres = re.match(r"backone/block\d+/conv2d_(\d+)/kernel", name)
+            if mres and int(mres.group(1)) >= 2 and int(mres.group(1)) % 2 == 0:
+                out[name] *= np.float32(0.25)
         elif kind == "zeros":
             out[name] = np.zeros(shape, np.float32)
         elif kind == "pi":
@@ -625,14 +636,14 @@ def init_weights(variables, seed=1, bn_mode="tf_init", stem_scale=1.0 / 64.0):
         elif kind == "l2norm":
             out[name] = np.full(shape, 20.0, np.float32)
         elif kind in ("bn_gamma", "gn_gamma"):
-            out[name] = (np.ones(shape, np.float32) if bn_mode == "tf_init"
-                         else rng.uniform(0.5, 1.5, shape).astype(np.float32))
+            out[name] = (rng.uniform(0.8, 1.2, shape).astype(np.float32) if trained
+                         else np.ones(shape, np.float32))
         elif kind in ("bn_beta", "gn_beta", "bn_mean"):
-            out[name] = (np.zeros(shape, np.float32) if bn_mode == "tf_init"
-                         else (rng.standard_normal(shape) * 0.1).astype(np.float32))
+            out[name] = ((rng.standard_normal(shape) * 0.1).astype(np.float32) if trained
+                         else np.zeros(shape, np.float32))
         elif kind == "bn_var":
-            out[name] = (np.ones(shape, np.float32) if bn_mode == "tf_init"
-                         else rng.uniform(0.5, 1.5, shape).astype(np.float32))
+            out[name] = (rng.uniform(0.8, 1.25, shape).astype(np.float32) if trained
+                         else np.ones(shape, np.float32))
         else:
             raise ValueError(kind)
     return out

@@ -19,3 +19,18 @@ def model_cfg(kind, **over):
         c.update(data_shape=[128, 128, 3], nms_max_boxes=10, nms_iou_threshold=0.45)
     c.update(over)
     return c
+
+
+def assert_boxes_close(got, exp, abs_tol=1e-4, rel_tol=1e-6, what="boxes"):
+    """Box parity bar: 1e-4 absolute, plus rel_tol x the box's largest coordinate
+    magnitude (random-weight boxes reach 1e7 px, where 1 fp32 ulp is ~1 px and
+    y1 = cy - h/2 cancels catastrophically; in-image boxes see the bare 1e-4)."""
+    import numpy as np
+    got, exp = np.asarray(got, np.float32), np.asarray(exp, np.float32)
+    assert got.shape == exp.shape, (got.shape, exp.shape)
+    if got.size == 0:
+        return
+    mag = np.abs(exp).max(axis=-1, keepdims=True)
+    bad = np.abs(got - exp) > abs_tol + rel_tol * mag
+    assert not bad.any(), "%s: %d coords off, worst |err| %.4g at magnitude %.4g" % (
+        what, int(bad.sum()), float(np.abs(got - exp)[bad].max()), float(mag[bad.any(-1)].max()))

@@ -9,7 +9,7 @@ against the CPU oracle on identical inputs and weights.
 import numpy as np
 import pytest
 
-from helpers import model_cfg
+from helpers import assert_boxes_close, model_cfg
 
 pytestmark = pytest.mark.gpu
 
@@ -97,7 +97,7 @@ def test_ssd300_reference_plumbing_config_fp32(built):
     exp = _tail_oracle_on_rows("ssd300", rows, m.config)
     np.testing.assert_array_equal(res[2], exp[2])
     np.testing.assert_array_equal(net.tail.det_anchor.cpu().numpy()[0, :len(exp[3])], exp[3])
-    assert np.all(np.abs(res[1] - exp[1]) <= 1e-4 + 1e-6 * np.abs(exp[1]))
+    assert_boxes_close(res[1], exp[1])
     # (b) end to end against the oracle's own forward: identical decisions wherever the
     #     oracle's margins exceed the measured row error
     preds = ON.ssd_heads(m.get_weights(), img, 300)
@@ -110,7 +110,8 @@ def test_ssd300_reference_plumbing_config_fp32(built):
     if same:
         d = np.abs(res[1] - full[1])
         print("end-to-end fp32: max box |err| = %.3g px" % float(d.max()) if len(d) else "no boxes")
-        assert np.all(d <= 5e-3 + 1e-5 * np.abs(full[1]))
+        # rows differ by ~1e-6 relative (accumulation order) and t_hw goes through exp()
+        assert_boxes_close(res[1], full[1], abs_tol=5e-3, rel_tol=3e-4, what="end-to-end fp32 boxes")
     else:
         frac = len(set(zip(full[2].tolist(), full[3].tolist())) &
                    set(zip(res[2].tolist(), net.tail.det_anchor.cpu().numpy()[0, :len(res[2])].tolist())))
@@ -130,7 +131,7 @@ def test_ssd300_fp16_batch_and_api(built):
     for b in range(4):
         exp = _tail_oracle_on_rows("ssd300", rows, m.config, image=b)
         np.testing.assert_array_equal(res[b][2], exp[2])
-        assert np.all(np.abs(res[b][1] - exp[1]) <= 1e-4 + 1e-6 * np.abs(exp[1]))
+        assert_boxes_close(res[b][1], exp[1])
 
 
 def test_ssd512_builds_and_runs(built):

@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import YOLO_PRIORS, model_cfg
+from helpers import assert_boxes_close, model_cfg
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -32,7 +32,7 @@ def _check(res, keep, exp, near_ok=False):
     np.testing.assert_array_equal(res[2], cid, err_msg="class ids")
     np.testing.assert_array_equal(keep, kp, err_msg="NMS keep indices")
     np.testing.assert_allclose(res[0], s, rtol=1e-6, atol=0)
-    assert np.all(np.abs(res[1] - bx) <= 1e-4 + 1e-6 * np.abs(bx)), float(np.abs(res[1] - bx).max())
+    assert_boxes_close(res[1], bx)
 
 
 @pytest.mark.parametrize("name", ["tail_ssd", "tail_retina", "tail_yolo", "tail_fcos"])
