@@ -97,28 +97,51 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+_CPU_STATE = {}
+
+
 def cpu_oracle_images_per_sec(n_images, repeats=1, threads=None):
     """The reference's CPU path as restated by the oracle (torch-CPU fp32 + C NMS):
-    full test_one_image semantics, batch-1 graph semantics looped over images."""
+    full test_one_image semantics, batch-1 graph semantics looped over images.
+    The thread count is the fastest of {all cores, 64, 32, 16, 8} on this host
+    (more threads than the 300x300 batch-1 convs can use only adds contention)."""
     import torch
     from odt_b200.engine import init_weights
     import SSD300
     from oracle import nets as ON
     from oracle import tails as OT
-    threads = threads or os.cpu_count()
-    torch.set_num_threads(threads)
     OT.build_nms_lib()
-    model = SSD300.SSD300(dict(CFG), None)
-    w = init_weights(model.variables(), seed=1)
-    img = synthetic_images(n_images, seed=0)
-    ON.ssd_heads(w, img[:1], SIZE)  # warm-up (thread pools, oneDNN primitives)
+    if "w" not in _CPU_STATE:
+        model = SSD300.SSD300(dict(CFG), None)
+        _CPU_STATE["w"] = init_weights(model.variables(), seed=1)
+    w = _CPU_STATE["w"]
+    img = synthetic_images(max(n_images, 1), seed=0)
+
+    def one(i):
+        preds = ON.ssd_heads(w, img[i:i + 1], SIZE)
+        OT.ssd_detect(preds, SIZE, CFG["nms_score_threshold"], CFG["nms_max_boxes"],
+                      CFG["nms_iou_threshold"])
+
+    if threads is None and "threads" not in _CPU_STATE:
+        ncpu = os.cpu_count() or 1
+        best_t, best_dt = ncpu, None
+        for t in sorted({ncpu, min(ncpu, 64), min(ncpu, 32), min(ncpu, 16), min(ncpu, 8)}, reverse=True):
+            torch.set_num_threads(t)
+            one(0)  # warm-up (thread pool, oneDNN primitive cache)
+            t0 = time.perf_counter()
+            one(0)
+            dt = time.perf_counter() - t0
+            if best_dt is None or dt < best_dt:
+                best_t, best_dt = t, dt
+        _CPU_STATE["threads"] = best_t
+    threads = threads or _CPU_STATE["threads"]
+    torch.set_num_threads(threads)
+    one(0)
     best = None
     for _ in range(repeats):
         t0 = time.perf_counter()
         for i in range(n_images):
-            preds = ON.ssd_heads(w, img[i:i + 1], SIZE)
-            OT.ssd_detect(preds, SIZE, CFG["nms_score_threshold"], CFG["nms_max_boxes"],
-                          CFG["nms_iou_threshold"])
+            one(i)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     return n_images / best, threads
@@ -132,8 +155,6 @@ def run_reference(args, rank, world):
         return
     sample = 4
     vals = []
-    for _ in range(max(args.warmup, 0) and 1):
-        cpu_oracle_images_per_sec(1)
     t_all = time.perf_counter()
     for _ in range(args.steps):
         v, threads = cpu_oracle_images_per_sec(sample)
@@ -227,17 +248,20 @@ def main():
     value = world * BATCH * K / (ms_total / 1e3)
 
     # ---------------- end to end through the public API ------------------------
-    def step_e2e():
+    def run_e2e(n):
+        # public API: pipelined stream of host batches (H2D of batch i+1 overlaps batch i),
+        # every step copies its inputs from pinned host memory and reads its detections back
         if world > 1:
-            return model.detect_batch_sharded(images)
-        return model.detect_batch(images)
+            for _ in range(n):
+                model.detect_batch_sharded(images)
+        else:
+            for _ in model.detect_stream(images for _ in range(n)):
+                pass
 
-    for _ in range(W):
-        step_e2e()
+    run_e2e(W)
     barrier()
     e0.record()
-    for _ in range(K):
-        out = step_e2e()
+    run_e2e(K)
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))

@@ -136,6 +136,51 @@ class _Detector:
         net.run()
         return net.tail.results()
 
+    def detect_stream(self, batches, precision=None):
+        """Pipelined inference over an iterable of host batches [B,H,W,3]: the
+        host->device copy of batch i+1 runs on a copy stream while the kernels of
+        batch i execute; every batch's detections are read back (D2H) before it is
+        yielded.  Sources in pinned memory make the H2D copies truly asynchronous."""
+        it = iter(batches)
+        try:
+            cur = _as_host_tensor(next(it))
+        except StopIteration:
+            return
+        net = self.engine(cur.shape[0], precision)
+        if not hasattr(net, "_stage"):
+            net._stage = [torch.empty_like(net.image_buf) for _ in range(2)]
+            net._copy_stream = torch.cuda.Stream()
+            net._h2d = [torch.cuda.Event() for _ in range(2)]
+            net._used = [torch.cuda.Event() for _ in range(2)]
+        main = torch.cuda.current_stream()
+        cs = net._copy_stream
+
+        def prefetch(t, slot):
+            cs.wait_event(net._used[slot])
+            with torch.cuda.stream(cs):
+                net._stage[slot].copy_(t, non_blocking=True)
+                net._h2d[slot].record(cs)
+
+        for ev in net._used:
+            ev.record(main)
+        prefetch(cur, 0)
+        i = 0
+        while cur is not None:
+            slot = i & 1
+            main.wait_event(net._h2d[slot])
+            net.image_buf.copy_(net._stage[slot], non_blocking=True)  # device-to-device
+            net._used[slot].record(main)
+            try:
+                nxt = _as_host_tensor(next(it))
+                assert nxt.shape == cur.shape, "all batches of a stream must share a shape"
+                prefetch(nxt, slot ^ 1)  # overlaps the launches below
+            except StopIteration:
+                nxt = None
+            net.run()
+            yield net.tail.results()
+            cur = nxt
+            i += 1
+
     def test_one_image(self, images):
         """ref SSD300.py:486-488: returns [scores, bbox, class_id]."""
         if self.data_format == "channels_first":
