@@ -235,6 +235,10 @@ extern "C" int odt_conv2d_stem(const float* images, const float* mean3_host, con
   ODT_CHECK_ARG(p->Cin == 3, "stem expects Cin == 3");
   ODT_CHECK_ARG(dtype == ODT_F16 || dtype == ODT_F32, "dtype");
   cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == ODT_F16) {  // tensor-core stem first (conv_stem_tc.cu)
+    int trc = odt_conv2d_stem_tc_try(images, mean3_host, weights, p, stream);
+    if (trc != ODT_ERR_UNSUPPORTED) return trc;
+  }
   const bool simple = p->out0 && !p->out1 && !p->residual && p->out0_group == 0 && p->R == p->S &&
                       p->dil == 1 && p->in_ld == 3 &&
                       p->out0_dtype == (dtype == ODT_F16 ? ODT_F16 : ODT_F32) &&

@@ -1,0 +1,293 @@
+// tcgen05 stem convolution (Cin = 3): the first layer of every backbone.
+//
+// K = KS*KS*3 is far below one TMA/UMMA channel chunk, so instead of im2col TMA
+// the A operand is BUILT in shared memory: 4 producer warps (one thread per
+// output pixel of the 128-row tile) gather the KS*KS*3 fp32 pixels, subtract the
+// RGB mean, convert to fp16 and store 16-byte chunks straight into the
+// 128B-swizzled K-major layout the UMMA descriptor expects (chunk c of row m at
+// ((c ^ (m & 7)) << 4)); a fence.proxy.async + mbarrier arrive hands the stage to
+// the single MMA-issuing thread.  Weights [COUT x Kpad] sit in shared memory for
+// the whole kernel.  Accumulators are double-buffered in TMEM; 4 epilogue warps
+// apply bias/BN/activation and write fp16 NHWC rows.  The layer is HBM-bound
+// (image read + activation write); the tensor pipe is idle most of the time.
+//
+// ref: conv1_1 SSD300.py:193-200 (+mean :52-66); YOLOv3.py:388; RetinaNet.py:260-265; FCOS.py:73-78.
+#include "epilogue.cuh"
+#include "tc_ptx.cuh"
+
+namespace odt {
+
+struct StemGeom {
+  int B, H, W, OH, OW, ohw, pad_t, pad_l, w_ld;
+  long long M;
+  int num_tiles;
+  float mean[3];
+};
+
+constexpr int ST_STAGES = 4;
+constexpr int ST_PROD_WARPS = 4, ST_EPI_WARPS = 4;
+constexpr int ST_THREADS = 32 * (ST_PROD_WARPS + 1 + ST_EPI_WARPS);
+
+template <int COUT, int KS, int STRIDE>
+__global__ void __launch_bounds__(ST_THREADS)
+    conv_stem_tc_kernel(const float* __restrict__ img, const __half* __restrict__ wgt,
+                        const __grid_constant__ StemGeom g, const __grid_constant__ Epi e) {
+  constexpr int KREAL = KS * KS * 3;
+  constexpr int KSTEPS = (KREAL + 15) / 16;        // UMMA k-steps issued
+  constexpr int NCHUNK = KSTEPS * 2;               // 16-byte chunks written per row
+  constexpr int NBLK = (KSTEPS * 16 + 63) / 64;    // 128-byte-row blocks per stage
+  constexpr int A_BYTES = NBLK * 128 * 128;
+  constexpr int B_BYTES = NBLK * COUT * 128;
+  constexpr int TMEM_COLS = (2 * COUT <= 32) ? 32 : (2 * COUT <= 64 ? 64 : (2 * COUT <= 128 ? 128 : 256));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  const uint32_t a_base = base;                               // ST_STAGES x A_BYTES
+  const uint32_t b_base = base + ST_STAGES * A_BYTES;         // weights (1024-aligned: A_BYTES % 16384 == 0)
+  const uint32_t bar_base = b_base + ((B_BYTES + 1023) & ~1023);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (ST_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * ST_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * ST_STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * ST_STAGES + 4);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+  float* s_scale = reinterpret_cast<float*>(smem_raw + (bar_base + 128u - raw));
+  float* s_shift = s_scale + COUT;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- one-time setup: weights -> swizzled smem, params, barriers, TMEM ----
+  {
+    uint8_t* bsm = gbase + (b_base - base);
+    // zero the K padding once, then scatter the real weights
+    for (int i = threadIdx.x; i < B_BYTES / 16; i += blockDim.x)
+      reinterpret_cast<uint4*>(bsm)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < COUT * KREAL; i += blockDim.x) {
+      const int n = i / KREAL, k = i - n * KREAL;
+      const int tap = k / 3, ch = k - tap * 3;
+      const __half v = wgt[((long long)n * KS * KS + tap) * g.w_ld + ch];
+      const int blk = k >> 6, kk = k & 63;
+      const uint32_t off = blk * COUT * 128 + n * 128 + ((((kk >> 3) ^ (n & 7))) << 4) + (kk & 7) * 2;
+      *reinterpret_cast<__half*>(bsm + off) = v;
+    }
+    for (int c = threadIdx.x; c < COUT; c += blockDim.x) {
+      s_scale[c] = e.scale ? e.scale[c] : 1.f;
+      s_shift[c] = e.shift ? e.shift[c] : 0.f;
+    }
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ST_STAGES; ++s) {
+      mbar_init(full_bar(s), ST_PROD_WARPS * 32);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), ST_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == ST_PROD_WARPS) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async_smem();  // weight tile written through the generic proxy
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp < ST_PROD_WARPS) {
+    // ===================== A-tile producers ====================================
+    const int t = threadIdx.x;  // row of the tile
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      const long long m = (long long)tile * 128 + t;
+      const bool ok = m < g.M;
+      int b = 0, oy = 0, ox = 0;
+      if (ok) {
+        b = (int)(m / g.ohw);
+        const int pix = (int)(m - (long long)b * g.ohw);
+        oy = pix / g.OW;
+        ox = pix - oy * g.OW;
+      }
+      const float* ib = img + (long long)b * g.H * g.W * 3;
+      const int iy0 = oy * STRIDE - g.pad_t, ix0 = ox * STRIDE - g.pad_l;
+      mbar_wait(empty_bar(stage), phase ^ 1u);
+      uint8_t* arow = gbase + (a_base - base) + (uint32_t)stage * A_BYTES + t * 128;
+#pragma unroll
+      for (int c = 0; c < NCHUNK; ++c) {
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int k = c * 8 + q;  // compile-time after unrolling
+          if (k < KREAL) {
+            const int tap = k / 3, ch = k - tap * 3;
+            const int r = tap / KS, s = tap - r * KS;
+            const int iy = iy0 + r, ix = ix0 + s;
+            const bool in = ok && iy >= 0 && iy < g.H && ix >= 0 && ix < g.W;
+            v[q] = in ? __fsub_rn(__ldg(ib + ((long long)iy * g.W + ix) * 3 + ch), g.mean[ch]) : 0.f;
+          } else {
+            v[q] = 0.f;
+          }
+        }
+        uint4 pk;
+        __half2* h = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) h[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+        const int blk = c >> 3, cc = c & 7;
+        *reinterpret_cast<uint4*>(arow + blk * (128 * 128) + ((cc ^ (t & 7)) << 4)) = pk;
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(full_bar(stage));
+      if (++stage == ST_STAGES) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  } else if (warp == ST_PROD_WARPS) {
+    // ===================== MMA issuer ==========================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(128, COUT);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase[2] = {0u, 0u};
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase[acc] ^ 1u);
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * COUT;
+#pragma unroll
+        for (int k = 0; k < KSTEPS; ++k) {
+          const uint32_t blk = k >> 2, kin = k & 3;
+          const uint64_t adesc =
+              make_desc_sw128(a_base + (uint32_t)stage * A_BYTES + blk * (128 * 128)) + (uint64_t)(2 * kin);
+          const uint64_t bdesc = make_desc_sw128(b_base + blk * (COUT * 128)) + (uint64_t)(2 * kin);
+          tc_mma_f16(d_tmem, adesc, bdesc, idesc, (uint32_t)(k != 0));
+        }
+        tc_commit(empty_bar(stage));
+        tc_commit(tfull_bar(acc));
+        acc_phase[acc] ^= 1u;
+        acc ^= 1;
+        if (++stage == ST_STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue ============================================
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase[2] = {0u, 0u};
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      const long long m = (long long)tile * 128 + quarter * 32 + lane;
+      const bool row_ok = m < g.M;
+      const int b = row_ok ? (int)(m / g.ohw) : 0;
+      const int pix = row_ok ? (int)(m - (long long)b * g.ohw) : 0;
+      mbar_wait(tfull_bar(acc), acc_phase[acc]);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)acc * COUT + ((uint32_t)(quarter * 32) << 16);
+      __half* orow = reinterpret_cast<__half*>(e.out0) + (long long)b * e.out0_img_stride +
+                     (long long)pix * e.out0_pix_stride;
+#pragma unroll
+      for (int j = 0; j < COUT / 16; ++j) {
+        uint32_t r[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+              "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]),
+              "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(taddr + (uint32_t)(j * 16))
+            : "memory");
+        tc_wait_ld();
+        uint4 pk[2];
+        __half2* h = reinterpret_cast<__half2*>(pk);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int c0 = j * 16 + 2 * q;
+          const float v0 = apply_act(fmaf(__uint_as_float(r[2 * q]), s_scale[c0], s_shift[c0]), e.act);
+          const float v1 =
+              apply_act(fmaf(__uint_as_float(r[2 * q + 1]), s_scale[c0 + 1], s_shift[c0 + 1]), e.act);
+          h[q] = __floats2half2_rn(v0, v1);
+        }
+        if (row_ok) {
+          uint4* op = reinterpret_cast<uint4*>(orow + j * 16);
+          op[0] = pk[0];
+          op[1] = pk[1];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      acc_phase[acc] ^= 1u;
+      acc ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == ST_PROD_WARPS) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS)
+                 : "memory");
+  }
+}
+
+template <int COUT, int KS, int STRIDE>
+static int launch_stem_tc(const float* img, const void* w, const StemGeom& g, const Epi& e,
+                          cudaStream_t st) {
+  constexpr int KSTEPS = (KS * KS * 3 + 15) / 16;
+  constexpr int NBLK = (KSTEPS * 16 + 63) / 64;
+  const int smem = ST_STAGES * NBLK * 128 * 128 + ((NBLK * COUT * 128 + 1023) & ~1023) + 1024 + 128 +
+                   2 * COUT * 4 + 64;
+  auto kern = conv_stem_tc_kernel<COUT, KS, STRIDE>;
+  static bool attr = false;
+  if (!attr) {
+    ODT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  const int per_sm = smem > 110000 ? 1 : 2;
+  int grid = kNumSMs * per_sm;
+  if (grid > g.num_tiles) grid = g.num_tiles;
+  kern<<<grid, ST_THREADS, smem, st>>>(img, (const __half*)w, g, e);
+  return ODT_OK;
+}
+
+}  // namespace odt
+
+using namespace odt;
+
+// Returns ODT_ERR_UNSUPPORTED when the shape has no tensor-core stem variant
+// (the caller then uses the CUDA-core stem).
+int odt_conv2d_stem_tc_try(const float* images, const float* mean3_host, const void* weights,
+                           const odt_conv_params* p, void* stream) {
+  const bool ok = p->out0 && !p->out1 && !p->residual && p->out0_group == 0 && p->R == p->S &&
+                  p->dil == 1 && p->in_ld == 3 && p->Cin == 3 && p->out0_dtype == ODT_F16 &&
+                  ((uintptr_t)p->out0 % 16) == 0 && p->out0_pix_stride % 8 == 0 &&
+                  p->out0_img_stride % 8 == 0;
+  int variant = 0;
+  if (ok && p->R == 3 && p->stride == 1 && p->Cout == 64) variant = 1;
+  if (ok && p->R == 3 && p->stride == 1 && p->Cout == 32) variant = 2;
+  if (ok && p->R == 7 && p->stride == 2 && p->Cout == 16) variant = 3;
+  if (!variant) return ODT_ERR_UNSUPPORTED;
+  StemGeom g;
+  g.B = p->B; g.H = p->H; g.W = p->W; g.OH = p->OH; g.OW = p->OW; g.ohw = p->OH * p->OW;
+  g.pad_t = p->pad_t; g.pad_l = p->pad_l; g.w_ld = p->w_ld;
+  g.M = (long long)p->B * p->OH * p->OW;
+  g.num_tiles = (int)((g.M + 127) / 128);
+  g.mean[0] = mean3_host[0]; g.mean[1] = mean3_host[1]; g.mean[2] = mean3_host[2];
+  Epi e = make_epi(*p);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = ODT_OK;
+  if (variant == 1) rc = launch_stem_tc<64, 3, 1>(images, weights, g, e, st);
+  if (variant == 2) rc = launch_stem_tc<32, 3, 1>(images, weights, g, e, st);
+  if (variant == 3) rc = launch_stem_tc<16, 7, 2>(images, weights, g, e, st);
+  if (rc) return rc;
+  ODT_LAUNCH_OK();
+  return ODT_OK;
+}

@@ -228,3 +228,58 @@ def test_glue_kernels_vs_oracle_ops(built, dtype):
                                     gd.data_ptr(), btd.data_ptr(), 1, st))
     np.testing.assert_allclose(y.float().cpu().numpy(), ref, atol=tol * 8, rtol=tol)
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("shape", [
+    (2, 300, 300, 64, 3, 1),   # SSD conv1_1
+    (3, 37, 53, 64, 3, 1),     # ragged tile tail
+    (2, 64, 64, 32, 3, 1),     # YOLOv3 stem
+    (2, 128, 128, 16, 7, 2),   # RetinaNet / FCOS stem (K = 147, 3 swizzle blocks)
+    (1, 33, 47, 16, 7, 2),
+    (1, 20, 20, 24, 5, 1),     # no specialised variant -> generic CUDA-core stem
+])
+@pytest.mark.parametrize("dtype", ["f16", "f32"])
+def test_stem_conv_vs_oracle(built, shape, dtype):
+    """odt_conv2d_stem: fp32 image - RGB mean -> conv -> bias/BN -> ReLU.  fp16 takes the
+    tcgen05 stem (A tile built in swizzled smem), fp32 the CUDA-core stem."""
+    from odt_b200 import lib as L
+    from odt_b200.engine import same_pad
+    from oracle import tfops as T
+    lib = L.load()
+    B, H, W, Cout, k, stride = shape
+    rng = np.random.default_rng(7)
+    img = rng.integers(0, 256, (B, H, W, 3)).astype(np.float32)
+    w = (rng.standard_normal((k, k, 3, Cout)) * np.sqrt(2.0 / (k * k * 3)) / 64).astype(np.float32)
+    f16 = dtype == "f16"
+    if f16:
+        w = w.astype(np.float16).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, Cout).astype(np.float32)
+    shift = (rng.standard_normal(Cout) * 0.2).astype(np.float32)
+    tdt = torch.float16 if f16 else torch.float32
+    ld = (Cout + 63) // 64 * 64 if f16 else Cout
+    OH, pt, _ = same_pad(H, k, stride)
+    OW, pl, _ = same_pad(W, k, stride)
+    imgd = torch.from_numpy(img).cuda()
+    wd = torch.from_numpy(np.ascontiguousarray(np.transpose(w, (3, 0, 1, 2)))).cuda().to(tdt)
+    sd, hd = torch.from_numpy(scale).cuda(), torch.from_numpy(shift).cuda()
+    yd = torch.zeros((B, OH, OW, ld), dtype=tdt, device="cuda")
+    p = L.ConvParams()
+    p.B, p.H, p.W, p.Cin, p.in_ld = B, H, W, 3, 3
+    p.OH, p.OW, p.Cout = OH, OW, Cout
+    p.R, p.S, p.stride, p.dil, p.pad_t, p.pad_l = k, k, stride, 1, pt, pl
+    p.w_ld, p.Cout_pad = 3, Cout
+    p.scale, p.shift, p.act = sd.data_ptr(), hd.data_ptr(), 1
+    p.out0, p.out0_dtype = yd.data_ptr(), (L.ODT_F16 if f16 else L.ODT_F32)
+    p.out0_img_stride, p.out0_pix_stride = OH * OW * ld, ld
+    mean = (C.c_float * 3)(123.68, 116.779, 103.979)
+    L.check(lib.odt_conv2d_stem(imgd.data_ptr(), mean, wd.data_ptr(), L.ODT_F16 if f16 else L.ODT_F32,
+                                C.byref(p), torch.cuda.current_stream().cuda_stream), "stem")
+    torch.cuda.synchronize()
+    x = img - T.RGB_MEAN.reshape(1, 1, 1, 3)
+    xr = x.astype(np.float16).astype(np.float32) if f16 else x  # the fp16 stem rounds the operand
+    ref = np.maximum(T.conv2d_same(xr, w, None, stride) * scale + shift, 0)
+    got = yd[..., :Cout].float().cpu().numpy()
+    tol = (3e-3 if f16 else 2e-5) * max(np.abs(ref).max(), 1.0)
+    assert np.abs(got - ref).max() <= tol, (shape, dtype, float(np.abs(got - ref).max()), float(np.abs(ref).max()))
+    if ld > Cout:
+        assert float(yd[..., Cout:].abs().max()) == 0.0
