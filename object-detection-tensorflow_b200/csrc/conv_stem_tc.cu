@@ -21,6 +21,7 @@ struct StemGeom {
   int B, H, W, OH, OW, ohw, pad_t, pad_l, w_ld;
   long long M;
   int num_tiles;
+  int bulk_store;  // output rows are 128 contiguous bytes (ld == 64, dense NHWC): smem-staged bulk stores
   float mean[3];
 };
 
@@ -54,6 +55,8 @@ __global__ void __launch_bounds__(ST_THREADS)
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
   float* s_scale = reinterpret_cast<float*>(smem_raw + (bar_base + 128u - raw));
   float* s_shift = s_scale + COUT;
+  // per-epilogue-warp staging for coalesced bulk stores: 32 rows x 128 B
+  const uint32_t stage_out = (bar_base + 128u + 2u * COUT * 4u + 127u) & ~127u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -193,6 +196,18 @@ __global__ void __launch_bounds__(ST_THREADS)
       const uint32_t taddr = tmem_base + (uint32_t)acc * COUT + ((uint32_t)(quarter * 32) << 16);
       __half* orow = reinterpret_cast<__half*>(e.out0) + (long long)b * e.out0_img_stride +
                      (long long)pix * e.out0_pix_stride;
+      const uint32_t my_stage = stage_out + (uint32_t)(warp - ST_PROD_WARPS - 1) * 4096u;
+      uint8_t* my_stage_ptr = smem_raw + (my_stage - raw);
+      if (g.bulk_store) {
+        // the previous tile's bulk store must have finished READING the staging buffer
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+        if (COUT < 64) {  // zero the pad lanes of the row (they must stay zero in HBM anyway)
+#pragma unroll
+          for (int c = COUT / 8; c < 8; ++c)
+            *reinterpret_cast<uint4*>(my_stage_ptr + lane * 128 + (c << 4)) = make_uint4(0, 0, 0, 0);
+        }
+      }
 #pragma unroll
       for (int j = 0; j < COUT / 16; ++j) {
         uint32_t r[16];
@@ -215,10 +230,30 @@ __global__ void __launch_bounds__(ST_THREADS)
               apply_act(fmaf(__uint_as_float(r[2 * q + 1]), s_scale[c0 + 1], s_shift[c0 + 1]), e.act);
           h[q] = __floats2half2_rn(v0, v1);
         }
-        if (row_ok) {
+        if (g.bulk_store) {
+          // row-major staging, linear as the bulk copy needs (the strided 16-byte writes
+          // bank-conflict, ~256 cycles per tile and warp, hidden behind the HBM stream)
+          *reinterpret_cast<uint4*>(my_stage_ptr + lane * 128 + ((2 * j) << 4)) = pk[0];
+          *reinterpret_cast<uint4*>(my_stage_ptr + lane * 128 + ((2 * j + 1) << 4)) = pk[1];
+        } else if (row_ok) {
           uint4* op = reinterpret_cast<uint4*>(orow + j * 16);
           op[0] = pk[0];
           op[1] = pk[1];
+        }
+      }
+      if (g.bulk_store) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        const long long m_first = (long long)tile * 128 + quarter * 32;
+        const long long rows_left = g.M - m_first;
+        if (lane == 0 && rows_left > 0) {
+          const uint32_t bytes = (uint32_t)(rows_left < 32 ? rows_left : 32) * 128u;
+          // rows of consecutive pixels are contiguous (dense NHWC, ld == 64)
+          const __half* gdst = reinterpret_cast<const __half*>(e.out0) + m_first * 64;
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                       "r"(my_stage), "r"(bytes)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
       tc_fence_before();
@@ -227,6 +262,7 @@ __global__ void __launch_bounds__(ST_THREADS)
       acc_phase[acc] ^= 1u;
       acc ^= 1;
     }
+    if (g.bulk_store && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -244,7 +280,7 @@ static int launch_stem_tc(const float* img, const void* w, const StemGeom& g, co
   constexpr int KSTEPS = (KS * KS * 3 + 15) / 16;
   constexpr int NBLK = (KSTEPS * 16 + 63) / 64;
   const int smem = ST_STAGES * NBLK * 128 * 128 + ((NBLK * COUT * 128 + 1023) & ~1023) + 1024 + 128 +
-                   2 * COUT * 4 + 64;
+                   2 * COUT * 4 + 64 + 128 + ST_EPI_WARPS * 4096;
   auto kern = conv_stem_tc_kernel<COUT, KS, STRIDE>;
   static bool attr = false;
   if (!attr) {
@@ -280,6 +316,7 @@ int odt_conv2d_stem_tc_try(const float* images, const float* mean3_host, const v
   g.pad_t = p->pad_t; g.pad_l = p->pad_l; g.w_ld = p->w_ld;
   g.M = (long long)p->B * p->OH * p->OW;
   g.num_tiles = (int)((g.M + 127) / 128);
+  g.bulk_store = (p->out0_pix_stride == 64 && p->out0_img_stride == (long long)p->OH * p->OW * 64) ? 1 : 0;
   g.mean[0] = mean3_host[0]; g.mean[1] = mean3_host[1]; g.mean[2] = mean3_host[2];
   Epi e = make_epi(*p);
   cudaStream_t st = (cudaStream_t)stream;

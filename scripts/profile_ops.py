@@ -62,6 +62,26 @@ def main():
     ms = float(np.median(rec[-1]))
     total += ms
     print("tail (decode+nms) %.4f ms ; sum of ops %.3f ms ; conv GFLOP %.1f" % (ms, total, net.conv_flops / 1e9))
+    # split the tail
+    import ctypes as C
+    from odt_b200 import lib as L
+    t = net.tail
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev[0].record()
+    L.check(net.lib.odt_decode_candidates(net.head_buf.data_ptr(), C.byref(t.p), net.batch, t.cand_keys.data_ptr(),
+                                          t.cand_count.data_ptr(), st))
+    ev[1].record()
+    L.check(net.lib.odt_nms_per_class(net.head_buf.data_ptr(), C.byref(t.p), net.batch, t.cand_keys.data_ptr(),
+                                      t.cand_count.data_ptr(), t.dets.data_ptr(), t.det_anchor.data_ptr(),
+                                      t.det_count.data_ptr(), t.scratch.data_ptr(), t.work.data_ptr(),
+                                      t.status.data_ptr(), st))
+    ev[2].record()
+    torch.cuda.synchronize()
+    cc = t.cand_count.cpu().numpy()
+    print("decode %.4f ms (%.1f MB rows -> %.0f GB/s) ; nms %.4f ms ; candidates/class max %d mean %.1f ; dets/img mean %.1f"
+          % (ev[0].elapsed_time(ev[1]), net.head_buf.numel() * 4 / 1e6,
+             net.head_buf.numel() * 4 / 1e6 / ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), cc.max(), cc.mean(),
+             t.det_count.float().mean().item()))
 
 
 if __name__ == "__main__":
