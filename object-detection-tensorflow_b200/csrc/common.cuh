@@ -60,4 +60,14 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Programmatic dependent launch (PDL).  Every kernel of the library signals its
+// dependents at entry; kernels launched with the programmatic-serialisation
+// attribute (the tensor-core convolutions) run their prologue early and block in
+// pdl_wait() until the preceding grid has completed and flushed its writes.
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();  // ODT_PDL=0 disables the launch attribute (api.cu)
+
 }  // namespace odt

@@ -18,6 +18,7 @@ template <typename T, bool STEM>
 __global__ void __launch_bounds__(DTHREADS)
     conv_direct_kernel(const void* __restrict__ in_, const T* __restrict__ wgt,
                        const __grid_constant__ DirectGeom g, const __grid_constant__ Epi e) {
+  pdl_launch_dependents();
   __shared__ float As[DK][DM + 4];
   __shared__ float Bs[DK][DN + 4];
   const int tid = threadIdx.x;
@@ -112,6 +113,7 @@ template <typename T, int COUT, int KS, int STRIDE>
 __global__ void __launch_bounds__(128)
     conv_stem_kernel(const float* __restrict__ img, const T* __restrict__ wgt,
                      const __grid_constant__ DirectGeom g, const __grid_constant__ Epi e) {
+  pdl_launch_dependents();
   constexpr int KK = KS * KS * 3;
   __shared__ __align__(16) float ws[KK][COUT];
   __shared__ float s_scale[COUT], s_shift[COUT];

@@ -102,6 +102,8 @@ __global__ void __launch_bounds__(ST_THREADS)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp < ST_PROD_WARPS) {
     // ===================== A-tile producers ====================================

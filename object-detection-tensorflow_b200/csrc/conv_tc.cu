@@ -27,7 +27,7 @@ constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = 32 * (2 + TC_EPI_WARPS);  // TMA, MMA, 8 epilogue warps
-constexpr int TC_EPI_SMEM = 2 * 4 * 256 * 4;  // double-buffered scale/shift/scale2/shift2
+constexpr int TC_EPI_SMEM = 2 * 5 * 256 * 4;  // double-buffered scale/shift/scale2/shift2/column offset
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KiB
 constexpr int TC_SMEM_LIMIT = 232448;          // 227 KiB
@@ -41,6 +41,7 @@ struct TcGeom {
   int num_m_tiles, num_n_tiles, BN;
   int stages;
   int fast_store;  // 1: fp16 out0, no regroup, 16-byte aligned rows
+  int fast_cols;   // columns that may be written by whole 32-column chunks (min channel stride)
 };
 
 // --------------------------------------------------------------- kernel ----
@@ -91,6 +92,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation,
+  // descriptor prefetch) overlapped the tail of the previous kernel in the stream;
+  // from here on we touch memory it produced.
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int num_tiles = g.num_m_tiles * g.num_n_tiles;
   const int kblocks = g.R * g.S * g.cchunks;
@@ -170,7 +176,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
     const int et = threadIdx.x - 64;  // 0..255 within the epilogue group
-    int acc = 0, local_tile = 0;
+    int acc = 0, local_tile = 0, staged_n_tile = -1, pbuf = 0;
     uint32_t acc_phase[2] = {0u, 0u};
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
       const int n_tile = tile % g.num_n_tiles, m_tile = tile / g.num_n_tiles;
@@ -179,17 +185,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const int img = row_ok ? (int)(m / g.ohw) : 0;
       const int pix = row_ok ? (int)(m - (long long)img * g.ohw) : 0;
       const int n0 = n_tile * g.BN;
-      // stage this tile's per-channel parameters (broadcast reads later)
-      float* par = epi_par + (local_tile & 1) * 1024;
-      {
+      // stage the per-channel parameters of this N tile once (broadcast reads later);
+      // consecutive tiles of single-N-tile layers reuse them
+      if (n_tile != staged_n_tile) {
+        staged_n_tile = n_tile;
+        pbuf ^= 1;
+        float* wpar = epi_par + pbuf * 1280;
         const int n = n0 + et;
         const bool ok = et < g.BN && n < e.Cout;
-        par[et] = (ok && e.scale) ? __ldg(e.scale + n) : 1.f;
-        par[256 + et] = (ok && e.shift) ? __ldg(e.shift + n) : 0.f;
-        par[512 + et] = (ok && e.scale2) ? __ldg(e.scale2 + n) : 1.f;
-        par[768 + et] = (ok && e.shift2) ? __ldg(e.shift2 + n) : 0.f;
+        wpar[et] = (ok && e.scale) ? __ldg(e.scale + n) : 1.f;
+        wpar[256 + et] = (ok && e.shift) ? __ldg(e.shift + n) : 0.f;
+        wpar[512 + et] = (ok && e.scale2) ? __ldg(e.scale2 + n) : 1.f;
+        wpar[768 + et] = (ok && e.shift2) ? __ldg(e.shift2 + n) : 0.f;
+        reinterpret_cast<int*>(wpar)[1024 + et] = ok ? regroup(e, n) : 0;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float* par = epi_par + pbuf * 1280;
       mbar_wait(tfull_bar(acc), acc_phase[acc]);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(quarter * 32) << 16);
@@ -203,7 +214,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         uint32_t r[32];
         tc_ld32(taddr0 + (uint32_t)(j * 32), r);
         tc_wait_ld();
-        if (g.fast_store && nb + 32 <= e.Cout) {
+        if (g.fast_store && nb + 32 <= g.fast_cols) {
           const float4* ps = reinterpret_cast<const float4*>(par + j * 32);
           const float4* ph4 = reinterpret_cast<const float4*>(par + 256 + j * 32);
           float v[32];
@@ -265,25 +276,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           // generic path: fp32 head outputs scattered into the candidate rows,
           // channel regrouping, ragged Cout; parameters come from shared memory
           const float* ps = par + j * 32;
+          const int* pofs = reinterpret_cast<const int*>(par) + 1024 + j * 32;
+          const int nvalid = min(32, e.Cout - nb);
+          if (e.out0_dtype == ODT_F32 && !e.residual && !e.out1) {
+            // head convolutions: fp32 scatter into the candidate rows
+            float* orow = reinterpret_cast<float*>(e.out0) + o0_row;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int n = nb + i;
-            if (n >= e.Cout) break;
-            float v = apply_act(fmaf(__uint_as_float(r[i]), ps[i], ps[256 + i]), e.act);
-            const long long o0 = o0_row + regroup(e, n);
-            if (e.residual) v += __half2float(reinterpret_cast<const __half*>(e.residual)[o0]);
-            if (e.out0) {
-              if (e.out0_dtype == ODT_F32) {
-                reinterpret_cast<float*>(e.out0)[o0] = v;
-              } else {
-                const __half hv = __float2half_rn(v);
-                reinterpret_cast<__half*>(e.out0)[o0] = hv;
-                v = __half2float(hv);
+            for (int i = 0; i < 32; ++i)
+              if (i < nvalid)
+                orow[pofs[i]] = apply_act(fmaf(__uint_as_float(r[i]), ps[i], ps[256 + i]), e.act);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (i >= nvalid) break;
+              const int n = nb + i;
+              float v = apply_act(fmaf(__uint_as_float(r[i]), ps[i], ps[256 + i]), e.act);
+              const long long o0 = o0_row + pofs[i];
+              if (e.residual) v += __half2float(reinterpret_cast<const __half*>(e.residual)[o0]);
+              if (e.out0) {
+                if (e.out0_dtype == ODT_F32) {
+                  reinterpret_cast<float*>(e.out0)[o0] = v;
+                } else {
+                  const __half hv = __float2half_rn(v);
+                  reinterpret_cast<__half*>(e.out0)[o0] = hv;
+                  v = __half2float(hv);
+                }
               }
+              if (e.out1)
+                reinterpret_cast<__half*>(e.out1)[o1_row + n] =
+                    __float2half_rn(apply_act(fmaf(v, ps[512 + i], ps[768 + i]), e.act2));
             }
-            if (e.out1)
-              reinterpret_cast<__half*>(e.out1)[o1_row + n] =
-                  __float2half_rn(apply_act(fmaf(v, ps[512 + i], ps[768 + i]), e.act2));
           }
         }
       }
@@ -409,6 +431,9 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
                  (!p->residual || ((uintptr_t)p->residual & 15) == 0) &&
                  (!p->out1 || (((uintptr_t)p->out1 & 15) == 0 && p->out1_pix_stride % 8 == 0 &&
                                p->out1_img_stride % 8 == 0));
+  g.fast_cols = p->out0 ? p->out0_pix_stride : (1 << 30);
+  if (p->out1 && p->out1_pix_stride < g.fast_cols) g.fast_cols = p->out1_pix_stride;
+
   CUtensorMap tmA, tmB;
   {
     cuuint64_t dims[4] = {(cuuint64_t)p->in_ld, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->B};
@@ -455,7 +480,17 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
   Epi e = make_epi(*p);
   const int num_tiles = g.num_m_tiles * g.num_n_tiles;
   const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
-  conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, g, e);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  ODT_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel, tmA, tmB, g, e));
   ODT_LAUNCH_OK();
   return ODT_OK;
 }

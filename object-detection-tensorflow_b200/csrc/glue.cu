@@ -75,6 +75,7 @@ static inline int grid_for(long long work, int threads) {
 template <typename T>
 __global__ void normalize_kernel(const float* __restrict__ img, T* __restrict__ out,
                                  long long pixels, int ld, float m0, float m1, float m2) {
+  pdl_launch_dependents();
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < pixels;
        p += (long long)gridDim.x * blockDim.x) {
     const float* s = img + p * 3;
@@ -90,6 +91,7 @@ __global__ void normalize_kernel(const float* __restrict__ img, T* __restrict__ 
 template <typename T, int V>
 __global__ void maxpool_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int H, int W,
                                int OH, int OW, int C, int ld, int k, int stride, int pt, int pl) {
+  pdl_launch_dependents();
   const int cv = C / V;
   const long long total = (long long)B * OH * OW * cv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -122,6 +124,7 @@ __global__ void maxpool_kernel(const T* __restrict__ in, T* __restrict__ out, in
 template <typename T>
 __global__ void l2norm_kernel(const T* __restrict__ in, T* __restrict__ out, long long pixels,
                               int C, int ld, float gamma) {
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -146,6 +149,7 @@ template <typename T, int V>
 __global__ void affine_act_kernel(const T* __restrict__ in, T* __restrict__ out, long long pixels,
                                   int C, int ld, const float* __restrict__ scale,
                                   const float* __restrict__ shift, int act) {
+  pdl_launch_dependents();
   const int cv = C / V;
   const long long total = pixels * cv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -172,6 +176,7 @@ __global__ void upsample_bilinear_add_kernel(const T* __restrict__ top, const T*
                                              const float* __restrict__ scale2,
                                              const float* __restrict__ shift2, int act2,
                                              T* __restrict__ out1) {
+  pdl_launch_dependents();
   const int cv = C / V;
   const long long total = (long long)B * H * W * cv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -221,6 +226,7 @@ __global__ void upsample_nearest_concat_kernel(const T* __restrict__ a, const T*
                                                T* __restrict__ out, int B, int H, int W, int Ca,
                                                int lda, int BH, int BW, int Cb, int ldb, int ldo,
                                                float hs, float ws) {
+  pdl_launch_dependents();
   const int CT = Ca + Cb;
   const long long total = (long long)B * H * W * CT;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -247,6 +253,7 @@ __global__ void upsample_nearest_concat_kernel(const T* __restrict__ a, const T*
 template <typename T>
 __global__ void groupnorm_stats_kernel(const T* __restrict__ in, float* __restrict__ stats,
                                        long long hw, int C, int ld, int groups, float eps) {
+  pdl_launch_dependents();
   const int g = blockIdx.x, b = blockIdx.y;
   const int cpg = C / groups;
   const T* base = in + (long long)b * hw * ld + g * cpg;
@@ -295,6 +302,7 @@ __global__ void groupnorm_apply_kernel(const T* __restrict__ in, T* __restrict__
                                        const float* __restrict__ stats, int B, long long hw, int C,
                                        int ld, int groups, const float* __restrict__ gamma,
                                        const float* __restrict__ beta, int act) {
+  pdl_launch_dependents();
   const int cv = C / V;
   const int cpg = C / groups;
   const long long total = (long long)B * hw * cv;

@@ -46,6 +46,7 @@ __device__ __forceinline__ int gt_count(const float* gt, int G) {
 __global__ void __launch_bounds__(kLossThreads)
     loss_best_anchor_kernel(const __grid_constant__ TailP tp, const float* __restrict__ gt, int G,
                             int* __restrict__ best) {
+  pdl_launch_dependents();
   const odt_tail_params& p = tp.p;
   const int g = blockIdx.x, b = blockIdx.y;
   const float* gb = gt + (long long)b * G * 5;
@@ -130,6 +131,7 @@ __global__ void __launch_bounds__(kLossThreads)
     loss_anchor_kernel(const float* __restrict__ head, const __grid_constant__ TailP tp,
                        const float* __restrict__ gt, int G, const int* __restrict__ best,
                        float alpha, float gamma, float* __restrict__ partial) {
+  pdl_launch_dependents();
   const odt_tail_params& p = tp.p;
   const int b = blockIdx.y, blk = blockIdx.x;
   const float* gb = gt + (long long)b * G * 5;
@@ -214,6 +216,7 @@ __global__ void __launch_bounds__(kLossThreads)
 }
 
 __global__ void loss_final_kernel(const float* __restrict__ partial, int B, float* __restrict__ out) {
+  pdl_launch_dependents();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   float conf = 0.f, coord = 0.f, npos = 0.f;

@@ -1,6 +1,6 @@
 // Inference tail of the five detectors on sm_100a: score activation, analytic
 // anchor/prior generation, box decode, thresholding, candidate compaction and
-// exact per-class TF NonMaxSuppressionV3.
+// exact per-class TF NonMaxSuppressionV3 (iterative arg-max + IoU suppress).
 //
 // All arithmetic that feeds a discrete decision (class id, keep index) is done
 // with explicitly rounded fp32 intrinsics (__fmul_rn/__fadd_rn/__fdiv_rn), in
@@ -21,6 +21,7 @@ __global__ void __launch_bounds__(kDecodeWarps * 32)
     decode_candidates_kernel(const float* __restrict__ head, const __grid_constant__ TailP tp,
                              long long total_rows, unsigned long long* __restrict__ cand_keys,
                              int* __restrict__ cand_count) {
+  pdl_launch_dependents();
   const odt_tail_params& p = tp.p;
   __shared__ __align__(16) float srow[kDecodeWarps][32 * kRow];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -128,48 +129,23 @@ __device__ __forceinline__ float iou_tf(const float4& a, const float4& b) {
 }
 
 constexpr int kNmsThreads = 256;
-constexpr int kNmsSmemKeys = 4096;  // per-class candidates sorted in shared memory
-
-// Normalised bitonic sort (descending): every compare-exchange puts the larger
-// key at the lower index, so virtual zero padding beyond `n` never moves.
-__device__ void bitonic_desc(unsigned long long* k, int n) {
-  int np2 = 1;
-  while (np2 < n) np2 <<= 1;
-  for (int size = 2; size <= np2; size <<= 1) {
-    // flip stage
-    for (int i = threadIdx.x; i < np2 / 2; i += blockDim.x) {
-      int blk = i / (size / 2), off = i % (size / 2);
-      int lo = blk * size + off, hi = blk * size + size - 1 - off;
-      if (hi < n) {
-        unsigned long long a = k[lo], b = k[hi];
-        if (a < b) {
-          k[lo] = b;
-          k[hi] = a;
-        }
-      }
-    }
-    __syncthreads();
-    for (int j = size / 4; j >= 1; j >>= 1) {
-      for (int i = threadIdx.x; i < np2 / 2; i += blockDim.x) {
-        int lo = (i / j) * 2 * j + (i % j), hi = lo + j;
-        if (hi < n) {
-          unsigned long long a = k[lo], b = k[hi];
-          if (a < b) {
-            k[lo] = b;
-            k[hi] = a;
-          }
-        }
-      }
-      __syncthreads();
-    }
-  }
-}
+constexpr int kNmsSmemKeys = 4096;  // per-class candidate lists kept (with boxes) in shared memory
 
 struct NmsSmem {
   unsigned long long keys[kNmsSmemKeys];
   float4 box[kNmsSmemKeys];
 };
 
+// Exact TF NonMaxSuppressionV3 without a sort: greedy NMS always picks the
+// highest-scoring candidate that no kept box suppresses, so each round is
+//   (1) block-wide arg-max over the still-alive keys   (key = score bits << 32 | ~row:
+//       unique, so "highest score, lowest row on ties" is a plain u64 max),
+//   (2) keep it, (3) kill every alive candidate whose IoU with it exceeds the
+//   threshold (strict >).
+// Rounds = number of kept boxes <= nms_max_boxes (10-20), work per round =
+// alive candidates / 256 threads -- no O(n log^2 n) sort, no capacity cliff: lists
+// longer than the shared-memory window are processed in place in global memory
+// with boxes decoded on the fly.
 __global__ void __launch_bounds__(kNmsThreads)
     nms_per_class_kernel(const float* __restrict__ head, const __grid_constant__ TailP tp, int B,
                          unsigned long long* __restrict__ cand_keys,
@@ -177,16 +153,21 @@ __global__ void __launch_bounds__(kNmsThreads)
                          int* __restrict__ det_anchor, int* __restrict__ det_count,
                          int* __restrict__ scratch, int* __restrict__ work,
                          int* __restrict__ status) {
+  pdl_launch_dependents();
   const odt_tail_params& p = tp.p;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   NmsSmem& sm = *reinterpret_cast<NmsSmem*>(smem_raw);
-  __shared__ int s_head;
+  __shared__ unsigned long long s_wkey[kNmsThreads / 32];
+  __shared__ int s_wpos[kNmsThreads / 32];
+  __shared__ unsigned long long s_best_key;
+  __shared__ int s_best_pos;
   __shared__ int s_last;
   const int c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
   const int C = p.nms_classes, MB = p.max_boxes;
   // staging: per (b,c): nsel + MB * (6 floats + anchor)
-  int* nsel_all = scratch;                                   // [B*C]
-  float* st_det = reinterpret_cast<float*>(scratch + B * C); // [B*C*MB*6]
+  int* nsel_all = scratch;                                       // [B*C]
+  float* st_det = reinterpret_cast<float*>(scratch + B * C);     // [B*C*MB*6]
   int* st_anchor = scratch + B * C + (long long)B * C * MB * 6;  // [B*C*MB]
   const long long bc = (long long)b * C + c;
 
@@ -198,38 +179,70 @@ __global__ void __launch_bounds__(kNmsThreads)
   unsigned long long* gkeys = cand_keys + ((long long)b * p.num_fg + c) * p.cap;
   const bool in_smem = cnt <= kNmsSmemKeys;
   unsigned long long* keys = in_smem ? sm.keys : gkeys;
-  if (in_smem) {
-    for (int i = tid; i < cnt; i += blockDim.x) sm.keys[i] = gkeys[i];
-  }
-  __syncthreads();
-  if (cnt > 1) bitonic_desc(keys, cnt);
   const float* hb = head + (long long)b * p.N * kRow;
   if (in_smem) {
     for (int i = tid; i < cnt; i += blockDim.x) {
-      int n = (int)(0xFFFFFFFFu - (unsigned)(sm.keys[i] & 0xFFFFFFFFull));
+      const unsigned long long k = gkeys[i];
+      sm.keys[i] = k;
+      const int n = (int)(0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull));
       Cell cell = locate(p, n);
       sm.box[i] = decode_box(p, cell, hb + (long long)n * kRow);
     }
   }
   __syncthreads();
 
-  // greedy selection: identical decisions to the sequential TF loop -- a
-  // candidate is kept iff no previously kept box has IoU > thr with it.
-  int head_pos = 0, nsel = 0;
-  while (nsel < MB) {
-    if (tid == 0) {
-      int h = head_pos;
-      while (h < cnt && keys[h] == 0ull) ++h;
-      s_head = h;
+  int nsel = 0;
+  while (nsel < MB && cnt > 0) {
+    // (1) arg-max over alive keys
+    unsigned long long bk = 0ull;
+    int bp = -1;
+    for (int i = tid; i < cnt; i += blockDim.x) {
+      const unsigned long long k = keys[i];
+      if (k > bk) {
+        bk = k;
+        bp = i;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const unsigned long long ok = __shfl_xor_sync(0xffffffffu, bk, o);
+      const int op = __shfl_xor_sync(0xffffffffu, bp, o);
+      if (ok > bk) {
+        bk = ok;
+        bp = op;
+      }
+    }
+    if (lane == 0) {
+      s_wkey[warp] = bk;
+      s_wpos[warp] = bp;
     }
     __syncthreads();
-    const int h = s_head;
-    if (h >= cnt) break;
-    const unsigned long long hk = keys[h];
+    if (warp == 0) {
+      bk = lane < kNmsThreads / 32 ? s_wkey[lane] : 0ull;
+      bp = lane < kNmsThreads / 32 ? s_wpos[lane] : -1;
+#pragma unroll
+      for (int o = 4; o; o >>= 1) {
+        const unsigned long long ok = __shfl_xor_sync(0xffffffffu, bk, o);
+        const int op = __shfl_xor_sync(0xffffffffu, bp, o);
+        if (ok > bk) {
+          bk = ok;
+          bp = op;
+        }
+      }
+      if (lane == 0) {
+        s_best_key = bk;
+        s_best_pos = bp;
+      }
+    }
+    __syncthreads();
+    const unsigned long long hk = s_best_key;
+    const int hp = s_best_pos;
+    if (hk == 0ull) break;  // nothing alive
+    // (2) keep it
     const int hn = (int)(0xFFFFFFFFu - (unsigned)(hk & 0xFFFFFFFFull));
     float4 cur;
     if (in_smem) {
-      cur = sm.box[h];
+      cur = sm.box[hp];
     } else {
       Cell cell = locate(p, hn);
       cur = decode_box(p, cell, hb + (long long)hn * kRow);
@@ -243,26 +256,27 @@ __global__ void __launch_bounds__(kNmsThreads)
       d[4] = cur.w;
       d[5] = (float)c;
       st_anchor[bc * MB + nsel] = hn;
+      keys[hp] = 0ull;
     }
     ++nsel;
-    if (nsel < MB) {
-      for (int j = h + 1 + tid; j < cnt; j += blockDim.x) {
-        const unsigned long long kj = keys[j];
-        if (kj == 0ull) continue;
-        float4 bj;
-        if (in_smem) {
-          bj = sm.box[j];
-        } else {
-          int n = (int)(0xFFFFFFFFu - (unsigned)(kj & 0xFFFFFFFFull));
-          Cell cell = locate(p, n);
-          bj = decode_box(p, cell, hb + (long long)n * kRow);
-        }
-        if (iou_tf(bj, cur) > p.iou_thr) keys[j] = 0ull;
+    if (nsel >= MB) break;
+    // (3) suppress (strict >, TF IoU)
+    for (int j = tid; j < cnt; j += blockDim.x) {
+      const unsigned long long kj = keys[j];
+      if (kj == 0ull || j == hp) continue;
+      float4 bj;
+      if (in_smem) {
+        bj = sm.box[j];
+      } else {
+        const int n = (int)(0xFFFFFFFFu - (unsigned)(kj & 0xFFFFFFFFull));
+        Cell cell = locate(p, n);
+        bj = decode_box(p, cell, hb + (long long)n * kRow);
       }
+      if (iou_tf(bj, cur) > p.iou_thr) keys[j] = 0ull;
     }
     __syncthreads();
-    head_pos = h + 1;
   }
+  __syncthreads();
   if (tid == 0) nsel_all[bc] = nsel;
 
   // class-major compaction by the last block of this image
