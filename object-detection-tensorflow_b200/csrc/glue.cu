@@ -221,30 +221,30 @@ __global__ void upsample_bilinear_add_kernel(const T* __restrict__ top, const T*
 }
 
 // ---- YOLOv3: concat([a, nearest(b)]) (a18) ----------------------------------
-template <typename T>
+template <typename T, int V>
 __global__ void upsample_nearest_concat_kernel(const T* __restrict__ a, const T* __restrict__ bsrc,
                                                T* __restrict__ out, int B, int H, int W, int Ca,
                                                int lda, int BH, int BW, int Cb, int ldb, int ldo,
                                                float hs, float ws) {
   pdl_launch_dependents();
-  const int CT = Ca + Cb;
-  const long long total = (long long)B * H * W * CT;
+  const int cv = (Ca + Cb) / V;
+  const long long total = (long long)B * H * W * cv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % CT);
-    long long pix = i / CT;
+    int c = (int)(i % cv) * V;
+    long long pix = i / cv;
     int x = (int)(pix % W);
     int y = (int)((pix / W) % H);
     int b = (int)(pix / ((long long)W * H));
-    T v;
+    float v[V];
     if (c < Ca) {
-      v = a[pix * lda + c];
+      VecIO<T, V>::ld(a + pix * lda + c, v);
     } else {
       int sy = min((int)floorf(__fmul_rn((float)y, hs)), BH - 1);
       int sx = min((int)floorf(__fmul_rn((float)x, ws)), BW - 1);
-      v = bsrc[(((long long)b * BH + sy) * BW + sx) * ldb + (c - Ca)];
+      VecIO<T, V>::ld(bsrc + (((long long)b * BH + sy) * BW + sx) * ldb + (c - Ca), v);
     }
-    out[pix * ldo + c] = v;
+    VecIO<T, V>::st(out + pix * ldo + c, v);
   }
 }
 
@@ -447,10 +447,19 @@ extern "C" int odt_upsample_nearest_concat(const void* a, const void* b, void* o
                 "args");
   cudaStream_t st = (cudaStream_t)stream;
   float hs = (float)BH / (float)H, ws = (float)BW / (float)W;
-  long long work = (long long)B * H * W * (Ca + Cb);
   DISPATCH_DTYPE(dtype, {
-    upsample_nearest_concat_kernel<T><<<grid_for(work, 256), 256, 0, st>>>(
-        (const T*)a, (const T*)b, (T*)out, B, H, W, Ca, lda, BH, BW, Cb, ldb, ldo, hs, ws);
+    constexpr int V = FullVec<T>::V;
+    const bool vec = Ca % V == 0 && Cb % V == 0 && lda % V == 0 && ldb % V == 0 && ldo % V == 0 &&
+                     ((uintptr_t)a % 16) == 0 && ((uintptr_t)b % 16) == 0 && ((uintptr_t)out % 16) == 0;
+    if (vec) {
+      long long work = (long long)B * H * W * ((Ca + Cb) / V);
+      upsample_nearest_concat_kernel<T, V><<<grid_for(work, 256), 256, 0, st>>>(
+          (const T*)a, (const T*)b, (T*)out, B, H, W, Ca, lda, BH, BW, Cb, ldb, ldo, hs, ws);
+    } else {
+      long long work = (long long)B * H * W * (Ca + Cb);
+      upsample_nearest_concat_kernel<T, 1><<<grid_for(work, 256), 256, 0, st>>>(
+          (const T*)a, (const T*)b, (T*)out, B, H, W, Ca, lda, BH, BW, Cb, ldb, ldo, hs, ws);
+    }
   })
   ODT_LAUNCH_OK();
   return ODT_OK;
