@@ -190,6 +190,8 @@ def main():
         run_reference(args, rank, world)
         return
 
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
     import torch
     import torch.distributed as tdist
     from odt_b200 import dist as od

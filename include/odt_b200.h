@@ -130,7 +130,9 @@ int odt_upsample_bilinear_add(const void* top, const void* a, void* out, int dty
 int odt_upsample_nearest_concat(const void* a, const void* b, void* out, int dtype, int B, int H,
                                 int W, int Ca, int lda, int BH, int BW, int Cb, int ldb, int ldo,
                                 void* stream);
-/* GroupNorm(groups) statistics: stats[b][g] = (mean, rstd), eps inside.  ref: FCOS.py:438-446 */
+/* GroupNorm(groups) statistics: stats[b][g] = (mean, rstd), eps inside.  `stats` must be
+ * 8-byte aligned and hold B*groups*6 floats: the B*groups*2 results followed by an fp64
+ * accumulation workspace.  ref: FCOS.py:438-446 */
 int odt_groupnorm_stats(const void* in, float* stats, int dtype, int B, long long hw, int C,
                         int ld, int groups, float eps, void* stream);
 /* y = act((x-mean)*rstd*gamma[c] + beta[c]) */
@@ -178,12 +180,16 @@ int odt_decode_candidates(const float* head, const odt_tail_params* p, int B,
  * dets: f32 [B, nms_classes*max_boxes, 6] rows (score,y1,x1,y2,x2,class);
  * det_anchor: i32 same rows (candidate row index = the keep index);
  * det_count: i32 [B]; status: i32 [1] (0 ok, ODT_ERR_OVERFLOW if any list
- * overflowed `cap`).  work: i32 [B] zero-initialised scratch (reset by the kernel).
+ * overflowed `cap`).  work: i32 [round_up(B,2) + 2] zero-initialised, 8-byte aligned scratch
+ * (per-image completion counters reset by the kernel, then the 64-bit bump pointer
+ * of the box pool).  box_pool: optional f32 [box_pool_entries][4]
+ * scratch where lists longer than the 4096-entry shared-memory window cache their
+ * decoded boxes (NULL / exhausted -> boxes are re-decoded every round).
  * ref: SSD300.py:173-190; RetinaNet.py:240-256; YOLOv3.py:352-368; FCOS.py:249-264 */
 int odt_nms_per_class(const float* head, const odt_tail_params* p, int B,
                       unsigned long long* cand_keys, const int* cand_count, float* dets,
                       int* det_anchor, int* det_count, int* sel_scratch, int* work, int* status,
-                      void* stream);
+                      float* box_pool, long long box_pool_entries, void* stream);
 /* bytes of sel_scratch needed by odt_nms_per_class */
 long long odt_nms_scratch_bytes(const odt_tail_params* p, int B);
 

@@ -297,6 +297,61 @@ __global__ void groupnorm_stats_kernel(const T* __restrict__ in, float* __restri
   }
 }
 
+// Parallel statistics: grid (blocks, B); every thread owns one channel vector
+// (so its group(s) are fixed) and a strided set of pixels; fp32 partials per
+// thread -> shared fp32 per group -> one fp64 atomicAdd per (block, group).
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+    groupnorm_partial_kernel(const T* __restrict__ in, double* __restrict__ acc, long long hw, int C,
+                             int ld, int groups, long long pix_per_block) {
+  pdl_launch_dependents();
+  constexpr int NGMAX = 8;
+  __shared__ float s_acc[64][2];
+  const int b = blockIdx.y;
+  const int cv = C / V, cpg = C / groups;
+  const int cvi = threadIdx.x % cv, pl = threadIdx.x / cv, pstep = blockDim.x / cv;
+  const int c0 = cvi * V;
+  const int ng = cpg >= V ? 1 : V / cpg;  // groups spanned by one vector
+  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) (&s_acc[0][0])[i] = 0.f;
+  __syncthreads();
+  float sum[NGMAX], sq[NGMAX];
+#pragma unroll
+  for (int q = 0; q < NGMAX; ++q) sum[q] = sq[q] = 0.f;
+  const long long p0 = (long long)blockIdx.x * pix_per_block;
+  const long long p1 = min(hw, p0 + pix_per_block);
+  const T* base = in + (long long)b * hw * ld + c0;
+  for (long long p = p0 + pl; p < p1; p += pstep) {
+    float v[V];
+    VecIO<T, V>::ld(base + p * ld, v);
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+      const int gl = cpg >= V ? 0 : q / cpg;
+      sum[gl] += v[q];
+      sq[gl] = fmaf(v[q], v[q], sq[gl]);
+    }
+  }
+  const int g0 = c0 / cpg;
+  for (int q = 0; q < ng; ++q) {
+    atomicAdd(&s_acc[g0 + q][0], sum[q]);
+    atomicAdd(&s_acc[g0 + q][1], sq[q]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x)
+    atomicAdd(acc + (long long)b * groups * 2 + i, (double)(&s_acc[0][0])[i]);
+}
+
+__global__ void groupnorm_finalize_kernel(const double* __restrict__ acc, float* __restrict__ stats,
+                                          int total, double n, float eps) {
+  pdl_launch_dependents();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const double mean = acc[2 * i] / n;
+  double var = acc[2 * i + 1] / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  stats[2 * i] = (float)mean;
+  stats[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
 template <typename T, int V>
 __global__ void groupnorm_apply_kernel(const T* __restrict__ in, T* __restrict__ out,
                                        const float* __restrict__ stats, int B, long long hw, int C,
@@ -470,9 +525,35 @@ extern "C" int odt_groupnorm_stats(const void* in, float* stats, int dtype, int 
   ODT_CHECK_ARG(in && stats && B > 0 && hw > 0 && C > 0 && ld >= C && groups > 0 && C % groups == 0,
                 "args");
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid(groups, B);
+  const int cpg = C / groups;
+  const bool pow2 = (C & (C - 1)) == 0 && (groups & (groups - 1)) == 0;
   DISPATCH_DTYPE(dtype, {
-    groupnorm_stats_kernel<T><<<grid, 1024, 0, st>>>((const T*)in, stats, hw, C, ld, groups, eps);
+    constexpr int V = FullVec<T>::V;
+    const int cv = C / V;
+    const bool fast = pow2 && C % V == 0 && cv <= 256 && groups <= 64 && ld % V == 0 &&
+                      ((uintptr_t)in % 16) == 0 && (cpg >= V ? cpg % V == 0 : V % cpg == 0) &&
+                      (cpg >= V || V / cpg <= 8);
+    if (fast) {
+      // workspace: B*groups*2 doubles behind the B*groups*2 result floats
+      double* acc = reinterpret_cast<double*>(stats + (long long)B * groups * 2);
+      ODT_CHECK_ARG(((uintptr_t)acc & 7) == 0, "stats must be 8-byte aligned");
+      ODT_CUDA_OK(cudaMemsetAsync(acc, 0, sizeof(double) * (size_t)B * groups * 2, st));
+      long long blocks = (long long)kNumSMs * 4 / B;
+      if (blocks < 1) blocks = 1;
+      long long ppb = (hw + blocks - 1) / blocks;
+      const long long min_ppb = 256 / cv * 8;  // at least 8 vectors per thread
+      if (ppb < min_ppb) ppb = min_ppb;
+      blocks = (hw + ppb - 1) / ppb;
+      groupnorm_partial_kernel<T, V><<<dim3((unsigned)blocks, B), 256, 0, st>>>(
+          (const T*)in, acc, hw, C, ld, groups, ppb);
+      ODT_LAUNCH_OK();
+      const int total = B * groups;
+      groupnorm_finalize_kernel<<<(total + 127) / 128, 128, 0, st>>>(acc, stats, total,
+                                                                     (double)hw * cpg, eps);
+    } else {
+      dim3 grid(groups, B);
+      groupnorm_stats_kernel<T><<<grid, 1024, 0, st>>>((const T*)in, stats, hw, C, ld, groups, eps);
+    }
   })
   ODT_LAUNCH_OK();
   return ODT_OK;

@@ -152,11 +152,13 @@ __global__ void __launch_bounds__(kNmsThreads)
                          const int* __restrict__ cand_count, float* __restrict__ dets,
                          int* __restrict__ det_anchor, int* __restrict__ det_count,
                          int* __restrict__ scratch, int* __restrict__ work,
-                         int* __restrict__ status) {
+                         int* __restrict__ status, float4* __restrict__ box_pool,
+                         long long box_pool_entries) {
   pdl_launch_dependents();
   const odt_tail_params& p = tp.p;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   NmsSmem& sm = *reinterpret_cast<NmsSmem*>(smem_raw);
+  __shared__ long long s_pool_start;
   __shared__ unsigned long long s_wkey[kNmsThreads / 32];
   __shared__ int s_wpos[kNmsThreads / 32];
   __shared__ unsigned long long s_best_key;
@@ -180,6 +182,10 @@ __global__ void __launch_bounds__(kNmsThreads)
   const bool in_smem = cnt <= kNmsSmemKeys;
   unsigned long long* keys = in_smem ? sm.keys : gkeys;
   const float* hb = head + (long long)b * p.N * kRow;
+  // boxes of a list longer than the shared-memory window are decoded ONCE into a
+  // slice of the global box pool (bump-allocated per launch); only if the pool is
+  // exhausted are they re-decoded on the fly every round (correct, slower)
+  const float4* pbox = nullptr;
   if (in_smem) {
     for (int i = tid; i < cnt; i += blockDim.x) {
       const unsigned long long k = gkeys[i];
@@ -187,6 +193,26 @@ __global__ void __launch_bounds__(kNmsThreads)
       const int n = (int)(0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull));
       Cell cell = locate(p, n);
       sm.box[i] = decode_box(p, cell, hb + (long long)n * kRow);
+    }
+  } else {
+    if (tid == 0) {
+      long long start = -1;
+      if (box_pool) {
+        start = (long long)atomicAdd(reinterpret_cast<unsigned long long*>(work + ((B + 1) & ~1)),
+                                     (unsigned long long)cnt);
+        if (start + cnt > box_pool_entries) start = -1;
+      }
+      s_pool_start = start;
+    }
+    __syncthreads();
+    if (s_pool_start >= 0) {
+      float4* wb = box_pool + s_pool_start;
+      for (int i = tid; i < cnt; i += blockDim.x) {
+        const int n = (int)(0xFFFFFFFFu - (unsigned)(gkeys[i] & 0xFFFFFFFFull));
+        Cell cell = locate(p, n);
+        wb[i] = decode_box(p, cell, hb + (long long)n * kRow);
+      }
+      pbox = wb;
     }
   }
   __syncthreads();
@@ -243,6 +269,8 @@ __global__ void __launch_bounds__(kNmsThreads)
     float4 cur;
     if (in_smem) {
       cur = sm.box[hp];
+    } else if (pbox) {
+      cur = pbox[hp];
     } else {
       Cell cell = locate(p, hn);
       cur = decode_box(p, cell, hb + (long long)hn * kRow);
@@ -267,6 +295,8 @@ __global__ void __launch_bounds__(kNmsThreads)
       float4 bj;
       if (in_smem) {
         bj = sm.box[j];
+      } else if (pbox) {
+        bj = pbox[j];
       } else {
         const int n = (int)(0xFFFFFFFFu - (unsigned)(kj & 0xFFFFFFFFull));
         Cell cell = locate(p, n);
@@ -363,7 +393,8 @@ extern "C" long long odt_nms_scratch_bytes(const odt_tail_params* p, int B) {
 extern "C" int odt_nms_per_class(const float* head, const odt_tail_params* p, int B,
                                  unsigned long long* cand_keys, const int* cand_count, float* dets,
                                  int* det_anchor, int* det_count, int* sel_scratch, int* work,
-                                 int* status, void* stream) {
+                                 int* status, float* box_pool, long long box_pool_entries,
+                                 void* stream) {
   int rc = check_tail(p);
   if (rc) return rc;
   ODT_CHECK_ARG(head && cand_keys && cand_count && dets && det_anchor && det_count &&
@@ -380,8 +411,13 @@ extern "C" int odt_nms_per_class(const float* head, const odt_tail_params* p, in
   TailP tp;
   tp.p = *p;
   dim3 grid(p->nms_classes, B);
+  int* pool_ctr = work + ((B + 1) & ~1);  // 64-bit bump pointer behind the per-image counters
+  ODT_CHECK_ARG(((uintptr_t)pool_ctr & 7) == 0 || !box_pool, "work must be 8-byte aligned");
+  ODT_CHECK_ARG(((uintptr_t)box_pool & 15) == 0, "box_pool must be 16-byte aligned");
+  if (box_pool) ODT_CUDA_OK(cudaMemsetAsync(pool_ctr, 0, 8, st));  // pool bump pointer
   nms_per_class_kernel<<<grid, kNmsThreads, sizeof(NmsSmem), st>>>(
-      head, tp, B, cand_keys, cand_count, dets, det_anchor, det_count, sel_scratch, work, status);
+      head, tp, B, cand_keys, cand_count, dets, det_anchor, det_count, sel_scratch, work, status,
+      reinterpret_cast<float4*>(box_pool), box_pool ? box_pool_entries : 0);
   ODT_LAUNCH_OK();
   return ODT_OK;
 }

@@ -250,7 +250,7 @@ class GroupNormActOp(Op):
         dev = net.device
         self.gamma = torch.from_numpy(np.asarray(net.weights[self.gn + "/gamma"], np.float32)).to(dev)
         self.beta = torch.from_numpy(np.asarray(net.weights[self.gn + "/beta"], np.float32)).to(dev)
-        self.stats = torch.empty(self.x.B * self.groups * 2, dtype=torch.float32, device=dev)
+        self.stats = torch.zeros(self.x.B * self.groups * 6, dtype=torch.float32, device=dev)
 
     def launch(self, net, stream):
         x = self.x
@@ -509,7 +509,7 @@ class Net:
     def num_launches(self):
         n = 0
         for op in self.ops:
-            n += 2 if isinstance(op, GroupNormActOp) else 1
+            n += 3 if isinstance(op, GroupNormActOp) else 1
         return n + self.tail.num_launches()
 
 
@@ -520,6 +520,7 @@ class Tail:
         self.kind, self.num_fg, self.nms_classes = kind, num_fg, nms_classes
         self.score_thr, self.iou_thr, self.max_boxes = score_thr, iou_thr, max_boxes
         self.level_fn, self.cap = level_fn, cap
+        self.pool_cap = 8 << 20  # box-pool entries (16 B each) for > 4096-candidate lists
 
     def prepare(self, net):
         dev = net.device
@@ -545,8 +546,13 @@ class Tail:
         self.det_count = torch.zeros((B,), dtype=torch.int32, device=dev)
         nbytes = net.lib.odt_nms_scratch_bytes(C.byref(p), B)
         self.scratch = torch.zeros((nbytes + 3) // 4, dtype=torch.int32, device=dev)
-        self.work = torch.zeros((B,), dtype=torch.int32, device=dev)
+        self.work = torch.zeros((B + (B & 1) + 2,), dtype=torch.int32, device=dev)
         self.status = torch.zeros((1,), dtype=torch.int32, device=dev)
+        # box cache for candidate lists longer than the NMS shared-memory window
+        total = B * self.nms_classes * p.cap
+        self.pool_entries = 0 if p.cap <= 4096 else min(total, self.pool_cap)
+        self.box_pool = (torch.empty((self.pool_entries, 4), dtype=torch.float32, device=dev)
+                         if self.pool_entries else None)
 
     def launch(self, net, stream):
         lib = net.lib
@@ -557,11 +563,13 @@ class Tail:
                                       self.cand_keys.data_ptr(), self.cand_count.data_ptr(),
                                       self.dets.data_ptr(), self.det_anchor.data_ptr(),
                                       self.det_count.data_ptr(), self.scratch.data_ptr(),
-                                      self.work.data_ptr(), self.status.data_ptr(), stream),
+                                      self.work.data_ptr(), self.status.data_ptr(),
+                                      self.box_pool.data_ptr() if self.box_pool is not None else None,
+                                      self.pool_entries, stream),
                 "nms_per_class")
 
     def num_launches(self):
-        return 3  # memset + decode + nms
+        return 2  # decode + nms kernels (plus 1-2 memset nodes)
 
     def results(self):
         """D2H read of the fixed-size detection records -> per-image python lists

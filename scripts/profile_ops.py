@@ -74,7 +74,8 @@ def main():
     L.check(net.lib.odt_nms_per_class(net.head_buf.data_ptr(), C.byref(t.p), net.batch, t.cand_keys.data_ptr(),
                                       t.cand_count.data_ptr(), t.dets.data_ptr(), t.det_anchor.data_ptr(),
                                       t.det_count.data_ptr(), t.scratch.data_ptr(), t.work.data_ptr(),
-                                      t.status.data_ptr(), st))
+                                      t.status.data_ptr(), t.box_pool.data_ptr() if t.box_pool is not None else None,
+                                      t.pool_entries, st))
     ev[2].record()
     torch.cuda.synchronize()
     cc = t.cand_count.cpu().numpy()

@@ -220,7 +220,7 @@ def test_glue_kernels_vs_oracle_ops(built, dtype):
     x = rnd(2, 11, 13, 64)
     g, bt = rng.uniform(.5, 1.5, 64).astype(np.float32), rng.standard_normal(64).astype(np.float32)
     ref = np.maximum(T.group_norm(x, g, bt), 0)
-    stats = torch.zeros(2 * 8 * 2, dtype=torch.float32, device="cuda")
+    stats = torch.zeros(2 * 8 * 6, dtype=torch.float32, device="cuda")
     y = torch.zeros(x.shape, dtype=dt, device="cuda")
     xd, gd, btd = _dev(x, dt), _dev(g, torch.float32), _dev(bt, torch.float32)
     L.check(lib.odt_groupnorm_stats(xd.data_ptr(), stats.data_ptr(), code, 2, 11 * 13, 64, 64, 8, 1e-6, st))
