@@ -156,15 +156,16 @@ __global__ void __launch_bounds__(ST_THREADS)
     }
   } else if (warp == ST_PROD_WARPS) {
     // ===================== MMA issuer ==========================================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(128, COUT);
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase[2] = {0u, 0u};
-      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
-        mbar_wait(tempty_bar(acc), acc_phase[acc] ^ 1u);
-        mbar_wait(full_bar(stage), phase);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * COUT;
+    // warp-uniform loop, one elected lane issues (see conv_tc.cu)
+    const uint32_t idesc = make_idesc_f16(128, COUT);
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase0 = 0u, acc_phase1 = 0u;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      mbar_wait(tempty_bar(acc), (acc ? acc_phase1 : acc_phase0) ^ 1u);
+      mbar_wait(full_bar(stage), phase);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)acc * COUT;
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < KSTEPS; ++k) {
           const uint32_t blk = k >> 2, kin = k & 3;
@@ -175,12 +176,13 @@ __global__ void __launch_bounds__(ST_THREADS)
         }
         tc_commit(empty_bar(stage));
         tc_commit(tfull_bar(acc));
-        acc_phase[acc] ^= 1u;
-        acc ^= 1;
-        if (++stage == ST_STAGES) {
-          stage = 0;
-          phase ^= 1u;
-        }
+      }
+      __syncwarp();
+      if (acc) acc_phase1 ^= 1u; else acc_phase0 ^= 1u;
+      acc ^= 1;
+      if (++stage == ST_STAGES) {
+        stage = 0;
+        phase ^= 1u;
       }
     }
   } else {

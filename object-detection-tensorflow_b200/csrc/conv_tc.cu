@@ -103,32 +103,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 
   if (warp == 0) {
     // ===================== TMA producer ======================================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_tile = tile % g.num_n_tiles, m_tile = tile / g.num_n_tiles;
-        const long long m0 = (long long)m_tile * TC_BM;
-        const int img = (int)(m0 / g.ohw);
-        const int rem = (int)(m0 - (long long)img * g.ohw);
-        const int p = rem / g.OW, q = rem - p * g.OW;
-        const int cw = q * g.stride + g.lower_w, ch = p * g.stride + g.lower_h;
-        const int n0 = n_tile * g.BN;
-        int kcol = 0;
-        for (int r = 0; r < g.R; ++r) {
-          for (int s = 0; s < g.S; ++s) {
-            for (int cc = 0; cc < g.cchunks; ++cc) {
-              mbar_wait(empty_bar(stage), phase ^ 1u);
+    // The whole warp runs the loop (warp-uniform control flow, operands stay in
+    // uniform registers); one elected lane issues the TMA instructions.
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_tile = tile % g.num_n_tiles, m_tile = tile / g.num_n_tiles;
+      const long long m0 = (long long)m_tile * TC_BM;
+      const int img = (int)(m0 / g.ohw);
+      const int rem = (int)(m0 - (long long)img * g.ohw);
+      const int p = rem / g.OW, q = rem - p * g.OW;
+      const int cw = q * g.stride + g.lower_w, ch = p * g.stride + g.lower_h;
+      const int n0 = n_tile * g.BN;
+      int kcol = 0;
+      for (int r = 0; r < g.R; ++r) {
+        for (int s = 0; s < g.S; ++s) {
+          for (int cc = 0; cc < g.cchunks; ++cc) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            if (elect_one()) {
               mbar_expect_tx(full_bar(stage), TC_A_BYTES + b_bytes);
               tma_load_im2col(a_base + (uint32_t)stage * TC_A_BYTES, &tmA, full_bar(stage),
                               cc * TC_BK, cw, ch, img, (uint16_t)(s * g.dil),
                               (uint16_t)(r * g.dil));
               tma_load_2d(b_base + (uint32_t)stage * b_bytes, &tmB, full_bar(stage), kcol, n0);
-              kcol += TC_BK;
-              if (++stage == stages) {
-                stage = 0;
-                phase ^= 1u;
-              }
+            }
+            __syncwarp();
+            kcol += TC_BK;
+            if (++stage == stages) {
+              stage = 0;
+              phase ^= 1u;
             }
           }
         }
@@ -136,22 +139,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =========================================
-    if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=f16, K-major both, N, M=128
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(g.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase[2] = {0u, 0u};
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(tempty_bar(acc), acc_phase[acc] ^ 1u);
+    // Warp-uniform loop; one elected lane issues tcgen05.mma / tcgen05.commit.  (With a
+    // single-lane branch around the whole loop ptxas has to bounce every descriptor
+    // through R2UR + an ELECT retry loop: ~170 cycles per MMA, measured.)
+    const uint32_t idesc = make_idesc_f16(TC_BM, g.BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase0 = 0u, acc_phase1 = 0u;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(tempty_bar(acc), (acc ? acc_phase1 : acc_phase0) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint64_t adesc = make_desc_sw128(a_base + (uint32_t)stage * TC_A_BYTES);
-          const uint64_t bdesc = make_desc_sw128(b_base + (uint32_t)stage * b_bytes);
+        const uint64_t adesc = make_desc_sw128(a_base + (uint32_t)stage * TC_A_BYTES);
+        const uint64_t bdesc = make_desc_sw128(b_base + (uint32_t)stage * b_bytes);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
             // advance 16 elements (32 bytes) along K inside the swizzle atom
@@ -159,15 +164,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                        (uint32_t)((kb | k) != 0));
           }
           tc_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
-          if (++stage == stages) {
-            stage = 0;
-            phase ^= 1u;
-          }
+          if (kb == kblocks - 1) tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
         }
-        tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
-        acc_phase[acc] ^= 1u;
-        acc ^= 1;
+        __syncwarp();
+        if (++stage == stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
       }
+      if (acc) acc_phase1 ^= 1u; else acc_phase0 ^= 1u;
+      acc ^= 1;
     }
   } else {
     // ===================== epilogue warps =====================================

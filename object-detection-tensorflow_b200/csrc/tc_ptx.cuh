@@ -110,6 +110,16 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
 }
 
 
+// one lane of the (converged) warp: elect.sync, as ptxas understands it natively
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async_smem() {
   // make generic-proxy shared-memory writes visible to the async proxy (UMMA / TMA reads)
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
