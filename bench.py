@@ -233,11 +233,14 @@ def main():
         return float(t.item())
 
     # ---------------- device-resident throughput (value) ----------------------
+    sampler = ClockSampler(local)
+    sampler.start()  # started before the warm-up so that samples exist for short timed regions
     for _ in range(W):
         step_resident()
-    sampler = ClockSampler(local)
+    t_spin = time.perf_counter()
+    while len(sampler.lines) < 1 and time.perf_counter() - t_spin < 3.0:
+        step_resident()  # keep the GPU under the same load until nvidia-smi has sampled once
     barrier()
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(K):

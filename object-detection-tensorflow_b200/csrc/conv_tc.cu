@@ -384,12 +384,30 @@ int check_conv_params(const odt_conv_params* p) {
 
 using namespace odt;
 
-static int pick_bn(int cout_pad) {
-  // largest N tile <= 256 that divides the padded Cout into equal 32-multiples
-  if (cout_pad <= 256) return cout_pad;
-  for (int bn = 256; bn >= 32; bn -= 32)
-    if (cout_pad % bn == 0) return bn;
-  return 256;
+static int pick_bn(int cout_pad, int m_tiles) {
+  // Largest N tile <= 256 that splits the padded Cout into equal 32-multiples ...
+  int bn = 256;
+  if (cout_pad <= 256) {
+    bn = cout_pad;
+  } else {
+    for (bn = 256; bn >= 32; bn -= 32)
+      if (cout_pad % bn == 0) break;
+    if (bn < 32) bn = 256;
+  }
+  // ... then narrowed while the launch would leave most SMs idle: a small-M layer
+  // (FPN P5-P7 towers, SSD extras) is bound by the per-SM TMA fill rate of the few
+  // CTAs that stream the whole weight matrix, so more, narrower tiles win.
+  while (bn > 32 && (long long)m_tiles * ((cout_pad + bn - 1) / bn) < kNumSMs) {
+    int nb = 0;
+    for (int c = bn - 32; c >= 32; c -= 32)
+      if (cout_pad % c == 0) {
+        nb = c;
+        break;
+      }
+    if (!nb) break;
+    bn = nb;
+  }
+  return bn;
 }
 
 extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_conv_params* p,
@@ -423,8 +441,8 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
   g.lower_w = -p->pad_l;
   g.lower_h = -p->pad_t;
   g.cchunks = p->in_ld / 64;
-  g.BN = pick_bn(p->Cout_pad);
   g.num_m_tiles = (int)((g.M + TC_BM - 1) / TC_BM);
+  g.BN = pick_bn(p->Cout_pad, g.num_m_tiles);
   g.num_n_tiles = (p->Cout_pad + g.BN - 1) / g.BN;
   const int stage_bytes = TC_A_BYTES + g.BN * 128;
   int stages = (TC_SMEM_LIMIT - 2048 - TC_EPI_SMEM) / stage_bytes;

@@ -161,8 +161,6 @@ __global__ void __launch_bounds__(kNmsThreads)
   __shared__ long long s_pool_start;
   __shared__ unsigned long long s_wkey[kNmsThreads / 32];
   __shared__ int s_wpos[kNmsThreads / 32];
-  __shared__ unsigned long long s_best_key;
-  __shared__ int s_best_pos;
   __shared__ int s_last;
   const int c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -219,9 +217,10 @@ __global__ void __launch_bounds__(kNmsThreads)
 
   int nsel = 0;
   while (nsel < MB && cnt > 0) {
-    // (1) arg-max over alive keys
+    // (1) arg-max over alive keys: per-thread scan, 3 redux.sync per warp, then every
+    //     thread folds the 8 warp partials itself (one barrier, no second shuffle tree)
     unsigned long long bk = 0ull;
-    int bp = -1;
+    int bp = 0x7fffffff;
     for (int i = tid; i < cnt; i += blockDim.x) {
       const unsigned long long k = keys[i];
       if (k > bk) {
@@ -229,38 +228,27 @@ __global__ void __launch_bounds__(kNmsThreads)
         bp = i;
       }
     }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      const unsigned long long ok = __shfl_xor_sync(0xffffffffu, bk, o);
-      const int op = __shfl_xor_sync(0xffffffffu, bp, o);
-      if (ok > bk) {
-        bk = ok;
-        bp = op;
-      }
-    }
-    if (lane == 0) {
-      s_wkey[warp] = bk;
-      s_wpos[warp] = bp;
-    }
-    __syncthreads();
-    if (warp == 0) {
-      bk = lane < kNmsThreads / 32 ? s_wkey[lane] : 0ull;
-      bp = lane < kNmsThreads / 32 ? s_wpos[lane] : -1;
-#pragma unroll
-      for (int o = 4; o; o >>= 1) {
-        const unsigned long long ok = __shfl_xor_sync(0xffffffffu, bk, o);
-        const int op = __shfl_xor_sync(0xffffffffu, bp, o);
-        if (ok > bk) {
-          bk = ok;
-          bp = op;
-        }
-      }
+    {
+      const unsigned hi = (unsigned)(bk >> 32), lo = (unsigned)bk;
+      const unsigned whi = __reduce_max_sync(0xffffffffu, hi);
+      const unsigned wlo = __reduce_max_sync(0xffffffffu, hi == whi ? lo : 0u);
+      const int wpos = __reduce_min_sync(0xffffffffu, (hi == whi && lo == wlo) ? bp : 0x7fffffff);
       if (lane == 0) {
-        s_best_key = bk;
-        s_best_pos = bp;
+        s_wkey[warp] = ((unsigned long long)whi << 32) | wlo;
+        s_wpos[warp] = wpos;
       }
     }
     __syncthreads();
+    unsigned long long s_best_key = 0ull;
+    int s_best_pos = -1;
+#pragma unroll
+    for (int w = 0; w < kNmsThreads / 32; ++w) {
+      const unsigned long long k = s_wkey[w];
+      if (k > s_best_key) {
+        s_best_key = k;
+        s_best_pos = s_wpos[w];
+      }
+    }
     const unsigned long long hk = s_best_key;
     const int hp = s_best_pos;
     if (hk == 0ull) break;  // nothing alive

@@ -78,6 +78,20 @@ def main():
                                       t.pool_entries, st))
     ev[2].record()
     torch.cuda.synchronize()
+    # whole forward as ONE CUDA graph replay (what the bench / API actually runs)
+    net.capture()
+    for _ in range(3):
+        net.run()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    g0.record()
+    for _ in range(10):
+        net.run()
+    g1.record()
+    torch.cuda.synchronize()
+    gms = g0.elapsed_time(g1) / 10
+    print("CUDA-graph replay: %.3f ms/step -> %.0f images/s (batch %d), %d launches, conv %.1f TFLOP/s whole-step"
+          % (gms, B / gms * 1e3, B, net.num_launches(), net.conv_flops / gms / 1e9))
     cc = t.cand_count.cpu().numpy()
     print("decode %.4f ms (%.1f MB rows -> %.0f GB/s) ; nms %.4f ms ; candidates/class max %d mean %.1f ; dets/img mean %.1f"
           % (ev[0].elapsed_time(ev[1]), net.head_buf.numel() * 4 / 1e6,
