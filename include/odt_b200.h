@@ -92,6 +92,14 @@ typedef struct {
   void* out1; /* or NULL */
   long long out1_img_stride;
   int out1_pix_stride;
+  /* halo layouts (tensor-core path only): 1 = the tensor is stored as
+   * [B][H+2][W+2][ld] with a zero 1-pixel border that the kernels never dirty.
+   * A halo input lets 3x3/stride-1 convolutions with Cout_pad <= 128 run in
+   * "flat" mode: one [136 x 64] slab per (filter row, channel chunk) feeds the
+   * three horizontal taps, cutting the activation traffic ~3x.  out0_img_stride
+   * must then be (OH+2)*(OW+2)*out0_pix_stride; `residual` shares out0's layout. */
+  int in_halo;
+  int out0_halo;
 } odt_conv_params;
 
 /* tcgen05 / TMA implicit-GEMM forward convolution, fp16 in, fp32 accumulate.
@@ -110,9 +118,11 @@ int odt_conv2d_stem(const float* images, const float* mean3_host, const void* we
                     const odt_conv_params* p, void* stream);
 
 /* --------------------------------------------------------------- glue ---- */
-/* max pooling, TF SAME (pads ignored).  ref: SSD300.py:539-547, RetinaNet.py:645-653 */
+/* max pooling, TF SAME (pads ignored).  in_halo / out_halo: the tensor is stored with a
+ * zero 1-pixel border ([B][H+2][W+2][ld], see odt_conv_params).
+ * ref: SSD300.py:539-547, RetinaNet.py:645-653 */
 int odt_maxpool(const void* in, void* out, int dtype, int B, int H, int W, int C, int ld, int k,
-                int stride, void* stream);
+                int stride, int in_halo, int out_halo, void* stream);
 /* x * rsqrt(max(sum_c x^2, 1e-12)) * gamma.  ref: SSD300.py:74-83 */
 int odt_l2norm_scale(const void* in, void* out, int dtype, long long pixels, int C, int ld,
                      float gamma, void* stream);

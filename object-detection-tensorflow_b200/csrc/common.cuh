@@ -68,6 +68,7 @@ __device__ __forceinline__ void pdl_launch_dependents() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-bool pdl_enabled();  // ODT_PDL=0 disables the launch attribute (api.cu)
+bool pdl_enabled();   // ODT_PDL=0 disables the launch attribute (api.cu)
+bool flat_enabled();  // ODT_TC_FLAT=0 disables the halo-flat 3x3 path (A/B measurements)
 
 }  // namespace odt

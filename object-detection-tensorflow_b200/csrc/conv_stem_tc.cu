@@ -22,6 +22,7 @@ struct StemGeom {
   long long M;
   int num_tiles;
   int bulk_store;  // output rows are 128 contiguous bytes (ld == 64, dense NHWC): smem-staged bulk stores
+  int out_halo;    // output stored as [B][OH+2][OW+2][ld]
   float mean[3];
 };
 
@@ -198,8 +199,13 @@ __global__ void __launch_bounds__(ST_THREADS)
       mbar_wait(tfull_bar(acc), acc_phase[acc]);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)acc * COUT + ((uint32_t)(quarter * 32) << 16);
+      long long opix = pix;
+      if (g.out_halo) {
+        const int oy = pix / g.OW, ox = pix - oy * g.OW;
+        opix = (long long)(oy + 1) * (g.OW + 2) + ox + 1;
+      }
       __half* orow = reinterpret_cast<__half*>(e.out0) + (long long)b * e.out0_img_stride +
-                     (long long)pix * e.out0_pix_stride;
+                     opix * e.out0_pix_stride;
       const uint32_t my_stage = stage_out + (uint32_t)(warp - ST_PROD_WARPS - 1) * 4096u;
       uint8_t* my_stage_ptr = smem_raw + (my_stage - raw);
       if (g.bulk_store) {
@@ -320,7 +326,11 @@ int odt_conv2d_stem_tc_try(const float* images, const float* mean3_host, const v
   g.pad_t = p->pad_t; g.pad_l = p->pad_l; g.w_ld = p->w_ld;
   g.M = (long long)p->B * p->OH * p->OW;
   g.num_tiles = (int)((g.M + 127) / 128);
-  g.bulk_store = (p->out0_pix_stride == 64 && p->out0_img_stride == (long long)p->OH * p->OW * 64) ? 1 : 0;
+  g.out_halo = p->out0_halo ? 1 : 0;
+  g.bulk_store = (!g.out_halo && p->out0_pix_stride == 64 &&
+                  p->out0_img_stride == (long long)p->OH * p->OW * 64)
+                     ? 1
+                     : 0;
   g.mean[0] = mean3_host[0]; g.mean[1] = mean3_host[1]; g.mean[2] = mean3_host[2];
   Epi e = make_epi(*p);
   cudaStream_t st = (cudaStream_t)stream;

@@ -18,6 +18,8 @@
 //
 // ref call sites: tf.nn.conv2d SSD300.py:519; tf.layers.conv2d SSD300.py:524,
 // RetinaNet.py:579,599,609, YOLOv3.py:495, FCOS.py:449,469,479.
+#include <string.h>
+
 #include "epilogue.cuh"
 #include "tc_ptx.cuh"
 
@@ -42,7 +44,18 @@ struct TcGeom {
   int stages;
   int fast_store;  // 1: fp16 out0, no regroup, 16-byte aligned rows
   int fast_cols;   // columns that may be written by whole 32-column chunks (min channel stride)
+  int a_bytes, b_bytes;  // shared memory per pipeline stage
+  // halo-flat mode (3x3, stride 1, input stored with a 1-pixel zero halo): M runs over
+  // the padded-linear positions, one [136 x 64] slab per (filter row, channel chunk)
+  // feeds the three horizontal taps through row-shifted UMMA descriptors
+  int flat;
+  int PW, PHW;     // padded row length W+2 and padded image size (H+2)*(W+2)
+  int H, W;        // real input (= output) size in flat mode
+  long long Q;     // B*(H+2)*(W+2)
+  int out_halo;    // out0 / residual are stored with a 1-pixel halo
 };
+constexpr int TC_FLAT_ROWS = 136;                    // 128 + 2 neighbours, padded to 1024 B
+constexpr int TC_FLAT_A_BYTES = TC_FLAT_ROWS * 128;  // 17408
 
 // --------------------------------------------------------------- kernel ----
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -53,9 +66,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const int stages = g.stages;
-  const uint32_t b_bytes = (uint32_t)g.BN * 128u;
+  const uint32_t a_bytes = (uint32_t)g.a_bytes, b_bytes = (uint32_t)g.b_bytes;
   const uint32_t a_base = base;
-  const uint32_t b_base = base + (uint32_t)stages * TC_A_BYTES;
+  const uint32_t b_base = base + (uint32_t)stages * a_bytes;
   const uint32_t bar_base = b_base + (uint32_t)stages * b_bytes;  // 8-byte aligned
   // barriers: full[stages], empty[stages], tfull[2], tempty[2], then tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -99,7 +112,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   pdl_wait();
 
   const int num_tiles = g.num_m_tiles * g.num_n_tiles;
-  const int kblocks = g.R * g.S * g.cchunks;
+  const int kblocks = g.flat ? 3 * g.cchunks : g.R * g.S * g.cchunks;  // pipeline stages per tile
 
   if (warp == 0) {
     // ===================== TMA producer ======================================
@@ -110,19 +123,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int n_tile = tile % g.num_n_tiles, m_tile = tile / g.num_n_tiles;
       const long long m0 = (long long)m_tile * TC_BM;
+      const int n0 = n_tile * g.BN;
+      if (g.flat) {
+        // one slab of 136 consecutive padded-linear rows per (filter row, chunk): rows
+        // m0 + (r-1)*PW - 1 ...; negative / past-the-end rows are TMA zero fill
+        for (int r = 0; r < 3; ++r) {
+          const int row0 = (int)m0 + (r - 1) * g.PW - 1;
+          for (int cc = 0; cc < g.cchunks; ++cc) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            if (elect_one()) {
+              mbar_expect_tx(full_bar(stage), a_bytes + b_bytes);
+              tma_load_2d(a_base + (uint32_t)stage * a_bytes, &tmA, full_bar(stage), cc * TC_BK, row0);
+#pragma unroll
+              for (int s = 0; s < 3; ++s)
+                tma_load_2d(b_base + (uint32_t)stage * b_bytes + (uint32_t)s * (uint32_t)g.BN * 128u, &tmB,
+                            full_bar(stage), ((r * 3 + s) * g.cchunks + cc) * TC_BK, n0);
+            }
+            __syncwarp();
+            if (++stage == stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+        continue;
+      }
       const int img = (int)(m0 / g.ohw);
       const int rem = (int)(m0 - (long long)img * g.ohw);
       const int p = rem / g.OW, q = rem - p * g.OW;
       const int cw = q * g.stride + g.lower_w, ch = p * g.stride + g.lower_h;
-      const int n0 = n_tile * g.BN;
       int kcol = 0;
       for (int r = 0; r < g.R; ++r) {
         for (int s = 0; s < g.S; ++s) {
           for (int cc = 0; cc < g.cchunks; ++cc) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             if (elect_one()) {
-              mbar_expect_tx(full_bar(stage), TC_A_BYTES + b_bytes);
-              tma_load_im2col(a_base + (uint32_t)stage * TC_A_BYTES, &tmA, full_bar(stage),
+              mbar_expect_tx(full_bar(stage), a_bytes + b_bytes);
+              tma_load_im2col(a_base + (uint32_t)stage * a_bytes, &tmA, full_bar(stage),
                               cc * TC_BK, cw, ch, img, (uint16_t)(s * g.dil),
                               (uint16_t)(r * g.dil));
               tma_load_2d(b_base + (uint32_t)stage * b_bytes, &tmB, full_bar(stage), kcol, n0);
@@ -154,14 +191,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint64_t adesc = make_desc_sw128(a_base + (uint32_t)stage * TC_A_BYTES);
+        const uint64_t adesc = make_desc_sw128(a_base + (uint32_t)stage * a_bytes);
         const uint64_t bdesc = make_desc_sw128(b_base + (uint32_t)stage * b_bytes);
         if (elect_one()) {
+          if (g.flat) {
+            // three horizontal taps from the same slab: operand rows s .. s+127, i.e. the
+            // descriptor start shifted by s*128 B inside the 1024 B swizzle pattern (the
+            // swizzle is a function of the absolute address: probed, scripts/probe_rowoffset.py)
+            const uint64_t bstep = (uint64_t)((g.BN * 128) >> 4);
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
-            // advance 16 elements (32 bytes) along K inside the swizzle atom
-            tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                       (uint32_t)((kb | k) != 0));
+            for (int s3 = 0; s3 < 3; ++s3) {
+#pragma unroll
+              for (int k = 0; k < TC_BK / 16; ++k)
+                tc_mma_f16(d_tmem, adesc + (uint64_t)(8 * s3 + 2 * k), bdesc + bstep * s3 + (uint64_t)(2 * k),
+                           idesc, (uint32_t)((kb | s3 | k) != 0));
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) {
+              // advance 16 elements (32 bytes) along K inside the swizzle atom
+              tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                         (uint32_t)((kb | k) != 0));
+            }
           }
           tc_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
           if (kb == kblocks - 1) tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
@@ -187,9 +238,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
       const int n_tile = tile % g.num_n_tiles, m_tile = tile / g.num_n_tiles;
       const long long m = (long long)m_tile * TC_BM + quarter * 32 + lane;
-      const bool row_ok = m < g.M;
-      const int img = row_ok ? (int)(m / g.ohw) : 0;
-      const int pix = row_ok ? (int)(m - (long long)img * g.ohw) : 0;
+      bool row_ok;
+      int img, pix;
+      if (g.flat) {
+        // padded-linear position -> (image, padded y, padded x); halo positions are not stored
+        img = m < g.Q ? (int)(m / g.PHW) : 0;
+        const int rem = (int)(m - (long long)img * g.PHW);
+        const int yp = rem / g.PW, xp = rem - yp * g.PW;
+        row_ok = m < g.Q && yp >= 1 && yp <= g.H && xp >= 1 && xp <= g.W;
+        pix = row_ok ? (yp - 1) * g.W + (xp - 1) : 0;
+      } else {
+        row_ok = m < g.M;
+        img = row_ok ? (int)(m / g.ohw) : 0;
+        pix = row_ok ? (int)(m - (long long)img * g.ohw) : 0;
+      }
       const int n0 = n_tile * g.BN;
       // stage the per-channel parameters of this N tile once (broadcast reads later);
       // consecutive tiles of single-N-tile layers reuse them
@@ -210,8 +272,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       mbar_wait(tfull_bar(acc), acc_phase[acc]);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(quarter * 32) << 16);
-      const long long o0_row =
-          (long long)img * e.out0_img_stride + (long long)pix * e.out0_pix_stride;
+      long long o0_row = (long long)img * e.out0_img_stride;
+      if (g.out_halo) {
+        const int oy = pix / g.OW, ox = pix - oy * g.OW;
+        o0_row += (long long)((oy + 1) * (g.OW + 2) + ox + 1) * e.out0_pix_stride;
+      } else {
+        o0_row += (long long)pix * e.out0_pix_stride;
+      }
       const long long o1_row =
           (long long)img * e.out1_img_stride + (long long)pix * e.out1_pix_stride;
       for (int j = half; j < g.BN / 32; j += 2) {
@@ -429,7 +496,11 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
   const int pad_r = max((p->OW - 1) * p->stride + (p->S - 1) * p->dil + 1 - p->W, 0) - p->pad_l;
   ODT_CHECK_ARG(pad_b >= 0 && pad_r >= 0, "pad_t/pad_l exceed the SAME total");
 
+  const int ih = p->in_halo ? 1 : 0;  // input stored as [B][H+2][W+2][ld] with zero borders
+  ODT_CHECK_ARG(p->in_halo == 0 || p->in_halo == 1, "in_halo must be 0 or 1");
+  ODT_CHECK_ARG(p->out0_halo == 0 || p->out0_halo == 1, "out0_halo must be 0 or 1");
   TcGeom g;
+  memset(&g, 0, sizeof(g));
   g.M = (long long)p->B * p->OH * p->OW;
   g.OH = p->OH;
   g.OW = p->OW;
@@ -438,13 +509,35 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
   g.S = p->S;
   g.stride = p->stride;
   g.dil = p->dil;
-  g.lower_w = -p->pad_l;
-  g.lower_h = -p->pad_t;
+  g.lower_w = -p->pad_l + ih;
+  g.lower_h = -p->pad_t + ih;
   g.cchunks = p->in_ld / 64;
-  g.num_m_tiles = (int)((g.M + TC_BM - 1) / TC_BM);
-  g.BN = pick_bn(p->Cout_pad, g.num_m_tiles);
-  g.num_n_tiles = (p->Cout_pad + g.BN - 1) / g.BN;
-  const int stage_bytes = TC_A_BYTES + g.BN * 128;
+  g.out_halo = p->out0_halo;
+  g.H = p->H;
+  g.W = p->W;
+  g.PW = p->W + 2;
+  g.PHW = (p->H + 2) * (p->W + 2);
+  g.Q = (long long)p->B * g.PHW;
+  // halo-flat path: 3x3 / stride 1 / dilation 1 with a halo input and a narrow N
+  g.flat = (ih && p->R == 3 && p->S == 3 && p->stride == 1 && p->dil == 1 && p->pad_t == 1 &&
+            p->pad_l == 1 && p->Cout_pad <= 128 && flat_enabled() && g.Q < (1ll << 31) - 4096)
+               ? 1
+               : 0;
+  int stage_bytes;
+  if (g.flat) {
+    g.num_m_tiles = (int)((g.Q + TC_BM - 1) / TC_BM);
+    g.BN = p->Cout_pad;
+    g.num_n_tiles = 1;
+    g.a_bytes = TC_FLAT_A_BYTES;
+    g.b_bytes = 3 * g.BN * 128;
+  } else {
+    g.num_m_tiles = (int)((g.M + TC_BM - 1) / TC_BM);
+    g.BN = pick_bn(p->Cout_pad, g.num_m_tiles);
+    g.num_n_tiles = (p->Cout_pad + g.BN - 1) / g.BN;
+    g.a_bytes = TC_A_BYTES;
+    g.b_bytes = g.BN * 128;
+  }
+  stage_bytes = g.a_bytes + g.b_bytes;
   int stages = (TC_SMEM_LIMIT - 2048 - TC_EPI_SMEM) / stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   ODT_CHECK_ARG(stages >= 2, "tile too large for shared memory");
@@ -459,12 +552,28 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
   if (p->out1 && p->out1_pix_stride < g.fast_cols) g.fast_cols = p->out1_pix_stride;
 
   CUtensorMap tmA, tmB;
-  {
-    cuuint64_t dims[4] = {(cuuint64_t)p->in_ld, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->B};
-    cuuint64_t strides[3] = {(cuuint64_t)p->in_ld * 2, (cuuint64_t)p->W * p->in_ld * 2,
-                             (cuuint64_t)p->H * p->W * p->in_ld * 2};
-    int lower[2] = {-p->pad_l, -p->pad_t};
-    int upper[2] = {pad_r - (p->S - 1) * p->dil, pad_b - (p->R - 1) * p->dil};
+  if (g.flat) {
+    // flat [Q][ld] view of the halo tensor, slabs of 136 consecutive padded-linear pixels
+    cuuint64_t dims[2] = {(cuuint64_t)p->in_ld, (cuuint64_t)g.Q};
+    cuuint64_t strides[1] = {(cuuint64_t)p->in_ld * 2};
+    cuuint32_t box[2] = {TC_BK, TC_FLAT_ROWS};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult cr = g_encode_tiled(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(in), dims,
+                                 strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(flat activations) failed (%d)", (int)cr);
+      return ODT_ERR_CUDA;
+    }
+  } else {
+    const int IW = p->W + 2 * ih, IH = p->H + 2 * ih;
+    cuuint64_t dims[4] = {(cuuint64_t)p->in_ld, (cuuint64_t)IW, (cuuint64_t)IH, (cuuint64_t)p->B};
+    cuuint64_t strides[3] = {(cuuint64_t)p->in_ld * 2, (cuuint64_t)IW * p->in_ld * 2,
+                             (cuuint64_t)IH * IW * p->in_ld * 2};
+    // the halo shifts the image origin by one pixel inside the stored tensor
+    int lower[2] = {-p->pad_l + ih, -p->pad_t + ih};
+    int upper[2] = {pad_r - (p->S - 1) * p->dil - ih, pad_b - (p->R - 1) * p->dil - ih};
     cuuint32_t estr[4] = {1, (cuuint32_t)p->stride, (cuuint32_t)p->stride, 1};
     CUresult cr = g_encode_im2col(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(in),
                                   dims, strides, lower, upper, TC_BK, TC_BM, estr,
@@ -473,7 +582,7 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) {
       set_error("cuTensorMapEncodeIm2col failed (%d): dims %d %d %d %d lower %d %d upper %d %d stride %d",
-                (int)cr, p->in_ld, p->W, p->H, p->B, lower[0], lower[1], upper[0], upper[1], p->stride);
+                (int)cr, p->in_ld, IW, IH, p->B, lower[0], lower[1], upper[0], upper[1], p->stride);
       return ODT_ERR_CUDA;
     }
   }

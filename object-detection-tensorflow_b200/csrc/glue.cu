@@ -90,8 +90,11 @@ __global__ void normalize_kernel(const float* __restrict__ img, T* __restrict__ 
 // ---- max pool, TF SAME (a4) -------------------------------------------------
 template <typename T, int V>
 __global__ void maxpool_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int H, int W,
-                               int OH, int OW, int C, int ld, int k, int stride, int pt, int pl) {
+                               int OH, int OW, int C, int ld, int k, int stride, int pt, int pl,
+                               int ih, int oh) {
   pdl_launch_dependents();
+  // ih / oh: 1-pixel halo of the stored input / output tensor (0 or 1)
+  const int IW = W + 2 * ih, IH = H + 2 * ih, PW = OW + 2 * oh, PH = OH + 2 * oh;
   const int cv = C / V;
   const long long total = (long long)B * OH * OW * cv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -111,12 +114,12 @@ __global__ void maxpool_kernel(const T* __restrict__ in, T* __restrict__ out, in
         int ix = ox * stride - pl + s;
         if (ix < 0 || ix >= W) continue;
         float v[V];
-        VecIO<T, V>::ld(in + (((long long)b * H + iy) * W + ix) * ld + c, v);
+        VecIO<T, V>::ld(in + (((long long)b * IH + iy + ih) * IW + ix + ih) * ld + c, v);
 #pragma unroll
         for (int q = 0; q < V; ++q) m[q] = fmaxf(m[q], v[q]);
       }
     }
-    VecIO<T, V>::st(out + pix * ld + c, m);
+    VecIO<T, V>::st(out + (((long long)b * PH + oy + oh) * PW + ox + oh) * ld + c, m);
   }
 }
 
@@ -414,9 +417,10 @@ extern "C" int odt_normalize_input(const float* images, void* out, int out_dtype
 }
 
 extern "C" int odt_maxpool(const void* in, void* out, int dtype, int B, int H, int W, int C,
-                           int ld, int k, int stride, void* stream) {
+                           int ld, int k, int stride, int in_halo, int out_halo, void* stream) {
   ODT_CHECK_ARG(in && out && B > 0 && H > 0 && W > 0 && C > 0 && ld >= C && k > 0 && stride > 0,
                 "args");
+  ODT_CHECK_ARG((in_halo == 0 || in_halo == 1) && (out_halo == 0 || out_halo == 1), "halo must be 0/1");
   int OH, OW, pt, pl, pa;
   odt_same_pad(H, k, stride, 1, &OH, &pt, &pa);
   odt_same_pad(W, k, stride, 1, &OW, &pl, &pa);
@@ -426,11 +430,11 @@ extern "C" int odt_maxpool(const void* in, void* out, int dtype, int B, int H, i
     if (can_vec(in, out, C, ld, V, sizeof(T))) {
       long long work = (long long)B * OH * OW * (C / V);
       maxpool_kernel<T, V><<<grid_for(work, 256), 256, 0, st>>>((const T*)in, (T*)out, B, H, W, OH,
-                                                               OW, C, ld, k, stride, pt, pl);
+                                                               OW, C, ld, k, stride, pt, pl, in_halo, out_halo);
     } else {
       long long work = (long long)B * OH * OW * C;
       maxpool_kernel<T, 1><<<grid_for(work, 256), 256, 0, st>>>((const T*)in, (T*)out, B, H, W, OH,
-                                                               OW, C, ld, k, stride, pt, pl);
+                                                               OW, C, ld, k, stride, pt, pl, in_halo, out_halo);
     }
   })
   ODT_LAUNCH_OK();

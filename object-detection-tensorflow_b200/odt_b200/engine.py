@@ -13,6 +13,7 @@ A model file (nets.py) describes its layers once through `Builder`; the builder
 """
 import ctypes as C
 import math
+import os
 import re
 
 import numpy as np
@@ -72,6 +73,11 @@ class Act:
         self.name, self.B, self.H, self.W, self.C, self.ld, self.dtype = name, B, H, W, C, ld, dtype
         self.buf = None
         self.needed = True  # False when only a fused second output is consumed
+        self.halo = 0       # 1: stored as [B, H+2, W+2, ld] with a zero border (halo-flat 3x3 convs)
+
+    @property
+    def img_stride(self):
+        return (self.H + 2 * self.halo) * (self.W + 2 * self.halo) * self.ld
 
     @property
     def pixels(self):
@@ -146,6 +152,8 @@ class ConvOp(Op):
         p.shift = self.shift.data_ptr()
         p.act = ACT[self.act]
         p.residual = self.residual.ptr() if self.residual is not None else None
+        p.in_halo = 0 if self.is_image else x.halo
+        p.out0_halo = 0
         if self.head is not None:
             hb = net.head_buf
             lvl_off, col, group, gstride, A = self.head
@@ -159,8 +167,10 @@ class ConvOp(Op):
             assert (y.H, y.W, y.C) == (OH, OW, cout)
             p.out0 = y.ptr() if y.needed else None
             p.out0_dtype = L.ODT_F16 if f16 else L.ODT_F32
-            p.out0_img_stride = y.H * y.W * y.ld
+            p.out0_img_stride = y.img_stride
             p.out0_pix_stride = y.ld
+            p.out0_halo = y.halo
+            assert self.residual is None or self.residual.halo == y.halo
             p.out0_group = p.out0_group_stride = 0
         if self.pre is not None:
             scope, act2, t = self.pre
@@ -200,7 +210,7 @@ class PoolOp(Op):
         x = self.x
         # pooled over the padded channel range so pad lanes stay zero
         L.check(net.lib.odt_maxpool(x.ptr(), self.y.ptr(), net.dt, x.B, x.H, x.W, x.ld, x.ld,
-                                    self.k, self.stride, stream), "maxpool")
+                                    self.k, self.stride, x.halo, self.y.halo, stream), "maxpool")
 
 
 class L2NormOp(Op):
@@ -319,6 +329,7 @@ class Net:
         self.levels = []    # (H, W, A) per head level, in candidate order
         self.tail = None
         self.mean3 = (C.c_float * 3)(123.68, 116.779, 103.979)  # ref SSD300.py:55
+        self.use_halo = os.environ.get("ODT_HALO", "1") != "0"
         self.weights = None
         self.graph = None
 
@@ -458,6 +469,51 @@ class Net:
             kept.append(op)
         self.ops = kept
 
+    # -------------------------------------------------------------- halos ----
+    STEM_TC_VARIANTS = {(3, 1, 64), (3, 1, 32), (7, 2, 16)}
+
+    def assign_halos(self):
+        """Give a zero 1-pixel halo to fp16 tensors that feed a flat-eligible 3x3 conv
+        (stride 1, dilation 1, padded Cout <= 128) when every producer / consumer of the
+        tensor understands the layout (tensor-core convs, the tcgen05 stems, max-pool)."""
+        if self.precision != "fp16" or not self.allow_tc:
+            return
+        readers, producer = {}, {}
+        for op in self.ops:
+            for t in op.reads:
+                readers.setdefault(id(t), []).append(op)
+            for t in op.writes:
+                producer[id(t)] = op
+            if getattr(op, "pre", None) is not None:
+                producer[id(op.pre[2])] = None  # fused second outputs stay dense
+        for t in self.acts:
+            prod = producer.get(id(t))
+            cons = readers.get(id(t), [])
+            if not cons or not t.needed:
+                continue
+            if isinstance(prod, ConvOp):
+                if prod.head is not None or prod.residual is not None:
+                    continue
+                if prod.is_image and (prod.k, prod.stride, t.C) not in self.STEM_TC_VARIANTS:
+                    continue
+                if prod.is_image and prod.pre is not None:
+                    continue
+            elif not isinstance(prod, PoolOp):
+                continue
+            ok, gain = True, False
+            for c in cons:
+                if isinstance(c, ConvOp) and c.x is t and c.residual is not t and not c.is_image:
+                    cout = self.vars[c.kernel][0][3]
+                    if (c.k == 3 and c.stride == 1 and c.dil == 1 and _round_up(cout, 32) <= 128
+                            and t.H >= 16 and t.W >= 16):
+                        gain = True  # small maps: the halo positions would dominate
+                elif isinstance(c, PoolOp):
+                    pass
+                else:
+                    ok = False
+            if ok and gain and self.batch * (t.H + 2) * (t.W + 2) < (1 << 31) - 4096:
+                t.halo = 1
+
     # ------------------------------------------------------------ finalize --
     def finalize(self, weights, tail, fuse=True):
         """Allocate buffers, upload weights, build the kernel parameter blocks."""
@@ -467,12 +523,15 @@ class Net:
             raise KeyError("weights missing %d variables, e.g. %s" % (len(missing), missing[:3]))
         if fuse:
             self.fuse()
+        if self.use_halo:
+            self.assign_halos()
         dev = self.device
         self.image_buf = torch.zeros((self.batch, self.in_h, self.in_w, 3), dtype=torch.float32,
                                      device=dev)
         for t in self.acts:
             if t.needed or True:  # unneeded raws are tiny bookkeeping; keep a buffer for residual addressing
-                t.buf = torch.zeros((t.B, t.H, t.W, t.ld), dtype=self.tdtype, device=dev)
+                t.buf = torch.zeros((t.B, t.H + 2 * t.halo, t.W + 2 * t.halo, t.ld), dtype=self.tdtype,
+                                    device=dev)
         self.N = sum(h * w * a for h, w, a in self.levels)
         self.head_buf = torch.zeros((self.batch, self.N, 25), dtype=torch.float32, device=dev)
         self.tail = tail

@@ -31,6 +31,7 @@ class ConvParams(C.Structure):
         ("out0_group", C.c_int), ("out0_group_stride", C.c_int),
         ("scale2", C.c_void_p), ("shift2", C.c_void_p), ("act2", C.c_int),
         ("out1", C.c_void_p), ("out1_img_stride", C.c_longlong), ("out1_pix_stride", C.c_int),
+        ("in_halo", C.c_int), ("out0_halo", C.c_int),
     ]
 
 
@@ -64,7 +65,7 @@ SYMBOLS = {
     "odt_conv2d_f16_tc": (_I, [_P, _P, C.POINTER(ConvParams), _P]),
     "odt_conv2d_direct": (_I, [_P, _P, _I, C.POINTER(ConvParams), _P]),
     "odt_conv2d_stem": (_I, [_P, C.POINTER(_F), _P, _I, C.POINTER(ConvParams), _P]),
-    "odt_maxpool": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "odt_maxpool": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "odt_l2norm_scale": (_I, [_P, _P, _I, _L, _I, _I, _F, _P]),
     "odt_affine_act": (_I, [_P, _P, _I, _L, _I, _I, _P, _P, _I, _P]),
     "odt_upsample_bilinear_add": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P]),

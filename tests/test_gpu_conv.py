@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _conv_case(B, H, W, Cin, Cout, k, stride, dil, mode, act="relu", residual=False, pre=False,
-               bn=True, f32_out=False, seed=0):
+               bn=True, f32_out=False, seed=0, in_halo=0, out_halo=0):
     """mode: 'tc' (fp16 tcgen05), 'direct16', 'direct32'.  Returns (got, ref, got1, ref1)."""
     from odt_b200 import lib as L
     from odt_b200.engine import same_pad
@@ -34,8 +34,8 @@ def _conv_case(B, H, W, Cin, Cout, k, stride, dil, mode, act="relu", residual=Fa
     OW, pl, _ = same_pad(W, k, stride, dil)
     old = (Cout + 63) // 64 * 64 if mode == "tc" else Cout
     dev = "cuda"
-    xd = torch.zeros((B, H, W, ld), dtype=tdt, device=dev)
-    xd[..., :Cin] = torch.from_numpy(x).to(dev).to(tdt)
+    xd = torch.zeros((B, H + 2 * in_halo, W + 2 * in_halo, ld), dtype=tdt, device=dev)
+    xd[:, in_halo:in_halo + H, in_halo:in_halo + W, :Cin] = torch.from_numpy(x).to(dev).to(tdt)
     ohwi = np.transpose(w, (3, 0, 1, 2))
     if mode == "tc":
         cpad = (Cout + 31) // 32 * 32
@@ -50,11 +50,12 @@ def _conv_case(B, H, W, Cin, Cout, k, stride, dil, mode, act="relu", residual=Fa
         if f16:
             res = res.astype(np.float16).astype(np.float32)
     out_dt = torch.float32 if (f32_out or not f16) else torch.float16
-    yd = torch.zeros((B, OH, OW, old), dtype=out_dt, device=dev)
+    oh = out_halo
+    yd = torch.zeros((B, OH + 2 * oh, OW + 2 * oh, old), dtype=out_dt, device=dev)
     rd = None
     if residual:
-        rd = torch.zeros((B, OH, OW, old), dtype=tdt, device=dev)
-        rd[..., :Cout] = torch.from_numpy(res).to(dev).to(tdt)
+        rd = torch.zeros((B, OH + 2 * oh, OW + 2 * oh, old), dtype=tdt, device=dev)
+        rd[:, oh:oh + OH, oh:oh + OW, :Cout] = torch.from_numpy(res).to(dev).to(tdt)
     p = L.ConvParams()
     p.B, p.H, p.W, p.Cin, p.in_ld = B, H, W, Cin, ld
     p.OH, p.OW, p.Cout = OH, OW, Cout
@@ -68,7 +69,8 @@ def _conv_case(B, H, W, Cin, Cout, k, stride, dil, mode, act="relu", residual=Fa
     p.residual = rd.data_ptr() if rd is not None else None
     p.out0 = yd.data_ptr()
     p.out0_dtype = L.ODT_F32 if out_dt == torch.float32 else L.ODT_F16
-    p.out0_img_stride, p.out0_pix_stride = OH * OW * old, old
+    p.out0_img_stride, p.out0_pix_stride = (OH + 2 * oh) * (OW + 2 * oh) * old, old
+    p.in_halo, p.out0_halo = in_halo, out_halo
     s2 = h2 = y1 = None
     if pre:
         s2 = rng.uniform(0.5, 1.5, Cout).astype(np.float32)
@@ -93,7 +95,11 @@ def _conv_case(B, H, W, Cin, Cout, k, stride, dil, mode, act="relu", residual=Fa
         ref = np.maximum(ref, 0.1 * ref)
     if residual:
         ref = ref + res
-    got = yd[..., :Cout].float().cpu().numpy()
+    got = yd[:, oh:oh + OH, oh:oh + OW, :Cout].float().cpu().numpy()
+    if oh:  # the zero border must never be dirtied
+        full = yd.float().cpu().numpy()
+        assert np.abs(full[:, 0]).max() == 0 and np.abs(full[:, -1]).max() == 0
+        assert np.abs(full[:, :, 0]).max() == 0 and np.abs(full[:, :, -1]).max() == 0
     got1 = ref1 = None
     if pre:
         base = got if f16 and not f32_out else ref
@@ -183,7 +189,7 @@ def test_glue_kernels_vs_oracle_ops(built, dtype):
         ref = T.max_pool_same(x, k, s)
         y = torch.zeros(ref.shape, dtype=dt, device="cuda")
         xd = _dev(x, dt)
-        L.check(lib.odt_maxpool(xd.data_ptr(), y.data_ptr(), code, 2, h, h, 64, 64, k, s, st))
+        L.check(lib.odt_maxpool(xd.data_ptr(), y.data_ptr(), code, 2, h, h, 64, 64, k, s, 0, 0, st))
         np.testing.assert_allclose(y.float().cpu().numpy(), ref, atol=0)
     # channel L2 norm x scale
     x = rnd(2, 9, 9, 512)
@@ -262,7 +268,8 @@ def test_stem_conv_vs_oracle(built, shape, dtype):
     imgd = torch.from_numpy(img).cuda()
     wd = torch.from_numpy(np.ascontiguousarray(np.transpose(w, (3, 0, 1, 2)))).cuda().to(tdt)
     sd, hd = torch.from_numpy(scale).cuda(), torch.from_numpy(shift).cuda()
-    yd = torch.zeros((B, OH, OW, ld), dtype=tdt, device="cuda")
+    oh = 1 if (f16 and (k, stride, Cout) in [(3, 1, 64), (7, 2, 16)] and B == 2) else 0  # halo output variants
+    yd = torch.zeros((B, OH + 2 * oh, OW + 2 * oh, ld), dtype=tdt, device="cuda")
     p = L.ConvParams()
     p.B, p.H, p.W, p.Cin, p.in_ld = B, H, W, 3, 3
     p.OH, p.OW, p.Cout = OH, OW, Cout
@@ -270,7 +277,8 @@ def test_stem_conv_vs_oracle(built, shape, dtype):
     p.w_ld, p.Cout_pad = 3, Cout
     p.scale, p.shift, p.act = sd.data_ptr(), hd.data_ptr(), 1
     p.out0, p.out0_dtype = yd.data_ptr(), (L.ODT_F16 if f16 else L.ODT_F32)
-    p.out0_img_stride, p.out0_pix_stride = OH * OW * ld, ld
+    p.out0_img_stride, p.out0_pix_stride = (OH + 2 * oh) * (OW + 2 * oh) * ld, ld
+    p.out0_halo = oh
     mean = (C.c_float * 3)(123.68, 116.779, 103.979)
     L.check(lib.odt_conv2d_stem(imgd.data_ptr(), mean, wd.data_ptr(), L.ODT_F16 if f16 else L.ODT_F32,
                                 C.byref(p), torch.cuda.current_stream().cuda_stream), "stem")
@@ -278,8 +286,68 @@ def test_stem_conv_vs_oracle(built, shape, dtype):
     x = img - T.RGB_MEAN.reshape(1, 1, 1, 3)
     xr = x.astype(np.float16).astype(np.float32) if f16 else x  # the fp16 stem rounds the operand
     ref = np.maximum(T.conv2d_same(xr, w, None, stride) * scale + shift, 0)
-    got = yd[..., :Cout].float().cpu().numpy()
+    got = yd[:, oh:oh + OH, oh:oh + OW, :Cout].float().cpu().numpy()
+    if oh:
+        assert float(yd[:, 0].abs().max()) == 0 and float(yd[:, :, 0].abs().max()) == 0
     tol = (3e-3 if f16 else 2e-5) * max(np.abs(ref).max(), 1.0)
     assert np.abs(got - ref).max() <= tol, (shape, dtype, float(np.abs(got - ref).max()), float(np.abs(ref).max()))
     if ld > Cout:
         assert float(yd[..., Cout:].abs().max()) == 0.0
+
+
+FLAT_SHAPES = [
+    # B, H, W, Cin, Cout, k, stride, dil : 3x3 s1 with a halo input -> halo-flat path (Cout_pad <= 128)
+    (2, 38, 38, 64, 64, 3, 1, 1),
+    (3, 75, 75, 64, 128, 3, 1, 1),     # odd width: tiles wrap padded rows and images
+    (1, 150, 150, 128, 128, 3, 1, 1),  # two channel chunks
+    (2, 20, 23, 192, 96, 3, 1, 1),     # non-square, three chunks, N = 96
+    (1, 16, 16, 64, 28, 3, 1, 1),      # ragged Cout
+]
+
+
+@pytest.mark.parametrize("shape", FLAT_SHAPES)
+@pytest.mark.parametrize("out_halo", [0, 1])
+def test_conv_tc_flat_halo_vs_fp32_reference(built, shape, out_halo):
+    got, ref, _, _ = _conv_case(*shape, mode="tc", in_halo=1, out_halo=out_halo, seed=sum(shape))
+    assert np.abs(got - ref).max() <= 2e-3 * max(np.abs(ref).max(), 1.0), (shape, out_halo)
+
+
+def test_conv_tc_flat_equals_im2col_path(built, monkeypatch):
+    """Same halo input through both tensor-core paths (ODT_TC_FLAT toggles per call)."""
+    shape = (2, 38, 38, 128, 128, 3, 1, 1)
+    a, ref, a1, r1 = _conv_case(*shape, mode="tc", in_halo=1, out_halo=1, act="leaky", residual=True, pre=True)
+    monkeypatch.setenv("ODT_TC_FLAT", "0")
+    b, _, b1, _ = _conv_case(*shape, mode="tc", in_halo=1, out_halo=1, act="leaky", residual=True, pre=True)
+    tol = 2e-3 * max(np.abs(ref).max(), 1.0)
+    assert np.abs(a - ref).max() <= tol and np.abs(b - ref).max() <= tol
+    assert np.abs(a1 - r1).max() <= 2 * tol and np.abs(b1 - r1).max() <= 2 * tol
+    # identical operand values and accumulation order per tap chunk -> (near) identical results
+    assert np.abs(a - b).max() <= 1e-3 * max(np.abs(ref).max(), 1.0)
+
+
+@pytest.mark.parametrize("shape", [
+    (2, 19, 19, 256, 512, 3, 2, 1),   # im2col path reading a halo input (stride 2)
+    (2, 38, 38, 256, 256, 3, 1, 1),   # 3x3 s1 but N = 256: im2col path with halo input
+    (2, 26, 26, 128, 64, 1, 1, 1),    # 1x1 writing a halo output
+])
+def test_conv_tc_im2col_with_halo_layouts(built, shape):
+    got, ref, _, _ = _conv_case(*shape, mode="tc", in_halo=1, out_halo=1)
+    assert np.abs(got - ref).max() <= 2e-3 * max(np.abs(ref).max(), 1.0), shape
+
+
+def test_maxpool_halo_layouts(built):
+    from odt_b200 import lib as L
+    from oracle import tfops as T
+    lib = L.load()
+    st = torch.cuda.current_stream().cuda_stream
+    x = np.random.default_rng(1).standard_normal((2, 75, 75, 64)).astype(np.float16).astype(np.float32)
+    ref = T.max_pool_same(x, 2, 2)
+    for ih, oh in [(1, 1), (1, 0), (0, 1)]:
+        xd = torch.zeros((2, 75 + 2 * ih, 75 + 2 * ih, 64), dtype=torch.float16, device="cuda")
+        xd[:, ih:ih + 75, ih:ih + 75] = torch.from_numpy(x).cuda().half()
+        yd = torch.zeros((2, 38 + 2 * oh, 38 + 2 * oh, 64), dtype=torch.float16, device="cuda")
+        L.check(lib.odt_maxpool(xd.data_ptr(), yd.data_ptr(), L.ODT_F16, 2, 75, 75, 64, 64, 2, 2, ih, oh, st))
+        got = yd[:, oh:oh + 38, oh:oh + 38].float().cpu().numpy()
+        np.testing.assert_array_equal(got, ref)
+        if oh:
+            assert float(yd[:, 0].abs().max()) == 0 and float(yd[:, :, -1].abs().max()) == 0
