@@ -21,6 +21,10 @@ bool pdl_enabled() {
   }
   return v == 1;
 }
+bool bulk_enabled() {
+  const char* e = getenv("ODT_TC_BULK");
+  return !(e && e[0] == '0');
+}
 bool flat_enabled() {
   const char* e = getenv("ODT_TC_FLAT");  // read every call: lets one process compare both paths
   return !(e && e[0] == '0');

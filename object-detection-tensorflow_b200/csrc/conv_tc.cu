@@ -53,6 +53,7 @@ struct TcGeom {
   int H, W;        // real input (= output) size in flat mode
   long long Q;     // B*(H+2)*(W+2)
   int out_halo;    // out0 / residual are stored with a 1-pixel halo
+  int bulk_store;  // tile rows are contiguous in out0: smem-staged cp.async.bulk stores
 };
 constexpr int TC_FLAT_ROWS = 136;                    // 128 + 2 neighbours, padded to 1024 B
 constexpr int TC_FLAT_A_BYTES = TC_FLAT_ROWS * 128;  // 17408
@@ -80,6 +81,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
   // per-tile epilogue parameters staged in smem: [buf][scale|shift|scale2|shift2][256]
   float* epi_par = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - raw));
+  // bulk-store staging: per TMEM lane quarter 32 rows x BN fp16 (only when g.bulk_store)
+  const uint32_t out_stage = bar_base + 256u + TC_EPI_SMEM;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -281,9 +284,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
       const long long o1_row =
           (long long)img * e.out1_img_stride + (long long)pix * e.out1_pix_stride;
+      const uint32_t row_bytes = (uint32_t)g.BN * 2u;
+      const uint32_t my_stage = out_stage + (uint32_t)quarter * 32u * row_bytes;
+      uint8_t* my_stage_ptr = smem_raw + (my_stage - raw) + lane * row_bytes;
+      if (g.bulk_store) {
+        // the previous tile's bulk store must have drained the staging rows of this quarter
+        if (half == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");
+      }
       for (int j = half; j < g.BN / 32; j += 2) {
         const int nb = n0 + j * 32;
-        if (nb >= e.Cout) break;  // fully padded chunk (uniform)
+        if (nb >= e.Cout && !g.bulk_store) break;  // fully padded chunk (uniform)
         uint32_t r[32];
         tc_ld32(taddr0 + (uint32_t)(j * 32), r);
         tc_wait_ld();
@@ -298,6 +309,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             v[4 * i + 1] = apply_act(fmaf(__uint_as_float(r[4 * i + 1]), sc.y, sh.y), e.act);
             v[4 * i + 2] = apply_act(fmaf(__uint_as_float(r[4 * i + 2]), sc.z, sh.z), e.act);
             v[4 * i + 3] = apply_act(fmaf(__uint_as_float(r[4 * i + 3]), sc.w, sh.w), e.act);
+          }
+          if (g.bulk_store && !row_ok) {  // halo / tail rows of the staged block are zeros
+            uint4* sp = reinterpret_cast<uint4*>(my_stage_ptr + j * 64);
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) sp[qd] = make_uint4(0, 0, 0, 0);
           }
           if (row_ok) {
             const long long o0 = o0_row + nb;
@@ -320,7 +336,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             __half2* ph = reinterpret_cast<__half2*>(packed);
 #pragma unroll
             for (int i = 0; i < 16; ++i) ph[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-            if (e.out0) {
+            if (g.bulk_store) {
+              uint4* sp = reinterpret_cast<uint4*>(my_stage_ptr + j * 64);
+#pragma unroll
+              for (int qd = 0; qd < 4; ++qd) sp[qd] = packed[qd];
+            } else if (e.out0) {
               uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out0) + o0);
 #pragma unroll
               for (int qd = 0; qd < 4; ++qd) op[qd] = packed[qd];
@@ -386,9 +406,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (g.bulk_store) {
+        // both warps of the quarter have staged their column chunks: one bulk copy writes
+        // the 32 x BN block, which is contiguous in out0 (rows = consecutive pixels)
+        fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");
+        if (half == 0 && lane == 0) {
+          const long long first = (long long)m_tile * TC_BM + quarter * 32;
+          const long long total = g.flat ? g.Q : g.M;
+          const long long left = total - first;
+          if (left > 0) {
+            const uint32_t bytes = (uint32_t)(left < 32 ? left : 32) * row_bytes;
+            const __half* gdst = reinterpret_cast<const __half*>(e.out0) + first * e.out0_pix_stride;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                         "r"(my_stage), "r"(bytes)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+      }
       acc_phase[acc] ^= 1u;
       acc ^= 1;
     }
+    if (g.bulk_store && half == 0 && lane == 0)
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
 
   // ---- teardown ----
@@ -538,7 +579,20 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
     g.b_bytes = g.BN * 128;
   }
   stage_bytes = g.a_bytes + g.b_bytes;
-  int stages = (TC_SMEM_LIMIT - 2048 - TC_EPI_SMEM) / stage_bytes;
+  // staged bulk stores: fp16 rows of exactly BN channels that are contiguous over the tile
+  // (flat mode writing a halo tensor of the same geometry, or im2col mode writing dense NHWC)
+  const bool linear_rows =
+      g.flat ? (p->out0_halo == 1 &&
+                p->out0_img_stride == (long long)(p->OH + 2) * (p->OW + 2) * p->out0_pix_stride)
+             : (p->out0_halo == 0 && p->out0_img_stride == (long long)p->OH * p->OW * p->out0_pix_stride);
+  g.bulk_store = (bulk_enabled() && p->out0 && !p->out1 && p->out0_dtype == ODT_F16 &&
+                  p->out0_group == 0 && g.num_n_tiles == 1 && g.BN <= 128 &&
+                  g.BN == p->out0_pix_stride && linear_rows && ((uintptr_t)p->out0 & 15) == 0 &&
+                  (!p->residual || ((uintptr_t)p->residual & 15) == 0))
+                     ? 1
+                     : 0;
+  const int out_stage_bytes = g.bulk_store ? 4 * 32 * g.BN * 2 : 0;
+  int stages = (TC_SMEM_LIMIT - 2048 - TC_EPI_SMEM - out_stage_bytes) / stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   ODT_CHECK_ARG(stages >= 2, "tile too large for shared memory");
   g.stages = stages;
@@ -603,7 +657,7 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
     }
   }
 
-  const int smem = stages * stage_bytes + 2048 + TC_EPI_SMEM;
+  const int smem = stages * stage_bytes + 2048 + TC_EPI_SMEM + out_stage_bytes;
   static int smem_set = 0;
   if (smem_set < smem) {
     ODT_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
