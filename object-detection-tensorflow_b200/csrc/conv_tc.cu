@@ -29,7 +29,8 @@ constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = 32 * (2 + TC_EPI_WARPS);  // TMA, MMA, 8 epilogue warps
-constexpr int TC_EPI_SMEM = 2 * 5 * 256 * 4;  // double-buffered scale/shift/scale2/shift2/column offset
+constexpr int TC_EPI_SMEM = 2 * 2 * 5 * 256 * 4;  // per epilogue group, double-buffered: scale/shift/scale2/shift2/column offset
+constexpr int TC_MAX_ACC = 4;  // TMEM accumulator stages (512 columns / BN, at most 4)
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KiB
 constexpr int TC_SMEM_LIMIT = 232448;          // 227 KiB
@@ -54,6 +55,7 @@ struct TcGeom {
   long long Q;     // B*(H+2)*(W+2)
   int out_halo;    // out0 / residual are stored with a 1-pixel halo
   int bulk_store;  // tile rows are contiguous in out0: smem-staged cp.async.bulk stores
+  int nacc;        // accumulator stages in TMEM (2 or 4), BN columns each
 };
 constexpr int TC_FLAT_ROWS = 136;                    // 128 + 2 neighbours, padded to 1024 B
 constexpr int TC_FLAT_A_BYTES = TC_FLAT_ROWS * 128;  // 17408
@@ -75,8 +77,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (TC_MAX_STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * TC_MAX_STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * TC_MAX_STAGES + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * TC_MAX_STAGES + 4);
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * TC_MAX_STAGES + TC_MAX_ACC + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * TC_MAX_STAGES + 2 * TC_MAX_ACC);
   uint32_t* tmem_slot_ptr =
       reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
   // per-tile epilogue parameters staged in smem: [buf][scale|shift|scale2|shift2][256]
@@ -93,9 +95,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < TC_MAX_ACC; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), TC_EPI_WARPS);
+      mbar_init(tempty_bar(a), TC_EPI_WARPS / 2);  // one epilogue group (4 warps) drains a stage
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -185,12 +187,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const uint32_t idesc = make_idesc_f16(TC_BM, g.BN);
     int stage = 0;
     uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase0 = 0u, acc_phase1 = 0u;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      mbar_wait(tempty_bar(acc), (acc ? acc_phase1 : acc_phase0) ^ 1u);
+    int local_tile = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
+      const int acc = local_tile % g.nacc;
+      const uint32_t use = (uint32_t)(local_tile / g.nacc);
+      mbar_wait(tempty_bar(acc), (use & 1u) ^ 1u);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * g.BN);
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
@@ -226,19 +229,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           phase ^= 1u;
         }
       }
-      if (acc) acc_phase1 ^= 1u; else acc_phase0 ^= 1u;
-      acc ^= 1;
     }
   } else {
     // ===================== epilogue warps =====================================
-    // 8 warps: TMEM lane quarter = warp % 4 (hardware restriction), the two warps
-    // of a quarter split the 32-column chunks even/odd.
+    // Two groups of four warps (one warp per TMEM lane quarter) drain alternate tiles
+    // from up to four accumulator stages: the latency of one epilogue pass (tcgen05.ld
+    // -> math -> stores -> fence -> arrive) no longer bounds the tile rate of short-K
+    // layers, it is overlapped with the next tile's pass by the other group.
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int et = threadIdx.x - 64;  // 0..255 within the epilogue group
-    int acc = 0, local_tile = 0, staged_n_tile = -1, pbuf = 0;
-    uint32_t acc_phase[2] = {0u, 0u};
+    const int group = (warp - 2) >> 2;
+    const int et = threadIdx.x - 64 - group * 128;  // 0..127 inside the group
+    int staged_n_tile = -1, pbuf = 0;
+    float* gpar = epi_par + group * 2 * 1280;
+    const uint32_t row_bytes = (uint32_t)g.BN * 2u;
+    const uint32_t my_stage = out_stage + (uint32_t)(group * 4 + quarter) * 32u * row_bytes;
+    uint8_t* my_stage_ptr = smem_raw + (my_stage - raw) + lane * row_bytes;
+    int local_tile = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
+      if ((local_tile & 1) != group) continue;
+      const int acc = local_tile % g.nacc;
+      const uint32_t use = (uint32_t)(local_tile / g.nacc);
       const int n_tile = tile % g.num_n_tiles, m_tile = tile / g.num_n_tiles;
       const long long m = (long long)m_tile * TC_BM + quarter * 32 + lane;
       bool row_ok;
@@ -256,25 +266,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         pix = row_ok ? (int)(m - (long long)img * g.ohw) : 0;
       }
       const int n0 = n_tile * g.BN;
-      // stage the per-channel parameters of this N tile once (broadcast reads later);
-      // consecutive tiles of single-N-tile layers reuse them
+      // stage the per-channel parameters of this N tile once per group (broadcast reads
+      // later); consecutive tiles of single-N-tile layers reuse them
       if (n_tile != staged_n_tile) {
         staged_n_tile = n_tile;
         pbuf ^= 1;
-        float* wpar = epi_par + pbuf * 1280;
-        const int n = n0 + et;
-        const bool ok = et < g.BN && n < e.Cout;
-        wpar[et] = (ok && e.scale) ? __ldg(e.scale + n) : 1.f;
-        wpar[256 + et] = (ok && e.shift) ? __ldg(e.shift + n) : 0.f;
-        wpar[512 + et] = (ok && e.scale2) ? __ldg(e.scale2 + n) : 1.f;
-        wpar[768 + et] = (ok && e.shift2) ? __ldg(e.shift2 + n) : 0.f;
-        reinterpret_cast<int*>(wpar)[1024 + et] = ok ? regroup(e, n) : 0;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        float* wpar = gpar + pbuf * 1280;
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int c = et + h2 * 128;
+          const int n = n0 + c;
+          const bool ok = c < g.BN && n < e.Cout;
+          wpar[c] = (ok && e.scale) ? __ldg(e.scale + n) : 1.f;
+          wpar[256 + c] = (ok && e.shift) ? __ldg(e.shift + n) : 0.f;
+          wpar[512 + c] = (ok && e.scale2) ? __ldg(e.scale2 + n) : 1.f;
+          wpar[768 + c] = (ok && e.shift2) ? __ldg(e.shift2 + n) : 0.f;
+          reinterpret_cast<int*>(wpar)[1024 + c] = ok ? regroup(e, n) : 0;
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
       }
-      const float* par = epi_par + pbuf * 1280;
-      mbar_wait(tfull_bar(acc), acc_phase[acc]);
-      tc_fence_after();
-      const uint32_t taddr0 = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(quarter * 32) << 16);
+      const float* par = gpar + pbuf * 1280;
       long long o0_row = (long long)img * e.out0_img_stride;
       if (g.out_halo) {
         const int oy = pix / g.OW, ox = pix - oy * g.OW;
@@ -284,15 +295,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
       const long long o1_row =
           (long long)img * e.out1_img_stride + (long long)pix * e.out1_pix_stride;
-      const uint32_t row_bytes = (uint32_t)g.BN * 2u;
-      const uint32_t my_stage = out_stage + (uint32_t)quarter * 32u * row_bytes;
-      uint8_t* my_stage_ptr = smem_raw + (my_stage - raw) + lane * row_bytes;
       if (g.bulk_store) {
-        // the previous tile's bulk store must have drained the staging rows of this quarter
-        if (half == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");
+        // this warp's previous bulk store must have drained its staging rows
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
       }
-      for (int j = half; j < g.BN / 32; j += 2) {
+      mbar_wait(tfull_bar(acc), use & 1u);
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + (uint32_t)(acc * g.BN) + ((uint32_t)(quarter * 32) << 16);
+      for (int j = 0; j < g.BN / 32; ++j) {
         const int nb = n0 + j * 32;
         if (nb >= e.Cout && !g.bulk_store) break;  // fully padded chunk (uniform)
         uint32_t r[32];
@@ -402,19 +413,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           }
         }
       }
-      // release the accumulator buffer
+      // release the accumulator stage
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (g.bulk_store) {
-        // both warps of the quarter have staged their column chunks: one bulk copy writes
-        // the 32 x BN block, which is contiguous in out0 (rows = consecutive pixels)
+        // the warp staged its 32 x BN block, contiguous in out0 (rows = consecutive pixels)
         fence_proxy_async_smem();
-        asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");
-        if (half == 0 && lane == 0) {
+        __syncwarp();
+        if (lane == 0) {
           const long long first = (long long)m_tile * TC_BM + quarter * 32;
-          const long long total = g.flat ? g.Q : g.M;
-          const long long left = total - first;
+          const long long left = (g.flat ? g.Q : g.M) - first;
           if (left > 0) {
             const uint32_t bytes = (uint32_t)(left < 32 ? left : 32) * row_bytes;
             const __half* gdst = reinterpret_cast<const __half*>(e.out0) + first * e.out0_pix_stride;
@@ -425,11 +434,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           }
         }
       }
-      acc_phase[acc] ^= 1u;
-      acc ^= 1;
     }
-    if (g.bulk_store && half == 0 && lane == 0)
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (g.bulk_store && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
 
   // ---- teardown ----
@@ -586,12 +592,13 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
                 p->out0_img_stride == (long long)(p->OH + 2) * (p->OW + 2) * p->out0_pix_stride)
              : (p->out0_halo == 0 && p->out0_img_stride == (long long)p->OH * p->OW * p->out0_pix_stride);
   g.bulk_store = (bulk_enabled() && p->out0 && !p->out1 && p->out0_dtype == ODT_F16 &&
-                  p->out0_group == 0 && g.num_n_tiles == 1 && g.BN <= 128 &&
+                  p->out0_group == 0 && g.num_n_tiles == 1 && g.BN <= 64 &&
                   g.BN == p->out0_pix_stride && linear_rows && ((uintptr_t)p->out0 & 15) == 0 &&
                   (!p->residual || ((uintptr_t)p->residual & 15) == 0))
                      ? 1
                      : 0;
-  const int out_stage_bytes = g.bulk_store ? 4 * 32 * g.BN * 2 : 0;
+  const int out_stage_bytes = g.bulk_store ? TC_EPI_WARPS * 32 * g.BN * 2 : 0;  // per-warp staging
+  g.nacc = (512 / g.BN >= 4) ? 4 : 2;
   int stages = (TC_SMEM_LIMIT - 2048 - TC_EPI_SMEM - out_stage_bytes) / stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   ODT_CHECK_ARG(stages >= 2, "tile too large for shared memory");
