@@ -56,6 +56,7 @@ struct TcGeom {
   int out_halo;    // out0 / residual are stored with a 1-pixel halo
   int bulk_store;  // tile rows are contiguous in out0: smem-staged cp.async.bulk stores
   int nacc;        // accumulator stages in TMEM (2 or 4), BN columns each
+  int epi_split;   // 1: the two epilogue groups drain alternate tiles (N <= 128); 0: all 8 warps share a tile
 };
 constexpr int TC_FLAT_ROWS = 136;                    // 128 + 2 neighbours, padded to 1024 B
 constexpr int TC_FLAT_A_BYTES = TC_FLAT_ROWS * 128;  // 17408
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
     for (int a = 0; a < TC_MAX_ACC; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), TC_EPI_WARPS / 2);  // one epilogue group (4 warps) drains a stage
+      mbar_init(tempty_bar(a), g.epi_split ? TC_EPI_WARPS / 2 : TC_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -232,21 +233,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
   } else {
     // ===================== epilogue warps =====================================
-    // Two groups of four warps (one warp per TMEM lane quarter) drain alternate tiles
-    // from up to four accumulator stages: the latency of one epilogue pass (tcgen05.ld
-    // -> math -> stores -> fence -> arrive) no longer bounds the tile rate of short-K
-    // layers, it is overlapped with the next tile's pass by the other group.
+    // Two groups of four warps (one warp per TMEM lane quarter).  N <= 128 ("split"): the
+    // groups drain alternate tiles from four accumulator stages, so the latency of one
+    // epilogue pass (tcgen05.ld -> math -> stores -> fence -> arrive) is overlapped with the
+    // other group's pass instead of bounding the tile rate of short-K layers.  N > 128: both
+    // groups share every tile (even / odd 32-column chunks) over two 256-column stages.
     const int quarter = warp & 3;
     const int group = (warp - 2) >> 2;
-    const int et = threadIdx.x - 64 - group * 128;  // 0..127 inside the group
+    const bool split = g.epi_split != 0;
+    const int et = split ? threadIdx.x - 64 - group * 128 : threadIdx.x - 64;  // index in the sync group
     int staged_n_tile = -1, pbuf = 0;
-    float* gpar = epi_par + group * 2 * 1280;
+    float* gpar = epi_par + (split ? group * 2 * 1280 : 0);
     const uint32_t row_bytes = (uint32_t)g.BN * 2u;
     const uint32_t my_stage = out_stage + (uint32_t)(group * 4 + quarter) * 32u * row_bytes;
     uint8_t* my_stage_ptr = smem_raw + (my_stage - raw) + lane * row_bytes;
     int local_tile = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
-      if ((local_tile & 1) != group) continue;
+      if (split && (local_tile & 1) != group) continue;
       const int acc = local_tile % g.nacc;
       const uint32_t use = (uint32_t)(local_tile / g.nacc);
       const int n_tile = tile % g.num_n_tiles, m_tile = tile / g.num_n_tiles;
@@ -274,7 +277,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         float* wpar = gpar + pbuf * 1280;
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
-          const int c = et + h2 * 128;
+          const int c = split ? et + h2 * 128 : et;
+          if (!split && h2) break;
           const int n = n0 + c;
           const bool ok = c < g.BN && n < e.Cout;
           wpar[c] = (ok && e.scale) ? __ldg(e.scale + n) : 1.f;
@@ -283,7 +287,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           wpar[768 + c] = (ok && e.shift2) ? __ldg(e.shift2 + n) : 0.f;
           reinterpret_cast<int*>(wpar)[1024 + c] = ok ? regroup(e, n) : 0;
         }
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
+        if (split)
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
+        else
+          asm volatile("bar.sync 3, 256;" ::: "memory");
       }
       const float* par = gpar + pbuf * 1280;
       long long o0_row = (long long)img * e.out0_img_stride;
@@ -303,7 +310,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       mbar_wait(tfull_bar(acc), use & 1u);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + (uint32_t)(acc * g.BN) + ((uint32_t)(quarter * 32) << 16);
-      for (int j = 0; j < g.BN / 32; ++j) {
+      for (int j = split ? 0 : group; j < g.BN / 32; j += split ? 1 : 2) {
         const int nb = n0 + j * 32;
         if (nb >= e.Cout && !g.bulk_store) break;  // fully padded chunk (uniform)
         uint32_t r[32];
@@ -598,7 +605,8 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
                      ? 1
                      : 0;
   const int out_stage_bytes = g.bulk_store ? TC_EPI_WARPS * 32 * g.BN * 2 : 0;  // per-warp staging
-  g.nacc = (512 / g.BN >= 4) ? 4 : 2;
+  g.epi_split = g.BN <= 128 ? 1 : 0;
+  g.nacc = g.epi_split ? 4 : 2;
   int stages = (TC_SMEM_LIMIT - 2048 - TC_EPI_SMEM - out_stage_bytes) / stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   ODT_CHECK_ARG(stages >= 2, "tile too large for shared memory");

@@ -178,3 +178,33 @@ def test_retinanet_loss_forward_vs_oracle(built):
         print("image %d: loss gpu %.6f oracle %.6f (%d pos, %d neg)" % (b, got[b], ref, info["num_pos"],
                                                                        info["num_neg"]))
         assert abs(got[b] - ref) <= 2e-5 * max(abs(ref), 1.0)
+
+
+def test_detect_stream_matches_detect_batch(built):
+    """Pipelined public API (H2D of batch i+1 overlaps batch i) == synchronous API."""
+    import torch
+    m = _model("ssd300", precision="fp16", nms_score_threshold=0.3)
+    batches = [_img(2, 300, 300, seed=s) for s in (21, 22, 23)]
+    ref = [m.detect_batch(b) for b in batches]
+    pinned = [torch.from_numpy(b).pin_memory() for b in batches]
+    got = list(m.detect_stream(pinned))
+    assert len(got) == 3
+    for g, r in zip(got, ref):
+        for gi, ri in zip(g, r):
+            for a, b in zip(gi, ri):
+                np.testing.assert_array_equal(a, b)
+
+
+def test_halo_layout_does_not_change_results(built, monkeypatch):
+    """ODT_HALO=0 (dense NHWC everywhere, im2col path only) vs the default halo-flat path."""
+    img = _img(2, 300, 300, seed=5)
+    m1 = _model("ssd300", precision="fp16", nms_score_threshold=0.3)
+    m1.detect_batch(img)
+    a = m1.engine(2).head_buf.cpu().numpy().copy()
+    assert any(t.halo for t in m1.engine(2).acts), "halo layout expected on conv1_1/pool1/conv2_1 outputs"
+    monkeypatch.setenv("ODT_HALO", "0")
+    m2 = _model("ssd300", precision="fp16", nms_score_threshold=0.3)
+    m2.detect_batch(img)
+    b = m2.engine(2).head_buf.cpu().numpy()
+    assert not any(t.halo for t in m2.engine(2).acts)
+    assert np.abs(a - b).max() <= 2e-3 * np.abs(b).max()
