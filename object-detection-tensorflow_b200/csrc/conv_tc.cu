@@ -57,7 +57,9 @@ struct TcGeom {
   int bulk_store;  // tile rows are contiguous in out0: smem-staged cp.async.bulk stores
   int nacc;        // accumulator stages in TMEM (2 or 4), BN columns each
   int epi_split;   // 1: the two epilogue groups drain alternate tiles (N <= 128); 0: all 8 warps share a tile
+  int head_mode;   // fp32 scatter into candidate rows: 32x32 smem transpose per warp, coalesced stores
 };
+constexpr int TC_HEAD_STAGE = TC_EPI_WARPS * 32 * 33 * 4;  // per-warp [32][33] fp32 transpose tiles
 constexpr int TC_FLAT_ROWS = 136;                    // 128 + 2 neighbours, padded to 1024 B
 constexpr int TC_FLAT_A_BYTES = TC_FLAT_ROWS * 128;  // 17408
 
@@ -383,19 +385,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               for (int qd = 0; qd < 4; ++qd) op[qd] = packed1[qd];
             }
           }
-        } else if (row_ok) {
+        } else if (row_ok || g.head_mode) {
           // generic path: fp32 head outputs scattered into the candidate rows,
           // channel regrouping, ragged Cout; parameters come from shared memory
           const float* ps = par + j * 32;
           const int* pofs = reinterpret_cast<const int*>(par) + 1024 + j * 32;
           const int nvalid = min(32, e.Cout - nb);
-          if (e.out0_dtype == ODT_F32 && !e.residual && !e.out1) {
-            // head convolutions: fp32 scatter into the candidate rows
-            float* orow = reinterpret_cast<float*>(e.out0) + o0_row;
+          if (g.head_mode) {
+            // head convolutions: fp32 scatter into the candidate rows.  Each lane holds one
+            // pixel row; a 32x32 transpose through shared memory lets the warp write one
+            // row per instruction with the lanes on consecutive channels (4-5 sectors per
+            // request instead of 32).
+            float* tb = reinterpret_cast<float*>(smem_raw + (out_stage - raw)) + (warp - 2) * (32 * 33);
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (i < nvalid)
-                orow[pofs[i]] = apply_act(fmaf(__uint_as_float(r[i]), ps[i], ps[256 + i]), e.act);
+              tb[lane * 33 + i] = apply_act(fmaf(__uint_as_float(r[i]), ps[i], ps[256 + i]), e.act);
+            __syncwarp();
+            const int my_ofs = pofs[lane];
+            const long long my_row = row_ok ? o0_row : -1;
+            float* obase = reinterpret_cast<float*>(e.out0);
+#pragma unroll 4
+            for (int rr = 0; rr < 32; ++rr) {
+              const long long orow_r = __shfl_sync(0xffffffffu, my_row, rr);
+              const float val = tb[rr * 33 + lane];
+              if (orow_r >= 0 && lane < nvalid) obase[orow_r + my_ofs] = val;
+            }
+            __syncwarp();
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
@@ -604,7 +619,9 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
                   (!p->residual || ((uintptr_t)p->residual & 15) == 0))
                      ? 1
                      : 0;
-  const int out_stage_bytes = g.bulk_store ? TC_EPI_WARPS * 32 * g.BN * 2 : 0;  // per-warp staging
+  g.head_mode = (p->out0 && p->out0_dtype == ODT_F32 && !p->residual && !p->out1) ? 1 : 0;
+  const int out_stage_bytes =
+      g.bulk_store ? TC_EPI_WARPS * 32 * g.BN * 2 : (g.head_mode ? TC_HEAD_STAGE : 0);  // per-warp staging
   g.epi_split = g.BN <= 128 ? 1 : 0;
   g.nacc = g.epi_split ? 4 : 2;
   int stages = (TC_SMEM_LIMIT - 2048 - TC_EPI_SMEM - out_stage_bytes) / stage_bytes;
