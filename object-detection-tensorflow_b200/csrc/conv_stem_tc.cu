@@ -257,12 +257,32 @@ __global__ void __launch_bounds__(ST_THREADS)
         const long long m_first = (long long)tile * 128 + quarter * 32;
         const long long rows_left = g.M - m_first;
         if (lane == 0 && rows_left > 0) {
-          const uint32_t bytes = (uint32_t)(rows_left < 32 ? rows_left : 32) * 128u;
-          // rows of consecutive pixels are contiguous (dense NHWC, ld == 64)
-          const __half* gdst = reinterpret_cast<const __half*>(e.out0) + m_first * 64;
-          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
-                       "r"(my_stage), "r"(bytes)
-                       : "memory");
+          int remaining = (int)(rows_left < 32 ? rows_left : 32);
+          if (!g.out_halo) {
+            // rows of consecutive pixels are contiguous (dense NHWC, ld == 64)
+            const __half* gdst = reinterpret_cast<const __half*>(e.out0) + m_first * 64;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                         "r"(my_stage), "r"((uint32_t)remaining * 128u)
+                         : "memory");
+          } else {
+            // halo layout: contiguous only inside one image row -> one bulk copy per row run
+            long long mm = m_first;
+            uint32_t src = my_stage;
+            while (remaining > 0) {
+              const int bb = (int)(mm / g.ohw);
+              const int pp = (int)(mm - (long long)bb * g.ohw);
+              const int oy = pp / g.OW, ox = pp - oy * g.OW;
+              const int run = min(remaining, g.OW - ox);
+              const __half* gdst = reinterpret_cast<const __half*>(e.out0) + (long long)bb * e.out0_img_stride +
+                                   ((long long)(oy + 1) * (g.OW + 2) + ox + 1) * 64;
+              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                           "r"(src), "r"((uint32_t)run * 128u)
+                           : "memory");
+              mm += run;
+              src += (uint32_t)run * 128u;
+              remaining -= run;
+            }
+          }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
@@ -327,8 +347,9 @@ int odt_conv2d_stem_tc_try(const float* images, const float* mean3_host, const v
   g.M = (long long)p->B * p->OH * p->OW;
   g.num_tiles = (int)((g.M + 127) / 128);
   g.out_halo = p->out0_halo ? 1 : 0;
-  g.bulk_store = (!g.out_halo && p->out0_pix_stride == 64 &&
-                  p->out0_img_stride == (long long)p->OH * p->OW * 64)
+  g.bulk_store = (p->out0_pix_stride == 64 &&
+                  p->out0_img_stride ==
+                      (long long)(p->OH + 2 * g.out_halo) * (p->OW + 2 * g.out_halo) * 64)
                      ? 1
                      : 0;
   g.mean[0] = mean3_host[0]; g.mean[1] = mean3_host[1]; g.mean[2] = mean3_host[2];
