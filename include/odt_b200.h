@@ -100,6 +100,13 @@ typedef struct {
    * must then be (OH+2)*(OW+2)*out0_pix_stride; `residual` shares out0's layout. */
   int in_halo;
   int out0_halo;
+  /* fused 2x2 / stride-2 max pooling (a4: SSD300.py:539-547 straight after the
+   * VGG conv): out0_pool = 2 makes out0 the pooled tensor [B][OH/2][OW/2]
+   * (strides and out0_halo describe THAT tensor; OH/OW stay the convolution's).
+   * Tensor-core path only, for the halo-flat shapes (in_halo, 3x3, stride 1,
+   * Cout_pad <= 128) with even OH and OW, fp16 out0, no residual / out1 /
+   * regrouping.  0 = off.                                                      */
+  int out0_pool;
 } odt_conv_params;
 
 /* tcgen05 / TMA implicit-GEMM forward convolution, fp16 in, fp32 accumulate.

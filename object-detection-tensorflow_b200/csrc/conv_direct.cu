@@ -224,7 +224,8 @@ extern "C" int odt_conv2d_direct(const void* in, const void* weights, int dtype,
   if (rc) return rc;
   ODT_CHECK_ARG(in && weights, "null tensor");
   ODT_CHECK_ARG(dtype == ODT_F16 || dtype == ODT_F32, "dtype");
-  ODT_CHECK_ARG(p->in_halo == 0 && p->out0_halo == 0, "halo layouts are tensor-core-path only");
+  ODT_CHECK_ARG(p->in_halo == 0 && p->out0_halo == 0 && p->out0_pool == 0,
+                "halo layouts / fused pooling are tensor-core-path only");
   launch_direct<false>(in, weights, dtype, p, nullptr, (cudaStream_t)stream);
   ODT_LAUNCH_OK();
   return ODT_OK;
@@ -242,7 +243,8 @@ extern "C" int odt_conv2d_stem(const float* images, const float* mean3_host, con
     int trc = odt_conv2d_stem_tc_try(images, mean3_host, weights, p, stream);
     if (trc != ODT_ERR_UNSUPPORTED) return trc;
   }
-  ODT_CHECK_ARG(p->out0_halo == 0 && p->in_halo == 0, "halo output needs the tensor-core stem");
+  ODT_CHECK_ARG(p->out0_halo == 0 && p->in_halo == 0 && p->out0_pool == 0,
+                "halo output needs the tensor-core stem");
   const bool simple = p->out0 && !p->out1 && !p->residual && p->out0_group == 0 && p->R == p->S &&
                       p->dil == 1 && p->in_ld == 3 &&
                       p->out0_dtype == (dtype == ODT_F16 ? ODT_F16 : ODT_F32) &&

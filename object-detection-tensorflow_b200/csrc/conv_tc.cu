@@ -58,6 +58,12 @@ struct TcGeom {
   int nacc;        // accumulator stages in TMEM (2 or 4), BN columns each
   int epi_split;   // 1: the two epilogue groups drain alternate tiles (N <= 128); 0: all 8 warps share a tile
   int head_mode;   // fp32 scatter into candidate rows: 32x32 smem transpose per warp, coalesced stores
+  // row-block flat mode (flat == 2, fused 2x2/2 max pooling): a tile is RP image rows x XB
+  // columns (RP*XB = 128); the slab of one filter row is a [XB+2 columns][RP rows][64 ch]
+  // box, column-major over the tile so that tap s is the slab shifted by s*RP rows and the
+  // four pixels of a pooling window sit in four lanes of one warp
+  int RP, lgRP, XB, xblocks, yblocks;
+  int a_tx;        // bytes one activation slab load delivers
 };
 constexpr int TC_HEAD_STAGE = TC_EPI_WARPS * 32 * 33 * 4;  // per-warp [32][33] fp32 transpose tiles
 constexpr int TC_FLAT_ROWS = 136;                    // 128 + 2 neighbours, padded to 1024 B
@@ -135,13 +141,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       if (g.flat) {
         // one slab of 136 consecutive padded-linear rows per (filter row, chunk): rows
         // m0 + (r-1)*PW - 1 ...; negative / past-the-end rows are TMA zero fill
+        int bb = 0, yq = 0, xq = 0;
+        if (g.flat == 2) {
+          const int per_img = g.yblocks * g.xblocks;
+          bb = m_tile / per_img;
+          const int rem = m_tile - bb * per_img;
+          yq = rem / g.xblocks;
+          xq = rem - yq * g.xblocks;
+        }
         for (int r = 0; r < 3; ++r) {
           const int row0 = (int)m0 + (r - 1) * g.PW - 1;
           for (int cc = 0; cc < g.cchunks; ++cc) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             if (elect_one()) {
-              mbar_expect_tx(full_bar(stage), a_bytes + b_bytes);
-              tma_load_2d(a_base + (uint32_t)stage * a_bytes, &tmA, full_bar(stage), cc * TC_BK, row0);
+              mbar_expect_tx(full_bar(stage), (uint32_t)g.a_tx + b_bytes);
+              if (g.flat == 2)  // padded rows RP*yq + r .., padded columns XB*xq .. (+2 for the taps)
+                tma_load_4d(a_base + (uint32_t)stage * a_bytes, &tmA, full_bar(stage), cc * TC_BK,
+                            g.RP * yq + r, g.XB * xq, bb);
+              else
+                tma_load_2d(a_base + (uint32_t)stage * a_bytes, &tmA, full_bar(stage), cc * TC_BK, row0);
 #pragma unroll
               for (int s = 0; s < 3; ++s)
                 tma_load_2d(b_base + (uint32_t)stage * b_bytes + (uint32_t)s * (uint32_t)g.BN * 128u, &tmB,
@@ -208,11 +226,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             // descriptor start shifted by s*128 B inside the 1024 B swizzle pattern (the
             // swizzle is a function of the absolute address: probed, scripts/probe_rowoffset.py)
             const uint64_t bstep = (uint64_t)((g.BN * 128) >> 4);
+            const uint64_t astep = (uint64_t)(g.flat == 2 ? 8 * g.RP : 8);  // rows per tap shift x 128 B >> 4
 #pragma unroll
             for (int s3 = 0; s3 < 3; ++s3) {
 #pragma unroll
               for (int k = 0; k < TC_BK / 16; ++k)
-                tc_mma_f16(d_tmem, adesc + (uint64_t)(8 * s3 + 2 * k), bdesc + bstep * s3 + (uint64_t)(2 * k),
+                tc_mma_f16(d_tmem, adesc + astep * s3 + (uint64_t)(2 * k), bdesc + bstep * s3 + (uint64_t)(2 * k),
                            idesc, (uint32_t)((kb | s3 | k) != 0));
             }
           } else {
@@ -258,7 +277,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const long long m = (long long)m_tile * TC_BM + quarter * 32 + lane;
       bool row_ok;
       int img, pix;
-      if (g.flat) {
+      long long pool_row = 0;  // element offset of this lane's pooled pixel (flat == 2)
+      int pool_q = 0;          // which 8-channel quarter of a 32-column chunk this lane stores
+      if (g.flat == 2) {
+        const int per_img = g.yblocks * g.xblocks;
+        img = m_tile / per_img;
+        const int rem = m_tile - img * per_img;
+        const int yq = rem / g.xblocks, xq = rem - yq * g.xblocks;
+        const int ml = quarter * 32 + lane;
+        const int x = g.XB * xq + (ml >> g.lgRP), y = g.RP * yq + (ml & (g.RP - 1));
+        row_ok = x < g.W && y < g.H;  // even sizes: a pooling window is valid or invalid as a whole
+        pix = 0;
+        const int oh = g.out_halo;
+        pool_row = (long long)img * e.out0_img_stride +
+                   (long long)(((y >> 1) + oh) * ((g.W >> 1) + 2 * oh) + (x >> 1) + oh) * e.out0_pix_stride;
+        pool_q = (ml & 1) | (((ml >> g.lgRP) & 1) << 1);
+      } else if (g.flat) {
         // padded-linear position -> (image, padded y, padded x); halo positions are not stored
         img = m < g.Q ? (int)(m / g.PHW) : 0;
         const int rem = (int)(m - (long long)img * g.PHW);
@@ -318,7 +352,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         uint32_t r[32];
         tc_ld32(taddr0 + (uint32_t)(j * 32), r);
         tc_wait_ld();
-        if (g.fast_store && nb + 32 <= g.fast_cols) {
+        if (g.flat == 2) {
+          // fused 2x2/2 max pooling: bias/BN + activation, round to fp16, then the maximum over
+          // the window's four lanes (vertical neighbour = lane^1, horizontal = lane^RP); each
+          // of the four lanes stores one 8-channel quarter of the pooled pixel
+          const float4* ps = reinterpret_cast<const float4*>(par + j * 32);
+          const float4* ph4 = reinterpret_cast<const float4*>(par + 256 + j * 32);
+          uint4 packed[4];
+          __half2* ph = reinterpret_cast<__half2*>(packed);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 sc = ps[i], sh = ph4[i];
+            ph[2 * i] = __floats2half2_rn(apply_act(fmaf(__uint_as_float(r[4 * i + 0]), sc.x, sh.x), e.act),
+                                          apply_act(fmaf(__uint_as_float(r[4 * i + 1]), sc.y, sh.y), e.act));
+            ph[2 * i + 1] = __floats2half2_rn(apply_act(fmaf(__uint_as_float(r[4 * i + 2]), sc.z, sh.z), e.act),
+                                              apply_act(fmaf(__uint_as_float(r[4 * i + 3]), sc.w, sh.w), e.act));
+          }
+          uint32_t* pw = reinterpret_cast<uint32_t*>(packed);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            uint32_t o = __shfl_xor_sync(0xffffffffu, pw[i], 1);
+            __half2 a = __hmax2(*reinterpret_cast<__half2*>(&pw[i]), *reinterpret_cast<__half2*>(&o));
+            pw[i] = *reinterpret_cast<uint32_t*>(&a);
+            o = __shfl_xor_sync(0xffffffffu, pw[i], g.RP);
+            a = __hmax2(a, *reinterpret_cast<__half2*>(&o));
+            pw[i] = *reinterpret_cast<uint32_t*>(&a);
+          }
+          const uint4 sel = pool_q == 0 ? packed[0] : pool_q == 1 ? packed[1] : pool_q == 2 ? packed[2] : packed[3];
+          if (row_ok && nb + 8 * pool_q < g.fast_cols)
+            *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out0) + pool_row + nb + 8 * pool_q) = sel;
+        } else if (g.fast_store && nb + 32 <= g.fast_cols) {
           const float4* ps = reinterpret_cast<const float4*>(par + j * 32);
           const float4* ph4 = reinterpret_cast<const float4*>(par + 256 + j * 32);
           float v[32];
@@ -588,12 +651,40 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
   g.PHW = (p->H + 2) * (p->W + 2);
   g.Q = (long long)p->B * g.PHW;
   // halo-flat path: 3x3 / stride 1 / dilation 1 with a halo input and a narrow N
-  g.flat = (ih && p->R == 3 && p->S == 3 && p->stride == 1 && p->dil == 1 && p->pad_t == 1 &&
-            p->pad_l == 1 && p->Cout_pad <= 128 && flat_enabled() && g.Q < (1ll << 31) - 4096)
-               ? 1
-               : 0;
+  const bool flat_shape = ih && p->R == 3 && p->S == 3 && p->stride == 1 && p->dil == 1 &&
+                          p->pad_t == 1 && p->pad_l == 1 && p->Cout_pad <= 128 &&
+                          g.Q < (1ll << 31) - 4096;
+  ODT_CHECK_ARG(p->out0_pool == 0 || p->out0_pool == 2, "out0_pool must be 0 or 2");
+  if (p->out0_pool) {
+    ODT_CHECK_ARG(flat_shape, "fused pooling needs a halo input and a 3x3/stride-1 filter with Cout_pad <= 128");
+    ODT_CHECK_ARG(p->OH % 2 == 0 && p->OW % 2 == 0, "fused pooling needs even OH and OW");
+    ODT_CHECK_ARG(p->out0 && p->out0_dtype == ODT_F16 && !p->residual && !p->out1 && p->out0_group == 0,
+                  "fused pooling: fp16 out0 only, no residual / out1 / regrouping");
+    ODT_CHECK_ARG(p->out0_pix_stride % 8 == 0 && p->out0_img_stride % 8 == 0 &&
+                      ((uintptr_t)p->out0 & 15) == 0 && p->out0_pix_stride >= p->Cout_pad,
+                  "fused pooling: out0 alignment / channel stride");
+  }
+  g.flat = p->out0_pool ? 2 : ((flat_shape && flat_enabled()) ? 1 : 0);
+  g.a_tx = TC_A_BYTES;
   int stage_bytes;
-  if (g.flat) {
+  if (g.flat == 2) {
+    // tile = RP rows x XB columns; take the split that wastes fewer tile positions
+    const long long t2 = (long long)((p->OH + 1) / 2) * ((p->OW + 63) / 64);
+    const long long t4 = (long long)((p->OH + 3) / 4) * ((p->OW + 31) / 32);
+    g.RP = t4 < t2 ? 4 : 2;
+    g.lgRP = g.RP == 4 ? 2 : 1;
+    g.XB = TC_BM / g.RP;
+    g.yblocks = (p->OH + g.RP - 1) / g.RP;
+    g.xblocks = (p->OW + g.XB - 1) / g.XB;
+    ODT_CHECK_ARG((long long)p->B * g.yblocks * g.xblocks < (1ll << 31), "too many tiles");
+    g.num_m_tiles = p->B * g.yblocks * g.xblocks;
+    g.BN = p->Cout_pad;
+    g.num_n_tiles = 1;
+    g.a_bytes = TC_FLAT_A_BYTES;
+    g.a_tx = (g.XB + 2) * g.RP * 128;
+    g.b_bytes = 3 * g.BN * 128;
+  } else if (g.flat) {
+    g.a_tx = TC_FLAT_A_BYTES;
     g.num_m_tiles = (int)((g.Q + TC_BM - 1) / TC_BM);
     g.BN = p->Cout_pad;
     g.num_n_tiles = 1;
@@ -613,7 +704,7 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
       g.flat ? (p->out0_halo == 1 &&
                 p->out0_img_stride == (long long)(p->OH + 2) * (p->OW + 2) * p->out0_pix_stride)
              : (p->out0_halo == 0 && p->out0_img_stride == (long long)p->OH * p->OW * p->out0_pix_stride);
-  g.bulk_store = (bulk_enabled() && p->out0 && !p->out1 && p->out0_dtype == ODT_F16 &&
+  g.bulk_store = (bulk_enabled() && g.flat != 2 && p->out0 && !p->out1 && p->out0_dtype == ODT_F16 &&
                   p->out0_group == 0 && g.num_n_tiles == 1 && g.BN <= 64 &&
                   g.BN == p->out0_pix_stride && linear_rows && ((uintptr_t)p->out0 & 15) == 0 &&
                   (!p->residual || ((uintptr_t)p->residual & 15) == 0))
@@ -638,7 +729,23 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
   if (p->out1 && p->out1_pix_stride < g.fast_cols) g.fast_cols = p->out1_pix_stride;
 
   CUtensorMap tmA, tmB;
-  if (g.flat) {
+  if (g.flat == 2) {
+    // [ld][H+2][W+2][B] view with the ROW dimension second, so that a {64, RP, XB+2, 1} box
+    // lands in shared memory column-major over the tile (smem row = column*RP + row)
+    const cuuint64_t PH = (cuuint64_t)p->H + 2, PW = (cuuint64_t)p->W + 2;
+    cuuint64_t dims[4] = {(cuuint64_t)p->in_ld, PH, PW, (cuuint64_t)p->B};
+    cuuint64_t strides[3] = {PW * p->in_ld * 2, (cuuint64_t)p->in_ld * 2, PH * PW * p->in_ld * 2};
+    cuuint32_t box[4] = {TC_BK, (cuuint32_t)g.RP, (cuuint32_t)(g.XB + 2), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult cr = g_encode_tiled(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(in), dims,
+                                 strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(row-block activations) failed (%d)", (int)cr);
+      return ODT_ERR_CUDA;
+    }
+  } else if (g.flat) {
     // flat [Q][ld] view of the halo tensor, slabs of 136 consecutive padded-linear pixels
     cuuint64_t dims[2] = {(cuuint64_t)p->in_ld, (cuuint64_t)g.Q};
     cuuint64_t strides[1] = {(cuuint64_t)p->in_ld * 2};

@@ -105,6 +105,7 @@ class ConvOp(Op):
         self.kernel, self.bias, self.bn, self.act = kernel, bias, bn, act
         self.residual, self.head, self.is_image = residual, head, is_image
         self.pre = None     # fused consumer pre-activation: (bn_scope, act, Act)
+        self.pool = 0       # 2: the 2x2/2 max-pool that follows is done in the epilogue (y is the pooled tensor)
         self.reads = tuple(t for t in (x, residual) if t is not None)
         self.writes = (y,) if y is not None else ()
         self.flops = 0
@@ -164,7 +165,11 @@ class ConvOp(Op):
             p.out0_group, p.out0_group_stride = group, gstride
         else:
             y = self.y
-            assert (y.H, y.W, y.C) == (OH, OW, cout)
+            if self.pool:
+                assert (y.H, y.W, y.C) == (OH // 2, OW // 2, cout) and OH % 2 == 0 and OW % 2 == 0
+            else:
+                assert (y.H, y.W, y.C) == (OH, OW, cout)
+            p.out0_pool = self.pool
             p.out0 = y.ptr() if y.needed else None
             p.out0_dtype = L.ODT_F16 if f16 else L.ODT_F32
             p.out0_img_stride = y.img_stride
@@ -514,6 +519,33 @@ class Net:
             if ok and gain and self.batch * (t.H + 2) * (t.W + 2) < (1 << 31) - 4096:
                 t.halo = 1
 
+    def fuse_pools(self):
+        """Fold a 2x2/2 max-pool into the epilogue of the halo-flat 3x3 conv that feeds it
+        (a4: SSD300.py:539-547 after conv1_2 / conv2_2): the unpooled tensor is never stored."""
+        if self.precision != "fp16" or not self.allow_tc or os.environ.get("ODT_POOL_FUSE", "1") == "0":
+            return
+        readers, producer = {}, {}
+        for op in self.ops:
+            for t in op.reads:
+                readers.setdefault(id(t), []).append(op)
+            for t in op.writes:
+                producer[id(t)] = op
+        kept = []
+        for op in self.ops:
+            if isinstance(op, PoolOp) and op.k == 2 and op.stride == 2:
+                q, t = producer.get(id(op.x)), op.x
+                ok = (isinstance(q, ConvOp) and q.y is t and readers.get(id(t)) == [op] and q.pre is None
+                      and q.head is None and q.residual is None and not q.is_image and q.pool == 0
+                      and q.x.halo == 1 and q.x.ld % 64 == 0 and q.k == 3 and q.stride == 1 and q.dil == 1
+                      and _round_up(t.C, 32) <= 128 and t.H % 2 == 0 and t.W % 2 == 0)
+                if ok:
+                    q.pool, q.y, q.writes = 2, op.y, (op.y,)
+                    producer[id(op.y)] = q
+                    t.needed, t.fused_away = False, True
+                    continue
+            kept.append(op)
+        self.ops = kept
+
     # ------------------------------------------------------------ finalize --
     def finalize(self, weights, tail, fuse=True):
         """Allocate buffers, upload weights, build the kernel parameter blocks."""
@@ -525,10 +557,13 @@ class Net:
             self.fuse()
         if self.use_halo:
             self.assign_halos()
+            self.fuse_pools()
         dev = self.device
         self.image_buf = torch.zeros((self.batch, self.in_h, self.in_w, 3), dtype=torch.float32,
                                      device=dev)
         for t in self.acts:
+            if getattr(t, "fused_away", False):
+                continue  # the pre-pool tensor of a conv with a fused max-pool is never materialised
             if t.needed or True:  # unneeded raws are tiny bookkeeping; keep a buffer for residual addressing
                 t.buf = torch.zeros((t.B, t.H + 2 * t.halo, t.W + 2 * t.halo, t.ld), dtype=self.tdtype,
                                     device=dev)

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _conv_case(B, H, W, Cin, Cout, k, stride, dil, mode, act="relu", residual=False, pre=False,
-               bn=True, f32_out=False, seed=0, in_halo=0, out_halo=0):
+               bn=True, f32_out=False, seed=0, in_halo=0, out_halo=0, pool=0):
     """mode: 'tc' (fp16 tcgen05), 'direct16', 'direct32'.  Returns (got, ref, got1, ref1)."""
     from odt_b200 import lib as L
     from odt_b200.engine import same_pad
@@ -51,6 +51,9 @@ def _conv_case(B, H, W, Cin, Cout, k, stride, dil, mode, act="relu", residual=Fa
             res = res.astype(np.float16).astype(np.float32)
     out_dt = torch.float32 if (f32_out or not f16) else torch.float16
     oh = out_halo
+    cOH, cOW = OH, OW                       # the convolution's own output size
+    if pool:                                # out0 is the 2x2/2 max-pooled tensor
+        OH, OW = OH // 2, OW // 2
     yd = torch.zeros((B, OH + 2 * oh, OW + 2 * oh, old), dtype=out_dt, device=dev)
     rd = None
     if residual:
@@ -58,7 +61,8 @@ def _conv_case(B, H, W, Cin, Cout, k, stride, dil, mode, act="relu", residual=Fa
         rd[:, oh:oh + OH, oh:oh + OW, :Cout] = torch.from_numpy(res).to(dev).to(tdt)
     p = L.ConvParams()
     p.B, p.H, p.W, p.Cin, p.in_ld = B, H, W, Cin, ld
-    p.OH, p.OW, p.Cout = OH, OW, Cout
+    p.OH, p.OW, p.Cout = cOH, cOW, Cout
+    p.out0_pool = pool
     p.R, p.S, p.stride, p.dil, p.pad_t, p.pad_l = k, k, stride, dil, pt, pl
     p.w_ld, p.Cout_pad = (ld if mode == "tc" else Cin), cpad
     sd = torch.from_numpy(scale).to(dev) if scale is not None else None
@@ -95,6 +99,8 @@ def _conv_case(B, H, W, Cin, Cout, k, stride, dil, mode, act="relu", residual=Fa
         ref = np.maximum(ref, 0.1 * ref)
     if residual:
         ref = ref + res
+    if pool:
+        ref = T.max_pool_same(ref, 2, 2)
     got = yd[:, oh:oh + OH, oh:oh + OW, :Cout].float().cpu().numpy()
     if oh:  # the zero border must never be dirtied
         full = yd.float().cpu().numpy()
@@ -310,6 +316,43 @@ FLAT_SHAPES = [
 def test_conv_tc_flat_halo_vs_fp32_reference(built, shape, out_halo):
     got, ref, _, _ = _conv_case(*shape, mode="tc", in_halo=1, out_halo=out_halo, seed=sum(shape))
     assert np.abs(got - ref).max() <= 2e-3 * max(np.abs(ref).max(), 1.0), (shape, out_halo)
+
+
+POOL_SHAPES = [
+    # 3x3 s1 halo-flat conv + fused 2x2/2 max-pool (SSD300 conv1_2 / conv2_2 and friends)
+    (2, 300, 300, 64, 64, 3, 1, 1),    # conv1_2: 2-row x 64-column tiles, ragged last column block
+    (2, 150, 150, 128, 128, 3, 1, 1),  # conv2_2: 4-row x 32-column tiles, ragged last row block
+    (3, 38, 38, 64, 96, 3, 1, 1),      # small map, N = 96
+    (1, 16, 130, 64, 28, 3, 1, 1),     # ragged Cout, non-square
+    (2, 6, 4, 64, 64, 3, 1, 1),        # tile larger than the image
+]
+
+
+@pytest.mark.parametrize("shape", POOL_SHAPES)
+@pytest.mark.parametrize("out_halo", [0, 1])
+def test_conv_tc_fused_maxpool(built, shape, out_halo):
+    """Pooled epilogue against max_pool(fp32 conv reference), and bit-exact against the
+    same conv followed by the stand-alone pooling kernel (max commutes with fp16 rounding)."""
+    from odt_b200 import lib as L
+    got, ref, _, _ = _conv_case(*shape, mode="tc", in_halo=1, out_halo=out_halo, pool=2, seed=sum(shape))
+    assert np.abs(got - ref).max() <= 2e-3 * max(np.abs(ref).max(), 1.0), (shape, out_halo)
+    full, _, _, _ = _conv_case(*shape, mode="tc", in_halo=1, out_halo=0, seed=sum(shape))
+    B, H, W, _, Cout = shape[:5]
+    ld = (Cout + 63) // 64 * 64
+    xd = torch.zeros((B, H, W, ld), dtype=torch.float16, device="cuda")
+    xd[..., :Cout] = torch.from_numpy(full).cuda().half()
+    yd = torch.zeros((B, H // 2, W // 2, ld), dtype=torch.float16, device="cuda")
+    L.check(L.load().odt_maxpool(xd.data_ptr(), yd.data_ptr(), L.ODT_F16, B, H, W, ld, ld, 2, 2, 0, 0,
+                                 torch.cuda.current_stream().cuda_stream))
+    np.testing.assert_array_equal(got, yd[..., :Cout].float().cpu().numpy())
+
+
+def test_conv_tc_fused_maxpool_rejects_bad_shapes(built):
+    from odt_b200 import lib as L
+    with pytest.raises(L.OdtError):   # odd size
+        _conv_case(1, 75, 75, 64, 64, 3, 1, 1, mode="tc", in_halo=1, pool=2)
+    with pytest.raises(L.OdtError):   # no halo input
+        _conv_case(1, 16, 16, 64, 64, 3, 1, 1, mode="tc", in_halo=0, pool=2)
 
 
 def test_conv_tc_flat_equals_im2col_path(built, monkeypatch):
