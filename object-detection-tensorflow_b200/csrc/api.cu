@@ -29,6 +29,10 @@ bool flat_enabled() {
   const char* e = getenv("ODT_TC_FLAT");  // read every call: lets one process compare both paths
   return !(e && e[0] == '0');
 }
+bool wres_enabled() {
+  const char* e = getenv("ODT_TC_WRES");
+  return !(e && e[0] == '0');
+}
 }  // namespace odt
 
 extern "C" int odt_abi_version(void) { return 1; }

@@ -21,7 +21,6 @@ struct StemGeom {
   int B, H, W, OH, OW, ohw, pad_t, pad_l, w_ld;
   long long M;
   int num_tiles;
-  int bulk_store;  // output rows are 128 contiguous bytes (ld == 64, dense NHWC): smem-staged bulk stores
   int out_halo;    // output stored as [B][OH+2][OW+2][ld]
   float mean[3];
 };
@@ -29,6 +28,8 @@ struct StemGeom {
 constexpr int ST_STAGES = 4;
 constexpr int ST_PROD_WARPS = 4, ST_EPI_WARPS = 4;
 constexpr int ST_THREADS = 32 * (ST_PROD_WARPS + 1 + ST_EPI_WARPS);
+constexpr int ST_PITCH = 144;                  // staging row pitch (bytes)
+constexpr int ST_WARP_STAGE = 32 * ST_PITCH;   // staging bytes per epilogue warp
 
 template <int COUT, int KS, int STRIDE>
 __global__ void __launch_bounds__(ST_THREADS)
@@ -56,7 +57,9 @@ __global__ void __launch_bounds__(ST_THREADS)
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
   float* s_scale = reinterpret_cast<float*>(smem_raw + (bar_base + 128u - raw));
   float* s_shift = s_scale + COUT;
-  // per-epilogue-warp staging for coalesced bulk stores: 32 rows x 128 B
+  // per-epilogue-warp store staging: 32 rows x 128 B at a 144 B pitch (ST_PITCH), so
+  // the one-row-per-lane 16-byte writes spread over all banks (4 wavefronts per STS.128,
+  // the minimum, instead of 32 at a 128 B pitch)
   const uint32_t stage_out = (bar_base + 128u + 2u * COUT * 4u + 127u) & ~127u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -125,28 +128,66 @@ __global__ void __launch_bounds__(ST_THREADS)
       const int iy0 = oy * STRIDE - g.pad_t, ix0 = ox * STRIDE - g.pad_l;
       mbar_wait(empty_bar(stage), phase ^ 1u);
       uint8_t* arow = gbase + (a_base - base) + (uint32_t)stage * A_BYTES + t * 128;
+      // Interior pixels (the whole KSxKS window inside the image) take a branch-free path:
+      // one row pointer per filter row, every tap at an immediate offset from it.  (The
+      // per-tap predicated form costs ~20 integer/branch instructions per load and made
+      // the producers issue-bound.)
+      const bool interior = ok && iy0 >= 0 && iy0 + KS <= g.H && ix0 >= 0 && ix0 + KS <= g.W;
+      const float* prow[KS];
+      {
+        const float* p0 = ib + ((long long)iy0 * g.W + ix0) * 3;
+        const int rs = g.W * 3;
 #pragma unroll
-      for (int c = 0; c < NCHUNK; ++c) {
-        float v[8];
+        for (int r = 0; r < KS; ++r) prow[r] = p0 + r * rs;
+      }
+      const float mean0 = g.mean[0], mean1 = g.mean[1], mean2 = g.mean[2];
+      if (interior) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int k = c * 8 + q;  // compile-time after unrolling
-          if (k < KREAL) {
-            const int tap = k / 3, ch = k - tap * 3;
-            const int r = tap / KS, s = tap - r * KS;
-            const int iy = iy0 + r, ix = ix0 + s;
-            const bool in = ok && iy >= 0 && iy < g.H && ix >= 0 && ix < g.W;
-            v[q] = in ? __fsub_rn(__ldg(ib + ((long long)iy * g.W + ix) * 3 + ch), g.mean[ch]) : 0.f;
-          } else {
-            v[q] = 0.f;
+        for (int c = 0; c < NCHUNK; ++c) {
+          float v[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int k = c * 8 + q;  // compile-time after unrolling
+            if (k < KREAL) {
+              const int tap = k / 3, ch = k - tap * 3;
+              const int r = tap / KS, sx = tap - r * KS;
+              v[q] = __fsub_rn(__ldg(prow[r] + sx * 3 + ch), ch == 0 ? mean0 : (ch == 1 ? mean1 : mean2));
+            } else {
+              v[q] = 0.f;
+            }
           }
-        }
-        uint4 pk;
-        __half2* h = reinterpret_cast<__half2*>(&pk);
+          uint4 pk;
+          __half2* h = reinterpret_cast<__half2*>(&pk);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) h[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
-        const int blk = c >> 3, cc = c & 7;
-        *reinterpret_cast<uint4*>(arow + blk * (128 * 128) + ((cc ^ (t & 7)) << 4)) = pk;
+          for (int q = 0; q < 4; ++q) h[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+          const int blk = c >> 3, cc = c & 7;
+          *reinterpret_cast<uint4*>(arow + blk * (128 * 128) + ((cc ^ (t & 7)) << 4)) = pk;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c) {
+          float v[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int k = c * 8 + q;
+            if (k < KREAL) {
+              const int tap = k / 3, ch = k - tap * 3;
+              const int r = tap / KS, sx = tap - r * KS;
+              const int iy = iy0 + r, ix = ix0 + sx;
+              const bool in = ok && iy >= 0 && iy < g.H && ix >= 0 && ix < g.W;
+              v[q] = in ? __fsub_rn(__ldg(prow[r] + sx * 3 + ch), ch == 0 ? mean0 : (ch == 1 ? mean1 : mean2))
+                        : 0.f;
+            } else {
+              v[q] = 0.f;
+            }
+          }
+          uint4 pk;
+          __half2* h = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) h[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+          const int blk = c >> 3, cc = c & 7;
+          *reinterpret_cast<uint4*>(arow + blk * (128 * 128) + ((cc ^ (t & 7)) << 4)) = pk;
+        }
       }
       fence_proxy_async_smem();
       mbar_arrive(full_bar(stage));
@@ -204,20 +245,13 @@ __global__ void __launch_bounds__(ST_THREADS)
         const int oy = pix / g.OW, ox = pix - oy * g.OW;
         opix = (long long)(oy + 1) * (g.OW + 2) + ox + 1;
       }
-      __half* orow = reinterpret_cast<__half*>(e.out0) + (long long)b * e.out0_img_stride +
-                     opix * e.out0_pix_stride;
-      const uint32_t my_stage = stage_out + (uint32_t)(warp - ST_PROD_WARPS - 1) * 4096u;
-      uint8_t* my_stage_ptr = smem_raw + (my_stage - raw);
-      if (g.bulk_store) {
-        // the previous tile's bulk store must have finished READING the staging buffer
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        __syncwarp();
-        if (COUT < 64) {  // zero the pad lanes of the row (they must stay zero in HBM anyway)
-#pragma unroll
-          for (int c = COUT / 8; c < 8; ++c)
-            *reinterpret_cast<uint4*>(my_stage_ptr + lane * 128 + (c << 4)) = make_uint4(0, 0, 0, 0);
-        }
-      }
+      // Stage the warp's 32 rows x COUT fp16 in shared memory (one row per lane, 144-byte
+      // pitch: conflict-free 16-byte writes), then store them with the lanes transposed:
+      // CPR consecutive lanes cover one row's COUT*2 bytes, so every STG.128 of the warp
+      // writes whole 32-byte sectors of 32/CPR rows -- in the dense and in the halo layout.
+      uint8_t* warp_stage = smem_raw + (stage_out - raw) + (uint32_t)(warp - ST_PROD_WARPS - 1) * ST_WARP_STAGE;
+      uint8_t* my_stage_ptr = warp_stage + lane * ST_PITCH;
+      const long long my_off = row_ok ? (long long)b * e.out0_img_stride + opix * e.out0_pix_stride : -1;
 #pragma unroll
       for (int j = 0; j < COUT / 16; ++j) {
         uint32_t r[16];
@@ -240,59 +274,27 @@ __global__ void __launch_bounds__(ST_THREADS)
               apply_act(fmaf(__uint_as_float(r[2 * q + 1]), s_scale[c0 + 1], s_shift[c0 + 1]), e.act);
           h[q] = __floats2half2_rn(v0, v1);
         }
-        if (g.bulk_store) {
-          // row-major staging, linear as the bulk copy needs (the strided 16-byte writes
-          // bank-conflict, ~256 cycles per tile and warp, hidden behind the HBM stream)
-          *reinterpret_cast<uint4*>(my_stage_ptr + lane * 128 + ((2 * j) << 4)) = pk[0];
-          *reinterpret_cast<uint4*>(my_stage_ptr + lane * 128 + ((2 * j + 1) << 4)) = pk[1];
-        } else if (row_ok) {
-          uint4* op = reinterpret_cast<uint4*>(orow + j * 16);
-          op[0] = pk[0];
-          op[1] = pk[1];
-        }
+        *reinterpret_cast<uint4*>(my_stage_ptr + ((2 * j) << 4)) = pk[0];
+        *reinterpret_cast<uint4*>(my_stage_ptr + ((2 * j + 1) << 4)) = pk[1];
       }
-      if (g.bulk_store) {
-        fence_proxy_async_smem();
-        __syncwarp();
-        const long long m_first = (long long)tile * 128 + quarter * 32;
-        const long long rows_left = g.M - m_first;
-        if (lane == 0 && rows_left > 0) {
-          int remaining = (int)(rows_left < 32 ? rows_left : 32);
-          if (!g.out_halo) {
-            // rows of consecutive pixels are contiguous (dense NHWC, ld == 64)
-            const __half* gdst = reinterpret_cast<const __half*>(e.out0) + m_first * 64;
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
-                         "r"(my_stage), "r"((uint32_t)remaining * 128u)
-                         : "memory");
-          } else {
-            // halo layout: contiguous only inside one image row -> one bulk copy per row run
-            long long mm = m_first;
-            uint32_t src = my_stage;
-            while (remaining > 0) {
-              const int bb = (int)(mm / g.ohw);
-              const int pp = (int)(mm - (long long)bb * g.ohw);
-              const int oy = pp / g.OW, ox = pp - oy * g.OW;
-              const int run = min(remaining, g.OW - ox);
-              const __half* gdst = reinterpret_cast<const __half*>(e.out0) + (long long)bb * e.out0_img_stride +
-                                   ((long long)(oy + 1) * (g.OW + 2) + ox + 1) * 64;
-              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
-                           "r"(src), "r"((uint32_t)run * 128u)
-                           : "memory");
-              mm += run;
-              src += (uint32_t)run * 128u;
-              remaining -= run;
-            }
-          }
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-      }
+      // the accumulator stage is drained: hand it back before the store phase
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       acc_phase[acc] ^= 1u;
       acc ^= 1;
+      constexpr int CPR = COUT / 8;    // 16-byte chunks per row (the pad channels stay zero in HBM)
+      constexpr int RPI = 32 / CPR;    // rows per store instruction
+      const int sub_row = lane / CPR, chunk = lane % CPR;
+#pragma unroll
+      for (int i = 0; i < CPR; ++i) {
+        const int rr = i * RPI + sub_row;
+        const uint4 val = *reinterpret_cast<const uint4*>(warp_stage + rr * ST_PITCH + (chunk << 4));
+        const long long ro = __shfl_sync(0xffffffffu, my_off, rr);
+        if (ro >= 0) *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out0) + ro + chunk * 8) = val;
+      }
+      __syncwarp();  // staging rows are rewritten by the next tile
     }
-    if (g.bulk_store && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -310,7 +312,7 @@ static int launch_stem_tc(const float* img, const void* w, const StemGeom& g, co
   constexpr int KSTEPS = (KS * KS * 3 + 15) / 16;
   constexpr int NBLK = (KSTEPS * 16 + 63) / 64;
   const int smem = ST_STAGES * NBLK * 128 * 128 + ((NBLK * COUT * 128 + 1023) & ~1023) + 1024 + 128 +
-                   2 * COUT * 4 + 64 + 128 + ST_EPI_WARPS * 4096;
+                   2 * COUT * 4 + 64 + 128 + ST_EPI_WARPS * ST_WARP_STAGE;
   auto kern = conv_stem_tc_kernel<COUT, KS, STRIDE>;
   static bool attr = false;
   if (!attr) {
@@ -335,6 +337,7 @@ int odt_conv2d_stem_tc_try(const float* images, const float* mean3_host, const v
   const bool ok = p->out0 && !p->out1 && !p->residual && p->out0_group == 0 && p->R == p->S &&
                   p->dil == 1 && p->in_ld == 3 && p->Cin == 3 && p->out0_dtype == ODT_F16 &&
                   p->out0_pool == 0 && ((uintptr_t)p->out0 % 16) == 0 && p->out0_pix_stride % 8 == 0 &&
+                  p->out0_pix_stride >= p->Cout &&
                   p->out0_img_stride % 8 == 0;
   int variant = 0;
   if (ok && p->R == 3 && p->stride == 1 && p->Cout == 64) variant = 1;
@@ -347,11 +350,6 @@ int odt_conv2d_stem_tc_try(const float* images, const float* mean3_host, const v
   g.M = (long long)p->B * p->OH * p->OW;
   g.num_tiles = (int)((g.M + 127) / 128);
   g.out_halo = p->out0_halo ? 1 : 0;
-  g.bulk_store = (p->out0_pix_stride == 64 &&
-                  p->out0_img_stride ==
-                      (long long)(p->OH + 2 * g.out_halo) * (p->OW + 2 * g.out_halo) * 64)
-                     ? 1
-                     : 0;
   g.mean[0] = mean3_host[0]; g.mean[1] = mean3_host[1]; g.mean[2] = mean3_host[2];
   Epi e = make_epi(*p);
   cudaStream_t st = (cudaStream_t)stream;

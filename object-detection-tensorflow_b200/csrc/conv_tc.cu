@@ -18,6 +18,7 @@
 //
 // ref call sites: tf.nn.conv2d SSD300.py:519; tf.layers.conv2d SSD300.py:524,
 // RetinaNet.py:579,599,609, YOLOv3.py:495, FCOS.py:449,469,479.
+#include <stdlib.h>
 #include <string.h>
 
 #include "epilogue.cuh"
@@ -64,6 +65,10 @@ struct TcGeom {
   // four pixels of a pooling window sit in four lanes of one warp
   int RP, lgRP, XB, xblocks, yblocks;
   int a_tx;        // bytes one activation slab load delivers
+  // flat modes with a small filter bank: all 9*cchunks weight tiles [BN x 64] stay resident
+  // in shared memory (loaded once per CTA); the pipeline stages then carry activations only
+  int bres;
+  int dbg_aligned;  // timing experiment only (ODT_TC_DEBUG_ALIGNED=1): all taps read the unshifted slab (wrong results)
 };
 constexpr int TC_HEAD_STAGE = TC_EPI_WARPS * 32 * 33 * 4;  // per-warp [32][33] fp32 transpose tiles
 constexpr int TC_FLAT_ROWS = 136;                    // 128 + 2 neighbours, padded to 1024 B
@@ -81,13 +86,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const uint32_t a_bytes = (uint32_t)g.a_bytes, b_bytes = (uint32_t)g.b_bytes;
   const uint32_t a_base = base;
   const uint32_t b_base = base + (uint32_t)stages * a_bytes;
-  const uint32_t bar_base = b_base + (uint32_t)stages * b_bytes;  // 8-byte aligned
+  const uint32_t wres_bytes = g.bres ? (uint32_t)(9 * g.cchunks * g.BN * 128) : 0u;
+  const uint32_t bar_base = b_base + (uint32_t)stages * b_bytes + wres_bytes;  // 8-byte aligned
   // barriers: full[stages], empty[stages], tfull[2], tempty[2], then tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (TC_MAX_STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * TC_MAX_STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * TC_MAX_STAGES + TC_MAX_ACC + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * TC_MAX_STAGES + 2 * TC_MAX_ACC);
+  const uint32_t wfull_bar = tmem_slot + 8u;  // resident weights landed
   uint32_t* tmem_slot_ptr =
       reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
   // per-tile epilogue parameters staged in smem: [buf][scale|shift|scale2|shift2][256]
@@ -108,6 +115,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), g.epi_split ? TC_EPI_WARPS / 2 : TC_EPI_WARPS);
     }
+    mbar_init(wfull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -119,6 +127,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  if (g.bres && warp == 0) {
+    // the filter bank is constant data: fetch it before waiting on the previous kernel
+    if (elect_one()) {
+      mbar_expect_tx(wfull_bar, wres_bytes);
+      for (int t = 0; t < 9 * g.cchunks; ++t)
+        tma_load_2d(b_base + (uint32_t)t * (uint32_t)g.BN * 128u, &tmB, wfull_bar, t * TC_BK, 0);
+    }
+    __syncwarp();
+  }
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation,
   // descriptor prefetch) overlapped the tail of the previous kernel in the stream;
   // from here on we touch memory it produced.
@@ -154,16 +171,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           for (int cc = 0; cc < g.cchunks; ++cc) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             if (elect_one()) {
-              mbar_expect_tx(full_bar(stage), (uint32_t)g.a_tx + b_bytes);
+              mbar_expect_tx(full_bar(stage), (uint32_t)g.a_tx + b_bytes);  // b_bytes == 0 when resident
               if (g.flat == 2)  // padded rows RP*yq + r .., padded columns XB*xq .. (+2 for the taps)
                 tma_load_4d(a_base + (uint32_t)stage * a_bytes, &tmA, full_bar(stage), cc * TC_BK,
                             g.RP * yq + r, g.XB * xq, bb);
               else
                 tma_load_2d(a_base + (uint32_t)stage * a_bytes, &tmA, full_bar(stage), cc * TC_BK, row0);
+              if (!g.bres) {
 #pragma unroll
-              for (int s = 0; s < 3; ++s)
-                tma_load_2d(b_base + (uint32_t)stage * b_bytes + (uint32_t)s * (uint32_t)g.BN * 128u, &tmB,
-                            full_bar(stage), ((r * 3 + s) * g.cchunks + cc) * TC_BK, n0);
+                for (int s = 0; s < 3; ++s)
+                  tma_load_2d(b_base + (uint32_t)stage * b_bytes + (uint32_t)s * (uint32_t)g.BN * 128u, &tmB,
+                              full_bar(stage), ((r * 3 + s) * g.cchunks + cc) * TC_BK, n0);
+              }
             }
             __syncwarp();
             if (++stage == stages) {
@@ -209,6 +228,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     int stage = 0;
     uint32_t phase = 0;
     int local_tile = 0;
+    if (g.bres) {
+      mbar_wait(wfull_bar, 0);
+      tc_fence_after();
+    }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
       const int acc = local_tile % g.nacc;
       const uint32_t use = (uint32_t)(local_tile / g.nacc);
@@ -219,14 +242,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         const uint64_t adesc = make_desc_sw128(a_base + (uint32_t)stage * a_bytes);
-        const uint64_t bdesc = make_desc_sw128(b_base + (uint32_t)stage * b_bytes);
+        // resident bank: tile ((r*3 + s)*cchunks + cc) with kb = r*cchunks + cc
+        const uint64_t bdesc = make_desc_sw128(
+            g.bres ? b_base + (uint32_t)((kb / g.cchunks) * 3 * g.cchunks + kb % g.cchunks) * (uint32_t)g.BN * 128u
+                   : b_base + (uint32_t)stage * b_bytes);
         if (elect_one()) {
           if (g.flat) {
             // three horizontal taps from the same slab: operand rows s .. s+127, i.e. the
             // descriptor start shifted by s*128 B inside the 1024 B swizzle pattern (the
             // swizzle is a function of the absolute address: probed, scripts/probe_rowoffset.py)
-            const uint64_t bstep = (uint64_t)((g.BN * 128) >> 4);
-            const uint64_t astep = (uint64_t)(g.flat == 2 ? 8 * g.RP : 8);  // rows per tap shift x 128 B >> 4
+            const uint64_t bstep = (uint64_t)(((g.bres ? g.cchunks : 1) * g.BN * 128) >> 4);
+            const uint64_t astep =
+                g.dbg_aligned ? 0ull : (uint64_t)(g.flat == 2 ? 8 * g.RP : 8);  // rows per tap shift x 128 B >> 4
 #pragma unroll
             for (int s3 = 0; s3 < 3; ++s3) {
 #pragma unroll
@@ -715,7 +742,20 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
       g.bulk_store ? TC_EPI_WARPS * 32 * g.BN * 2 : (g.head_mode ? TC_HEAD_STAGE : 0);  // per-warp staging
   g.epi_split = g.BN <= 128 ? 1 : 0;
   g.nacc = g.epi_split ? 4 : 2;
-  int stages = (TC_SMEM_LIMIT - 2048 - TC_EPI_SMEM - out_stage_bytes) / stage_bytes;
+  // small filter banks of the flat modes stay resident in shared memory if at least three
+  // activation stages still fit beside them
+  const long long wres = 9ll * g.cchunks * g.BN * 128;
+  if (g.flat && wres_enabled() &&
+      wres + 3 * TC_FLAT_A_BYTES + 2048 + TC_EPI_SMEM + out_stage_bytes <= TC_SMEM_LIMIT) {
+    g.bres = 1;
+    g.b_bytes = 0;
+    stage_bytes = g.a_bytes;
+  }
+  {
+    const char* dbg = getenv("ODT_TC_DEBUG_ALIGNED");
+    g.dbg_aligned = (dbg && dbg[0] == '1') ? 1 : 0;
+  }
+  int stages = (TC_SMEM_LIMIT - 2048 - TC_EPI_SMEM - out_stage_bytes - (g.bres ? (int)wres : 0)) / stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   ODT_CHECK_ARG(stages >= 2, "tile too large for shared memory");
   g.stages = stages;
@@ -796,7 +836,7 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
     }
   }
 
-  const int smem = stages * stage_bytes + 2048 + TC_EPI_SMEM + out_stage_bytes;
+  const int smem = stages * stage_bytes + (g.bres ? (int)wres : 0) + 2048 + TC_EPI_SMEM + out_stage_bytes;
   static int smem_set = 0;
   if (smem_set < smem) {
     ODT_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

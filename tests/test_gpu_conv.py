@@ -355,6 +355,18 @@ def test_conv_tc_fused_maxpool_rejects_bad_shapes(built):
         _conv_case(1, 16, 16, 64, 64, 3, 1, 1, mode="tc", in_halo=0, pool=2)
 
 
+@pytest.mark.parametrize("shape,pool", [((2, 38, 38, 64, 64, 3, 1, 1), 0), ((3, 75, 75, 64, 128, 3, 1, 1), 0),
+                                        ((2, 300, 300, 64, 64, 3, 1, 1), 2), ((1, 40, 40, 128, 64, 3, 1, 1), 2)])
+def test_conv_tc_resident_filter_bank_is_bit_identical(built, monkeypatch, shape, pool):
+    """Shared-memory-resident weights (ODT_TC_WRES, default on) change where the B operand
+    lives, not the arithmetic: identical MMA sequence -> identical bits."""
+    a, ref, _, _ = _conv_case(*shape, mode="tc", in_halo=1, out_halo=1, pool=pool)
+    monkeypatch.setenv("ODT_TC_WRES", "0")
+    b, _, _, _ = _conv_case(*shape, mode="tc", in_halo=1, out_halo=1, pool=pool)
+    assert np.abs(a - ref).max() <= 2e-3 * max(np.abs(ref).max(), 1.0)
+    np.testing.assert_array_equal(a, b)
+
+
 def test_conv_tc_flat_equals_im2col_path(built, monkeypatch):
     """Same halo input through both tensor-core paths (ODT_TC_FLAT toggles per call)."""
     shape = (2, 38, 38, 128, 128, 3, 1, 1)
