@@ -584,13 +584,75 @@ class Net:
             op.launch(self, st)
         self.tail.launch(self, st)
 
+    # Independent branches of the op list (FPN levels, the two towers, SSD/YOLO heads
+    # next to the rest of the backbone) are captured on separate stream lanes so that
+    # launches with fewer CTAs than SMs overlap inside the graph.
+    def plan_lanes(self, max_lanes=None):
+        """Dataflow -> (lane of every op, cross-lane waits).  Pure host logic."""
+        if max_lanes is None:
+            max_lanes = int(os.environ.get("ODT_STREAMS", "12"))
+        producer, deps = {}, []
+        for i, op in enumerate(self.ops):
+            deps.append(sorted({producer[id(t)] for t in op.reads if id(t) in producer}))
+            outs = list(op.writes)
+            if getattr(op, "pre", None) is not None:
+                outs.append(op.pre[2])
+            for t in outs:
+                producer[id(t)] = i
+        lane_of, tails, waits = [], [], []   # tails[l] = index of the last op put on lane l
+        for i, d in enumerate(deps):
+            lane = None
+            for p in reversed(d):             # continue the lane of a producer that is still its tail
+                if tails[lane_of[p]] == p:
+                    lane = lane_of[p]
+                    break
+            if lane is None:
+                if not tails or not d:        # roots stay on the capturing stream
+                    lane = 0
+                    if not tails:
+                        tails.append(-1)
+                elif len(tails) < max(1, max_lanes):
+                    lane = len(tails)
+                    tails.append(-1)
+                else:                         # reuse the lane that has been idle longest
+                    lane = min(range(len(tails)), key=lambda l: tails[l])
+            waits.append([p for p in d if lane_of[p] != lane])
+            lane_of.append(lane)
+            tails[lane] = i
+        return lane_of, waits, tails
+
+    def forward_lanes(self):
+        """Multi-lane launch of the op list (used under graph capture)."""
+        lane_of, waits, tails = self.plan_lanes()
+        main = torch.cuda.current_stream()
+        if len(tails) <= 1:
+            return self.forward()
+        if getattr(self, "_lanes", None) is None or len(self._lanes) < len(tails):
+            self._lanes = [None] + [torch.cuda.Stream(device=self.device) for _ in range(len(tails) - 1)]
+        streams = [main] + self._lanes[1:len(tails)]
+        need_event = {p for w in waits for p in w} | {t for l, t in enumerate(tails) if l != 0 and t >= 0}
+        events = {}
+        for i, op in enumerate(self.ops):
+            st = streams[lane_of[i]]
+            for p in waits[i]:
+                st.wait_event(events[p])
+            op.launch(self, st.cuda_stream)
+            if i in need_event:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                events[i] = ev
+        for l, t in enumerate(tails):         # join every lane back before the tail
+            if l != 0 and t >= 0:
+                main.wait_event(events[t])
+        self.tail.launch(self, main.cuda_stream)
+
     def capture(self):
         """Capture the whole forward in a CUDA graph (launch-bound tail + 30-130 convs)."""
         self.forward()  # warm-up outside capture (lazy attribute sets, driver entry points)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self.forward()
+            self.forward_lanes()
         self.graph = g
         return g
 

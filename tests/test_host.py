@@ -175,6 +175,40 @@ def test_fusion_plan_retinanet():
     assert dropped >= 40  # the 4x2x5 tower intermediates at least
 
 
+@pytest.mark.parametrize("model,min_lanes", [("ssd300", 2), ("retinanet", 4), ("yolov3", 2), ("fcos", 4)])
+def test_lane_plan_respects_dataflow(model, min_lanes):
+    """Multi-stream capture plan: every producer is either earlier on the same lane or
+    waited on through an event; independent heads / pyramid levels get their own lanes."""
+    import importlib
+    from odt_b200 import engine as E
+    mod = {"ssd300": "SSD300", "retinanet": "RetinaNet", "yolov3": "YOLOv3", "fcos": "FCOS"}[model]
+    m = getattr(importlib.import_module(mod), mod)(model_cfg(model), None)
+    E.Net.spec_only = True
+    try:
+        net, _ = m._build(1, "fp16", True)
+    finally:
+        E.Net.spec_only = False
+    net.fuse()
+    lane_of, waits, tails = net.plan_lanes(8)
+    assert len(lane_of) == len(net.ops) and max(lane_of) < 8 and lane_of[0] == 0
+    assert len(tails) >= min_lanes
+    producer = {}
+    for i, op in enumerate(net.ops):
+        for t in op.reads:
+            p = producer.get(id(t))
+            if p is None:
+                continue
+            assert p < i
+            assert lane_of[p] == lane_of[i] or p in waits[i]
+        for w in waits[i]:
+            assert w < i and lane_of[w] != lane_of[i]
+        outs = list(op.writes) + ([op.pre[2]] if getattr(op, "pre", None) is not None else [])
+        for t in outs:
+            producer[id(t)] = i
+    one, w1, t1 = net.plan_lanes(1)
+    assert set(one) == {0} and not any(w1)
+
+
 def _gloo_worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
