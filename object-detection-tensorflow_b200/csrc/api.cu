@@ -29,6 +29,10 @@ bool flat_enabled() {
   const char* e = getenv("ODT_TC_FLAT");  // read every call: lets one process compare both paths
   return !(e && e[0] == '0');
 }
+bool pair_enabled() {
+  const char* e = getenv("ODT_TC_PAIR");  // read every call: A/B inside one process
+  return !(e && e[0] == '0');
+}
 bool wres_enabled() {
   const char* e = getenv("ODT_TC_WRES");
   return !(e && e[0] == '0');

@@ -71,6 +71,7 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 bool pdl_enabled();   // ODT_PDL=0 disables the launch attribute (api.cu)
 bool bulk_enabled();  // ODT_TC_BULK=0 disables the smem-staged bulk-store epilogue
 bool flat_enabled();  // ODT_TC_FLAT=0 disables the halo-flat 3x3 path (A/B measurements)
+bool pair_enabled();  // ODT_TC_PAIR=0 disables the CTA-pair (cta_group::2) launch of large im2col-mode convs
 bool wres_enabled();  // ODT_TC_WRES=0 disables shared-memory-resident filter banks in the flat path
 
 }  // namespace odt

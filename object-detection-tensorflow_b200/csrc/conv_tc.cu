@@ -68,6 +68,7 @@ struct TcGeom {
   // flat modes with a small filter bank: all 9*cchunks weight tiles [BN x 64] stay resident
   // in shared memory (loaded once per CTA); the pipeline stages then carry activations only
   int bres;
+  int pair;         // 1: launched as CTA pairs (conv_tc_kernel<2>)
   int dbg_aligned;  // timing experiment only (ODT_TC_DEBUG_ALIGNED=1): all taps read the unshifted slab (wrong results)
 };
 constexpr int TC_HEAD_STAGE = TC_EPI_WARPS * 32 * 33 * 4;  // per-warp [32][33] fp32 transpose tiles
@@ -75,6 +76,13 @@ constexpr int TC_FLAT_ROWS = 136;                    // 128 + 2 neighbours, padd
 constexpr int TC_FLAT_A_BYTES = TC_FLAT_ROWS * 128;  // 17408
 
 // --------------------------------------------------------------- kernel ----
+// CG = 1: one CTA per tile.  CG = 2 (im2col mode only): the two CTAs of a cluster (one TPC)
+// share every MMA -- tcgen05.mma.cta_group::2, M = 256 = two M tiles, each CTA stages its own
+// 128 activation rows and HALF of the weight tile, so the shared-memory operand traffic per
+// SM and MMA drops from A+B to A+B/2 (the UMMA operand fetch, ~64 B/clk, is what bounds the
+// N = 256 layers at ~2/3 of the tensor peak with CG = 1).  Rank 0 issues the MMAs; its
+// commits are multicast to both CTAs' barriers.
+template <int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ TcGeom g, const __grid_constant__ Epi e) {
@@ -103,6 +111,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const uint32_t out_stage = bar_base + 256u + TC_EPI_SMEM;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -113,18 +122,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
     for (int a = 0; a < TC_MAX_ACC; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), g.epi_split ? TC_EPI_WARPS / 2 : TC_EPI_WARPS);
+      mbar_init(tempty_bar(a), CG * (g.epi_split ? TC_EPI_WARPS / 2 : TC_EPI_WARPS));  // both CTAs' epilogues
     }
     mbar_init(wfull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG == 2) {  // warp 1 of both CTAs, same slot offset
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2)
+    cluster_sync_all();  // barrier inits of both CTAs visible before any cross-CTA arrival
+  else
+    __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   if (g.bres && warp == 0) {
@@ -142,7 +160,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   pdl_launch_dependents();
   pdl_wait();
 
-  const int num_tiles = g.num_m_tiles * g.num_n_tiles;
+  // CG = 2: a "tile" is a pair of M tiles (2*pair + rank) x one N tile, one pair per cluster
+  const int num_tiles = CG == 2 ? ((g.num_m_tiles + 1) / 2) * g.num_n_tiles : g.num_m_tiles * g.num_n_tiles;
+  const int tile_first = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int kblocks = g.flat ? 3 * g.cchunks : g.R * g.S * g.cchunks;  // pipeline stages per tile
 
   if (warp == 0) {
@@ -151,8 +172,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     // uniform registers); one elected lane issues the TMA instructions.
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int n_tile = tile % g.num_n_tiles, m_tile = tile / g.num_n_tiles;
+    const uint32_t full_rank0 = CG == 2 ? mapa_u32(bar_base, 0) : 0u;  // rank 0's barrier block
+    for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+      const int n_tile = tile % g.num_n_tiles;
+      int m_tile = CG == 2 ? 2 * (tile / g.num_n_tiles) + (int)cta_rank : tile / g.num_n_tiles;
+      if (CG == 2 && m_tile >= g.num_m_tiles) m_tile = g.num_m_tiles - 1;  // phantom half of the last pair: valid loads, no stores
       const long long m0 = (long long)m_tile * TC_BM;
       const int n0 = n_tile * g.BN;
       if (g.flat) {
@@ -203,11 +227,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           for (int cc = 0; cc < g.cchunks; ++cc) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             if (elect_one()) {
-              mbar_expect_tx(full_bar(stage), a_bytes + b_bytes);
-              tma_load_im2col(a_base + (uint32_t)stage * a_bytes, &tmA, full_bar(stage),
-                              cc * TC_BK, cw, ch, img, (uint16_t)(s * g.dil),
-                              (uint16_t)(r * g.dil));
-              tma_load_2d(b_base + (uint32_t)stage * b_bytes, &tmB, full_bar(stage), kcol, n0);
+              if (CG == 2) {
+                // both CTAs' bytes are credited to rank 0's full barrier; this CTA loads its own
+                // 128 rows of A and its half (rank * BN/2 ...) of the weight tile
+                const uint32_t fb = full_rank0 + 8u * stage;
+                if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2u * (a_bytes + b_bytes));
+                tma_load_im2col_cg2(a_base + (uint32_t)stage * a_bytes, &tmA, fb, cc * TC_BK, cw, ch, img,
+                                    (uint16_t)(s * g.dil), (uint16_t)(r * g.dil));
+                tma_load_2d_cg2(b_base + (uint32_t)stage * b_bytes, &tmB, fb, kcol,
+                                n0 + (int)cta_rank * (g.BN / 2));
+              } else {
+                mbar_expect_tx(full_bar(stage), a_bytes + b_bytes);
+                tma_load_im2col(a_base + (uint32_t)stage * a_bytes, &tmA, full_bar(stage),
+                                cc * TC_BK, cw, ch, img, (uint16_t)(s * g.dil),
+                                (uint16_t)(r * g.dil));
+                tma_load_2d(b_base + (uint32_t)stage * b_bytes, &tmB, full_bar(stage), kcol, n0);
+              }
             }
             __syncwarp();
             kcol += TC_BK;
@@ -224,7 +259,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     // Warp-uniform loop; one elected lane issues tcgen05.mma / tcgen05.commit.  (With a
     // single-lane branch around the whole loop ptxas has to bounce every descriptor
     // through R2UR + an ELECT retry loop: ~170 cycles per MMA, measured.)
-    const uint32_t idesc = make_idesc_f16(TC_BM, g.BN);
+    const uint32_t idesc = make_idesc_f16(CG * TC_BM, g.BN);
     int stage = 0;
     uint32_t phase = 0;
     int local_tile = 0;
@@ -232,7 +267,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       mbar_wait(wfull_bar, 0);
       tc_fence_after();
     }
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
+    for (int tile = (CG == 2 && cta_rank != 0) ? num_tiles : tile_first; tile < num_tiles;
+         tile += tile_step, ++local_tile) {
       const int acc = local_tile % g.nacc;
       const uint32_t use = (uint32_t)(local_tile / g.nacc);
       mbar_wait(tempty_bar(acc), (use & 1u) ^ 1u);
@@ -265,12 +301,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k) {
               // advance 16 elements (32 bytes) along K inside the swizzle atom
-              tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                         (uint32_t)((kb | k) != 0));
+              if (CG == 2)
+                tc_mma_f16_cg2(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                               (uint32_t)((kb | k) != 0));
+              else
+                tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                           (uint32_t)((kb | k) != 0));
             }
           }
-          tc_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
-          if (kb == kblocks - 1) tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+          if (CG == 2) {
+            tc_commit_cg2(empty_bar(stage), 3);  // both CTAs' smem slots
+            if (kb == kblocks - 1) tc_commit_cg2(tfull_bar(acc), 3);
+          } else {
+            tc_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+            if (kb == kblocks - 1) tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+          }
         }
         __syncwarp();
         if (++stage == stages) {
@@ -296,11 +341,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const uint32_t my_stage = out_stage + (uint32_t)(group * 4 + quarter) * 32u * row_bytes;
     uint8_t* my_stage_ptr = smem_raw + (my_stage - raw) + lane * row_bytes;
     int local_tile = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
+    const uint32_t tempty_rank0 = CG == 2 ? mapa_u32(tempty_bar(0), 0) : 0u;
+    for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++local_tile) {
       if (split && (local_tile & 1) != group) continue;
       const int acc = local_tile % g.nacc;
       const uint32_t use = (uint32_t)(local_tile / g.nacc);
-      const int n_tile = tile % g.num_n_tiles, m_tile = tile / g.num_n_tiles;
+      const int n_tile = tile % g.num_n_tiles;
+      const int m_tile = CG == 2 ? 2 * (tile / g.num_n_tiles) + (int)cta_rank : tile / g.num_n_tiles;
       const long long m = (long long)m_tile * TC_BM + quarter * 32 + lane;
       bool row_ok;
       int img, pix;
@@ -528,7 +575,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       // release the accumulator stage
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (CG == 2)
+          mbar_arrive_cluster(tempty_rank0 + 8u * acc);  // the MMA issuer (rank 0) waits for both CTAs
+        else
+          mbar_arrive(tempty_bar(acc));
+      }
       if (g.bulk_store) {
         // the warp staged its 32 x BN block, contiguous in out0 (rows = consecutive pixels)
         fence_proxy_async_smem();
@@ -552,10 +604,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 
   // ---- teardown ----
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2)
+    cluster_sync_all();  // the peer's shared memory / TMEM stay alive until every MMA has retired
+  else
+    __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    if (CG == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
 }
 
@@ -722,7 +780,10 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
     g.BN = pick_bn(p->Cout_pad, g.num_m_tiles);
     g.num_n_tiles = (p->Cout_pad + g.BN - 1) / g.BN;
     g.a_bytes = TC_A_BYTES;
-    g.b_bytes = g.BN * 128;
+    // CTA pairs (cta_group::2) once the launch has at least two full waves of tiles: each CTA
+    // then stages only half of the weight tile
+    g.pair = (pair_enabled() && g.BN >= 64 && (long long)g.num_m_tiles * g.num_n_tiles >= 2 * kNumSMs) ? 1 : 0;
+    g.b_bytes = (g.pair ? g.BN / 2 : g.BN) * 128;
   }
   stage_bytes = g.a_bytes + g.b_bytes;
   // staged bulk stores: fp16 rows of exactly BN channels that are contiguous over the tile
@@ -745,7 +806,7 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
   // small filter banks of the flat modes stay resident in shared memory if at least three
   // activation stages still fit beside them
   const long long wres = 9ll * g.cchunks * g.BN * 128;
-  if (g.flat && wres_enabled() &&
+  if (g.flat && wres_enabled() && g.BN >= 128 &&  // measured: a win at N = 128 (conv2_1), a loss at N <= 64
       wres + 3 * TC_FLAT_A_BYTES + 2048 + TC_EPI_SMEM + out_stage_bytes <= TC_SMEM_LIMIT) {
     g.bres = 1;
     g.b_bytes = 0;
@@ -823,7 +884,7 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
     const cuuint64_t ktot = (cuuint64_t)p->R * p->S * p->w_ld;
     cuuint64_t dims[2] = {ktot, (cuuint64_t)p->Cout_pad};
     cuuint64_t strides[1] = {ktot * 2};
-    cuuint32_t box[2] = {TC_BK, (cuuint32_t)g.BN};
+    cuuint32_t box[2] = {TC_BK, (cuuint32_t)(g.pair ? g.BN / 2 : g.BN)};
     cuuint32_t estr[2] = {1, 1};
     CUresult cr = g_encode_tiled(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
                                  const_cast<void*>(weights), dims, strides, box, estr,
@@ -839,24 +900,38 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
   const int smem = stages * stage_bytes + (g.bres ? (int)wres : 0) + 2048 + TC_EPI_SMEM + out_stage_bytes;
   static int smem_set = 0;
   if (smem_set < smem) {
-    ODT_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ODT_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     TC_SMEM_LIMIT));
+    ODT_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      TC_SMEM_LIMIT));
     smem_set = TC_SMEM_LIMIT;
   }
   Epi e = make_epi(*p);
-  const int num_tiles = g.num_m_tiles * g.num_n_tiles;
-  const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  ODT_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel, tmA, tmB, g, e));
+  if (g.pair) {
+    // one cluster (two CTAs on one TPC) per pair of M tiles; persistent over at most 74 clusters
+    const int num_pairs = ((g.num_m_tiles + 1) / 2) * g.num_n_tiles;
+    const int clusters = num_pairs < kNumSMs / 2 ? num_pairs : kNumSMs / 2;
+    cfg.gridDim = dim3(2 * clusters);
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.numAttrs = 1;
+    ODT_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<2>, tmA, tmB, g, e));
+  } else {
+    const int num_tiles = g.num_m_tiles * g.num_n_tiles;
+    cfg.gridDim = dim3(num_tiles < kNumSMs ? num_tiles : kNumSMs);
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    ODT_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<1>, tmA, tmB, g, e));
+  }
   ODT_LAUNCH_OK();
   return ODT_OK;
 }

@@ -1,0 +1,13 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python __graft_entry__.py > gpurun_out/build.log 2>&1 || { echo BUILD FAILED; tail -20 gpurun_out/build.log; }
+for t in conv tail models; do
+  timeout 900 python -m pytest tests/test_gpu_$t.py -q -m gpu --timeout 300 > gpurun_out/test_$t.log 2>&1
+  echo "test_gpu_$t exit $?"; grep -E "passed|failed|FAILED|Error|assert" gpurun_out/test_$t.log | tail -n 14
+done
+for m in "ssd300 64" "retinanet 16" "yolov3 32" "fcos 4"; do
+  n=$(echo $m | tr ' ' '_')
+  timeout 600 python scripts/profile_ops.py $m > gpurun_out/ops_$n.txt 2>&1; echo "== $m: $(grep -E 'CUDA-graph' gpurun_out/ops_$n.txt)"
+  ODT_TC_PAIR=0 timeout 600 python scripts/profile_ops.py $m > gpurun_out/ops_${n}_nopair.txt 2>&1; echo "== $m nopair: $(grep -E 'CUDA-graph' gpurun_out/ops_${n}_nopair.txt)"
+done
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -c 1500 gpurun_out/bench_n1.json

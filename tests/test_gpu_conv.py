@@ -367,6 +367,40 @@ def test_conv_tc_resident_filter_bank_is_bit_identical(built, monkeypatch, shape
     np.testing.assert_array_equal(a, b)
 
 
+PAIR_SHAPES = [
+    # >= 296 tiles -> CTA-pair launch (tcgen05 cta_group::2): B, H, W, Cin, Cout, k, stride, dil
+    (5, 88, 88, 128, 256, 3, 1, 1),    # 303 M tiles: odd count (phantom half pair) + ragged last tile
+    (4, 69, 69, 128, 512, 3, 1, 1),    # two N tiles of 256, 149 M tiles
+    (8, 75, 75, 256, 128, 1, 1, 1),    # 1x1, N = 128 (64 weight rows per CTA)
+    (8, 150, 150, 64, 192, 3, 2, 1),   # stride 2, N = 192
+    (6, 80, 80, 64, 96, 3, 1, 2),      # dilation 2, N = 96
+]
+
+
+@pytest.mark.parametrize("shape", PAIR_SHAPES)
+def test_conv_tc_cta_pairs(built, monkeypatch, shape):
+    """cta_group::2 path against the fp32 reference and bit-identical to the one-CTA path
+    (same K order, same accumulator precision)."""
+    a, ref, a1, r1 = _conv_case(*shape, mode="tc", act="leaky", residual=True, pre=True, seed=sum(shape))
+    tol = 2e-3 * max(np.abs(ref).max(), 1.0)
+    assert np.abs(a - ref).max() <= tol and np.abs(a1 - r1).max() <= 2 * tol
+    monkeypatch.setenv("ODT_TC_PAIR", "0")
+    b, _, b1, _ = _conv_case(*shape, mode="tc", act="leaky", residual=True, pre=True, seed=sum(shape))
+    np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(a1, b1)
+
+
+def test_conv_tc_cta_pairs_head_scatter_and_halo(built, monkeypatch):
+    # fp32 head rows (RetinaNet cls head shape class) and halo in/out layouts through the pair path
+    g, ref, _, _ = _conv_case(4, 100, 100, 256, 189, 3, 1, 1, mode="tc", act=None, f32_out=True)
+    assert np.abs(g - ref).max() <= 2e-3 * max(np.abs(ref).max(), 1.0)
+    h, ref2, _, _ = _conv_case(4, 100, 100, 128, 256, 3, 1, 1, mode="tc", in_halo=1, out_halo=1)
+    assert np.abs(h - ref2).max() <= 2e-3 * max(np.abs(ref2).max(), 1.0)
+    monkeypatch.setenv("ODT_TC_PAIR", "0")
+    h0, _, _, _ = _conv_case(4, 100, 100, 128, 256, 3, 1, 1, mode="tc", in_halo=1, out_halo=1)
+    np.testing.assert_array_equal(h, h0)
+
+
 def test_conv_tc_flat_equals_im2col_path(built, monkeypatch):
     """Same halo input through both tensor-core paths (ODT_TC_FLAT toggles per call)."""
     shape = (2, 38, 38, 128, 128, 3, 1, 1)
