@@ -668,30 +668,37 @@ int check_conv_params(const odt_conv_params* p) {
 
 using namespace odt;
 
-static int pick_bn(int cout_pad, int m_tiles) {
-  // Largest N tile <= 256 that splits the padded Cout into equal 32-multiples ...
-  int bn = 256;
-  if (cout_pad <= 256) {
-    bn = cout_pad;
-  } else {
-    for (bn = 256; bn >= 32; bn -= 32)
-      if (cout_pad % bn == 0) break;
-    if (bn < 32) bn = 256;
-  }
-  // ... then narrowed while the launch would leave most SMs idle: a small-M layer
-  // (FPN P5-P7 towers, SSD extras) is bound by the per-SM TMA fill rate of the few
-  // CTAs that stream the whole weight matrix, so more, narrower tiles win.
-  while (bn > 32 && (long long)m_tiles * ((cout_pad + bn - 1) / bn) < kNumSMs) {
-    int nb = 0;
-    for (int c = bn - 32; c >= 32; c -= 32)
-      if (cout_pad % c == 0) {
-        nb = c;
-        break;
+// N tile and launch shape of an im2col-mode layer from a two-term cost model:
+//   time ~ rounds * (kblocks * cost_kb + fixed),
+//   cost_kb = 256 + 2*BN cycles per 64-deep K block with one CTA per tile (UMMA operand
+//             fetch of A and B at ~64 B/clk -- the same figure as the per-SM L2->smem fill),
+//           = 256 +   BN with CTA pairs (each CTA stages half of the weight tile),
+//   rounds  = tiles per CTA (or pair-tiles per cluster) of the slowest SM.
+// Small-M layers (FPN P5-P7 towers, SSD extras) come out with narrow tiles spread over many
+// SMs, large ones with 256-wide pair tiles.
+static void pick_tiling(int cout_pad, int m_tiles, int kblocks, bool allow_pair, int* bn_out, int* pair_out) {
+  long long best = -1;
+  int best_bn = 32, best_pair = 0;
+  for (int bn = 256; bn >= 32; bn -= 32) {
+    if (cout_pad % bn != 0) continue;
+    const long long n_tiles = cout_pad / bn;
+    for (int pair = allow_pair ? 1 : 0; pair >= 0; --pair) {
+      if (pair && (bn < 64 || m_tiles < 2)) continue;
+      const long long units = pair ? (long long)((m_tiles + 1) / 2) * n_tiles : (long long)m_tiles * n_tiles;
+      const long long slots = pair ? kNumSMs / 2 : kNumSMs;
+      const long long rounds = (units + slots - 1) / slots;
+      // + a per-launch constant for the cluster launch / cluster barriers of the pair kernel
+      const long long cost =
+          rounds * ((long long)kblocks * (256 + (pair ? bn : 2 * bn)) + 2000) + (pair ? 4000 : 0);
+      if (best < 0 || cost < best) {  // ties keep the wider tile / the pair launch (visited first)
+        best = cost;
+        best_bn = bn;
+        best_pair = pair;
       }
-    if (!nb) break;
-    bn = nb;
+    }
   }
-  return bn;
+  *bn_out = best_bn;
+  *pair_out = best_pair;
 }
 
 extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_conv_params* p,
@@ -777,12 +784,9 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
     g.b_bytes = 3 * g.BN * 128;
   } else {
     g.num_m_tiles = (int)((g.M + TC_BM - 1) / TC_BM);
-    g.BN = pick_bn(p->Cout_pad, g.num_m_tiles);
+    pick_tiling(p->Cout_pad, g.num_m_tiles, p->R * p->S * g.cchunks, pair_enabled(), &g.BN, &g.pair);
     g.num_n_tiles = (p->Cout_pad + g.BN - 1) / g.BN;
     g.a_bytes = TC_A_BYTES;
-    // CTA pairs (cta_group::2) once the launch has at least two full waves of tiles: each CTA
-    // then stages only half of the weight tile
-    g.pair = (pair_enabled() && g.BN >= 64 && (long long)g.num_m_tiles * g.num_n_tiles >= 2 * kNumSMs) ? 1 : 0;
     g.b_bytes = (g.pair ? g.BN / 2 : g.BN) * 128;
   }
   stage_bytes = g.a_bytes + g.b_bytes;
