@@ -33,6 +33,10 @@ bool pair_enabled() {
   const char* e = getenv("ODT_TC_PAIR");  // read every call: A/B inside one process
   return !(e && e[0] == '0');
 }
+bool flat_pair_enabled() {
+  const char* e = getenv("ODT_TC_FLAT_PAIR");
+  return pair_enabled() && !(e && e[0] == '0');
+}
 bool wres_enabled() {
   const char* e = getenv("ODT_TC_WRES");
   return !(e && e[0] == '0');

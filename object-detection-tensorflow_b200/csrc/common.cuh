@@ -72,6 +72,7 @@ bool pdl_enabled();   // ODT_PDL=0 disables the launch attribute (api.cu)
 bool bulk_enabled();  // ODT_TC_BULK=0 disables the smem-staged bulk-store epilogue
 bool flat_enabled();  // ODT_TC_FLAT=0 disables the halo-flat 3x3 path (A/B measurements)
 bool pair_enabled();  // ODT_TC_PAIR=0 disables the CTA-pair (cta_group::2) launch of large im2col-mode convs
+bool flat_pair_enabled();  // ODT_TC_FLAT_PAIR=0: no CTA pairs in the halo-flat modes
 bool wres_enabled();  // ODT_TC_WRES=0 disables shared-memory-resident filter banks in the flat path
 
 }  // namespace odt

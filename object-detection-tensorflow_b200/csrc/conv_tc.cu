@@ -94,7 +94,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const uint32_t a_bytes = (uint32_t)g.a_bytes, b_bytes = (uint32_t)g.b_bytes;
   const uint32_t a_base = base;
   const uint32_t b_base = base + (uint32_t)stages * a_bytes;
-  const uint32_t wres_bytes = g.bres ? (uint32_t)(9 * g.cchunks * g.BN * 128) : 0u;
+  const uint32_t bn_cta = (uint32_t)(g.BN / CG);  // weight-tile rows staged by this CTA
+  const uint32_t wres_bytes = g.bres ? (uint32_t)(9 * g.cchunks) * bn_cta * 128u : 0u;
   const uint32_t bar_base = b_base + (uint32_t)stages * b_bytes + wres_bytes;  // 8-byte aligned
   // barriers: full[stages], empty[stages], tfull[2], tempty[2], then tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -148,9 +149,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   if (g.bres && warp == 0) {
     // the filter bank is constant data: fetch it before waiting on the previous kernel
     if (elect_one()) {
-      mbar_expect_tx(wfull_bar, wres_bytes);
-      for (int t = 0; t < 9 * g.cchunks; ++t)
-        tma_load_2d(b_base + (uint32_t)t * (uint32_t)g.BN * 128u, &tmB, wfull_bar, t * TC_BK, 0);
+      if (CG == 2) {  // both CTAs' halves are credited to rank 0's barrier (its MMA issuer waits there)
+        const uint32_t wb = mapa_u32(wfull_bar, 0);
+        if (cta_rank == 0) mbar_expect_tx(wfull_bar, 2u * wres_bytes);
+        for (int t = 0; t < 9 * g.cchunks; ++t)
+          tma_load_2d_cg2(b_base + (uint32_t)t * bn_cta * 128u, &tmB, wb, t * TC_BK, (int)(cta_rank * bn_cta));
+      } else {
+        mbar_expect_tx(wfull_bar, wres_bytes);
+        for (int t = 0; t < 9 * g.cchunks; ++t)
+          tma_load_2d(b_base + (uint32_t)t * (uint32_t)g.BN * 128u, &tmB, wfull_bar, t * TC_BK, 0);
+      }
     }
     __syncwarp();
   }
@@ -195,17 +203,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           for (int cc = 0; cc < g.cchunks; ++cc) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             if (elect_one()) {
-              mbar_expect_tx(full_bar(stage), (uint32_t)g.a_tx + b_bytes);  // b_bytes == 0 when resident
-              if (g.flat == 2)  // padded rows RP*yq + r .., padded columns XB*xq .. (+2 for the taps)
-                tma_load_4d(a_base + (uint32_t)stage * a_bytes, &tmA, full_bar(stage), cc * TC_BK,
-                            g.RP * yq + r, g.XB * xq, bb);
-              else
-                tma_load_2d(a_base + (uint32_t)stage * a_bytes, &tmA, full_bar(stage), cc * TC_BK, row0);
-              if (!g.bres) {
+              const uint32_t adst = a_base + (uint32_t)stage * a_bytes, bdst = b_base + (uint32_t)stage * b_bytes;
+              if (CG == 2) {
+                const uint32_t fb = full_rank0 + 8u * stage;
+                if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2u * ((uint32_t)g.a_tx + b_bytes));
+                if (g.flat == 2)
+                  tma_load_4d_cg2(adst, &tmA, fb, cc * TC_BK, g.RP * yq + r, g.XB * xq, bb);
+                else
+                  tma_load_2d_cg2(adst, &tmA, fb, cc * TC_BK, row0);
+                if (!g.bres) {
 #pragma unroll
-                for (int s = 0; s < 3; ++s)
-                  tma_load_2d(b_base + (uint32_t)stage * b_bytes + (uint32_t)s * (uint32_t)g.BN * 128u, &tmB,
-                              full_bar(stage), ((r * 3 + s) * g.cchunks + cc) * TC_BK, n0);
+                  for (int s = 0; s < 3; ++s)
+                    tma_load_2d_cg2(bdst + (uint32_t)s * bn_cta * 128u, &tmB, fb,
+                                    ((r * 3 + s) * g.cchunks + cc) * TC_BK, n0 + (int)(cta_rank * bn_cta));
+                }
+              } else {
+                mbar_expect_tx(full_bar(stage), (uint32_t)g.a_tx + b_bytes);  // b_bytes == 0 when resident
+                if (g.flat == 2)  // padded rows RP*yq + r .., padded columns XB*xq .. (+2 for the taps)
+                  tma_load_4d(adst, &tmA, full_bar(stage), cc * TC_BK, g.RP * yq + r, g.XB * xq, bb);
+                else
+                  tma_load_2d(adst, &tmA, full_bar(stage), cc * TC_BK, row0);
+                if (!g.bres) {
+#pragma unroll
+                  for (int s = 0; s < 3; ++s)
+                    tma_load_2d(bdst + (uint32_t)s * (uint32_t)g.BN * 128u, &tmB, full_bar(stage),
+                                ((r * 3 + s) * g.cchunks + cc) * TC_BK, n0);
+                }
               }
             }
             __syncwarp();
@@ -263,7 +286,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     int stage = 0;
     uint32_t phase = 0;
     int local_tile = 0;
-    if (g.bres) {
+    if (g.bres && (CG == 1 || cta_rank == 0)) {  // the issuing CTA's barrier collects both halves
       mbar_wait(wfull_bar, 0);
       tc_fence_after();
     }
@@ -280,22 +303,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         const uint64_t adesc = make_desc_sw128(a_base + (uint32_t)stage * a_bytes);
         // resident bank: tile ((r*3 + s)*cchunks + cc) with kb = r*cchunks + cc
         const uint64_t bdesc = make_desc_sw128(
-            g.bres ? b_base + (uint32_t)((kb / g.cchunks) * 3 * g.cchunks + kb % g.cchunks) * (uint32_t)g.BN * 128u
+            g.bres ? b_base + (uint32_t)((kb / g.cchunks) * 3 * g.cchunks + kb % g.cchunks) * bn_cta * 128u
                    : b_base + (uint32_t)stage * b_bytes);
         if (elect_one()) {
           if (g.flat) {
             // three horizontal taps from the same slab: operand rows s .. s+127, i.e. the
             // descriptor start shifted by s*128 B inside the 1024 B swizzle pattern (the
             // swizzle is a function of the absolute address: probed, scripts/probe_rowoffset.py)
-            const uint64_t bstep = (uint64_t)(((g.bres ? g.cchunks : 1) * g.BN * 128) >> 4);
+            const uint64_t bstep = (uint64_t)(((uint32_t)(g.bres ? g.cchunks : 1) * bn_cta * 128u) >> 4);
             const uint64_t astep =
                 g.dbg_aligned ? 0ull : (uint64_t)(g.flat == 2 ? 8 * g.RP : 8);  // rows per tap shift x 128 B >> 4
 #pragma unroll
             for (int s3 = 0; s3 < 3; ++s3) {
 #pragma unroll
-              for (int k = 0; k < TC_BK / 16; ++k)
-                tc_mma_f16(d_tmem, adesc + astep * s3 + (uint64_t)(2 * k), bdesc + bstep * s3 + (uint64_t)(2 * k),
-                           idesc, (uint32_t)((kb | s3 | k) != 0));
+              for (int k = 0; k < TC_BK / 16; ++k) {
+                if (CG == 2)
+                  tc_mma_f16_cg2(d_tmem, adesc + astep * s3 + (uint64_t)(2 * k),
+                                 bdesc + bstep * s3 + (uint64_t)(2 * k), idesc, (uint32_t)((kb | s3 | k) != 0));
+                else
+                  tc_mma_f16(d_tmem, adesc + astep * s3 + (uint64_t)(2 * k),
+                             bdesc + bstep * s3 + (uint64_t)(2 * k), idesc, (uint32_t)((kb | s3 | k) != 0));
+              }
             }
           } else {
 #pragma unroll
@@ -360,7 +388,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         const int yq = rem / g.xblocks, xq = rem - yq * g.xblocks;
         const int ml = quarter * 32 + lane;
         const int x = g.XB * xq + (ml >> g.lgRP), y = g.RP * yq + (ml & (g.RP - 1));
-        row_ok = x < g.W && y < g.H;  // even sizes: a pooling window is valid or invalid as a whole
+        row_ok = x < g.W && y < g.H && m_tile < g.num_m_tiles;  // even sizes: a window is valid or invalid as a whole
         pix = 0;
         const int oh = g.out_halo;
         pool_row = (long long)img * e.out0_img_stride +
@@ -774,14 +802,20 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
     g.num_n_tiles = 1;
     g.a_bytes = TC_FLAT_A_BYTES;
     g.a_tx = (g.XB + 2) * g.RP * 128;
-    g.b_bytes = 3 * g.BN * 128;
+    // CTA pairs (half of each tap tile per CTA) pay off once a tile is long enough to hide the
+    // cross-CTA handshakes: measured +21 % at Cin = 128 (conv2_2), -10 % at Cin <= 64 (conv2_1)
+    g.pair = (flat_pair_enabled() && g.num_m_tiles >= 2 && g.cchunks >= 2) ? 1 : 0;
+    g.b_bytes = 3 * (g.pair ? g.BN / 2 : g.BN) * 128;
   } else if (g.flat) {
     g.a_tx = TC_FLAT_A_BYTES;
     g.num_m_tiles = (int)((g.Q + TC_BM - 1) / TC_BM);
     g.BN = p->Cout_pad;
     g.num_n_tiles = 1;
     g.a_bytes = TC_FLAT_A_BYTES;
-    g.b_bytes = 3 * g.BN * 128;
+    // CTA pairs (half of each tap tile per CTA) pay off once a tile is long enough to hide the
+    // cross-CTA handshakes: measured +21 % at Cin = 128 (conv2_2), -10 % at Cin <= 64 (conv2_1)
+    g.pair = (flat_pair_enabled() && g.num_m_tiles >= 2 && g.cchunks >= 2) ? 1 : 0;
+    g.b_bytes = 3 * (g.pair ? g.BN / 2 : g.BN) * 128;
   } else {
     g.num_m_tiles = (int)((g.M + TC_BM - 1) / TC_BM);
     pick_tiling(p->Cout_pad, g.num_m_tiles, p->R * p->S * g.cchunks, pair_enabled(), &g.BN, &g.pair);
@@ -809,7 +843,7 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
   g.nacc = g.epi_split ? 4 : 2;
   // small filter banks of the flat modes stay resident in shared memory if at least three
   // activation stages still fit beside them
-  const long long wres = 9ll * g.cchunks * g.BN * 128;
+  const long long wres = 9ll * g.cchunks * (g.pair ? g.BN / 2 : g.BN) * 128;  // per CTA
   if (g.flat && wres_enabled() && g.BN >= 128 &&  // measured: a win at N = 128 (conv2_1), a loss at N <= 64
       wres + 3 * TC_FLAT_A_BYTES + 2048 + TC_EPI_SMEM + out_stage_bytes <= TC_SMEM_LIMIT) {
     g.bres = 1;

@@ -401,6 +401,18 @@ def test_conv_tc_cta_pairs_head_scatter_and_halo(built, monkeypatch):
     np.testing.assert_array_equal(h, h0)
 
 
+@pytest.mark.parametrize("shape,pool", [((2, 38, 38, 64, 64, 3, 1, 1), 0), ((3, 75, 75, 64, 128, 3, 1, 1), 0),
+                                        ((2, 300, 300, 64, 64, 3, 1, 1), 2), ((2, 150, 150, 128, 128, 3, 1, 1), 2),
+                                        ((1, 150, 150, 128, 128, 3, 1, 1), 0), ((1, 17, 23, 64, 28, 3, 1, 1), 0)])
+def test_conv_tc_flat_cta_pairs_bit_identical(built, monkeypatch, shape, pool):
+    """Halo-flat / row-block modes launched as CTA pairs vs one CTA per tile: same bits."""
+    a, ref, _, _ = _conv_case(*shape, mode="tc", in_halo=1, out_halo=1, pool=pool)
+    assert np.abs(a - ref).max() <= 2e-3 * max(np.abs(ref).max(), 1.0)
+    monkeypatch.setenv("ODT_TC_FLAT_PAIR", "0")
+    b, _, _, _ = _conv_case(*shape, mode="tc", in_halo=1, out_halo=1, pool=pool)
+    np.testing.assert_array_equal(a, b)
+
+
 def test_conv_tc_flat_equals_im2col_path(built, monkeypatch):
     """Same halo input through both tensor-core paths (ODT_TC_FLAT toggles per call)."""
     shape = (2, 38, 38, 128, 128, 3, 1, 1)
