@@ -298,9 +298,16 @@ def main():
     peaks, peak_src = measured_peaks()
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
     achieved_tf = tc_flops / (tc_ms * 1e-3) / 1e12
+    traffic, traffic_src = None, None
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_conv_traffic.json")
+    if os.path.exists(tpath):  # committed ncu measurement of the same command (scripts/conv_traffic.py)
+        with open(tpath) as f:
+            tj = json.load(f)
+        if tj.get("launches_per_step") == len(tc_ops):
+            traffic, traffic_src = tj["dram_bytes_per_launch_avg"], "profiles/r01_conv_traffic.json (ncu dram__bytes_read+write)"
     roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM)",
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf, "traffic": None,
+                "frac": achieved_tf / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_src + " cuBLAS bf16 sustained (kernel timed inside a long step)",
                 "launches_per_step": len(tc_ops), "tc_ms_per_step": tc_ms,
                 "algorithmic_gflop_per_step": tc_flops / 1e9,
@@ -311,7 +318,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "per_gpu_batch": BATCH,
                        "parallelism": "dp%d (image shards, 1 all-gather of detections)" % world,
-                       "l2": "per-step activation working set ~2.9 GB >> 126 MB L2 (no reuse between steps)",
+                       "l2": "per-step activation working set ~2 GB >> 126 MB L2 (no reuse between steps)",
                        "cuda_graph": True, "conv_gflop_per_img": CONV_GFLOP_PER_IMG,
                        "conv_roofline_frac_whole_step":
                            (BATCH * CONV_GFLOP_PER_IMG * 1e9 / (ms_step * 1e-3)) / (peak_tf * 1e12)},
