@@ -147,6 +147,15 @@ def cpu_oracle_images_per_sec(n_images, repeats=1, threads=None):
     return n_images / best, threads
 
 
+_OUT = None
+
+
+def emit(line):
+    out = _OUT if _OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path.  TF 1.13
     is not installable here and SSD300.py does not parse, so this times the oracle
@@ -171,7 +180,7 @@ def run_reference(args, rank, world):
                              "sample": "%d images per step, batch-1 graph semantics, torch-CPU fp32 "
                                        "convs + C NMS" % sample},
             "e2e": {"value": v, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -186,6 +195,12 @@ def main():
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout carries exactly ONE JSON line: keep the real stdout aside and point fd 1 at stderr so
+    # that libraries writing to stdout (NCCL's version banner, ...) cannot pollute it
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -333,7 +348,7 @@ def main():
                                 "sample": "8 of the 64 images, oracle port (torch-CPU fp32 + C NMS), "
                                           "batch-1 graph semantics like the reference"}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         tdist.barrier()
         tdist.destroy_process_group()
