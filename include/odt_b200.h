@@ -78,7 +78,7 @@ typedef struct {
   const float* shift; /* [Cout] or NULL (=0)  bias / folded BN beta           */
   int act;
   const void* residual; /* activation dtype, same addressing as out0, or NULL */
-  void* out0;           /* may be NULL when only out1 is wanted               */
+  void* out0;           /* may be NULL when only out1 / out2 are wanted       */
   int out0_dtype;       /* ODT_F16 / ODT_F32                                  */
   long long out0_img_stride; /* elements between images                       */
   int out0_pix_stride;       /* elements between pixels                       */
@@ -92,6 +92,15 @@ typedef struct {
   void* out1; /* or NULL */
   long long out1_img_stride;
   int out1_pix_stride;
+  /* epilogue 3: a second consumer pre-activation of the same value (RetinaNet's
+   * identity and conv branches normalise the block input with different BNs,
+   * RetinaNet.py:634-643):  out2 = act3(v*scale3[c] + shift3[c])              */
+  const float* scale3;
+  const float* shift3;
+  int act3;
+  void* out2; /* or NULL */
+  long long out2_img_stride;
+  int out2_pix_stride;
   /* halo layouts (tensor-core path only): 1 = the tensor is stored as
    * [B][H+2][W+2][ld] with a zero 1-pixel border that the kernels never dirty.
    * A halo input lets 3x3/stride-1 convolutions with Cout_pad <= 128 run in

@@ -245,7 +245,7 @@ extern "C" int odt_conv2d_stem(const float* images, const float* mean3_host, con
   }
   ODT_CHECK_ARG(p->out0_halo == 0 && p->in_halo == 0 && p->out0_pool == 0,
                 "halo output needs the tensor-core stem");
-  const bool simple = p->out0 && !p->out1 && !p->residual && p->out0_group == 0 && p->R == p->S &&
+  const bool simple = p->out0 && !p->out1 && !p->out2 && !p->residual && p->out0_group == 0 && p->R == p->S &&
                       p->dil == 1 && p->in_ld == 3 &&
                       p->out0_dtype == (dtype == ODT_F16 ? ODT_F16 : ODT_F32) &&
                       ((uintptr_t)p->out0 % 16) == 0 &&

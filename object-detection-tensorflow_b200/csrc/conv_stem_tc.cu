@@ -334,7 +334,7 @@ using namespace odt;
 // (the caller then uses the CUDA-core stem).
 int odt_conv2d_stem_tc_try(const float* images, const float* mean3_host, const void* weights,
                            const odt_conv_params* p, void* stream) {
-  const bool ok = p->out0 && !p->out1 && !p->residual && p->out0_group == 0 && p->R == p->S &&
+  const bool ok = p->out0 && !p->out1 && !p->out2 && !p->residual && p->out0_group == 0 && p->R == p->S &&
                   p->dil == 1 && p->in_ld == 3 && p->Cin == 3 && p->out0_dtype == ODT_F16 &&
                   p->out0_pool == 0 && ((uintptr_t)p->out0 % 16) == 0 && p->out0_pix_stride % 8 == 0 &&
                   p->out0_pix_stride >= p->Cout &&

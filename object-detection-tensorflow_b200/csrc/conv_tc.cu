@@ -30,7 +30,8 @@ constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = 32 * (2 + TC_EPI_WARPS);  // TMA, MMA, 8 epilogue warps
-constexpr int TC_EPI_SMEM = 2 * 2 * 5 * 256 * 4;  // per epilogue group, double-buffered: scale/shift/scale2/shift2/column offset
+constexpr int TC_EPI_PAR = 7 * 256;               // floats per parameter block: scale/shift/scale2/shift2/column offset/scale3/shift3
+constexpr int TC_EPI_SMEM = 2 * 2 * TC_EPI_PAR * 4;  // per epilogue group, double-buffered
 constexpr int TC_MAX_ACC = 4;  // TMEM accumulator stages (512 columns / BN, at most 4)
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KiB
@@ -364,7 +365,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const bool split = g.epi_split != 0;
     const int et = split ? threadIdx.x - 64 - group * 128 : threadIdx.x - 64;  // index in the sync group
     int staged_n_tile = -1, pbuf = 0;
-    float* gpar = epi_par + (split ? group * 2 * 1280 : 0);
+    float* gpar = epi_par + (split ? group * 2 * TC_EPI_PAR : 0);
     const uint32_t row_bytes = (uint32_t)g.BN * 2u;
     const uint32_t my_stage = out_stage + (uint32_t)(group * 4 + quarter) * 32u * row_bytes;
     uint8_t* my_stage_ptr = smem_raw + (my_stage - raw) + lane * row_bytes;
@@ -412,7 +413,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       if (n_tile != staged_n_tile) {
         staged_n_tile = n_tile;
         pbuf ^= 1;
-        float* wpar = gpar + pbuf * 1280;
+        float* wpar = gpar + pbuf * TC_EPI_PAR;
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
           const int c = split ? et + h2 * 128 : et;
@@ -424,13 +425,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           wpar[512 + c] = (ok && e.scale2) ? __ldg(e.scale2 + n) : 1.f;
           wpar[768 + c] = (ok && e.shift2) ? __ldg(e.shift2 + n) : 0.f;
           reinterpret_cast<int*>(wpar)[1024 + c] = ok ? regroup(e, n) : 0;
+          wpar[1280 + c] = (ok && e.scale3) ? __ldg(e.scale3 + n) : 1.f;
+          wpar[1536 + c] = (ok && e.shift3) ? __ldg(e.shift3 + n) : 0.f;
         }
         if (split)
           asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
         else
           asm volatile("bar.sync 3, 256;" ::: "memory");
       }
-      const float* par = gpar + pbuf * 1280;
+      const float* par = gpar + pbuf * TC_EPI_PAR;
       long long o0_row = (long long)img * e.out0_img_stride;
       if (g.out_halo) {
         const int oy = pix / g.OW, ox = pix - oy * g.OW;
@@ -440,6 +443,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
       const long long o1_row =
           (long long)img * e.out1_img_stride + (long long)pix * e.out1_pix_stride;
+      const long long o2_row =
+          (long long)img * e.out2_img_stride + (long long)pix * e.out2_pix_stride;
       if (g.bulk_store) {
         // this warp's previous bulk store must have drained its staging rows
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -549,6 +554,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
               for (int qd = 0; qd < 4; ++qd) op[qd] = packed1[qd];
             }
+            if (e.out2) {
+              const float4* ps3 = reinterpret_cast<const float4*>(par + 1280 + j * 32);
+              const float4* ph3 = reinterpret_cast<const float4*>(par + 1536 + j * 32);
+              uint4 packed2[4];
+              __half2* p2 = reinterpret_cast<__half2*>(packed2);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 sc = ps3[i], sh = ph3[i];
+                const float2 fa = __half22float2(ph[2 * i]);
+                const float2 fb = __half22float2(ph[2 * i + 1]);
+                p2[2 * i] = __floats2half2_rn(apply_act(fmaf(fa.x, sc.x, sh.x), e.act3),
+                                              apply_act(fmaf(fa.y, sc.y, sh.y), e.act3));
+                p2[2 * i + 1] = __floats2half2_rn(apply_act(fmaf(fb.x, sc.z, sh.z), e.act3),
+                                                  apply_act(fmaf(fb.y, sc.w, sh.w), e.act3));
+              }
+              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out2) + o2_row + nb);
+#pragma unroll
+              for (int qd = 0; qd < 4; ++qd) op[qd] = packed2[qd];
+            }
           }
         } else if (row_ok || g.head_mode) {
           // generic path: fp32 head outputs scattered into the candidate rows,
@@ -596,6 +620,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               if (e.out1)
                 reinterpret_cast<__half*>(e.out1)[o1_row + n] =
                     __float2half_rn(apply_act(fmaf(v, ps[512 + i], ps[768 + i]), e.act2));
+              if (e.out2)
+                reinterpret_cast<__half*>(e.out2)[o2_row + n] =
+                    __float2half_rn(apply_act(fmaf(v, ps[1280 + i], ps[1536 + i]), e.act3));
             }
           }
         }
@@ -686,8 +713,9 @@ int check_conv_params(const odt_conv_params* p) {
   ODT_CHECK_ARG(p->OH > 0 && p->OW > 0 && p->Cout > 0, "output geometry");
   ODT_CHECK_ARG(p->R > 0 && p->S > 0 && p->stride > 0 && p->dil > 0, "filter geometry");
   ODT_CHECK_ARG(p->w_ld >= p->Cin && p->Cout_pad >= p->Cout, "weight geometry");
-  ODT_CHECK_ARG(p->out0 || p->out1, "no output");
-  ODT_CHECK_ARG(p->act >= 0 && p->act <= 2 && p->act2 >= 0 && p->act2 <= 2, "activation code");
+  ODT_CHECK_ARG(p->out0 || p->out1 || p->out2, "no output");
+  ODT_CHECK_ARG(p->act >= 0 && p->act <= 2 && p->act2 >= 0 && p->act2 <= 2 && p->act3 >= 0 && p->act3 <= 2,
+                "activation code");
   ODT_CHECK_ARG(p->out0_dtype == ODT_F16 || p->out0_dtype == ODT_F32, "out0 dtype");
   return ODT_OK;
 }
@@ -778,7 +806,7 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
   if (p->out0_pool) {
     ODT_CHECK_ARG(flat_shape, "fused pooling needs a halo input and a 3x3/stride-1 filter with Cout_pad <= 128");
     ODT_CHECK_ARG(p->OH % 2 == 0 && p->OW % 2 == 0, "fused pooling needs even OH and OW");
-    ODT_CHECK_ARG(p->out0 && p->out0_dtype == ODT_F16 && !p->residual && !p->out1 && p->out0_group == 0,
+    ODT_CHECK_ARG(p->out0 && p->out0_dtype == ODT_F16 && !p->residual && !p->out1 && !p->out2 && p->out0_group == 0,
                   "fused pooling: fp16 out0 only, no residual / out1 / regrouping");
     ODT_CHECK_ARG(p->out0_pix_stride % 8 == 0 && p->out0_img_stride % 8 == 0 &&
                       ((uintptr_t)p->out0 & 15) == 0 && p->out0_pix_stride >= p->Cout_pad,
@@ -830,13 +858,13 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
       g.flat ? (p->out0_halo == 1 &&
                 p->out0_img_stride == (long long)(p->OH + 2) * (p->OW + 2) * p->out0_pix_stride)
              : (p->out0_halo == 0 && p->out0_img_stride == (long long)p->OH * p->OW * p->out0_pix_stride);
-  g.bulk_store = (bulk_enabled() && g.flat != 2 && p->out0 && !p->out1 && p->out0_dtype == ODT_F16 &&
+  g.bulk_store = (bulk_enabled() && g.flat != 2 && p->out0 && !p->out1 && !p->out2 && p->out0_dtype == ODT_F16 &&
                   p->out0_group == 0 && g.num_n_tiles == 1 && g.BN <= 64 &&
                   g.BN == p->out0_pix_stride && linear_rows && ((uintptr_t)p->out0 & 15) == 0 &&
                   (!p->residual || ((uintptr_t)p->residual & 15) == 0))
                      ? 1
                      : 0;
-  g.head_mode = (p->out0 && p->out0_dtype == ODT_F32 && !p->residual && !p->out1) ? 1 : 0;
+  g.head_mode = (p->out0 && p->out0_dtype == ODT_F32 && !p->residual && !p->out1 && !p->out2) ? 1 : 0;
   const int out_stage_bytes =
       g.bulk_store ? TC_EPI_WARPS * 32 * g.BN * 2 : (g.head_mode ? TC_HEAD_STAGE : 0);  // per-warp staging
   g.epi_split = g.BN <= 128 ? 1 : 0;
@@ -863,9 +891,12 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
                  (!p->out0 || ((uintptr_t)p->out0 & 15) == 0) &&
                  (!p->residual || ((uintptr_t)p->residual & 15) == 0) &&
                  (!p->out1 || (((uintptr_t)p->out1 & 15) == 0 && p->out1_pix_stride % 8 == 0 &&
-                               p->out1_img_stride % 8 == 0));
+                               p->out1_img_stride % 8 == 0)) &&
+                 (!p->out2 || (((uintptr_t)p->out2 & 15) == 0 && p->out2_pix_stride % 8 == 0 &&
+                               p->out2_img_stride % 8 == 0));
   g.fast_cols = p->out0 ? p->out0_pix_stride : (1 << 30);
   if (p->out1 && p->out1_pix_stride < g.fast_cols) g.fast_cols = p->out1_pix_stride;
+  if (p->out2 && p->out2_pix_stride < g.fast_cols) g.fast_cols = p->out2_pix_stride;
 
   CUtensorMap tmA, tmB;
   if (g.flat == 2) {

@@ -1,6 +1,6 @@
 // Fused convolution epilogue shared by the tensor-core and the CUDA-core
 // convolution kernels.  v = act(acc*scale[c]+shift[c]) (+residual) -> out0 ;
-// out1 = act2(v*scale2[c]+shift2[c]) (the consumer's pre-activation).
+// out1 = act2(v*scale2[c]+shift2[c]), out2 = act3(v*scale3[c]+shift3[c]) (consumer pre-activations).
 // ref: bias_add+ReLU SSD300.py:520-521; BN(+act) SSD300.py:534-537,
 // YOLOv3.py:504-507; pre-activation BN+ReLU RetinaNet.py:594-597;
 // residual adds RetinaNet.py:643, YOLOv3.py:491.
@@ -25,6 +25,12 @@ struct Epi {
   void* out1;
   long long out1_img_stride;
   int out1_pix_stride;
+  const float* scale3;
+  const float* shift3;
+  int act3;
+  void* out2;
+  long long out2_img_stride;
+  int out2_pix_stride;
   int Cout;
 };
 
@@ -53,6 +59,12 @@ inline Epi make_epi(const odt_conv_params& p) {
   e.out1 = p.out1;
   e.out1_img_stride = p.out1_img_stride;
   e.out1_pix_stride = p.out1_pix_stride;
+  e.scale3 = p.scale3;
+  e.shift3 = p.shift3;
+  e.act3 = p.act3;
+  e.out2 = p.out2;
+  e.out2_img_stride = p.out2_img_stride;
+  e.out2_pix_stride = p.out2_pix_stride;
   e.Cout = p.Cout;
   return e;
 }
@@ -85,6 +97,13 @@ __device__ __forceinline__ void epi_store_one(const Epi& e, int b, int pix, int 
     float w = apply_act(fmaf(v, s2, h2), e.act2);
     const long long o1 = (long long)b * e.out1_img_stride + (long long)pix * e.out1_pix_stride + n;
     Elem<T>::st(reinterpret_cast<T*>(e.out1) + o1, w);
+  }
+  if (e.out2) {
+    float s3 = e.scale3 ? __ldg(e.scale3 + n) : 1.f;
+    float h3 = e.shift3 ? __ldg(e.shift3 + n) : 0.f;
+    float w = apply_act(fmaf(v, s3, h3), e.act3);
+    const long long o2 = (long long)b * e.out2_img_stride + (long long)pix * e.out2_pix_stride + n;
+    Elem<T>::st(reinterpret_cast<T*>(e.out2) + o2, w);
   }
 }
 

@@ -105,6 +105,7 @@ class ConvOp(Op):
         self.kernel, self.bias, self.bn, self.act = kernel, bias, bn, act
         self.residual, self.head, self.is_image = residual, head, is_image
         self.pre = None     # fused consumer pre-activation: (bn_scope, act, Act)
+        self.pre2 = None    # a second one (tensor-core path): RetinaNet block inputs feed two BNs
         self.pool = 0       # 2: the 2x2/2 max-pool that follows is done in the epilogue (y is the pooled tensor)
         self.reads = tuple(t for t in (x, residual) if t is not None)
         self.writes = (y,) if y is not None else ()
@@ -188,6 +189,17 @@ class ConvOp(Op):
             p.out1 = t.ptr()
             p.out1_img_stride = t.H * t.W * t.ld
             p.out1_pix_stride = t.ld
+        if self.pre2 is not None:
+            scope, act3, t = self.pre2
+            if scope is not None:
+                s3, h3 = net.bn_fold(scope)
+                self.scale3 = torch.from_numpy(s3).to(dev)
+                self.shift3 = torch.from_numpy(h3).to(dev)
+                p.scale3, p.shift3 = self.scale3.data_ptr(), self.shift3.data_ptr()
+            p.act3 = ACT[act3]
+            p.out2 = t.ptr()
+            p.out2_img_stride = t.H * t.W * t.ld
+            p.out2_pix_stride = t.ld
         self.p = p
         self.flops = 2 * B * OH * OW * cout * R * S * cin
 
@@ -464,8 +476,15 @@ class Net:
                 ok = isinstance(q, (ConvOp, UpsampleAddOp)) and q.pre is None
                 if ok and isinstance(q, ConvOp):
                     ok = q.head is None
-                if ok:
-                    q.pre = (op.bn, op.act, op.y)
+                # second pre-activation of the same tensor: tensor-core convs only (third epilogue output)
+                second = (not ok and isinstance(q, ConvOp) and q.head is None and q.pre is not None
+                          and q.pre2 is None and not q.is_image and self.precision == "fp16" and self.allow_tc
+                          and q.x.ld % 64 == 0 and os.environ.get("ODT_FUSE_PRE2", "1") != "0")
+                if ok or second:
+                    if ok:
+                        q.pre = (op.bn, op.act, op.y)
+                    else:
+                        q.pre2 = (op.bn, op.act, op.y)
                     producer[id(op.y)] = q
                     consumers[id(op.x)].remove(op)
                     if not consumers[id(op.x)] and isinstance(q, ConvOp):
@@ -489,8 +508,9 @@ class Net:
                 readers.setdefault(id(t), []).append(op)
             for t in op.writes:
                 producer[id(t)] = op
-            if getattr(op, "pre", None) is not None:
-                producer[id(op.pre[2])] = None  # fused second outputs stay dense
+            for pr in (getattr(op, "pre", None), getattr(op, "pre2", None)):
+                if pr is not None:
+                    producer[id(pr[2])] = None  # fused second / third outputs stay dense
         for t in self.acts:
             prod = producer.get(id(t))
             cons = readers.get(id(t), [])
@@ -535,6 +555,7 @@ class Net:
             if isinstance(op, PoolOp) and op.k == 2 and op.stride == 2:
                 q, t = producer.get(id(op.x)), op.x
                 ok = (isinstance(q, ConvOp) and q.y is t and readers.get(id(t)) == [op] and q.pre is None
+                      and q.pre2 is None
                       and q.head is None and q.residual is None and not q.is_image and q.pool == 0
                       and q.x.halo == 1 and q.x.ld % 64 == 0 and q.k == 3 and q.stride == 1 and q.dil == 1
                       and _round_up(t.C, 32) <= 128 and t.H % 2 == 0 and t.W % 2 == 0)
@@ -595,8 +616,9 @@ class Net:
         for i, op in enumerate(self.ops):
             deps.append(sorted({producer[id(t)] for t in op.reads if id(t) in producer}))
             outs = list(op.writes)
-            if getattr(op, "pre", None) is not None:
-                outs.append(op.pre[2])
+            for pr in (getattr(op, "pre", None), getattr(op, "pre2", None)):
+                if pr is not None:
+                    outs.append(pr[2])
             for t in outs:
                 producer[id(t)] = i
         lane_of, tails, waits = [], [], []   # tails[l] = index of the last op put on lane l

@@ -31,6 +31,8 @@ class ConvParams(C.Structure):
         ("out0_group", C.c_int), ("out0_group_stride", C.c_int),
         ("scale2", C.c_void_p), ("shift2", C.c_void_p), ("act2", C.c_int),
         ("out1", C.c_void_p), ("out1_img_stride", C.c_longlong), ("out1_pix_stride", C.c_int),
+        ("scale3", C.c_void_p), ("shift3", C.c_void_p), ("act3", C.c_int),
+        ("out2", C.c_void_p), ("out2_img_stride", C.c_longlong), ("out2_pix_stride", C.c_int),
         ("in_halo", C.c_int), ("out0_halo", C.c_int), ("out0_pool", C.c_int),
     ]
 

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _conv_case(B, H, W, Cin, Cout, k, stride, dil, mode, act="relu", residual=False, pre=False,
-               bn=True, f32_out=False, seed=0, in_halo=0, out_halo=0, pool=0):
+               bn=True, f32_out=False, seed=0, in_halo=0, out_halo=0, pool=0, pre2=False, no_out0=False):
     """mode: 'tc' (fp16 tcgen05), 'direct16', 'direct32'.  Returns (got, ref, got1, ref1)."""
     from odt_b200 import lib as L
     from odt_b200.engine import same_pad
@@ -83,6 +83,16 @@ def _conv_case(B, H, W, Cin, Cout, k, stride, dil, mode, act="relu", residual=Fa
         y1 = torch.zeros((B, OH, OW, old), dtype=tdt, device=dev)
         p.scale2, p.shift2, p.act2 = s2d.data_ptr(), h2d.data_ptr(), 1
         p.out1, p.out1_img_stride, p.out1_pix_stride = y1.data_ptr(), OH * OW * old, old
+    s3 = h3 = y2 = None
+    if pre2:  # third epilogue output (checked in here against the rounded out0 like out1)
+        s3 = rng.uniform(0.5, 1.5, Cout).astype(np.float32)
+        h3 = (rng.standard_normal(Cout) * 0.2).astype(np.float32)
+        s3d, h3d = torch.from_numpy(s3).to(dev), torch.from_numpy(h3).to(dev)
+        y2 = torch.zeros((B, OH, OW, old), dtype=tdt, device=dev)
+        p.scale3, p.shift3, p.act3 = s3d.data_ptr(), h3d.data_ptr(), 2
+        p.out2, p.out2_img_stride, p.out2_pix_stride = y2.data_ptr(), OH * OW * old, old
+    if no_out0:
+        p.out0 = None
     st = torch.cuda.current_stream().cuda_stream
     if mode == "tc":
         rc = lib.odt_conv2d_f16_tc(xd.data_ptr(), wd.data_ptr(), C.byref(p), st)
@@ -108,9 +118,16 @@ def _conv_case(B, H, W, Cin, Cout, k, stride, dil, mode, act="relu", residual=Fa
         assert np.abs(full[:, :, 0]).max() == 0 and np.abs(full[:, :, -1]).max() == 0
     got1 = ref1 = None
     if pre:
-        base = got if f16 and not f32_out else ref
+        base = got if (f16 and not f32_out and not no_out0) else ref
         ref1 = np.maximum(base * s2 + h2, 0)
         got1 = y1[..., :Cout].float().cpu().numpy()
+    if pre2:
+        base = got if (f16 and not f32_out and not no_out0) else ref
+        t = base * s3 + h3
+        ref2 = np.maximum(t, 0.1 * t)
+        got2 = y2[..., :Cout].float().cpu().numpy()
+        tol2 = (6e-3 if f16 else 4e-5) * max(np.abs(ref2).max(), 1.0)
+        assert np.abs(got2 - ref2).max() <= tol2, ("out2", float(np.abs(got2 - ref2).max()))
     if mode == "tc" and old > Cout and not f32_out:
         assert float(yd[..., Cout:].abs().max()) == 0.0, "pad channels must stay zero"
     return got, ref.astype(np.float32), got1, ref1
@@ -411,6 +428,26 @@ def test_conv_tc_flat_cta_pairs_bit_identical(built, monkeypatch, shape, pool):
     monkeypatch.setenv("ODT_TC_FLAT_PAIR", "0")
     b, _, _, _ = _conv_case(*shape, mode="tc", in_halo=1, out_halo=1, pool=pool)
     np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("shape,kw", [
+    ((2, 38, 38, 128, 256, 3, 1, 1), {}),                       # im2col mode
+    ((8, 75, 75, 128, 256, 3, 1, 1), {"residual": True}),       # CTA pairs + residual
+    ((2, 40, 40, 64, 96, 3, 1, 1), {"in_halo": 1}),             # halo-flat mode
+    ((2, 26, 26, 512, 28, 1, 1, 1), {"no_out0": True}),         # ragged Cout, only the two pre-activations wanted
+])
+def test_conv_tc_two_preactivation_outputs(built, shape, kw):
+    """out1 and out2 (two consumer BN+activation variants of the same conv output)."""
+    got, ref, g1, r1 = _conv_case(*shape, mode="tc", pre=True, pre2=True, **kw)
+    tol = 2e-3 * max(np.abs(ref).max(), 1.0)
+    if not kw.get("no_out0"):
+        assert np.abs(got - ref).max() <= tol
+    assert np.abs(g1 - r1).max() <= 3 * tol
+
+
+def test_conv_direct_two_preactivation_outputs(built):
+    got, ref, g1, r1 = _conv_case(2, 20, 20, 24, 40, 3, 1, 1, mode="direct32", pre=True, pre2=True)
+    assert np.abs(got - ref).max() <= 2e-5 * max(np.abs(ref).max(), 1.0)
 
 
 def test_conv_tc_flat_equals_im2col_path(built, monkeypatch):

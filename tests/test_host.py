@@ -168,9 +168,10 @@ def test_fusion_plan_retinanet():
     n_aff = sum(isinstance(o, E.AffineActOp) for o in net.ops)
     net.fuse()
     n_aff2 = sum(isinstance(o, E.AffineActOp) for o in net.ops)
-    fused = sum(1 for o in net.ops if isinstance(o, (E.ConvOp, E.UpsampleAddOp)) and o.pre is not None)
+    fused = sum((o.pre is not None) + (getattr(o, "pre2", None) is not None)
+                for o in net.ops if isinstance(o, (E.ConvOp, E.UpsampleAddOp)))
     assert n_aff == 122 - 1  # every conv but the stem is pre-activated
-    assert fused + n_aff2 == n_aff and n_aff2 < 40
+    assert fused + n_aff2 == n_aff and n_aff2 <= 8  # the BNs on the max-pool output and third consumers stay
     dropped = sum(1 for t in net.acts if not t.needed)
     assert dropped >= 40  # the 4x2x5 tower intermediates at least
 
@@ -202,7 +203,7 @@ def test_lane_plan_respects_dataflow(model, min_lanes):
             assert lane_of[p] == lane_of[i] or p in waits[i]
         for w in waits[i]:
             assert w < i and lane_of[w] != lane_of[i]
-        outs = list(op.writes) + ([op.pre[2]] if getattr(op, "pre", None) is not None else [])
+        outs = list(op.writes) + [pr[2] for pr in (getattr(op, "pre", None), getattr(op, "pre2", None)) if pr]
         for t in outs:
             producer[id(t)] = i
     one, w1, t1 = net.plan_lanes(1)
