@@ -146,6 +146,17 @@ struct NmsSmem {
 // alive candidates / 256 threads -- no O(n log^2 n) sort, no capacity cliff: lists
 // longer than the shared-memory window are processed in place in global memory
 // with boxes decoded on the fly.
+//
+// Long lists (> kNmsPrefilter) first try an exact prefilter: a radix select on the score
+// bits finds a threshold T with kNmsSelectMin..kNmsSmemKeys candidates at or above it, and
+// the rounds run on that subset S in shared memory.  Greedy NMS visits candidates in
+// descending score order, so if nms_max_boxes boxes are kept inside S the result is the
+// exact global one (every kept box and every candidate that could have suppressed or
+// preceded it has score >= T and therefore is in S).  Only if S runs dry first is the full
+// list processed (correct, slower).
+constexpr int kNmsPrefilter = 1024;
+constexpr int kNmsSelectMin = 512;
+
 __global__ void __launch_bounds__(kNmsThreads)
     nms_per_class_kernel(const float* __restrict__ head, const __grid_constant__ TailP tp, int B,
                          unsigned long long* __restrict__ cand_keys,
@@ -162,6 +173,8 @@ __global__ void __launch_bounds__(kNmsThreads)
   __shared__ unsigned long long s_wkey[kNmsThreads / 32];
   __shared__ int s_wpos[kNmsThreads / 32];
   __shared__ int s_last;
+  __shared__ int s_hist[256];
+  __shared__ unsigned s_ctl[4];  // radix select: [0] done flag, [1] prefix / threshold, [2] count above the bin, [3] subset fill
   const int c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int C = p.nms_classes, MB = p.max_boxes;
@@ -177,14 +190,72 @@ __global__ void __launch_bounds__(kNmsThreads)
     cnt = p.cap;
   }
   unsigned long long* gkeys = cand_keys + ((long long)b * p.num_fg + c) * p.cap;
-  const bool in_smem = cnt <= kNmsSmemKeys;
-  unsigned long long* keys = in_smem ? sm.keys : gkeys;
   const float* hb = head + (long long)b * p.N * kRow;
+  const int cnt_all = cnt;
+  int nsel = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+  // ---- attempt 0 on a long list: exact prefilter (see the kernel comment) ----
+  bool subset = false;
+  cnt = cnt_all;
+  if (attempt == 0 && cnt_all > kNmsPrefilter) {
+    unsigned prefix = 0u, prefix_mask = 0u;
+    bool done = false;
+    for (int shift = 24; shift >= 0 && !done; shift -= 8) {
+      s_hist[tid] = 0;  // kNmsThreads == 256 bins
+      if (tid == 0 && shift == 24) s_ctl[2] = 0u;
+      __syncthreads();
+      for (int i = tid; i < cnt_all; i += blockDim.x) {
+        const unsigned sc = (unsigned)(gkeys[i] >> 32);
+        if ((sc & prefix_mask) == prefix) atomicAdd(&s_hist[(sc >> shift) & 255u], 1);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        unsigned cum = s_ctl[2];
+        s_ctl[0] = 0u;
+        for (int bin = 255; bin >= 0; --bin) {
+          const unsigned h = (unsigned)s_hist[bin];
+          if (cum + h >= (unsigned)kNmsSelectMin) {
+            s_ctl[1] = prefix | ((unsigned)bin << shift);
+            if (cum + h <= (unsigned)kNmsSmemKeys) s_ctl[0] = 1u;  // threshold = low end of this bin
+            else s_ctl[2] = cum;                                    // refine inside this bin
+            break;
+          }
+          cum += h;
+        }
+      }
+      __syncthreads();
+      done = s_ctl[0] != 0u;
+      prefix = s_ctl[1];
+      prefix_mask |= 0xFFu << shift;
+    }
+    if (done) {  // (more than kNmsSmemKeys identical scores otherwise: full path)
+      const unsigned thr_bits = prefix;
+      if (tid == 0) s_ctl[3] = 0u;
+      __syncthreads();
+      for (int i = tid; i < cnt_all; i += blockDim.x) {
+        const unsigned long long k = gkeys[i];
+        if ((unsigned)(k >> 32) >= thr_bits) {
+          const unsigned slot = atomicAdd(&s_ctl[3], 1u);
+          sm.keys[slot] = k;
+          const int n = (int)(0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull));
+          Cell cell = locate(p, n);
+          sm.box[slot] = decode_box(p, cell, hb + (long long)n * kRow);
+        }
+      }
+      __syncthreads();
+      cnt = (int)s_ctl[3];
+      subset = true;
+    }
+  }
+  const bool in_smem = subset || cnt <= kNmsSmemKeys;
+  unsigned long long* keys = in_smem ? sm.keys : gkeys;
   // boxes of a list longer than the shared-memory window are decoded ONCE into a
   // slice of the global box pool (bump-allocated per launch); only if the pool is
   // exhausted are they re-decoded on the fly every round (correct, slower)
   const float4* pbox = nullptr;
-  if (in_smem) {
+  if (subset) {
+    // already staged
+  } else if (in_smem) {
     for (int i = tid; i < cnt; i += blockDim.x) {
       const unsigned long long k = gkeys[i];
       sm.keys[i] = k;
@@ -215,7 +286,7 @@ __global__ void __launch_bounds__(kNmsThreads)
   }
   __syncthreads();
 
-  int nsel = 0;
+  nsel = 0;
   while (nsel < MB && cnt > 0) {
     // (1) arg-max over alive keys: per-thread scan, 3 redux.sync per warp, then every
     //     thread folds the 8 warp partials itself (one barrier, no second shuffle tree)
@@ -295,6 +366,9 @@ __global__ void __launch_bounds__(kNmsThreads)
     __syncthreads();
   }
   __syncthreads();
+  // the subset ran dry before nms_max_boxes boxes were kept: redo on the full list
+  if (!(subset && nsel < MB && cnt < cnt_all)) break;
+  }  // attempt
   if (tid == 0) nsel_all[bc] = nsel;
 
   // class-major compaction by the last block of this image

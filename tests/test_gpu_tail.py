@@ -102,6 +102,33 @@ def test_tail_spill_path_more_than_smem_candidates(built):
         del mg.CASES["_spill"]
 
 
+def test_tail_prefilter_falls_back_when_subset_runs_dry(built):
+    """Long lists run NMS on the top-scoring subset first (exact when nms_max_boxes boxes are kept inside
+    it).  Here the ~700 best candidates of class 0 are huge, mutually suppressing boxes, so the subset
+    yields one box and the kernel must redo the class on the full list."""
+    from golden import make_golden as mg
+    from odt_b200.engine import RowsHarness
+    name = "tail_yolo"
+    case = dict(mg.CASES[name], levels=[(48, 48, 3)], score_thr=0.0, max_boxes=25, iou_thr=0.6)
+    mg.CASES["_dry"] = case
+    try:
+        rows = mg.make_rows("_dry", batch=2, seed=9)
+        rng = np.random.default_rng(4)
+        idx = rng.choice(rows.shape[1], 700, replace=False)
+        for b in range(2):
+            rows[b, idx, 0] = np.linspace(4.0, 8.0, 700, dtype=np.float32)[rng.permutation(700)]
+            rows[b, idx, 24] = 8.0            # objectness
+            rows[b, idx, 22:24] = 7.0         # exp(7) grid units high and wide: IoU among them > 0.8
+        h = RowsHarness(_tail_for(name, case), case["levels"], rows)
+        res, keep = h.run(), h.keep_indices()
+        for b in range(2):
+            exp = mg.run_case("_dry", rows, image=b)
+            assert (exp[2] == 0).sum() == 25   # the oracle does reach max_boxes for class 0
+            _check(res[b], keep[b], exp)
+    finally:
+        del mg.CASES["_dry"]
+
+
 def test_tail_overflow_is_reported(built):
     from golden import make_golden as mg
     from odt_b200 import lib
