@@ -129,7 +129,7 @@ __device__ __forceinline__ float iou_tf(const float4& a, const float4& b) {
 }
 
 constexpr int kNmsThreads = 256;
-constexpr int kNmsSmemKeys = 4096;  // per-class candidate lists kept (with boxes) in shared memory
+constexpr int kNmsSmemKeys = 1024;  // candidates (keys + boxes, 24 KB) a CTA works on in shared memory: 8 CTAs / SM
 
 struct NmsSmem {
   unsigned long long keys[kNmsSmemKeys];
@@ -154,8 +154,8 @@ struct NmsSmem {
 // exact global one (every kept box and every candidate that could have suppressed or
 // preceded it has score >= T and therefore is in S).  Only if S runs dry first is the full
 // list processed (correct, slower).
-constexpr int kNmsPrefilter = 1024;
-constexpr int kNmsSelectMin = 512;
+constexpr int kNmsPrefilter = kNmsSmemKeys;  // longer lists: prefilter first
+constexpr int kNmsSelectMin = 384;
 
 __global__ void __launch_bounds__(kNmsThreads)
     nms_per_class_kernel(const float* __restrict__ head, const __grid_constant__ TailP tp, int B,

@@ -698,7 +698,7 @@ class Tail:
         self.kind, self.num_fg, self.nms_classes = kind, num_fg, nms_classes
         self.score_thr, self.iou_thr, self.max_boxes = score_thr, iou_thr, max_boxes
         self.level_fn, self.cap = level_fn, cap
-        self.pool_cap = 8 << 20  # box-pool entries (16 B each) for > 4096-candidate lists
+        self.pool_cap = 8 << 20  # box-pool entries (16 B each) for lists beyond the shared-memory window
 
     def prepare(self, net):
         dev = net.device
@@ -728,7 +728,7 @@ class Tail:
         self.status = torch.zeros((1,), dtype=torch.int32, device=dev)
         # box cache for candidate lists longer than the NMS shared-memory window
         total = B * self.nms_classes * p.cap
-        self.pool_entries = 0 if p.cap <= 4096 else min(total, self.pool_cap)
+        self.pool_entries = 0 if p.cap <= 1024 else min(total, self.pool_cap)
         self.box_pool = (torch.empty((self.pool_entries, 4), dtype=torch.float32, device=dev)
                          if self.pool_entries else None)
 
