@@ -1,8 +1,8 @@
 // tcgen05 stem convolution (Cin = 3): the first layer of every backbone.
 //
 // K = KS*KS*3 is far below one TMA/UMMA channel chunk, so instead of im2col TMA
-// the A operand is BUILT in shared memory: 4 producer warps (one thread per
-// output pixel of the 128-row tile) gather the KS*KS*3 fp32 pixels, subtract the
+// the A operand is BUILT in shared memory: two groups of 4 producer warps (one thread per
+// output pixel of a 128-row tile, the groups take alternate tiles) gather the KS*KS*3 fp32 pixels, subtract the
 // RGB mean, convert to fp16 and store 16-byte chunks straight into the
 // 128B-swizzled K-major layout the UMMA descriptor expects (chunk c of row m at
 // ((c ^ (m & 7)) << 4)); a fence.proxy.async + mbarrier arrive hands the stage to
@@ -22,11 +22,13 @@ struct StemGeom {
   long long M;
   int num_tiles;
   int out_halo;    // output stored as [B][OH+2][OW+2][ld]
+  int vec2_ok;     // 7x7/2: filter rows start 8-byte aligned (even W, even left pad, aligned image base)
   float mean[3];
 };
 
 constexpr int ST_STAGES = 4;
-constexpr int ST_PROD_WARPS = 4, ST_EPI_WARPS = 4;
+constexpr int ST_PROD_GROUPS = 2;                    // producer groups of 4 warps, round-robin over the CTA's tiles
+constexpr int ST_PROD_WARPS = 4 * ST_PROD_GROUPS, ST_EPI_WARPS = 4;
 constexpr int ST_THREADS = 32 * (ST_PROD_WARPS + 1 + ST_EPI_WARPS);
 constexpr int ST_PITCH = 144;                  // staging row pitch (bytes)
 constexpr int ST_WARP_STAGE = 32 * ST_PITCH;   // staging bytes per epilogue warp
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(ST_THREADS)
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < ST_STAGES; ++s) {
-      mbar_init(full_bar(s), ST_PROD_WARPS * 32);
+      mbar_init(full_bar(s), 128);  // one producer group (one thread per tile row)
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -111,10 +113,14 @@ __global__ void __launch_bounds__(ST_THREADS)
 
   if (warp < ST_PROD_WARPS) {
     // ===================== A-tile producers ====================================
-    const int t = threadIdx.x;  // row of the tile
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+    const int t = threadIdx.x & 127;  // row of the tile
+    const int pgroup = threadIdx.x >> 7;
+    // group i builds the CTA's tiles i, i + G, i + 2G, ...: G gathers in flight per CTA
+    int local = pgroup;
+    for (int tile = blockIdx.x + pgroup * gridDim.x; tile < g.num_tiles;
+         tile += ST_PROD_GROUPS * gridDim.x, local += ST_PROD_GROUPS) {
+      const int stage = local % ST_STAGES;
+      const uint32_t phase = (uint32_t)(local / ST_STAGES) & 1u;
       const long long m = (long long)tile * 128 + t;
       const bool ok = m < g.M;
       int b = 0, oy = 0, ox = 0;
@@ -141,7 +147,44 @@ __global__ void __launch_bounds__(ST_THREADS)
         for (int r = 0; r < KS; ++r) prow[r] = p0 + r * rs;
       }
       const float mean0 = g.mean[0], mean1 = g.mean[1], mean2 = g.mean[2];
-      if (interior) {
+      if (KS == 7 && STRIDE == 2 && interior && g.vec2_ok) {
+        // 7x7 / stride 2: the 21 floats of one filter row are contiguous and 8-byte aligned
+        // (even W, even left pad): 10 LDG.64 + 1 LDG.32 per row instead of 21 scalar loads
+        // (the 24-byte lane stride costs ~7 L1 wavefronts per load instruction either way)
+        constexpr int RW = KS * 3;
+        float v[NCHUNK * 8];
+#pragma unroll
+        for (int k = KREAL; k < NCHUNK * 8; ++k) v[k] = 0.f;
+#pragma unroll
+        for (int r = 0; r < KS; ++r) {
+          const float2* p2 = reinterpret_cast<const float2*>(prow[r]);
+#pragma unroll
+          for (int j = 0; j < RW / 2; ++j) {
+            const float2 t2 = __ldg(p2 + j);
+            const int c0 = (2 * j) % 3, c1 = (2 * j + 1) % 3;
+            v[RW * r + 2 * j] = __fsub_rn(t2.x, c0 == 0 ? mean0 : (c0 == 1 ? mean1 : mean2));
+            v[RW * r + 2 * j + 1] = __fsub_rn(t2.y, c1 == 0 ? mean0 : (c1 == 1 ? mean1 : mean2));
+          }
+          if (RW & 1) {
+            const int cl = (RW - 1) % 3;
+            v[RW * r + RW - 1] = __fsub_rn(__ldg(prow[r] + RW - 1), cl == 0 ? mean0 : (cl == 1 ? mean1 : mean2));
+          }
+          // store every 16-byte chunk completed by this row (the last row also flushes the zero-padded tail)
+#pragma unroll
+          for (int c = 0; c < NCHUNK; ++c) {
+            const bool ready = (8 * c + 7 < RW * (r + 1)) || (r == KS - 1);
+            const bool before = (r > 0) && (8 * c + 7 < RW * r);
+            if (ready && !before) {
+              uint4 pk;
+              __half2* h = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) h[q] = __floats2half2_rn(v[8 * c + 2 * q], v[8 * c + 2 * q + 1]);
+              const int blk = c >> 3, cc = c & 7;
+              *reinterpret_cast<uint4*>(arow + blk * (128 * 128) + ((cc ^ (t & 7)) << 4)) = pk;
+            }
+          }
+        }
+      } else if (interior) {
 #pragma unroll
         for (int c = 0; c < NCHUNK; ++c) {
           float v[8];
@@ -191,10 +234,6 @@ __global__ void __launch_bounds__(ST_THREADS)
       }
       fence_proxy_async_smem();
       mbar_arrive(full_bar(stage));
-      if (++stage == ST_STAGES) {
-        stage = 0;
-        phase ^= 1u;
-      }
     }
   } else if (warp == ST_PROD_WARPS) {
     // ===================== MMA issuer ==========================================
@@ -350,6 +389,7 @@ int odt_conv2d_stem_tc_try(const float* images, const float* mean3_host, const v
   g.M = (long long)p->B * p->OH * p->OW;
   g.num_tiles = (int)((g.M + 127) / 128);
   g.out_halo = p->out0_halo ? 1 : 0;
+  g.vec2_ok = ((p->W & 1) == 0 && (p->pad_l & 1) == 0 && ((uintptr_t)images & 7) == 0) ? 1 : 0;
   g.mean[0] = mean3_host[0]; g.mean[1] = mean3_host[1]; g.mean[2] = mean3_host[2];
   Epi e = make_epi(*p);
   cudaStream_t st = (cudaStream_t)stream;
