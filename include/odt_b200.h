@@ -49,6 +49,10 @@ extern "C" {
 
 /* ---------------------------------------------------------------- misc --- */
 int odt_abi_version(void);
+/* host utility: CRC-32C of a host buffer continuing from `crc` (0 = fresh).  Used by the
+ * tf.train.Saver V2 (TensorBundle) reader / writer that replaces NewCheckpointReader /
+ * Saver.save / Saver.restore (SSD300.py:31,490-504; RetinaNet.py:505-557; YOLOv3.py:376-385). */
+unsigned int odt_crc32c(unsigned int crc, const void* data, unsigned long long n);
 const char* odt_last_error(void);
 /* TF "SAME" geometry: out = ceil(in/stride); pad_before = pad_total/2.
  * ref: every tf.layers.conv2d/max_pooling2d(padding='same'), e.g. SSD300.py:524,540 */

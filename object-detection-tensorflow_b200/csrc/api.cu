@@ -43,7 +43,39 @@ bool wres_enabled() {
 }
 }  // namespace odt
 
-extern "C" int odt_abi_version(void) { return 1; }
+extern "C" int odt_abi_version(void) { return 2; }
+
+// CRC-32C (Castagnoli, reflected 0x82F63B78) of a host buffer, continuing from `crc`
+// (0 for a fresh sum): the checksum of TensorBundle index blocks and tensor payloads
+// (tf.train.Saver V2 files read / written by odt_b200/tf_checkpoint.py).  Host-only utility.
+extern "C" unsigned int odt_crc32c(unsigned int crc, const void* data, unsigned long long n) {
+  static unsigned int table[8][256];
+  static bool init = false;
+  if (!init) {
+    for (unsigned int i = 0; i < 256; ++i) {
+      unsigned int c = i;
+      for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ 0x82F63B78u : (c >> 1);
+      table[0][i] = c;
+    }
+    for (unsigned int i = 0; i < 256; ++i)
+      for (int t = 1; t < 8; ++t) table[t][i] = (table[t - 1][i] >> 8) ^ table[0][table[t - 1][i] & 0xFFu];
+    init = true;
+  }
+  const unsigned char* p = static_cast<const unsigned char*>(data);
+  unsigned int c = ~crc;
+  while (n >= 8) {
+    unsigned int lo, hi;
+    memcpy(&lo, p, 4);
+    memcpy(&hi, p + 4, 4);
+    lo ^= c;
+    c = table[7][lo & 0xFFu] ^ table[6][(lo >> 8) & 0xFFu] ^ table[5][(lo >> 16) & 0xFFu] ^ table[4][lo >> 24] ^
+        table[3][hi & 0xFFu] ^ table[2][(hi >> 8) & 0xFFu] ^ table[1][(hi >> 16) & 0xFFu] ^ table[0][hi >> 24];
+    p += 8;
+    n -= 8;
+  }
+  while (n--) c = table[0][(c ^ *p++) & 0xFFu] ^ (c >> 8);
+  return ~c;
+}
 extern "C" const char* odt_last_error(void) { return odt::g_err; }
 
 // TF SAME padding: out = ceil(in/stride),

@@ -16,8 +16,16 @@ import sys
 import numpy as np
 import torch
 
-from . import nets
+from . import nets, tf_checkpoint
 from .engine import init_weights
+
+# VGG-16 classification checkpoint scope -> (kernel variable, bias variable) as the reference
+# names them, typos included (SSD300.py:195-301: 'kenrel_conv2_1', 'bias_conv_3_1')
+VGG16_CKPT_NAMES = {
+    "conv%d/conv%d_%d" % (blk, blk, i): ("feature_extractor/" + kv, "feature_extractor/" + bv)
+    for (blk, i, kv, bv) in [
+        (int(e[0][4]), int(e[0][6]), e[1], e[2]) for e in nets._VGG if isinstance(e, tuple)]
+}
 
 
 def _as_host_tensor(images):
@@ -101,10 +109,38 @@ class _Detector:
         path = self.config.get("pretraining_weight")
         if path and os.path.exists(path) and path.endswith(".npz"):
             self._load_npz_into(w, path)
+        elif path and tf_checkpoint.is_v2_checkpoint(path):
+            self._load_bundle_into(w, path)
         elif path:
-            sys.stderr.write("[odt_b200] pretraining weight %r not readable here (TF checkpoint "
-                             "reader is a follow-on); using seeded random init\n" % (path,))
+            # the reference throws inside NewCheckpointReader (SSD300.py:31); BASELINE config 1
+            # asks for random-init VGG-16, so a missing file falls back to the seeded init
+            sys.stderr.write("[odt_b200] pretraining weight %r not found as a TF V2 bundle or .npz; "
+                             "using seeded random init\n" % (path,))
         return w
+
+    @staticmethod
+    def _load_bundle_into(w, prefix):
+        """Variables by their own names (checkpoints written by save_weight / the reference's
+        Saver), plus the VGG-16 classification names the SSD constructors read
+        (`vgg_16/convN/convN_M/{weights,biases}`, SSD300.py:195-301)."""
+        r = tf_checkpoint.CheckpointReader(prefix)
+        n = 0
+        for k in w:
+            if r.has_tensor(k):
+                t = r.get_tensor(k)
+                assert tuple(t.shape) == tuple(w[k].shape), (k, t.shape, w[k].shape)
+                w[k] = t.astype(np.float32)
+                n += 1
+        for ck_name, (kvar, bvar) in VGG16_CKPT_NAMES.items():
+            for src, dst in (("vgg_16/%s/weights" % ck_name, kvar), ("vgg_16/%s/biases" % ck_name, bvar)):
+                if dst in w and r.has_tensor(src):
+                    t = r.get_tensor(src)
+                    assert tuple(t.shape) == tuple(w[dst].shape), (src, t.shape, w[dst].shape)
+                    w[dst] = t.astype(np.float32)
+                    n += 1
+        if n == 0:
+            raise tf_checkpoint.CheckpointError("%s holds none of this model's variables" % prefix)
+        return n
 
     @staticmethod
     def _load_npz_into(w, path):
@@ -207,16 +243,24 @@ class _Detector:
         if d and not os.path.exists(d):
             os.makedirs(d)
             print(d, "does not exist, create it done")
-        out = "%s-%d.npz" % (path, self.global_step)
-        np.savez(out, **self.get_weights())
+        # `saver.save(sess, path, global_step=...)` (SSD300.py:499): a V2 bundle `<path>-<step>`
+        out = "%s-%d" % (path, self.global_step)
+        tensors = dict(self.get_weights())
+        tensors["global_step"] = np.asarray(self.global_step, np.int64)
+        tf_checkpoint.write_checkpoint(out, tensors)
         print("save", mode, "model in", out, "successfully")
         return out
 
     def load_weight(self, path):
-        if not path.endswith(".npz"):
-            path = path + ".npz"
+        """`saver.restore(sess, path)` (SSD300.py:503): a TF V2 bundle prefix (or an .npz)."""
         w = dict(self.get_weights())
-        self._load_npz_into(w, path)
+        if path.endswith(".npz"):
+            self._load_npz_into(w, path)
+        else:
+            self._load_bundle_into(w, path)
+            r = tf_checkpoint.CheckpointReader(path)
+            if r.has_tensor("global_step"):
+                self.global_step = int(r.get_tensor("global_step"))
         self.set_weights(w)
         print("load weight", path, "successfully")
 

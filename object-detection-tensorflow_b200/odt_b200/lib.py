@@ -61,6 +61,7 @@ class TailParams(C.Structure):
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 SYMBOLS = {
     "odt_abi_version": (_I, []),
+    "odt_crc32c": (C.c_uint, [C.c_uint, _P, C.c_ulonglong]),
     "odt_last_error": (C.c_char_p, []),
     "odt_same_pad": (_I, [_I, _I, _I, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "odt_normalize_input": (_I, [_P, _P, _I, _I, _I, _I, _I, C.POINTER(_F), _P]),

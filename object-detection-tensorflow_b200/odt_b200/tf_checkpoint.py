@@ -1,0 +1,473 @@
+"""Reader / writer for TensorFlow V2 checkpoints (TensorBundle: `<prefix>.index` +
+`<prefix>.data-SSSSS-of-NNNNN`), the format `tf.train.Saver().save / .restore` and
+`NewCheckpointReader` use in the reference (SSD300.py:31,195-301,490-504;
+RetinaNet.py:505-557; YOLOv3.py:376-385; FCOS.py:384-436).  No TensorFlow needed.
+
+Format restated from the public definitions (nothing copied):
+* `.index` is an SSTable in the LevelDB table format: data blocks of prefix-compressed
+  (shared, non_shared, value_len varint32 + key suffix + value) entries with a restart
+  array, each followed by a 5-byte trailer (compression type, masked CRC-32C of block +
+  type); a metaindex block, an index block (last key of a data block -> BlockHandle) and a
+  48-byte footer (two BlockHandles, padding, magic 0xdb4775248b80fb57).
+* key "" holds a BundleHeaderProto {1: num_shards, 2: endianness, 3: version{1: producer}};
+  every other key is a tensor name with a BundleEntryProto {1: dtype, 2: shape{2: dim{1:
+  size}}, 3: shard_id, 4: offset, 5: size, 6: fixed32 masked crc32c of the bytes}.
+* tensor bytes are raw little-endian, row-major, at [offset, offset+size) of the shard.
+
+PARITY UNPINNED: no TensorFlow and no TF-written checkpoint exists in this environment; the
+reader is exercised against this module's own writer plus hand-assembled blocks
+(tests/test_checkpoint.py).  V1 checkpoints (one SSTable of SavedTensorSlices protos, e.g.
+the 2016 slim `vgg_16.ckpt`) are detected and rejected with a clear message.
+"""
+import os
+import struct
+
+import numpy as np
+
+TABLE_MAGIC = 0xDB4775248B80FB57
+_MASK_DELTA = 0xA282EAD8
+
+# tensorflow DataType enum <-> numpy
+_DTYPES = {1: np.float32, 2: np.float64, 3: np.int32, 4: np.uint8, 5: np.int16, 6: np.int8, 9: np.int64,
+           10: np.bool_, 17: np.uint16, 19: np.float16, 22: np.uint32, 23: np.uint64}
+_DTYPE_OF = {np.dtype(v): k for k, v in _DTYPES.items()}
+
+
+class CheckpointError(RuntimeError):
+    pass
+
+
+# ------------------------------------------------------------------ crc32c ---
+_crc_table = None
+_crc_native = None
+
+
+def crc32c(data, crc=0):
+    """CRC-32C (Castagnoli).  Uses the C-ABI helper of libodt_b200.so when it is built,
+    a table-driven Python loop otherwise (index blocks are small)."""
+    global _crc_table, _crc_native
+    if _crc_native is None:
+        try:
+            from . import lib as L
+            fn = L.load().odt_crc32c
+            _crc_native = fn
+        except Exception:  # library not built: host-only fallback
+            _crc_native = False
+    mv = data if isinstance(data, bytes) else bytes(data)
+    if _crc_native:
+        return int(_crc_native(crc, mv, len(mv)))
+    if _crc_table is None:
+        t = []
+        for i in range(256):
+            c = i
+            for _ in range(8):
+                c = (c >> 1) ^ 0x82F63B78 if c & 1 else c >> 1
+            t.append(c)
+        _crc_table = t
+    c = crc ^ 0xFFFFFFFF
+    for b in bytes(mv):
+        c = _crc_table[(c ^ b) & 0xFF] ^ (c >> 8)
+    return c ^ 0xFFFFFFFF
+
+
+def mask_crc(c):
+    return (((c >> 15) | (c << 17)) + _MASK_DELTA) & 0xFFFFFFFF
+
+
+# ----------------------------------------------------------------- varints ---
+def _put_varint(out, v):
+    v &= (1 << 64) - 1
+    while v >= 0x80:
+        out.append((v & 0x7F) | 0x80)
+        v >>= 7
+    out.append(v)
+
+
+def _get_varint(buf, pos):
+    shift, v = 0, 0
+    while True:
+        if pos >= len(buf):
+            raise CheckpointError("truncated varint")
+        b = buf[pos]
+        pos += 1
+        v |= (b & 0x7F) << shift
+        if b < 0x80:
+            return v, pos
+        shift += 7
+        if shift > 63:
+            raise CheckpointError("varint too long")
+
+
+# ---------------------------------------------------------------- protobuf ---
+def _pb_fields(buf):
+    """Yield (field number, wire type, value) of one message; value = int or bytes."""
+    pos, n = 0, len(buf)
+    while pos < n:
+        tag, pos = _get_varint(buf, pos)
+        f, wt = tag >> 3, tag & 7
+        if wt == 0:
+            v, pos = _get_varint(buf, pos)
+        elif wt == 1:
+            v = struct.unpack_from("<Q", buf, pos)[0]
+            pos += 8
+        elif wt == 2:
+            ln, pos = _get_varint(buf, pos)
+            v = bytes(buf[pos:pos + ln])
+            pos += ln
+        elif wt == 5:
+            v = struct.unpack_from("<I", buf, pos)[0]
+            pos += 4
+        else:
+            raise CheckpointError("unsupported protobuf wire type %d" % wt)
+        yield f, wt, v
+
+
+def _pb_varint(out, field, v):
+    _put_varint(out, (field << 3) | 0)
+    _put_varint(out, v)
+
+
+def _pb_bytes(out, field, b):
+    _put_varint(out, (field << 3) | 2)
+    _put_varint(out, len(b))
+    out.extend(b)
+
+
+def _signed64(v):
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
+def _parse_shape(buf):
+    dims = []
+    for f, _, v in _pb_fields(buf):
+        if f == 2:  # Dim
+            size = 0
+            for f2, _, v2 in _pb_fields(v):
+                if f2 == 1:
+                    size = _signed64(v2)
+            dims.append(size)
+    return tuple(dims)
+
+
+def _parse_entry(buf):
+    e = {"dtype": 0, "shape": (), "shard_id": 0, "offset": 0, "size": 0, "crc32c": None, "sliced": False}
+    for f, _, v in _pb_fields(buf):
+        if f == 1:
+            e["dtype"] = v
+        elif f == 2:
+            e["shape"] = _parse_shape(v)
+        elif f == 3:
+            e["shard_id"] = v
+        elif f == 4:
+            e["offset"] = v
+        elif f == 5:
+            e["size"] = v
+        elif f == 6:
+            e["crc32c"] = v
+        elif f == 7:
+            e["sliced"] = True
+    return e
+
+
+def _encode_entry(dtype, shape, shard_id, offset, size, crc):
+    out = bytearray()
+    _pb_varint(out, 1, dtype)
+    sh = bytearray()
+    for d in shape:
+        dim = bytearray()
+        _pb_varint(dim, 1, int(d))
+        _pb_bytes(sh, 2, dim)
+    _pb_bytes(out, 2, sh)
+    if shard_id:
+        _pb_varint(out, 3, shard_id)
+    if offset:
+        _pb_varint(out, 4, offset)
+    _pb_varint(out, 5, size)
+    _put_varint(out, (6 << 3) | 5)
+    out.extend(struct.pack("<I", crc))
+    return bytes(out)
+
+
+def _encode_header(num_shards):
+    out = bytearray()
+    _pb_varint(out, 1, num_shards)
+    # endianness LITTLE = 0 is the default and omitted; version {producer: 1}
+    ver = bytearray()
+    _pb_varint(ver, 1, 1)
+    _pb_bytes(out, 3, ver)
+    return bytes(out)
+
+
+# ------------------------------------------------------------------ snappy ---
+def _snappy_decompress(buf):
+    """Raw snappy block format (index blocks written with compression enabled)."""
+    n, pos = _get_varint(buf, 0)
+    out = bytearray()
+    while pos < len(buf):
+        tag = buf[pos]
+        pos += 1
+        kind = tag & 3
+        if kind == 0:
+            ln = tag >> 2
+            if ln >= 60:
+                nb = ln - 59
+                ln = int.from_bytes(buf[pos:pos + nb], "little")
+                pos += nb
+            ln += 1
+            out.extend(buf[pos:pos + ln])
+            pos += ln
+            continue
+        if kind == 1:
+            ln = ((tag >> 2) & 7) + 4
+            off = ((tag >> 5) << 8) | buf[pos]
+            pos += 1
+        elif kind == 2:
+            ln = (tag >> 2) + 1
+            off = buf[pos] | (buf[pos + 1] << 8)
+            pos += 2
+        else:
+            ln = (tag >> 2) + 1
+            off = int.from_bytes(buf[pos:pos + 4], "little")
+            pos += 4
+        if off == 0 or off > len(out):
+            raise CheckpointError("corrupt snappy block")
+        for _ in range(ln):  # may overlap
+            out.append(out[-off])
+    if len(out) != n:
+        raise CheckpointError("snappy length mismatch")
+    return bytes(out)
+
+
+# ------------------------------------------------------------------- table ---
+def _read_block(f, offset, size, verify=True):
+    f.seek(offset)
+    raw = f.read(size + 5)
+    if len(raw) != size + 5:
+        raise CheckpointError("truncated table block")
+    body, ctype = raw[:size], raw[size]
+    stored = struct.unpack_from("<I", raw, size + 1)[0]
+    if verify and mask_crc(crc32c(raw[:size + 1])) != stored:
+        raise CheckpointError("table block checksum mismatch at offset %d" % offset)
+    if ctype == 0:
+        return body
+    if ctype == 1:
+        return _snappy_decompress(body)
+    raise CheckpointError("unknown block compression %d" % ctype)
+
+
+def _block_entries(block):
+    if len(block) < 4:
+        raise CheckpointError("bad block")
+    num_restarts = struct.unpack_from("<I", block, len(block) - 4)[0]
+    limit = len(block) - 4 - 4 * num_restarts
+    if limit < 0:
+        raise CheckpointError("bad restart array")
+    pos, key = 0, b""
+    while pos < limit:
+        shared, pos = _get_varint(block, pos)
+        non_shared, pos = _get_varint(block, pos)
+        vlen, pos = _get_varint(block, pos)
+        key = key[:shared] + bytes(block[pos:pos + non_shared])
+        pos += non_shared
+        yield key, bytes(block[pos:pos + vlen])
+        pos += vlen
+
+
+def _read_table(path, verify=True):
+    """All (key, value) pairs of an SSTable file, in key order."""
+    with open(path, "rb") as f:
+        f.seek(0, os.SEEK_END)
+        size = f.tell()
+        if size < 48:
+            raise CheckpointError("%s: too short for a table" % path)
+        f.seek(size - 48)
+        footer = f.read(48)
+        if struct.unpack_from("<Q", footer, 40)[0] != TABLE_MAGIC:
+            raise CheckpointError("%s: not an SSTable (bad magic)" % path)
+        pos = 0
+        _, pos = _get_varint(footer, pos)       # metaindex handle
+        _, pos = _get_varint(footer, pos)
+        ioff, pos = _get_varint(footer, pos)    # index handle
+        isz, pos = _get_varint(footer, pos)
+        out = []
+        for _, handle in _block_entries(_read_block(f, ioff, isz, verify)):
+            boff, p2 = _get_varint(handle, 0)
+            bsz, _ = _get_varint(handle, p2)
+            out.extend(_block_entries(_read_block(f, boff, bsz, verify)))
+    return out
+
+
+class _BlockBuilder:
+    def __init__(self, restart_interval=16):
+        self.buf, self.restarts, self.count, self.last = bytearray(), [0], 0, b""
+        self.interval = restart_interval
+
+    def add(self, key, value):
+        shared = 0
+        if self.count % self.interval == 0 and self.count:
+            self.restarts.append(len(self.buf))
+        elif self.count:
+            m = min(len(key), len(self.last))
+            while shared < m and key[shared] == self.last[shared]:
+                shared += 1
+        _put_varint(self.buf, shared)
+        _put_varint(self.buf, len(key) - shared)
+        _put_varint(self.buf, len(value))
+        self.buf.extend(key[shared:])
+        self.buf.extend(value)
+        self.last = key
+        self.count += 1
+
+    def finish(self):
+        out = bytearray(self.buf)
+        for r in self.restarts:
+            out.extend(struct.pack("<I", r))
+        out.extend(struct.pack("<I", len(self.restarts)))
+        return bytes(out)
+
+
+def _write_table(path, items, block_size=4096):
+    """items: list of (key bytes, value bytes) sorted by key."""
+    with open(path, "wb") as f:
+        index = _BlockBuilder(restart_interval=1)
+
+        def emit(block):
+            off = f.tell()
+            f.write(block)
+            f.write(b"\x00")
+            f.write(struct.pack("<I", mask_crc(crc32c(block + b"\x00"))))
+            return off, len(block)
+
+        def handle(off, size):
+            h = bytearray()
+            _put_varint(h, off)
+            _put_varint(h, size)
+            return bytes(h)
+
+        bb = _BlockBuilder()
+        for key, value in items:
+            bb.add(key, value)
+            if len(bb.buf) >= block_size:
+                off, size = emit(bb.finish())
+                index.add(bb.last, handle(off, size))
+                bb = _BlockBuilder()
+        if bb.count:
+            off, size = emit(bb.finish())
+            index.add(bb.last, handle(off, size))
+        moff, msize = emit(_BlockBuilder().finish())   # empty metaindex
+        ioff, isize = emit(index.finish())
+        footer = bytearray(handle(moff, msize) + handle(ioff, isize))
+        footer.extend(b"\x00" * (40 - len(footer)))
+        footer.extend(struct.pack("<Q", TABLE_MAGIC))
+        f.write(footer)
+
+
+# ------------------------------------------------------------------ public ---
+def is_v2_checkpoint(prefix):
+    return os.path.exists(prefix + ".index")
+
+
+def _shard_path(prefix, shard, num):
+    return "%s.data-%05d-of-%05d" % (prefix, shard, num)
+
+
+class CheckpointReader:
+    """`tf.train.NewCheckpointReader(prefix)` for V2 bundles: has_tensor / get_tensor /
+    get_variable_to_shape_map (SSD300.py:31,195-301 call sites)."""
+
+    def __init__(self, prefix, verify_index=True):
+        self.prefix = prefix
+        if not os.path.exists(prefix + ".index"):
+            if os.path.isfile(prefix):
+                with open(prefix, "rb") as f:
+                    f.seek(0, os.SEEK_END)
+                    n = f.tell()
+                    magic = 0
+                    if n >= 48:
+                        f.seek(n - 8)
+                        magic = struct.unpack("<Q", f.read(8))[0]
+                if magic == TABLE_MAGIC:
+                    raise CheckpointError(
+                        "%s is a V1 checkpoint (SavedTensorSlices table); only V2 bundles "
+                        "(<prefix>.index + .data-*) are supported -- re-save it with "
+                        "tf.train.Saver(write_version=V2)" % prefix)
+            raise CheckpointError("no checkpoint at %r (expected %s.index)" % (prefix, prefix))
+        self.entries, self.num_shards = {}, 1
+        for key, value in _read_table(prefix + ".index", verify_index):
+            if key == b"":
+                for f, _, v in _pb_fields(value):
+                    if f == 1:
+                        self.num_shards = v
+                    elif f == 2 and v != 0:
+                        raise CheckpointError("big-endian bundles are not supported")
+            else:
+                self.entries[key.decode("utf-8")] = _parse_entry(value)
+
+    def has_tensor(self, name):
+        return name in self.entries
+
+    def get_variable_to_shape_map(self):
+        return {k: list(e["shape"]) for k, e in self.entries.items()}
+
+    def get_tensor(self, name, verify=False):
+        e = self.entries.get(name)
+        if e is None:
+            raise CheckpointError("tensor %r not found in %s" % (name, self.prefix))
+        if e["sliced"]:
+            raise CheckpointError("partitioned variable %r is not supported" % name)
+        if e["dtype"] not in _DTYPES:
+            raise CheckpointError("dtype %d of %r is not supported" % (e["dtype"], name))
+        dt = np.dtype(_DTYPES[e["dtype"]])
+        count = int(np.prod(e["shape"])) if e["shape"] else 1
+        if count * dt.itemsize != e["size"]:
+            raise CheckpointError("size of %r does not match its shape" % name)
+        with open(_shard_path(self.prefix, e["shard_id"], self.num_shards), "rb") as f:
+            f.seek(e["offset"])
+            raw = f.read(e["size"])
+        if len(raw) != e["size"]:
+            raise CheckpointError("truncated data shard for %r" % name)
+        if verify and e["crc32c"] is not None and mask_crc(crc32c(raw)) != e["crc32c"]:
+            raise CheckpointError("payload checksum mismatch for %r" % name)
+        return np.frombuffer(raw, dtype=dt.newbyteorder("<")).astype(dt).reshape(e["shape"])
+
+
+def read_checkpoint(prefix, verify=False):
+    r = CheckpointReader(prefix)
+    return {k: r.get_tensor(k, verify) for k in r.entries}
+
+
+def write_checkpoint(prefix, tensors):
+    """Write {name: array} as a one-shard V2 bundle + update the `checkpoint` state file
+    the way `Saver.save` does (SSD300.py:499)."""
+    d = os.path.dirname(prefix)
+    if d:
+        os.makedirs(d, exist_ok=True)
+    items = [(b"", _encode_header(1))]
+    offset = 0
+    with open(_shard_path(prefix, 0, 1), "wb") as f:
+        for name in sorted(tensors, key=lambda s: s.encode("utf-8")):
+            a = np.asarray(tensors[name], order="C")  # (ascontiguousarray would turn scalars into shape (1,))
+            if a.dtype not in _DTYPE_OF:
+                raise CheckpointError("dtype %s of %r cannot be stored" % (a.dtype, name))
+            raw = a.astype(a.dtype.newbyteorder("<")).tobytes()
+            f.write(raw)
+            items.append((name.encode("utf-8"),
+                          _encode_entry(_DTYPE_OF[a.dtype], a.shape, 0, offset, len(raw), mask_crc(crc32c(raw)))))
+            offset += len(raw)
+    _write_table(prefix + ".index", items)
+    base = os.path.basename(prefix)
+    with open(os.path.join(d or ".", "checkpoint"), "w") as f:
+        f.write('model_checkpoint_path: "%s"\nall_model_checkpoint_paths: "%s"\n' % (base, base))
+    return prefix
+
+
+def latest_checkpoint(directory):
+    """tf.train.latest_checkpoint: the prefix named by the `checkpoint` state file."""
+    p = os.path.join(directory, "checkpoint")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        for ln in f:
+            if ln.startswith("model_checkpoint_path:"):
+                return os.path.join(directory, ln.split(":", 1)[1].strip().strip('"'))
+    return None

@@ -1,0 +1,159 @@
+"""TF V2 checkpoint (TensorBundle) reader / writer: SURVEY §8(f) row 1.  CPU only.
+PARITY UNPINNED (no TensorFlow, no TF-written checkpoint here): round trips through the
+module's own writer, hand-assembled table blocks, and published known answers of the
+building blocks (CRC-32C test vector, LevelDB crc mask, snappy literal/copy decoding)."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from helpers import model_cfg
+
+
+@pytest.fixture()
+def ck():
+    from odt_b200 import tf_checkpoint
+    return tf_checkpoint
+
+
+def test_crc32c_known_answers(ck):
+    assert ck.crc32c(b"123456789") == 0xE3069283            # the standard check value
+    assert ck.crc32c(b"") == 0
+    assert ck.crc32c(bytes(32)) == 0x8A9136AA               # RFC 3720 B.4: 32 zero bytes
+    assert ck.crc32c(bytes([0xFF] * 32)) == 0x62A8AB43      # RFC 3720 B.4: 32 x 0xFF
+    assert ck.crc32c(b"6789", ck.crc32c(b"12345")) == 0xE3069283   # continuation
+    c = 0x8A9136AA
+    assert ck.mask_crc(c) == (((c >> 15) | (c << 17)) + 0xA282EAD8) & 0xFFFFFFFF
+
+
+def test_python_crc_fallback_matches_native(ck, monkeypatch):
+    data = np.random.default_rng(0).integers(0, 256, 4099, dtype=np.uint8).tobytes()
+    native = ck.crc32c(data)
+    monkeypatch.setattr(ck, "_crc_native", False)
+    assert ck.crc32c(data) == native
+
+
+def test_round_trip_all_dtypes_and_many_blocks(ck, tmp_path):
+    rng = np.random.default_rng(1)
+    t = {"feature_extractor/kernel_conv1_1": rng.standard_normal((3, 3, 3, 64)).astype(np.float32),
+         "feature_extractor/bias_conv1_1": rng.standard_normal(64).astype(np.float32),
+         "global_step": np.asarray(1234, np.int64), "flags/b": np.asarray([True, False]),
+         "h": rng.standard_normal((2, 5)).astype(np.float16), "empty": np.zeros((0, 4), np.float32)}
+    for i in range(600):   # enough keys for several 4 KB data blocks with shared prefixes
+        t["regressor/conv2d_%d/batch_normalization/moving_variance" % i] = rng.standard_normal(3).astype(np.float32)
+    prefix = str(tmp_path / "run" / "model-77")
+    ck.write_checkpoint(prefix, t)
+    assert os.path.exists(prefix + ".index") and os.path.exists(prefix + ".data-00000-of-00001")
+    r = ck.CheckpointReader(prefix)
+    assert set(r.get_variable_to_shape_map()) == set(t)
+    assert r.get_variable_to_shape_map()["feature_extractor/kernel_conv1_1"] == [3, 3, 3, 64]
+    for k, v in t.items():
+        got = r.get_tensor(k, verify=True)
+        assert got.dtype == v.dtype and got.shape == v.shape
+        np.testing.assert_array_equal(got, v)
+    assert ck.latest_checkpoint(str(tmp_path / "run")) == prefix
+    with pytest.raises(ck.CheckpointError, match="not found"):
+        r.get_tensor("nope")
+
+
+def test_corruption_is_detected(ck, tmp_path):
+    prefix = str(tmp_path / "m")
+    ck.write_checkpoint(prefix, {"a": np.arange(10, dtype=np.float32), "b": np.ones(3, np.float32)})
+    raw = bytearray(open(prefix + ".index", "rb").read())
+    raw[10] ^= 0x40
+    open(prefix + ".index", "wb").write(bytes(raw))
+    with pytest.raises(ck.CheckpointError, match="checksum"):
+        ck.CheckpointReader(prefix)
+    ck.write_checkpoint(prefix, {"a": np.arange(10, dtype=np.float32)})
+    d = bytearray(open(prefix + ".data-00000-of-00001", "rb").read())
+    d[3] ^= 1
+    open(prefix + ".data-00000-of-00001", "wb").write(bytes(d))
+    with pytest.raises(ck.CheckpointError, match="payload checksum"):
+        ck.CheckpointReader(prefix).get_tensor("a", verify=True)
+
+
+def test_hand_assembled_table_with_restarts_and_snappy(ck, tmp_path):
+    """A table built byte by byte here (not by the module's writer): prefix compression
+    across a restart point, and a snappy-compressed data block."""
+    def varint(v):
+        out = bytearray()
+        while v >= 0x80:
+            out.append((v & 0x7F) | 0x80)
+            v >>= 7
+        out.append(v)
+        return bytes(out)
+
+    def entry(shared, suffix, value):
+        return varint(shared) + varint(len(suffix)) + varint(len(value)) + suffix + value
+
+    blk = entry(0, b"apple", b"1") + entry(3, b"ly", b"22")       # "apple", "apply"
+    r1 = len(blk)
+    blk += entry(0, b"banana", b"333")                             # restart point
+    blk += struct.pack("<III", 0, r1, 2)
+    # snappy: uncompressed length, one literal of the whole block
+    comp = varint(len(blk)) + bytes([(len(blk) - 1) << 2]) + blk if len(blk) <= 60 else None
+    assert comp is not None
+    f = bytearray()
+
+    def emit(body, ctype):
+        off = len(f)
+        f.extend(body)
+        f.append(ctype)
+        f.extend(struct.pack("<I", ck.mask_crc(ck.crc32c(bytes(body) + bytes([ctype])))))
+        return varint(off) + varint(len(body))
+
+    h_data = emit(comp, 1)
+    h_meta = emit(struct.pack("<II", 0, 1), 0)
+    idx = entry(0, b"banana", h_data) + struct.pack("<II", 0, 1)
+    h_idx = emit(idx, 0)
+    footer = h_meta + h_idx
+    f.extend(footer + b"\x00" * (40 - len(footer)) + struct.pack("<Q", ck.TABLE_MAGIC))
+    p = tmp_path / "t.index"
+    p.write_bytes(bytes(f))
+    assert ck._read_table(str(p)) == [(b"apple", b"1"), (b"apply", b"22"), (b"banana", b"333")]
+    # snappy copies (overlapping run): "ab" + copy(offset 2, len 6) -> "abababab"
+    s = varint(8) + bytes([(2 - 1) << 2]) + b"ab" + bytes([((6 - 4) << 2) | 1, 2])
+    assert ck._snappy_decompress(s) == b"abababab"
+
+
+def test_v1_checkpoint_is_rejected_with_a_clear_message(ck, tmp_path):
+    p = tmp_path / "vgg_16.ckpt"
+    ck._write_table(str(p), [(b"", b"x")])           # any SSTable without a .index sibling looks like V1
+    with pytest.raises(ck.CheckpointError, match="V1 checkpoint"):
+        ck.CheckpointReader(str(p))
+    with pytest.raises(ck.CheckpointError, match="no checkpoint"):
+        ck.CheckpointReader(str(tmp_path / "missing"))
+
+
+def test_model_save_load_and_vgg_pretraining_names(ck, tmp_path):
+    """save_weight writes `<path>-<global_step>` as a V2 bundle with the reference's variable
+    names (SSD300.py:490-504); load_weight restores it; a vgg_16-named bundle feeds the
+    `pretraining_weight` constructor argument (SSD300.py:31,195-301)."""
+    import SSD300
+    from odt_b200.api import VGG16_CKPT_NAMES
+    cfg = model_cfg("ssd300")
+    m = SSD300.SSD300(cfg, None)
+    w = m.get_weights()
+    out = m.save_weight("latest", str(tmp_path / "ssd" / "model"))
+    assert out.endswith("model-0") and ck.is_v2_checkpoint(out)
+    r = ck.CheckpointReader(out)
+    assert r.has_tensor("global_step") and r.has_tensor("feature_extractor/kenrel_conv2_1")
+    m2 = SSD300.SSD300(dict(cfg), None)
+    m2.seed = 99                                      # different random init, then restore
+    m2.load_weight(out)
+    for k, v in w.items():
+        np.testing.assert_array_equal(m2.get_weights()[k], v)
+    # VGG-16 classification checkpoint names -> the 13 backbone convs
+    rng = np.random.default_rng(5)
+    vgg = {}
+    for ck_name, (kvar, bvar) in VGG16_CKPT_NAMES.items():
+        vgg["vgg_16/%s/weights" % ck_name] = rng.standard_normal(w[kvar].shape).astype(np.float32)
+        vgg["vgg_16/%s/biases" % ck_name] = rng.standard_normal(w[bvar].shape).astype(np.float32)
+    vgg["vgg_16/fc8/weights"] = np.zeros((1, 1, 8, 4), np.float32)   # ignored extras
+    ck.write_checkpoint(str(tmp_path / "vgg_16.ckpt"), vgg)
+    m3 = SSD300.SSD300(dict(cfg, pretraining_weight=str(tmp_path / "vgg_16.ckpt")), None)
+    w3 = m3.get_weights()
+    np.testing.assert_array_equal(w3["feature_extractor/kernel_conv1_1"], vgg["vgg_16/conv1/conv1_1/weights"])
+    np.testing.assert_array_equal(w3["feature_extractor/bias_conv_3_1"], vgg["vgg_16/conv3/conv3_1/biases"])
+    np.testing.assert_array_equal(w3["feature_extractor/kernel_conv5_3"], vgg["vgg_16/conv5/conv5_3/weights"])
