@@ -234,6 +234,16 @@ int odt_retina_loss_fwd(const float* head, const odt_tail_params* p, int B, cons
                         float alpha, float gamma, float* partial_scratch, int* match_scratch,
                         float* loss_out, void* stream);
 long long odt_retina_loss_scratch_floats(int B);
+/* SSD300 / SSD512 training-loss forward (matching, cross-entropy, smooth-L1, hard-negative mining by
+ * NonMaxSuppressionV3 over the negative anchors): replaces `_compute_one_image_loss`
+ * SSD300.py:345-453 (SSD512.py same body) on the candidate rows the inference tail reads.
+ * gt [B,G,5] = (y, x, h, w, class) padded with -1 rows, G <= 128.  loss_out [B] fp32, one value per
+ * image.  `scratch`: odt_ssd_loss_scratch_bytes(p, B) bytes, 8-byte aligned; after the call the ints at
+ * byte offset odt_ssd_loss_info_offset(p, B) hold (#positives, #negatives, #mined negatives) per image. */
+long long odt_ssd_loss_scratch_bytes(const odt_tail_params* p, int B);
+long long odt_ssd_loss_info_offset(const odt_tail_params* p, int B);
+int odt_ssd_loss_fwd(const float* head, const odt_tail_params* p, int B, const float* gt, int G,
+                     void* scratch, float* loss_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -229,6 +229,213 @@ __global__ void loss_final_kernel(const float* __restrict__ partial, int B, floa
   out[b] = conf / npos + coord / npos;
 }
 
+// ============================ SSD loss forward ==============================
+// Restates SSD300.py:345-453 / SSD512.py (never copied):
+//   * matching as above but with ONE threshold: other anchors with best IoU > 0.5 are
+//     positives, all the rest are negatives;
+//   * cross-entropy (sparse_softmax_cross_entropy = logsumexp(x) - x[label]), positives
+//     averaged; smooth-L1 box term averaged over the positives;
+//   * hard-negative mining: tf.image.non_max_suppression over the negative ANCHOR boxes
+//     (yx -+ hw/2 of the anchor's centre form) scored by their background cross-entropy,
+//     max_output = min(#neg, 3 * #pos), IoU 0.7; the loss is the mean of the selected ones.
+__device__ __forceinline__ float xent21(const float* r, int label) {
+  float m = r[0];
+#pragma unroll
+  for (int i = 1; i < 21; ++i) m = fmaxf(m, r[i]);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 21; ++i) s = __fadd_rn(s, expf(__fsub_rn(r[i], m)));
+  return __fsub_rn(logf(s), __fsub_rn(r[label], m));
+}
+
+// K2': per-anchor assignment; positives -> partial sums, negatives -> (loss, row) keys
+__global__ void __launch_bounds__(kLossThreads)
+    ssd_loss_anchor_kernel(const float* __restrict__ head, const __grid_constant__ TailP tp,
+                           const float* __restrict__ gt, int G, const int* __restrict__ best,
+                           float* __restrict__ partial, unsigned long long* __restrict__ neg_keys,
+                           int* __restrict__ neg_count) {
+  pdl_launch_dependents();
+  const odt_tail_params& p = tp.p;
+  const int b = blockIdx.y, blk = blockIdx.x;
+  const float* gb = gt + (long long)b * G * 5;
+  __shared__ float s_gt[kMaxGT][6];
+  __shared__ int s_best[kMaxGT];
+  __shared__ int s_cnt;
+  __shared__ float s_red[3][kLossThreads];
+  if (threadIdx.x == 0) s_cnt = gt_count(gb, G);
+  __syncthreads();
+  const int cnt = s_cnt;
+  for (int g = threadIdx.x; g < cnt; g += blockDim.x) {
+    float gy = gb[g * 5], gx = gb[g * 5 + 1], gh = gb[g * 5 + 2], gw = gb[g * 5 + 3];
+    float hh = __fmul_rn(gh, 0.5f), hw = __fmul_rn(gw, 0.5f);
+    s_gt[g][0] = __fsub_rn(gy, hh);
+    s_gt[g][1] = __fsub_rn(gx, hw);
+    s_gt[g][2] = __fadd_rn(gy, hh);
+    s_gt[g][3] = __fadd_rn(gx, hw);
+    s_gt[g][4] = __fmul_rn(gh, gw);
+    s_best[g] = best[b * G + g];
+  }
+  __syncthreads();
+  const float* hb = head + (long long)b * p.N * kRow;
+  unsigned long long* nk = neg_keys + (long long)b * p.N;
+  float conf = 0.f, coord = 0.f, npos = 0.f;
+  const int per = (p.N + kLossBlocks - 1) / kLossBlocks;
+  const int n_begin = blk * per, n_end = min(p.N, n_begin + per);
+  for (int n0 = n_begin; n0 < n_end; n0 += blockDim.x) {
+    const int n = n0 + threadIdx.x;
+    bool is_neg = false;
+    float nloss = 0.f;
+    if (n < n_end) {
+      bool is_best = false;
+      for (int g = 0; g < cnt; ++g) is_best |= (s_best[g] == n);
+      if (!is_best) {
+        Cell c = locate(p, n);
+        Anchor a = anchor_ssd(p, c);
+        float bv = -1.f;
+        int bg = 0;
+        for (int g = 0; g < cnt; ++g) {
+          float v = iou_match(a, s_gt[g][0], s_gt[g][1], s_gt[g][2], s_gt[g][3], s_gt[g][4]);
+          if (v > bv) {
+            bv = v;
+            bg = g;
+          }
+        }
+        const float* r = hb + (long long)n * kRow;
+        if (bv > 0.5f) {
+          conf += xent21(r, (int)gb[bg * 5 + 4]);
+          coord += coord_loss(r, a, gb[bg * 5], gb[bg * 5 + 1], gb[bg * 5 + 2], gb[bg * 5 + 3]);
+          npos += 1.f;
+        } else {
+          is_neg = true;
+          nloss = xent21(r, 20);
+        }
+      }
+    }
+    // warp-aggregated append of the negatives (order is irrelevant: keys are unique)
+    const unsigned mask = __ballot_sync(0xffffffffu, is_neg);
+    if (mask) {
+      const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(&neg_count[b], __popc(mask));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (is_neg)
+        nk[base + __popc(mask & ((1u << lane) - 1))] =
+            ((unsigned long long)__float_as_uint(nloss) << 32) | (0xFFFFFFFFu - (unsigned)n);
+    }
+  }
+  if (blk == 0) {  // the G "best anchor" positives (duplicates kept)
+    for (int g = threadIdx.x; g < cnt; g += blockDim.x) {
+      int n = s_best[g];
+      Cell c = locate(p, n);
+      Anchor a = anchor_ssd(p, c);
+      const float* r = hb + (long long)n * kRow;
+      conf += xent21(r, (int)gb[g * 5 + 4]);
+      coord += coord_loss(r, a, gb[g * 5], gb[g * 5 + 1], gb[g * 5 + 2], gb[g * 5 + 3]);
+      npos += 1.f;
+    }
+  }
+  s_red[0][threadIdx.x] = conf;
+  s_red[1][threadIdx.x] = coord;
+  s_red[2][threadIdx.x] = npos;
+  __syncthreads();
+  for (int o = kLossThreads / 2; o; o >>= 1) {
+    if (threadIdx.x < o) {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) s_red[q][threadIdx.x] += s_red[q][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 3) partial[((long long)b * kLossBlocks + blk) * 4 + threadIdx.x] = s_red[threadIdx.x][0];
+}
+
+// negative anchor box in the reference's op order: yx -+ hw/2 of the centre form (:419)
+__device__ __forceinline__ float4 neg_anchor_box(const odt_tail_params& p, int n) {
+  Cell c = locate(p, n);
+  Anchor a = anchor_ssd(p, c);
+  const float hh = __fdiv_rn(a.h, 2.f), hw = __fdiv_rn(a.w, 2.f);
+  return make_float4(__fsub_rn(a.cy, hh), __fsub_rn(a.cx, hw), __fadd_rn(a.cy, hh), __fadd_rn(a.cx, hw));
+}
+
+// K3': one CTA per image: hard-negative mining (exact greedy NMS by repeated arg-max, as in
+// tail.cu) + the final combination.  loss_out[b] = mean(selected neg) + conf/npos + coord/npos
+__global__ void __launch_bounds__(kLossThreads)
+    ssd_loss_mine_kernel(const __grid_constant__ TailP tp, const float* __restrict__ partial,
+                         unsigned long long* __restrict__ neg_keys, const int* __restrict__ neg_count,
+                         float* __restrict__ loss_out, int* __restrict__ info_out) {
+  pdl_launch_dependents();
+  const odt_tail_params& p = tp.p;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ unsigned long long s_wkey[kLossThreads / 32];
+  __shared__ int s_wpos[kLossThreads / 32];
+  float conf = 0.f, coord = 0.f, nposf = 0.f;
+  for (int i = 0; i < kLossBlocks; ++i) {
+    const float* q = partial + ((long long)b * kLossBlocks + i) * 4;
+    conf += q[0];
+    coord += q[1];
+    nposf += q[2];
+  }
+  const int npos = (int)nposf, cnt = neg_count[b];
+  const int chosen = cnt > 3 * npos ? 3 * npos : cnt;
+  unsigned long long* keys = neg_keys + (long long)b * p.N;
+  double neg_sum = 0.0;  // thread 0 only
+  int nsel = 0;
+  while (nsel < chosen) {
+    unsigned long long bk = 0ull;
+    int bp = 0x7fffffff;
+    for (int i = tid; i < cnt; i += blockDim.x) {
+      const unsigned long long k = keys[i];
+      if (k > bk) {
+        bk = k;
+        bp = i;
+      }
+    }
+    {
+      const unsigned hi = (unsigned)(bk >> 32), lo = (unsigned)bk;
+      const unsigned whi = __reduce_max_sync(0xffffffffu, hi);
+      const unsigned wlo = __reduce_max_sync(0xffffffffu, hi == whi ? lo : 0u);
+      const int wpos = __reduce_min_sync(0xffffffffu, (hi == whi && lo == wlo) ? bp : 0x7fffffff);
+      if (lane == 0) {
+        s_wkey[warp] = ((unsigned long long)whi << 32) | wlo;
+        s_wpos[warp] = wpos;
+      }
+    }
+    __syncthreads();
+    unsigned long long hk = 0ull;
+    int hp = -1;
+#pragma unroll
+    for (int w = 0; w < kLossThreads / 32; ++w) {
+      if (s_wkey[w] > hk) {
+        hk = s_wkey[w];
+        hp = s_wpos[w];
+      }
+    }
+    if (hk == 0ull) break;  // every negative is selected or suppressed
+    const int hn = (int)(0xFFFFFFFFu - (unsigned)(hk & 0xFFFFFFFFull));
+    const float4 cur = neg_anchor_box(p, hn);
+    if (tid == 0) {
+      neg_sum += (double)__uint_as_float((unsigned)(hk >> 32));
+      keys[hp] = 0ull;
+    }
+    ++nsel;
+    if (nsel >= chosen) break;
+    for (int j = tid; j < cnt; j += blockDim.x) {
+      const unsigned long long kj = keys[j];
+      if (kj == 0ull || j == hp) continue;
+      const int n = (int)(0xFFFFFFFFu - (unsigned)(kj & 0xFFFFFFFFull));
+      if (iou_tf(neg_anchor_box(p, n), cur) > 0.7f) keys[j] = 0ull;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    loss_out[b] = (float)(neg_sum / (double)nsel) + conf / nposf + coord / nposf;
+    if (info_out) {
+      info_out[b * 3 + 0] = npos;
+      info_out[b * 3 + 1] = cnt;
+      info_out[b * 3 + 2] = nsel;
+    }
+  }
+}
+
 }  // namespace odt
 
 using namespace odt;
@@ -253,6 +460,59 @@ extern "C" int odt_retina_loss_fwd(const float* head, const odt_tail_params* p, 
                                                                   alpha, gamma, partial_scratch);
   ODT_LAUNCH_OK();
   loss_final_kernel<<<(B + 63) / 64, 64, 0, st>>>(partial_scratch, B, loss_out);
+  ODT_LAUNCH_OK();
+  return ODT_OK;
+}
+
+// ---- SSD ----
+static long long ssd_loss_layout(const odt_tail_params* p, int B, long long* o_match, long long* o_count,
+                                 long long* o_info, long long* o_keys) {
+  long long off = (long long)B * kLossBlocks * 4 * 4;             // partial sums (floats)
+  *o_match = off;  off += (long long)B * kMaxGT * 4;              // best anchor per GT (ints)
+  *o_count = off;  off += (((long long)B + 1) & ~1ll) * 4;        // negatives per image
+  *o_info = off;   off += (((long long)B * 3 + 1) & ~1ll) * 4;    // (#pos, #neg, #selected) per image
+  off = (off + 7) & ~7ll;
+  *o_keys = off;   off += (long long)B * p->N * 8;                // negative keys (u64)
+  return off;
+}
+
+extern "C" long long odt_ssd_loss_scratch_bytes(const odt_tail_params* p, int B) {
+  if (!p || B <= 0 || p->N <= 0) return -1;
+  long long a, b2, c, d;
+  return ssd_loss_layout(p, B, &a, &b2, &c, &d);
+}
+
+extern "C" long long odt_ssd_loss_info_offset(const odt_tail_params* p, int B) {
+  if (!p || B <= 0 || p->N <= 0) return -1;
+  long long a, b2, c, d;
+  ssd_loss_layout(p, B, &a, &b2, &c, &d);
+  return c;
+}
+
+extern "C" int odt_ssd_loss_fwd(const float* head, const odt_tail_params* p, int B, const float* gt, int G,
+                                void* scratch, float* loss_out, void* stream) {
+  ODT_CHECK_ARG(head && p && gt && scratch && loss_out, "null pointer");
+  ODT_CHECK_ARG(p->kind == ODT_DECODE_SSD, "softmax-family head expected");
+  ODT_CHECK_ARG(B > 0 && G > 0 && G <= kMaxGT, "B/G (G <= 128)");
+  ODT_CHECK_ARG(((uintptr_t)scratch & 7) == 0, "scratch must be 8-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long o_match, o_count, o_info, o_keys;
+  ssd_loss_layout(p, B, &o_match, &o_count, &o_info, &o_keys);
+  char* sb = static_cast<char*>(scratch);
+  float* partial = reinterpret_cast<float*>(sb);
+  int* match = reinterpret_cast<int*>(sb + o_match);
+  int* count = reinterpret_cast<int*>(sb + o_count);
+  int* info = reinterpret_cast<int*>(sb + o_info);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(sb + o_keys);
+  ODT_CUDA_OK(cudaMemsetAsync(count, 0, sizeof(int) * (size_t)B, st));
+  TailP tp;
+  tp.p = *p;
+  loss_best_anchor_kernel<<<dim3(G, B), kLossThreads, 0, st>>>(tp, gt, G, match);
+  ODT_LAUNCH_OK();
+  ssd_loss_anchor_kernel<<<dim3(kLossBlocks, B), kLossThreads, 0, st>>>(head, tp, gt, G, match, partial, keys,
+                                                                      count);
+  ODT_LAUNCH_OK();
+  ssd_loss_mine_kernel<<<B, kLossThreads, 0, st>>>(tp, partial, keys, count, loss_out, info);
   ODT_LAUNCH_OK();
   return ODT_OK;
 }

@@ -113,21 +113,6 @@ __global__ void __launch_bounds__(kDecodeWarps * 32)
 }
 
 // ----------------------------------------------------------------- NMS ----
-// TF NonMaxSuppressionV3 IoU, float32, no contraction.
-__device__ __forceinline__ float iou_tf(const float4& a, const float4& b) {
-  float ymin_i = fminf(a.x, a.z), xmin_i = fminf(a.y, a.w);
-  float ymax_i = fmaxf(a.x, a.z), xmax_i = fmaxf(a.y, a.w);
-  float ymin_j = fminf(b.x, b.z), xmin_j = fminf(b.y, b.w);
-  float ymax_j = fmaxf(b.x, b.z), xmax_j = fmaxf(b.y, b.w);
-  float area_i = __fmul_rn(__fsub_rn(ymax_i, ymin_i), __fsub_rn(xmax_i, xmin_i));
-  float area_j = __fmul_rn(__fsub_rn(ymax_j, ymin_j), __fsub_rn(xmax_j, xmin_j));
-  if (area_i <= 0.f || area_j <= 0.f) return 0.f;
-  float iy1 = fmaxf(ymin_i, ymin_j), ix1 = fmaxf(xmin_i, xmin_j);
-  float iy2 = fminf(ymax_i, ymax_j), ix2 = fminf(xmax_i, xmax_j);
-  float inter = __fmul_rn(fmaxf(__fsub_rn(iy2, iy1), 0.f), fmaxf(__fsub_rn(ix2, ix1), 0.f));
-  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_i, area_j), inter));
-}
-
 constexpr int kNmsThreads = 256;
 constexpr int kNmsSmemKeys = 1024;  // candidates (keys + boxes, 24 KB) a CTA works on in shared memory: 8 CTAs / SM
 

@@ -284,6 +284,34 @@ class SSD300(_Detector):
         return nets.build_ssd(self.input_size, batch, self.config, precision, self.device, allow_tc)
 
 
+    def loss_forward(self, images, ground_truth, precision=None, return_info=False):
+        """Forward of the per-image training loss (matching, cross-entropy, smooth-L1, hard-negative
+        mining by NMS over the negative anchors) on the head rows the inference tail reads.
+        ground_truth: [B,G,5] (y,x,h,w,id) padded with -1.  ref SSD300.py:345-453."""
+        import ctypes as C
+        from . import lib as L
+        images = np.ascontiguousarray(images, dtype=np.float32)
+        gt = np.ascontiguousarray(ground_truth, dtype=np.float32)
+        net = self.engine(images.shape[0], precision)
+        B, G = gt.shape[0], gt.shape[1]
+        net.image_buf.copy_(torch.from_numpy(images))
+        net.run()
+        dev = net.device
+        gtd = torch.from_numpy(gt).to(dev)
+        nbytes = net.lib.odt_ssd_loss_scratch_bytes(C.byref(net.tail.p), B)
+        scratch = torch.zeros((nbytes + 7) // 8, dtype=torch.int64, device=dev)
+        out = torch.zeros(B, dtype=torch.float32, device=dev)
+        L.check(net.lib.odt_ssd_loss_fwd(net.head_buf.data_ptr(), C.byref(net.tail.p), B, gtd.data_ptr(), G,
+                                         scratch.data_ptr(), out.data_ptr(),
+                                         torch.cuda.current_stream().cuda_stream), "ssd_loss")
+        loss = out.cpu().numpy()
+        if not return_info:
+            return loss
+        off = net.lib.odt_ssd_loss_info_offset(C.byref(net.tail.p), B)
+        info = scratch.view(torch.int32)[off // 4: off // 4 + 3 * B].cpu().numpy().reshape(B, 3)
+        return loss, info
+
+
 class SSD512(SSD300):
     name, input_size = "SSD512", 512
 

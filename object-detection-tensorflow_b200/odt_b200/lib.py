@@ -80,6 +80,9 @@ SYMBOLS = {
     "odt_nms_scratch_bytes": (_L, [C.POINTER(TailParams), _I]),
     "odt_retina_loss_fwd": (_I, [_P, C.POINTER(TailParams), _I, _P, _I, _F, _F, _P, _P, _P, _P]),
     "odt_retina_loss_scratch_floats": (_L, [_I]),
+    "odt_ssd_loss_scratch_bytes": (_L, [C.POINTER(TailParams), _I]),
+    "odt_ssd_loss_info_offset": (_L, [C.POINTER(TailParams), _I]),
+    "odt_ssd_loss_fwd": (_I, [_P, C.POINTER(TailParams), _I, _P, _I, _P, _P, _P]),
 }
 
 

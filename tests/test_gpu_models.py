@@ -180,6 +180,36 @@ def test_retinanet_loss_forward_vs_oracle(built):
         assert abs(got[b] - ref) <= 2e-5 * max(abs(ref), 1.0)
 
 
+@pytest.mark.parametrize("size", [300, 512])
+def test_ssd_loss_forward_vs_oracle(built, size):
+    """SSD training-loss forward on the fp32 head rows: matching counts and the mined
+    negative count exact, loss within 2e-5 relative (float summation order)."""
+    from oracle import loss as OL
+    from oracle import tails as OT
+    name = "ssd300" if size == 300 else "ssd512"
+    m = _model(name, precision="fp32", bn_init="trained")
+    B, G = 2, 20
+    img = _img(B, size, size, seed=16)
+    rng = np.random.default_rng(8)
+    gt = np.full((B, G, 5), -1.0, np.float32)
+    for b in range(B):
+        n = 2 + 5 * b
+        gt[b, :n, 0:2] = rng.uniform(0.15 * size, 0.85 * size, (n, 2))
+        gt[b, :n, 2:4] = rng.uniform(0.1 * size, 0.5 * size, (n, 2))
+        gt[b, :n, 4] = rng.integers(0, 20, n)
+    got, info = m.loss_forward(img, gt, return_info=True)
+    net = m.engine(B)
+    rows = net.head_buf.cpu().numpy()
+    shapes = [(h, w) for h, w, _ in net.levels]
+    a1, a2, ayx, ahw = OT.ssd_anchors(size, shapes)
+    for b in range(B):
+        ref, ri = OL.ssd_image_loss(rows[b, :, :21], rows[b, :, 21:23], rows[b, :, 23:], a1, a2, ayx, ahw, gt[b])
+        print("image %d: loss gpu %.6f oracle %.6f (%d pos, %d neg, %d mined)" % (
+            b, got[b], ref, ri["num_pos"], ri["num_neg"], ri["selected"]))
+        assert tuple(info[b]) == (ri["num_pos"], ri["num_neg"], ri["selected"])
+        assert abs(got[b] - ref) <= 2e-5 * max(abs(ref), 1.0)
+
+
 def test_detect_stream_matches_detect_batch(built):
     """Pipelined public API (H2D of batch i+1 overlaps batch i) == synchronous API."""
     import torch
