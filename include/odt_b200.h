@@ -244,6 +244,13 @@ long long odt_ssd_loss_scratch_bytes(const odt_tail_params* p, int B);
 long long odt_ssd_loss_info_offset(const odt_tail_params* p, int B);
 int odt_ssd_loss_fwd(const float* head, const odt_tail_params* p, int B, const float* gt, int G,
                      void* scratch, float* loss_out, void* stream);
+/* FCOS training-loss forward (level assignment by GT size, inside-box targets, IoU loss, centre-ness
+ * BCE, sigmoid focal loss): replaces FCOS.py:153-187 + `_compute_one_image_loss` FCOS.py:266-348 on
+ * the candidate rows [20 cls, ctr, l, r, t, b (pre-exp)].  gt as above; loss_out [B]; scratch:
+ * odt_fcos_loss_scratch_bytes(B) bytes, 4-byte aligned. */
+long long odt_fcos_loss_scratch_bytes(int B);
+int odt_fcos_loss_fwd(const float* head, const odt_tail_params* p, int B, const float* gt, int G,
+                      void* scratch, float* loss_out, void* stream);
 
 #ifdef __cplusplus
 }

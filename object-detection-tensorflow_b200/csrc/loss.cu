@@ -436,6 +436,165 @@ __global__ void __launch_bounds__(kLossThreads)
   }
 }
 
+// ============================ FCOS loss forward =============================
+// Restates FCOS.py:153-187 (level assignment) and :266-348 (per-level loss), never copied:
+//   * GT rows go to pyramid levels by sqrt(h*w) with inclusive, overlapping bounds
+//     (<=64 | 64..128 | 128..256 | 256..512 | >=512); a level without GT contributes 0;
+//   * per location (grid without +0.5, stride units): inside-box mask per GT; the regression
+//     target is the inside GT of minimal area (ties: element-wise max of l,r,t,b);
+//   * IoU loss -log(iou + 1e-12) over inside locations, centre-ness BCE-with-logits over ALL
+//     locations of the level, sigmoid focal loss (alpha .25, gamma 2) on the per-class inside mask;
+//   * level loss = (iou + focal + centre) / #(positive class cells); image loss = sum of levels.
+constexpr int kFcosLevels = 5;
+
+__device__ __forceinline__ float softplus_f(float x) {  // log(1 + exp(x)), stable
+  return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x)));
+}
+
+__global__ void __launch_bounds__(kLossThreads)
+    fcos_loss_kernel(const float* __restrict__ head, const __grid_constant__ TailP tp,
+                     const float* __restrict__ gt, int G, float* __restrict__ partial,
+                     int* __restrict__ level_cnt) {
+  pdl_launch_dependents();
+  const odt_tail_params& p = tp.p;
+  const int b = blockIdx.y, blk = blockIdx.x;
+  const float* gb = gt + (long long)b * G * 5;
+  __shared__ float s_box[kMaxGT][kFcosLevels][4];  // y1,x1,y2,x2 in stride units of each level
+  __shared__ int s_cls[kMaxGT];
+  __shared__ int s_lv[kMaxGT];                      // level membership bits
+  __shared__ int s_cnt;
+  __shared__ float s_red[kLossThreads];
+  if (threadIdx.x == 0) s_cnt = gt_count(gb, G);
+  __syncthreads();
+  const int cnt = s_cnt;
+  for (int g = threadIdx.x; g < cnt; g += blockDim.x) {
+    const float gy = gb[g * 5], gx = gb[g * 5 + 1], gh = gb[g * 5 + 2], gw = gb[g * 5 + 3];
+    const float size = __fsqrt_rn(__fmul_rn(gh, gw));
+    int bits = 0;
+    if (size <= 64.f) bits |= 1;
+    if (size >= 64.f && size <= 128.f) bits |= 2;
+    if (size >= 128.f && size <= 256.f) bits |= 4;
+    if (size >= 256.f && size <= 512.f) bits |= 8;
+    if (size >= 512.f) bits |= 16;
+    s_lv[g] = bits;
+    s_cls[g] = (int)gb[g * 5 + 4];
+    for (int l = 0; l < kFcosLevels; ++l) {
+      const float st = p.level[l].out_mul;
+      const float y = __fdiv_rn(gy, st), x = __fdiv_rn(gx, st), h = __fdiv_rn(gh, st), w = __fdiv_rn(gw, st);
+      const float hh = __fdiv_rn(h, 2.f), hw = __fdiv_rn(w, 2.f);
+      s_box[g][l][0] = __fsub_rn(y, hh);
+      s_box[g][l][1] = __fsub_rn(x, hw);
+      s_box[g][l][2] = __fadd_rn(y, hh);
+      s_box[g][l][3] = __fadd_rn(x, hw);
+    }
+  }
+  __syncthreads();
+  if (blk == 0 && threadIdx.x < kFcosLevels) {  // GT count per level (a level without GT contributes nothing)
+    int c = 0;
+    for (int g = 0; g < cnt; ++g) c += (s_lv[g] >> threadIdx.x) & 1;
+    level_cnt[b * kFcosLevels + threadIdx.x] = c;
+  }
+  const float* hb = head + (long long)b * p.N * kRow;
+  float acc[kFcosLevels][4];  // iou, focal, centre, #positive class cells
+#pragma unroll
+  for (int l = 0; l < kFcosLevels; ++l)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[l][q] = 0.f;
+  const int per = (p.N + kLossBlocks - 1) / kLossBlocks;
+  const int n_begin = blk * per, n_end = min(p.N, n_begin + per);
+  for (int n = n_begin + threadIdx.x; n < n_end; n += blockDim.x) {
+    const Cell c = locate(p, n);
+    const int l = c.lvl;
+    const float yy = (float)c.y, xx = (float)c.x;
+    bool loc = false;
+    float amin = 3.0e38f, dl = 0.f, dr = 0.f, dt = 0.f, db = 0.f;
+    unsigned cmask = 0u;
+    for (int g = 0; g < cnt; ++g) {
+      if (!((s_lv[g] >> l) & 1)) continue;
+      const float l_ = __fsub_rn(xx, s_box[g][l][1]), r_ = __fsub_rn(s_box[g][l][3], xx);
+      const float t_ = __fsub_rn(yy, s_box[g][l][0]), b_ = __fsub_rn(s_box[g][l][2], yy);
+      if (!(l_ > 0.f && r_ > 0.f && t_ > 0.f && b_ > 0.f)) continue;
+      loc = true;
+      cmask |= 1u << s_cls[g];
+      const float area = __fmul_rn(__fadd_rn(l_, r_), __fadd_rn(t_, b_));
+      if (area < amin) {
+        amin = area;
+        dl = l_; dr = r_; dt = t_; db = b_;
+      } else if (area == amin) {  // tied minimal areas: element-wise maximum (:300-307)
+        dl = fmaxf(dl, l_); dr = fmaxf(dr, r_); dt = fmaxf(dt, t_); db = fmaxf(db, b_);
+      }
+    }
+    const float* r = hb + (long long)n * kRow;
+    // centre-ness BCE with logits, every location (:331-334); target 0 where no GT covers the cell
+    const float lrmin = fminf(dl, dr), tbmin = fminf(dt, db), lrmax = fmaxf(dl, dr), tbmax = fmaxf(dt, db);
+    const float cgt = __fsqrt_rn(__fdiv_rn(__fmul_rn(lrmin, tbmin), __fadd_rn(__fmul_rn(lrmax, tbmax), 1e-12f)));
+    const float cx = r[20];
+    float centre = fmaxf(cx, 0.f) - cx * cgt + log1pf(expf(-fabsf(cx)));
+    float iou_l = 0.f;
+    if (loc) {
+      const float pl = expf(r[21]), pr = expf(r[22]), pt = expf(r[23]), pb = expf(r[24]);
+      const float iw = __fadd_rn(fminf(dl, pl), fminf(dr, pr)), ih = __fadd_rn(fminf(dt, pt), fminf(db, pb));
+      const float inter = __fmul_rn(iw, ih);
+      const float uni = __fsub_rn(__fadd_rn(__fmul_rn(__fadd_rn(dl, dr), __fadd_rn(dt, db)),
+                                            __fmul_rn(__fadd_rn(pl, pr), __fadd_rn(pt, pb))), inter);
+      const float iou = __fdiv_rn(inter, __fadd_rn(uni, 1e-12f));
+      iou_l = -logf(__fadd_rn(iou, 1e-12f));
+    }
+    float focal_l = 0.f, npos = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < 20; ++k) {
+      const float x = r[k];
+      const float ls = -softplus_f(-x);                 // log sigmoid(x)
+      const float sg = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-x)));
+      if ((cmask >> k) & 1u) {
+        const float om = 1.f - sg;
+        focal_l += -0.25f * om * om * ls;
+        npos += 1.f;
+      } else {
+        focal_l += -0.25f * sg * sg * (-x + ls);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < kFcosLevels; ++q) {
+      if (q == l) {
+        acc[q][0] += iou_l;
+        acc[q][1] += focal_l;
+        acc[q][2] += centre;
+        acc[q][3] += npos;
+      }
+    }
+  }
+  // fixed-order block reduction of the 5 x 4 sums
+  for (int l = 0; l < kFcosLevels; ++l) {
+    for (int q = 0; q < 4; ++q) {
+      s_red[threadIdx.x] = acc[l][q];
+      __syncthreads();
+      for (int o = kLossThreads / 2; o; o >>= 1) {
+        if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) partial[(((long long)b * kLossBlocks + blk) * kFcosLevels + l) * 4 + q] = s_red[0];
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void fcos_loss_final_kernel(const float* __restrict__ partial, const int* __restrict__ level_cnt,
+                                       int B, float* __restrict__ out) {
+  pdl_launch_dependents();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float total = 0.f;
+  for (int l = 0; l < kFcosLevels; ++l) {
+    if (level_cnt[b * kFcosLevels + l] == 0) continue;
+    double s3[4] = {0, 0, 0, 0};
+    for (int i = 0; i < kLossBlocks; ++i)
+      for (int q = 0; q < 4; ++q) s3[q] += (double)partial[(((long long)b * kLossBlocks + i) * kFcosLevels + l) * 4 + q];
+    total += (float)((s3[0] + s3[1] + s3[2]) / s3[3]);
+  }
+  out[b] = total;
+}
+
 }  // namespace odt
 
 using namespace odt;
@@ -513,6 +672,29 @@ extern "C" int odt_ssd_loss_fwd(const float* head, const odt_tail_params* p, int
                                                                       count);
   ODT_LAUNCH_OK();
   ssd_loss_mine_kernel<<<B, kLossThreads, 0, st>>>(tp, partial, keys, count, loss_out, info);
+  ODT_LAUNCH_OK();
+  return ODT_OK;
+}
+
+// ---- FCOS ----
+extern "C" long long odt_fcos_loss_scratch_bytes(int B) {
+  return B > 0 ? (long long)B * kLossBlocks * kFcosLevels * 4 * 4 + (long long)B * kFcosLevels * 4 : -1;
+}
+
+extern "C" int odt_fcos_loss_fwd(const float* head, const odt_tail_params* p, int B, const float* gt, int G,
+                                 void* scratch, float* loss_out, void* stream) {
+  ODT_CHECK_ARG(head && p && gt && scratch && loss_out, "null pointer");
+  ODT_CHECK_ARG(p->kind == ODT_DECODE_FCOS && p->num_levels == kFcosLevels && p->num_fg == 20,
+                "FCOS head with 5 levels and 20 classes expected");
+  ODT_CHECK_ARG(B > 0 && G > 0 && G <= kMaxGT, "B/G (G <= 128)");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* partial = static_cast<float*>(scratch);
+  int* level_cnt = reinterpret_cast<int*>(partial + (long long)B * kLossBlocks * kFcosLevels * 4);
+  TailP tp;
+  tp.p = *p;
+  fcos_loss_kernel<<<dim3(kLossBlocks, B), kLossThreads, 0, st>>>(head, tp, gt, G, partial, level_cnt);
+  ODT_LAUNCH_OK();
+  fcos_loss_final_kernel<<<(B + 63) / 64, 64, 0, st>>>(partial, level_cnt, B, loss_out);
   ODT_LAUNCH_OK();
   return ODT_OK;
 }

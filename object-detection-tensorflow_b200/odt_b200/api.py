@@ -388,3 +388,24 @@ class FCOS(_Detector):
     def _build(self, batch, precision, allow_tc=True):
         return nets.build_fcos(batch, self.config, precision, self.device, allow_tc,
                                share_heads=self.config.get("share_heads", True))
+
+    def loss_forward(self, images, ground_truth, precision=None):
+        """Forward of the per-image training loss (level assignment, IoU loss, centre-ness BCE, sigmoid
+        focal loss) on the head rows the inference tail reads.  ground_truth: [B,G,5] (y,x,h,w,id) padded
+        with -1.  ref FCOS.py:153-187,266-348."""
+        import ctypes as C
+        from . import lib as L
+        images = np.ascontiguousarray(images, dtype=np.float32)
+        gt = np.ascontiguousarray(ground_truth, dtype=np.float32)
+        net = self.engine(images.shape[0], precision)
+        B, G = gt.shape[0], gt.shape[1]
+        net.image_buf.copy_(torch.from_numpy(images))
+        net.run()
+        dev = net.device
+        gtd = torch.from_numpy(gt).to(dev)
+        scratch = torch.zeros((net.lib.odt_fcos_loss_scratch_bytes(B) + 3) // 4, dtype=torch.int32, device=dev)
+        out = torch.zeros(B, dtype=torch.float32, device=dev)
+        L.check(net.lib.odt_fcos_loss_fwd(net.head_buf.data_ptr(), C.byref(net.tail.p), B, gtd.data_ptr(), G,
+                                          scratch.data_ptr(), out.data_ptr(),
+                                          torch.cuda.current_stream().cuda_stream), "fcos_loss")
+        return out.cpu().numpy()

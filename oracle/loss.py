@@ -127,3 +127,71 @@ def ssd_image_loss(pconf, pyx, phw, a_y1x1, a_y2x2, a_yx, a_hw, gt):
     per = _smooth_l1(pos_pyx - tyx).sum(-1) + _smooth_l1(pos_phw - thw).sum(-1)
     coord = per.mean(dtype=np.float64)
     return float(neg_loss + pos_conf_loss + coord), dict(num_pos=num_pos, num_neg=num_neg, selected=len(sel))
+
+
+def _log_sigmoid(x):
+    # tf.log_sigmoid(x) = -softplus(-x)
+    return (-(np.maximum(-x, F32(0)) + np.log1p(np.exp(-np.abs(x))))).astype(F32)
+
+
+def fcos_level_loss(cls, reg_raw, ctr, gt, stride):
+    """One pyramid level of one image (FCOS.py:266-348).  cls [H,W,20] logits, reg_raw [H,W,4]
+    pre-exp (l,r,t,b) (the head applies exp, :363), ctr [H,W] logit, gt [g,5] rows of THIS level."""
+    h, w, nc = cls.shape
+    s = F32(stride)
+    gy, gx, gh, gw = [(gt[:, i] / s).astype(F32) for i in range(4)]
+    cid = gt[:, 4].astype(np.int32)
+    y1, y2 = (gy - gh / F32(2.0)).astype(F32), (gy + gh / F32(2.0)).astype(F32)
+    x1, x2 = (gx - gw / F32(2.0)).astype(F32), (gx + gw / F32(2.0)).astype(F32)
+    yy = np.arange(h, dtype=F32).reshape(h, 1, 1)
+    xx = np.arange(w, dtype=F32).reshape(1, w, 1)
+    dl, dr = (xx - x1).astype(F32) + np.zeros((h, 1, 1), F32), (x2 - xx).astype(F32) + np.zeros((h, 1, 1), F32)
+    dt, db = (yy - y1).astype(F32) + np.zeros((1, w, 1), F32), (y2 - yy).astype(F32) + np.zeros((1, w, 1), F32)
+    heat = ((dt > 0) & (db > 0) & (dl > 0) & (dr > 0)).astype(F32)       # :288-290
+    dl, dr, dt, db = dl * heat, dr * heat, dt * heat, db * heat
+    loc = heat.max(axis=-1)
+    area = ((dl + dr) * (dt + db)).astype(F32)
+    area_ = (area + (F32(1.0) - heat) * F32(1e8)).astype(F32)
+    amin = area_.min(axis=-1, keepdims=True)
+    dmask = (area == amin).astype(F32) * loc[..., None]                   # :299
+    dl, dr, dt, db = [(d * dmask).max(axis=-1) for d in (dl, dr, dt, db)]
+    p = np.exp(reg_raw.astype(F32)).astype(F32)
+    pl, pr, pt, pb = p[..., 0], p[..., 1], p[..., 2], p[..., 3]
+    iw = np.minimum(dl, pl) + np.minimum(dr, pr)
+    ih = np.minimum(dt, pt) + np.minimum(db, pb)
+    inter = (iw * ih).astype(F32)
+    union = ((dl + dr) * (dt + db) + (pl + pr) * (pt + pb) - inter).astype(F32)
+    iou = (inter / (union + F32(1e-12))).astype(F32)
+    iou_loss = (-np.log(iou + F32(1e-12)) * loc).sum(dtype=np.float64)
+    lrmin, tbmin = np.minimum(dl, dr), np.minimum(dt, db)
+    lrmax, tbmax = np.maximum(dl, dr), np.maximum(dt, db)
+    cgt = np.sqrt((lrmin * tbmin / (lrmax * tbmax + F32(1e-12))).astype(F32)).astype(F32)
+    x = ctr.astype(F32)
+    bce = (np.maximum(x, F32(0)) - x * cgt + np.log1p(np.exp(-np.abs(x)))).astype(F32)   # from_logits=True
+    center_loss = bce.sum(dtype=np.float64)
+    hgt = np.zeros((h, w, nc), F32)
+    for c in range(nc):
+        m = cid == c
+        if m.any():
+            hgt[..., c] = heat[..., m].max(axis=-1)
+    sg = T.sigmoid(cls.astype(F32))
+    ls = _log_sigmoid(cls.astype(F32))
+    pos = (F32(-0.25) * np.power(F32(1.0) - sg, F32(2.0)) * ls * hgt).sum(dtype=np.float64)
+    neg = (F32(-0.25) * np.power(sg, F32(2.0)) * (-cls.astype(F32) + ls) * (F32(1.0) - hgt)).sum(dtype=np.float64)
+    return (iou_loss + pos + neg + center_loss) / hgt.sum(dtype=np.float64)
+
+
+def fcos_image_loss(heads, gt, image=0):
+    """heads: [(cls [B,H,W,20], ctr [B,H,W,1], reg_raw [B,H,W,4])] x 5; gt [G,5] padded with -1.
+    GTs go to levels by sqrt(h*w) with the reference's inclusive, overlapping bounds (FCOS.py:158-164)."""
+    gt = np.asarray(gt, F32)
+    cnt = int(np.argmin(gt, axis=0)[0])
+    g = gt[:cnt]
+    size = np.sqrt((g[:, 2] * g[:, 3]).astype(F32)).astype(F32)
+    sel = [size <= 64, (size >= 64) & (size <= 128), (size >= 128) & (size <= 256),
+           (size >= 256) & (size <= 512), size >= 512]
+    total = 0.0
+    for (cls, ctr, reg), m, s in zip(heads, sel, [8, 16, 32, 64, 128]):
+        if m.any():
+            total += fcos_level_loss(cls[image], reg[image], ctr[image, ..., 0], g[m], s)
+    return float(total)
