@@ -251,6 +251,16 @@ int odt_ssd_loss_fwd(const float* head, const odt_tail_params* p, int B, const f
 long long odt_fcos_loss_scratch_bytes(int B);
 int odt_fcos_loss_fwd(const float* head, const odt_tail_params* p, int B, const float* gt, int G,
                       void* scratch, float* loss_out, void* stream);
+/* YOLOv3 training-loss forward (per-GT level / prior assignment by anchor IoU at the GT's cell,
+ * sigmoid-CE centre / class / objectness terms, squared log-size term, no-object term over the cells
+ * without a GT centre): replaces the loss section of `_build_graph` YOLOv3.py:115-318 on the candidate
+ * rows [20 cls, y, x, h, w, obj].  The four scales are config['coord_scale' | 'noobj_scale' |
+ * 'obj_scale' | 'class_scale'].  loss_out [B] is pos_loss + neg_loss per image (the graph then takes
+ * 0.5 x the batch mean).  scratch: odt_yolo_loss_scratch_bytes(p, B) bytes, 4-byte aligned. */
+long long odt_yolo_loss_scratch_bytes(const odt_tail_params* p, int B);
+int odt_yolo_loss_fwd(const float* head, const odt_tail_params* p, int B, const float* gt, int G,
+                      float coord_scale, float noobj_scale, float obj_scale, float class_scale,
+                      void* scratch, float* loss_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -595,6 +595,170 @@ __global__ void fcos_loss_final_kernel(const float* __restrict__ partial, const 
   out[b] = total;
 }
 
+// ============================ YOLOv3 loss forward ===========================
+// Restates YOLOv3.py:115-318 (+ :37-41 priors, :419-433 anchors, :435-442 GT normalisation), never copied.
+// Quirks kept: level k divides the GT by 32 / 16 / 8 while its priors are priors[k] / (8, 16, 32)[k];
+// the GT x anchor intersections are products of UNCLAMPED differences; the no-object anchors are built
+// from (yx - hw/2, yx + hw/2) re-used as (centre, size).
+__device__ __forceinline__ float sig_xent(float z, float x) {  // sigmoid_cross_entropy_with_logits(labels=z, logits=x)
+  return fmaxf(x, 0.f) - x * z + log1pf(expf(-fabsf(x)));
+}
+__device__ __forceinline__ float iou_unclamped(float gy1, float gx1, float gy2, float gx2, float ay1, float ax1,
+                                               float ay2, float ax2, float aarea) {
+  const float ih = __fsub_rn(fminf(gy2, ay2), fmaxf(gy1, ay1)), iw = __fsub_rn(fminf(gx2, ax2), fmaxf(gx1, ax1));
+  const float inter = __fmul_rn(ih, iw);
+  const float garea = __fmul_rn(__fsub_rn(gy2, gy1), __fsub_rn(gx2, gx1));
+  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(aarea, garea), inter));
+}
+constexpr int kYoloLevels = 3;
+
+// K1: one block per image, one thread per GT: level / prior assignment, positive terms, cell occupancy
+__global__ void __launch_bounds__(kMaxGT)
+    yolo_loss_pos_kernel(const float* __restrict__ head, const __grid_constant__ TailP tp,
+                         const float* __restrict__ gt, int G, unsigned char* __restrict__ occ,
+                         float* __restrict__ pos_out) {
+  pdl_launch_dependents();
+  const odt_tail_params& p = tp.p;
+  const int b = blockIdx.x, g = threadIdx.x;
+  const float* gb = gt + (long long)b * G * 5;
+  __shared__ int s_cnt;
+  __shared__ float s_red[3][kMaxGT];
+  if (threadIdx.x == 0) s_cnt = gt_count(gb, G);
+  __syncthreads();
+  const int cnt = s_cnt;
+  const float norm[kYoloLevels] = {32.f, 16.f, 8.f};
+  const long long cells = p.N / 3;
+  float coord = 0.f, cls = 0.f, obj = 0.f;
+  if (g < cnt) {
+    float mx[kYoloLevels];
+    int arg[kYoloLevels], cy[kYoloLevels], cx[kYoloLevels];
+    float ny[kYoloLevels], nx[kYoloLevels], nh[kYoloLevels], nw[kYoloLevels];
+#pragma unroll
+    for (int k = 0; k < kYoloLevels; ++k) {
+      const odt_level& L = p.level[k];
+      ny[k] = __fdiv_rn(gb[g * 5], norm[k]);
+      nx[k] = __fdiv_rn(gb[g * 5 + 1], norm[k]);
+      nh[k] = __fdiv_rn(gb[g * 5 + 2], norm[k]);
+      nw[k] = __fdiv_rn(gb[g * 5 + 3], norm[k]);
+      cy[k] = min(max((int)floorf(ny[k]), 0), L.H - 1);
+      cx[k] = min(max((int)floorf(nx[k]), 0), L.W - 1);
+      occ[(long long)b * cells + L.offset / 3 + cy[k] * L.W + cx[k]] = 1;  // every GT marks its cell on every level
+      const float gy1 = __fsub_rn(ny[k], __fdiv_rn(nh[k], 2.f)), gx1 = __fsub_rn(nx[k], __fdiv_rn(nw[k], 2.f));
+      const float gy2 = __fadd_rn(ny[k], __fdiv_rn(nh[k], 2.f)), gx2 = __fadd_rn(nx[k], __fdiv_rn(nw[k], 2.f));
+      const float ay = (float)cy[k] + 0.5f, ax = (float)cx[k] + 0.5f;
+      float bv = 0.f;
+      int bi = 0;
+      for (int a = 0; a < 3; ++a) {
+        const float hh = __fdiv_rn(L.prior_h[a], 2.f), hw = __fdiv_rn(L.prior_w[a], 2.f);
+        const float v = iou_unclamped(gy1, gx1, gy2, gx2, __fsub_rn(ay, hh), __fsub_rn(ax, hw), __fadd_rn(ay, hh),
+                                      __fadd_rn(ax, hw), __fmul_rn(L.prior_h[a], L.prior_w[a]));
+        if (a == 0 || v > bv) {
+          bv = v;
+          bi = a;
+        }
+      }
+      mx[k] = bv;
+      arg[k] = bi;
+    }
+    int k = 2;
+    if (mx[0] > mx[1] && mx[0] > mx[2]) k = 0;
+    else if (mx[1] > mx[0] && mx[1] > mx[2]) k = 1;
+    const odt_level& L = p.level[k];
+    const float* r = head + ((long long)b * p.N + L.offset + (long long)(cy[k] * L.W + cx[k]) * 3 + arg[k]) * kRow;
+    const float ty = __fsub_rn(ny[k], floorf(ny[k])), tx = __fsub_rn(nx[k], floorf(nx[k]));
+    const float th = logf(__fdiv_rn(nh[k], L.prior_h[arg[k]])), tw = logf(__fdiv_rn(nw[k], L.prior_w[arg[k]]));
+    coord = sig_xent(ty, r[20]) + sig_xent(tx, r[21]);
+    const float dh = __fsub_rn(r[22], th), dw = __fsub_rn(r[23], tw);
+    coord += 0.5f * (dh * dh + dw * dw);
+    const int label = (int)gb[g * 5 + 4];
+    for (int c = 0; c < 20; ++c) cls += sig_xent(c == label ? 1.f : 0.f, r[c]);
+    obj = sig_xent(1.f, r[24]);
+  }
+  s_red[0][threadIdx.x] = coord;
+  s_red[1][threadIdx.x] = cls;
+  s_red[2][threadIdx.x] = obj;
+  __syncthreads();
+  for (int o = kMaxGT / 2; o; o >>= 1) {
+    if (threadIdx.x < o) {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) s_red[q][threadIdx.x] += s_red[q][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 3) pos_out[b * 4 + threadIdx.x] = s_red[threadIdx.x][0];
+  if (threadIdx.x == 3) pos_out[b * 4 + 3] = (float)cnt;
+}
+
+// K2: no-object term over every (cell, prior) whose cell holds no GT centre
+__global__ void __launch_bounds__(kLossThreads)
+    yolo_loss_noobj_kernel(const float* __restrict__ head, const __grid_constant__ TailP tp,
+                           const float* __restrict__ gt, int G, const unsigned char* __restrict__ occ,
+                           float* __restrict__ partial) {
+  pdl_launch_dependents();
+  const odt_tail_params& p = tp.p;
+  const int b = blockIdx.y, blk = blockIdx.x;
+  const float* gb = gt + (long long)b * G * 5;
+  __shared__ float s_g[kMaxGT][kYoloLevels][4];
+  __shared__ int s_cnt;
+  __shared__ float s_red[kLossThreads];
+  if (threadIdx.x == 0) s_cnt = gt_count(gb, G);
+  __syncthreads();
+  const int cnt = s_cnt;
+  const float norm[kYoloLevels] = {32.f, 16.f, 8.f};
+  for (int g = threadIdx.x; g < cnt; g += blockDim.x) {
+#pragma unroll
+    for (int k = 0; k < kYoloLevels; ++k) {
+      const float ny = __fdiv_rn(gb[g * 5], norm[k]), nx = __fdiv_rn(gb[g * 5 + 1], norm[k]);
+      const float nh = __fdiv_rn(gb[g * 5 + 2], norm[k]), nw = __fdiv_rn(gb[g * 5 + 3], norm[k]);
+      s_g[g][k][0] = __fsub_rn(ny, __fdiv_rn(nh, 2.f));
+      s_g[g][k][1] = __fsub_rn(nx, __fdiv_rn(nw, 2.f));
+      s_g[g][k][2] = __fadd_rn(ny, __fdiv_rn(nh, 2.f));
+      s_g[g][k][3] = __fadd_rn(nx, __fdiv_rn(nw, 2.f));
+    }
+  }
+  __syncthreads();
+  const long long cells = p.N / 3;
+  const float* hb = head + (long long)b * p.N * kRow;
+  float acc = 0.f;
+  const int per = (p.N + kLossBlocks - 1) / kLossBlocks;
+  const int n_begin = blk * per, n_end = min(p.N, n_begin + per);
+  for (int n = n_begin + threadIdx.x; n < n_end; n += blockDim.x) {
+    const Cell c = locate(p, n);
+    const odt_level& L = p.level[c.lvl];
+    if (occ[(long long)b * cells + L.offset / 3 + c.y * L.W + c.x]) continue;
+    const float ay = (float)c.y + 0.5f, ax = (float)c.x + 0.5f;
+    const float ph = L.prior_h[c.a], pw = L.prior_w[c.a];
+    const float cyy = __fsub_rn(ay, __fdiv_rn(ph, 2.f)), cxx = __fsub_rn(ax, __fdiv_rn(pw, 2.f));  // "centre" = y1x1
+    const float sh = __fadd_rn(ay, __fdiv_rn(ph, 2.f)), sw = __fadd_rn(ax, __fdiv_rn(pw, 2.f));   // "size"   = y2x2
+    const float by1 = __fsub_rn(cyy, __fdiv_rn(sh, 2.f)), bx1 = __fsub_rn(cxx, __fdiv_rn(sw, 2.f));
+    const float by2 = __fadd_rn(cyy, __fdiv_rn(sh, 2.f)), bx2 = __fadd_rn(cxx, __fdiv_rn(sw, 2.f));
+    const float aarea = __fmul_rn(__fsub_rn(by2, by1), __fsub_rn(bx2, bx1));
+    float best = -3.0e38f;
+    for (int g = 0; g < cnt; ++g)
+      best = fmaxf(best, iou_unclamped(s_g[g][c.lvl][0], s_g[g][c.lvl][1], s_g[g][c.lvl][2], s_g[g][c.lvl][3], by1,
+                                       bx1, by2, bx2, aarea));
+    if (best <= 0.5f) acc += sig_xent(0.f, hb[(long long)n * kRow + 24]);
+  }
+  s_red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = kLossThreads / 2; o; o >>= 1) {
+    if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[(long long)b * kLossBlocks + blk] = s_red[0];
+}
+
+__global__ void yolo_loss_final_kernel(const float* __restrict__ pos, const float* __restrict__ partial, int B,
+                                       float cs, float ns, float os, float ks, float* __restrict__ out) {
+  pdl_launch_dependents();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double noobj = 0.0;
+  for (int i = 0; i < kLossBlocks; ++i) noobj += (double)partial[(long long)b * kLossBlocks + i];
+  const float ng = pos[b * 4 + 3];
+  out[b] = (cs * pos[b * 4 + 0] + ks * pos[b * 4 + 1] + os * pos[b * 4 + 2]) / ng + ns * (float)noobj / ng;
+}
+
 }  // namespace odt
 
 using namespace odt;
@@ -695,6 +859,37 @@ extern "C" int odt_fcos_loss_fwd(const float* head, const odt_tail_params* p, in
   fcos_loss_kernel<<<dim3(kLossBlocks, B), kLossThreads, 0, st>>>(head, tp, gt, G, partial, level_cnt);
   ODT_LAUNCH_OK();
   fcos_loss_final_kernel<<<(B + 63) / 64, 64, 0, st>>>(partial, level_cnt, B, loss_out);
+  ODT_LAUNCH_OK();
+  return ODT_OK;
+}
+
+// ---- YOLOv3 ----
+extern "C" long long odt_yolo_loss_scratch_bytes(const odt_tail_params* p, int B) {
+  if (!p || B <= 0 || p->N <= 0) return -1;
+  return (long long)B * 4 * 4 + (long long)B * kLossBlocks * 4 + (((long long)B * (p->N / 3) + 3) & ~3ll);
+}
+
+extern "C" int odt_yolo_loss_fwd(const float* head, const odt_tail_params* p, int B, const float* gt, int G,
+                                 float coord_scale, float noobj_scale, float obj_scale, float class_scale,
+                                 void* scratch, float* loss_out, void* stream) {
+  ODT_CHECK_ARG(head && p && gt && scratch && loss_out, "null pointer");
+  ODT_CHECK_ARG(p->kind == ODT_DECODE_YOLO3 && p->num_levels == kYoloLevels && p->num_fg == 20,
+                "YOLOv3 head with 3 levels and 20 classes expected");
+  for (int i = 0; i < kYoloLevels; ++i) ODT_CHECK_ARG(p->level[i].A == 3, "3 priors per level expected");
+  ODT_CHECK_ARG(B > 0 && G > 0 && G <= kMaxGT, "B/G (G <= 128)");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* pos = static_cast<float*>(scratch);
+  float* partial = pos + (long long)B * 4;
+  unsigned char* occ = reinterpret_cast<unsigned char*>(partial + (long long)B * kLossBlocks);
+  ODT_CUDA_OK(cudaMemsetAsync(occ, 0, (size_t)B * (p->N / 3), st));
+  TailP tp;
+  tp.p = *p;
+  yolo_loss_pos_kernel<<<B, kMaxGT, 0, st>>>(head, tp, gt, G, occ, pos);
+  ODT_LAUNCH_OK();
+  yolo_loss_noobj_kernel<<<dim3(kLossBlocks, B), kLossThreads, 0, st>>>(head, tp, gt, G, occ, partial);
+  ODT_LAUNCH_OK();
+  yolo_loss_final_kernel<<<(B + 63) / 64, 64, 0, st>>>(pos, partial, B, coord_scale, noobj_scale, obj_scale,
+                                                       class_scale, loss_out);
   ODT_LAUNCH_OK();
   return ODT_OK;
 }

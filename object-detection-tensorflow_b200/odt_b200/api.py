@@ -376,6 +376,29 @@ class YOLOv3(_Detector):
     def _build(self, batch, precision, allow_tc=True):
         return nets.build_yolov3(batch, self.config, precision, self.device, allow_tc)
 
+    def loss_forward(self, images, ground_truth, precision=None):
+        """Forward of the per-image training loss (level / prior assignment, sigmoid-CE centre, class and
+        objectness terms, squared log-size term, no-object term) on the head rows the inference tail
+        reads.  ground_truth: [B,G,5] (y,x,h,w,id) padded with -1.  ref YOLOv3.py:115-318."""
+        import ctypes as C
+        from . import lib as L
+        images = np.ascontiguousarray(images, dtype=np.float32)
+        gt = np.ascontiguousarray(ground_truth, dtype=np.float32)
+        net = self.engine(images.shape[0], precision)
+        B, G = gt.shape[0], gt.shape[1]
+        net.image_buf.copy_(torch.from_numpy(images))
+        net.run()
+        dev = net.device
+        gtd = torch.from_numpy(gt).to(dev)
+        nbytes = net.lib.odt_yolo_loss_scratch_bytes(C.byref(net.tail.p), B)
+        scratch = torch.zeros((nbytes + 3) // 4, dtype=torch.int32, device=dev)
+        out = torch.zeros(B, dtype=torch.float32, device=dev)
+        L.check(net.lib.odt_yolo_loss_fwd(net.head_buf.data_ptr(), C.byref(net.tail.p), B, gtd.data_ptr(), G,
+                                          float(self.coord_sacle), float(self.noobj_scale), float(self.obj_scale),
+                                          float(self.class_scale), scratch.data_ptr(), out.data_ptr(),
+                                          torch.cuda.current_stream().cuda_stream), "yolo_loss")
+        return out.cpu().numpy()
+
 
 class FCOS(_Detector):
     name = "FCOS"

@@ -83,6 +83,8 @@ SYMBOLS = {
     "odt_ssd_loss_scratch_bytes": (_L, [C.POINTER(TailParams), _I]),
     "odt_ssd_loss_info_offset": (_L, [C.POINTER(TailParams), _I]),
     "odt_ssd_loss_fwd": (_I, [_P, C.POINTER(TailParams), _I, _P, _I, _P, _P, _P]),
+    "odt_yolo_loss_scratch_bytes": (_L, [C.POINTER(TailParams), _I]),
+    "odt_yolo_loss_fwd": (_I, [_P, C.POINTER(TailParams), _I, _P, _I, _F, _F, _F, _F, _P, _P, _P]),
     "odt_fcos_loss_scratch_bytes": (_L, [_I]),
     "odt_fcos_loss_fwd": (_I, [_P, C.POINTER(TailParams), _I, _P, _I, _P, _P, _P]),
 }

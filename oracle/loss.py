@@ -195,3 +195,81 @@ def fcos_image_loss(heads, gt, image=0):
         if m.any():
             total += fcos_level_loss(cls[image], reg[image], ctr[image, ..., 0], g[m], s)
     return float(total)
+
+
+def _sig_xent(labels, logits):
+    # tf.nn.sigmoid_cross_entropy_with_logits: max(x,0) - x*z + log(1 + exp(-|x|))
+    x, z = logits.astype(F32), labels.astype(F32)
+    return (np.maximum(x, F32(0)) - x * z + np.log1p(np.exp(-np.abs(x)))).astype(F32)
+
+
+def yolo_image_loss(preds, priors, gt, coord_scale=1.0, noobj_scale=1.0, obj_scale=5.0, class_scale=1.0,
+                    image=0, num_classes=20):
+    """YOLOv3 per-image training loss, forward only (YOLOv3.py:115-318, priors :37-41,419-433, GT
+    normalisation :435-442).  preds: 3 tensors [B,H,W,3*25] (13, 26, 52 grids for 416), rows
+    [cls(20), y, x, h, w, obj].  Quirks kept: level k normalises the GT with strides 32,16,8 but its
+    priors are priors[k]/(8,16,32)[k]; the GT/anchor intersections are NOT clamped at 0; the
+    "no-object" anchors are built from (yx - hw/2, yx + hw/2) re-used as (centre, size)."""
+    nc = num_classes
+    gt = np.asarray(gt, F32)
+    cnt = int(np.argmin(gt, axis=0)[0])
+    g = gt[:cnt]
+    norm = [32.0, 16.0, 8.0]
+    pstride = [8.0, 16.0, 32.0]
+    lv = []
+    for k, p in enumerate(preds):
+        _, h, w, _ = p.shape
+        r = p[image].reshape(h, w, 3, nc + 5).astype(F32)
+        pri = (np.array(priors[k], dtype=F32) / F32(pstride[k])).astype(F32)      # [3,2] (h,w)
+        gn = (g / np.array([norm[k]] * 4 + [1.0], F32).reshape(1, 5)).astype(F32)
+        gyx, ghw, lab = gn[:, :2], gn[:, 2:4], gn[:, 4].astype(np.int32)
+        fl = np.floor(gyx).astype(np.int64)
+        ayx = (fl.astype(F32) + F32(0.5))[:, None, :]                                 # [G,1,2] cell centre
+        a1 = (ayx - pri[None] / F32(2)).astype(F32)                                    # [G,3,2]
+        a2 = (ayx + pri[None] / F32(2)).astype(F32)
+        g1 = (gyx - ghw / F32(2.0)).astype(F32)[:, None, :]
+        g2 = (gyx + ghw / F32(2.0)).astype(F32)[:, None, :]
+        inter = np.prod(np.minimum(g2, a2) - np.maximum(g1, a1), axis=-1).astype(F32)  # no clamp (:171-173)
+        garea = np.prod(g2 - g1, axis=-1).astype(F32)
+        aarea = np.prod(pri, axis=-1).astype(F32)[None]
+        iou = (inter / (aarea + garea - inter)).astype(F32)                            # [G,3]
+        lv.append(dict(r=r, pri=pri, gyx=gyx, ghw=ghw, lab=lab, fl=fl, g1=g1[:, 0], g2=g2[:, 0],
+                       idx=np.argmax(iou, axis=-1), mx=iou.max(axis=-1), h=h, w=w))
+    m1 = (lv[0]["mx"] > lv[1]["mx"]) & (lv[0]["mx"] > lv[2]["mx"])
+    m2 = (lv[1]["mx"] > lv[0]["mx"]) & (lv[1]["mx"] > lv[2]["mx"])
+    m3 = ~(m1 | m2)
+    coord = cls_l = obj_l = noobj = 0.0
+    for L_, m in zip(lv, (m1, m2, m3)):
+        r, pri = L_["r"], L_["pri"]
+        for gi in np.nonzero(m)[0]:
+            y, x = L_["fl"][gi]
+            a = L_["idx"][gi]
+            row = r[y, x, a]
+            tyx = (L_["gyx"][gi] - np.floor(L_["gyx"][gi])).astype(F32)
+            thw = np.log((L_["ghw"][gi] / pri[a]).astype(F32)).astype(F32)
+            coord += float(_sig_xent(tyx, row[nc:nc + 2]).sum(dtype=np.float64))
+            coord += 0.5 * float(np.square(row[nc + 2:nc + 4] - thw).astype(F32).sum(dtype=np.float64))
+            onehot = np.zeros(nc, F32)
+            onehot[L_["lab"][gi]] = 1.0
+            cls_l += float(_sig_xent(onehot, row[:nc]).sum(dtype=np.float64))
+            obj_l += float(_sig_xent(np.ones(1, F32), row[nc + 4:nc + 5]).sum(dtype=np.float64))
+        # no-object term over the cells that hold no GT centre (:249-311)
+        h, w = L_["h"], L_["w"]
+        occ = np.zeros((h, w), bool)
+        occ[L_["fl"][:, 0], L_["fl"][:, 1]] = True
+        cy = (np.arange(h, dtype=F32) + F32(0.5)).reshape(h, 1, 1, 1)
+        cx = (np.arange(w, dtype=F32) + F32(0.5)).reshape(1, w, 1, 1)
+        ayx = np.concatenate([cy + np.zeros((1, w, 3, 1), F32), cx + np.zeros((h, 1, 3, 1), F32)], -1).astype(F32)
+        yx_nb = (ayx - pri.reshape(1, 1, 3, 2) / F32(2.0)).astype(F32)      # really y1x1
+        hw_nb = (ayx + pri.reshape(1, 1, 3, 2) / F32(2.0)).astype(F32)      # really y2x2
+        b1 = (yx_nb - hw_nb / F32(2.0)).astype(F32)[..., None, :]             # [h,w,3,1,2]
+        b2 = (yx_nb + hw_nb / F32(2.0)).astype(F32)[..., None, :]
+        gg1, gg2 = L_["g1"].reshape(1, 1, 1, -1, 2), L_["g2"].reshape(1, 1, 1, -1, 2)
+        inter = np.prod(np.minimum(gg2, b2) - np.maximum(gg1, b1), axis=-1).astype(F32)
+        aarea = np.prod(b2 - b1, axis=-1).astype(F32)
+        garea = np.prod(gg2 - gg1, axis=-1).astype(F32)
+        iou = (inter / (aarea + garea - inter)).astype(F32).max(axis=-1)       # [h,w,3]
+        mask = (iou <= F32(0.5)) & (~occ)[..., None]
+        noobj += float((_sig_xent(np.zeros_like(r[..., nc + 4]), r[..., nc + 4]) * mask).sum(dtype=np.float64))
+    ng = float(cnt)
+    return (coord_scale * coord + class_scale * cls_l + obj_scale * obj_l) / ng + noobj_scale * noobj / ng

@@ -236,6 +236,37 @@ def test_fcos_loss_forward_vs_oracle(built):
         assert abs(got[b] - ref) <= 2e-5 * max(abs(ref), 1.0)
 
 
+def test_yolov3_loss_forward_vs_oracle(built):
+    """YOLOv3 training-loss forward incl. the reference's quirks (unclamped
+    intersections, mismatched GT / prior strides, the re-used no-object anchor form)."""
+    from helpers import YOLO_PRIORS
+    from oracle import loss as OL
+    m = _model("yolov3", precision="fp32", bn_init="trained", data_shape=[416, 416, 3], obj_scale=5,
+               coord_scale=2, noobj_scale=0.5, class_scale=1.5)
+    B, G = 2, 12
+    img = _img(B, 416, 416, seed=41)
+    rng = np.random.default_rng(12)
+    gt = np.full((B, G, 5), -1.0, np.float32)
+    for b in range(B):
+        n = 3 + 5 * b
+        gt[b, :n, 0:2] = rng.uniform(30, 380, (n, 2))
+        gt[b, :n, 2:4] = rng.uniform(12, 300, (n, 2))
+        gt[b, :n, 4] = rng.integers(0, 20, n)
+    got = m.loss_forward(img, gt)
+    net = m.engine(B)
+    rows = net.head_buf.cpu().numpy()
+    off, preds = 0, []
+    for h, w, a in net.levels:
+        preds.append(rows[:, off:off + h * w * a].reshape(B, h, w, a * 25))
+        off += h * w * a
+    assert [p.shape[1] for p in preds] == [13, 26, 52]
+    for b in range(B):
+        ref = OL.yolo_image_loss(preds, YOLO_PRIORS, gt[b], coord_scale=2, noobj_scale=0.5, obj_scale=5,
+                                 class_scale=1.5, image=b)
+        print("image %d: loss gpu %.5f oracle %.5f" % (b, got[b], ref))
+        assert abs(got[b] - ref) <= 2e-5 * max(abs(ref), 1.0)
+
+
 def test_detect_stream_matches_detect_batch(built):
     """Pipelined public API (H2D of batch i+1 overlaps batch i) == synchronous API."""
     import torch
