@@ -9,6 +9,8 @@
 //
 // Reference call sites restated here (never copied): SSD300.py:157-190,323-343;
 // RetinaNet.py:224-256,328-355; YOLOv3.py:320-368,419-433; FCOS.py:130-150,197-264.
+#include <stdlib.h>
+
 #include "tail_common.cuh"
 
 namespace odt {
@@ -28,17 +30,39 @@ __global__ void __launch_bounds__(kDecodeWarps * 32)
   float* my = srow[warp];
   const long long warps_total = (long long)gridDim.x * kDecodeWarps;
   const long long groups = (total_rows + 31) / 32;
-  for (long long g = (long long)blockIdx.x * kDecodeWarps + warp; g < groups; g += warps_total) {
+  // Software pipeline per warp: the 128-bit loads of the NEXT 32-row group are issued into registers
+  // before the current group (already staged in shared memory) is decoded, so every warp keeps
+  // ~3 KB in flight while it computes.
+  constexpr int kVecPerLane = (32 * kRow / 4 + 31) / 32;  // 7
+  float4 pre[kVecPerLane];
+  auto fetch = [&](long long gg) {
+    const long long r0 = gg * 32;
+    const int nr = (int)min((long long)32, total_rows - r0);
+    const int nv = nr * kRow / 4;
+    const float4* s4 = reinterpret_cast<const float4*>(head + r0 * kRow);
+#pragma unroll
+    for (int i = 0; i < kVecPerLane; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nv) pre[i] = __ldcs(s4 + idx);
+    }
+  };
+  long long g = (long long)blockIdx.x * kDecodeWarps + warp;
+  if (g < groups) fetch(g);
+  for (; g < groups; g += warps_total) {
     const long long row0 = g * 32;
     const int nrows = (int)min((long long)32, total_rows - row0);
     const float* src = head + row0 * kRow;
     // row0*25 floats: 32-row groups start at a multiple of 800 floats = 3200 B -> 16 B aligned
     const int nvec = nrows * kRow / 4;
-    const float4* src4 = reinterpret_cast<const float4*>(src);
     float4* dst4 = reinterpret_cast<float4*>(my);
-    for (int i = lane; i < nvec; i += 32) dst4[i] = __ldg(src4 + i);
+#pragma unroll
+    for (int i = 0; i < kVecPerLane; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nvec) dst4[idx] = pre[i];
+    }
     for (int i = nvec * 4 + lane; i < nrows * kRow; i += 32) my[i] = __ldg(src + i);
     __syncwarp();
+    if (g + warps_total < groups) fetch(g + warps_total);
 
     const bool active = lane < nrows;
     const long long row = row0 + lane;
@@ -82,30 +106,61 @@ __global__ void __launch_bounds__(kDecodeWarps * 32)
 #pragma unroll
       for (int i = 0; i < 20; ++i) conf[i] = __fmul_rn(sigmoid_rn(r[i]), sc);
     }
+    // Threshold + append.  Fast path (all rows of the warp in one image, i.e. everywhere but at image
+    // boundaries): the 20 per-class ballots are taken first, then lane c reserves the slots of class c
+    // with ONE atomic -- 20 independent atomics in flight instead of 20 dependent round trips.
+    const int b0 = __shfl_sync(0xffffffffu, b, 0);
+    const bool one_image = __all_sync(0xffffffffu, !active || b == b0);
+    if (one_image) {
+      unsigned my_mask = 0u;  // lane c keeps the ballot of class c
+      unsigned pass_bits = 0u;
 #pragma unroll
-    for (int c = 0; c < 20; ++c) {
-      if (c >= p.num_fg) break;
-      const bool pass = keep_row && (conf[c] >= p.score_thr);
-      const unsigned mask = __ballot_sync(0xffffffffu, pass);
-      if (mask == 0) continue;
-      // rows of one warp may straddle several images: aggregate the counter
-      // update per image (warp-uniform loop)
-      unsigned rem = mask;
-      int slot = -1;
-      while (rem) {
-        const int leader = __ffs(rem) - 1;
-        const int bl = __shfl_sync(0xffffffffu, b, leader);
-        const unsigned grp = __ballot_sync(0xffffffffu, pass && b == bl);
-        int base = 0;
-        if (lane == leader) base = atomicAdd(&cand_count[bl * p.num_fg + c], __popc(grp));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (pass && b == bl) slot = base + __popc(grp & ((1u << lane) - 1));
-        rem &= ~grp;
+      for (int c = 0; c < 20; ++c) {
+        const bool pass = c < p.num_fg && keep_row && (conf[c] >= p.score_thr);
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (lane == c) my_mask = m;
+        pass_bits |= pass ? (1u << c) : 0u;
       }
-      if (pass && slot < p.cap) {
-        const unsigned long long key =
-            ((unsigned long long)__float_as_uint(conf[c]) << 32) | (0xFFFFFFFFu - (unsigned)n);
-        cand_keys[((long long)b * p.num_fg + c) * p.cap + slot] = key;
+      int my_base = 0;
+      if (my_mask) my_base = atomicAdd(&cand_count[b0 * p.num_fg + lane], __popc(my_mask));
+      const unsigned any = __ballot_sync(0xffffffffu, my_mask != 0u);  // classes with candidates
+#pragma unroll
+      for (int c = 0; c < 20; ++c) {
+        if (!((any >> c) & 1u)) continue;  // warp-uniform
+        const unsigned m = __shfl_sync(0xffffffffu, my_mask, c);
+        const int base = __shfl_sync(0xffffffffu, my_base, c);
+        if ((pass_bits >> c) & 1u) {
+          const int slot = base + __popc(m & ((1u << lane) - 1));
+          if (slot < p.cap)
+            cand_keys[((long long)b0 * p.num_fg + c) * p.cap + slot] =
+                ((unsigned long long)__float_as_uint(conf[c]) << 32) | (0xFFFFFFFFu - (unsigned)n);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 20; ++c) {
+        if (c >= p.num_fg) break;
+        const bool pass = keep_row && (conf[c] >= p.score_thr);
+        const unsigned mask = __ballot_sync(0xffffffffu, pass);
+        if (mask == 0) continue;
+        // rows of this warp straddle two images: aggregate the counter update per image
+        unsigned rem = mask;
+        int slot = -1;
+        while (rem) {
+          const int leader = __ffs(rem) - 1;
+          const int bl = __shfl_sync(0xffffffffu, b, leader);
+          const unsigned grp = __ballot_sync(0xffffffffu, pass && b == bl);
+          int base = 0;
+          if (lane == leader) base = atomicAdd(&cand_count[bl * p.num_fg + c], __popc(grp));
+          base = __shfl_sync(0xffffffffu, base, leader);
+          if (pass && b == bl) slot = base + __popc(grp & ((1u << lane) - 1));
+          rem &= ~grp;
+        }
+        if (pass && slot < p.cap) {
+          const unsigned long long key =
+              ((unsigned long long)__float_as_uint(conf[c]) << 32) | (0xFFFFFFFFu - (unsigned)n);
+          cand_keys[((long long)b * p.num_fg + c) * p.cap + slot] = key;
+        }
       }
     }
     __syncwarp();
@@ -423,7 +478,9 @@ extern "C" int odt_decode_candidates(const float* head, const odt_tail_params* p
   long long rows = (long long)B * p->N;
   long long groups = (rows + 31) / 32;
   int blocks = (int)((groups + kDecodeWarps - 1) / kDecodeWarps);
-  int maxb = kNumSMs * 8;
+  int per_sm = 8;  // measured best of 2/4/8 (80 registers: 3 blocks resident, the rest back-fills the tail)
+  if (const char* e = getenv("ODT_DECODE_BLOCKS_PER_SM")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;
+  int maxb = kNumSMs * per_sm;
   if (blocks > maxb) blocks = maxb;
   decode_candidates_kernel<<<blocks, kDecodeWarps * 32, 0, st>>>(head, tp, rows, cand_keys,
                                                                  cand_count);
