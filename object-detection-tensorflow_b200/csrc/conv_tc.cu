@@ -70,7 +70,6 @@ struct TcGeom {
   // in shared memory (loaded once per CTA); the pipeline stages then carry activations only
   int bres;
   int pair;         // 1: launched as CTA pairs (conv_tc_kernel<2>)
-  int dbg_aligned;  // timing experiment only (ODT_TC_DEBUG_ALIGNED=1): all taps read the unshifted slab (wrong results)
 };
 constexpr int TC_HEAD_STAGE = TC_EPI_WARPS * 32 * 33 * 4;  // per-warp [32][33] fp32 transpose tiles
 constexpr int TC_FLAT_ROWS = 136;                    // 128 + 2 neighbours, padded to 1024 B
@@ -312,8 +311,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             // descriptor start shifted by s*128 B inside the 1024 B swizzle pattern (the
             // swizzle is a function of the absolute address: probed, scripts/probe_rowoffset.py)
             const uint64_t bstep = (uint64_t)(((uint32_t)(g.bres ? g.cchunks : 1) * bn_cta * 128u) >> 4);
-            const uint64_t astep =
-                g.dbg_aligned ? 0ull : (uint64_t)(g.flat == 2 ? 8 * g.RP : 8);  // rows per tap shift x 128 B >> 4
+            const uint64_t astep = (uint64_t)(g.flat == 2 ? 8 * g.RP : 8);  // rows per tap shift x 128 B >> 4
 #pragma unroll
             for (int s3 = 0; s3 < 3; ++s3) {
 #pragma unroll
@@ -877,10 +875,6 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
     g.bres = 1;
     g.b_bytes = 0;
     stage_bytes = g.a_bytes;
-  }
-  {
-    const char* dbg = getenv("ODT_TC_DEBUG_ALIGNED");
-    g.dbg_aligned = (dbg && dbg[0] == '1') ? 1 : 0;
   }
   int stages = (TC_SMEM_LIMIT - 2048 - TC_EPI_SMEM - out_stage_bytes - (g.bres ? (int)wres : 0)) / stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;

@@ -585,9 +585,9 @@ class Net:
         for t in self.acts:
             if getattr(t, "fused_away", False):
                 continue  # the pre-pool tensor of a conv with a fused max-pool is never materialised
-            if t.needed or True:  # unneeded raws are tiny bookkeeping; keep a buffer for residual addressing
-                t.buf = torch.zeros((t.B, t.H + 2 * t.halo, t.W + 2 * t.halo, t.ld), dtype=self.tdtype,
-                                    device=dev)
+            if not t.needed:
+                continue  # raw output nobody reads (only its fused pre-activations are consumed)
+            t.buf = torch.zeros((t.B, t.H + 2 * t.halo, t.W + 2 * t.halo, t.ld), dtype=self.tdtype, device=dev)
         self.N = sum(h * w * a for h, w, a in self.levels)
         self.head_buf = torch.zeros((self.batch, self.N, 25), dtype=torch.float32, device=dev)
         self.tail = tail
