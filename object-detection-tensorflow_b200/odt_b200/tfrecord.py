@@ -1,0 +1,252 @@
+"""TFRecord + tf.train.Example reader / writer and the VOC record schema of the reference's
+input pipeline (utils/tfrecord_voc_utils.py:30-113), without TensorFlow.  Host-side IO for
+SURVEY section 8(f) row 3; not on the accelerated hot path.
+
+* TFRecord framing: u64 length | u32 masked crc32c(length) | payload | u32 masked crc32c(payload).
+* tf.train.Example: Example{1: Features{1: map<string, Feature>}}, Feature = oneof
+  {1: BytesList{1: bytes...}, 2: FloatList{1: packed float}, 3: Int64List{1: packed varint}}.
+* VOC schema written by `xml_to_example` (:30-62): 'image' = JPEG bytes, 'shape' = int32[3]
+  (h, w, c) as bytes, 'ground_truth' = float32[n,5] rows (ymin, ymax, xmin, xmax, class id).
+* `preprocess` is the deterministic core of `image_augmentor` (utils/image_augmentor.py) for
+  keep_aspect_ratios=False: resize to `output_shape`, boxes scaled and converted to
+  (y_centre, x_centre, h, w, id), padded with -1 rows to `pad_truth_to`; optional left-right flip
+  with a seeded numpy generator.  Random zoom/crop, colour jitter and rotation are training
+  augmentations and are not restated (a warning is printed when the config asks for them).
+PARITY UNPINNED: no TensorFlow and no TF-written record here; JPEG decoding goes through
+OpenCV (libjpeg-turbo), TF uses libjpeg -- pixels can differ by a few levels.
+"""
+import struct
+import sys
+
+import numpy as np
+
+from .tf_checkpoint import (CheckpointError, _get_varint, _pb_bytes, _pb_fields, _put_varint, crc32c,
+                            mask_crc)
+
+
+class RecordError(CheckpointError):
+    pass
+
+
+# ---------------------------------------------------------------- framing ---
+def write_records(path, payloads):
+    with open(path, "wb") as f:
+        for p in payloads:
+            head = struct.pack("<Q", len(p))
+            f.write(head)
+            f.write(struct.pack("<I", mask_crc(crc32c(head))))
+            f.write(p)
+            f.write(struct.pack("<I", mask_crc(crc32c(p))))
+
+
+def read_records(path, verify=True):
+    with open(path, "rb") as f:
+        while True:
+            head = f.read(8)
+            if not head:
+                return
+            if len(head) != 8:
+                raise RecordError("%s: truncated record header" % path)
+            (n,) = struct.unpack("<Q", head)
+            (hc,) = struct.unpack("<I", f.read(4))
+            if verify and mask_crc(crc32c(head)) != hc:
+                raise RecordError("%s: record length checksum mismatch" % path)
+            data = f.read(n)
+            tail = f.read(4)
+            if len(data) != n or len(tail) != 4:
+                raise RecordError("%s: truncated record" % path)
+            if verify and mask_crc(crc32c(data)) != struct.unpack("<I", tail)[0]:
+                raise RecordError("%s: record payload checksum mismatch" % path)
+            yield data
+
+
+# ---------------------------------------------------------------- Example ---
+def encode_example(features):
+    """features: {name: bytes | list of bytes | float array | int array}."""
+    fmap = bytearray()
+    for key in sorted(features):
+        v = features[key]
+        feat = bytearray()
+        if isinstance(v, (bytes, bytearray)):
+            v = [bytes(v)]
+        if isinstance(v, (list, tuple)) and v and isinstance(v[0], (bytes, bytearray)):
+            bl = bytearray()
+            for b in v:
+                _pb_bytes(bl, 1, bytes(b))
+            _pb_bytes(feat, 1, bl)
+        else:
+            a = np.asarray(v)
+            inner = bytearray()
+            if a.dtype.kind == "f":
+                _pb_bytes(inner, 1, a.astype("<f4").tobytes())
+                _pb_bytes(feat, 2, inner)
+            else:
+                packed = bytearray()
+                for x in a.reshape(-1).tolist():
+                    _put_varint(packed, int(x))
+                _pb_bytes(inner, 1, packed)
+                _pb_bytes(feat, 3, inner)
+        entry = bytearray()
+        _pb_bytes(entry, 1, key.encode("utf-8"))
+        _pb_bytes(entry, 2, feat)
+        _pb_bytes(fmap, 1, entry)
+    out = bytearray()
+    _pb_bytes(out, 1, fmap)
+    return bytes(out)
+
+
+def parse_example(data):
+    """-> {name: list of bytes | float32 array | int64 array}."""
+    out = {}
+    for f, _, features in _pb_fields(data):
+        if f != 1:
+            continue
+        for f2, _, entry in _pb_fields(features):
+            if f2 != 1:
+                continue
+            key, feat = None, b""
+            for f3, _, v in _pb_fields(entry):
+                if f3 == 1:
+                    key = v.decode("utf-8")
+                elif f3 == 2:
+                    feat = v
+            val = []
+            for kind, _, lst in _pb_fields(feat):
+                if kind == 1:
+                    val = [v for f4, _, v in _pb_fields(lst) if f4 == 1]
+                elif kind == 2:
+                    parts = []
+                    for f4, wt, v in _pb_fields(lst):
+                        if f4 == 1:
+                            parts.append(np.frombuffer(v, "<f4") if wt == 2 else
+                                         np.frombuffer(struct.pack("<I", v), "<f4"))
+                    val = np.concatenate(parts).astype(np.float32) if parts else np.zeros(0, np.float32)
+                elif kind == 3:
+                    ints = []
+                    for f4, wt, v in _pb_fields(lst):
+                        if f4 != 1:
+                            continue
+                        if wt == 2:
+                            pos = 0
+                            while pos < len(v):
+                                x, pos = _get_varint(v, pos)
+                                ints.append(x - (1 << 64) if x >= (1 << 63) else x)
+                        else:
+                            ints.append(v - (1 << 64) if v >= (1 << 63) else v)
+                    val = np.asarray(ints, np.int64)
+            if key is not None:
+                out[key] = val
+    return out
+
+
+# ------------------------------------------------------------- VOC schema ---
+def encode_voc_example(jpeg_bytes, shape, ground_truth):
+    return encode_example({"image": jpeg_bytes, "shape": np.asarray(shape, "<i4").tobytes(),
+                           "ground_truth": np.asarray(ground_truth, "<f4").tobytes()})
+
+
+def decode_voc_example(data):
+    """-> (image uint8 [H,W,3] RGB, ground_truth float32 [n,5] = (ymin, ymax, xmin, xmax, id))."""
+    import cv2
+    ex = parse_example(data)
+    for k in ("image", "shape", "ground_truth"):
+        if k not in ex or not ex[k]:
+            raise RecordError("record lacks the %r feature" % k)
+    shape = np.frombuffer(ex["shape"][0], "<i4")
+    gt = np.frombuffer(ex["ground_truth"][0], "<f4").reshape(-1, 5).astype(np.float32)
+    img = cv2.imdecode(np.frombuffer(ex["image"][0], np.uint8), cv2.IMREAD_COLOR)
+    if img is None:
+        raise RecordError("image bytes are not decodable")
+    img = cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
+    if tuple(img.shape) != tuple(int(x) for x in shape):
+        raise RecordError("decoded image %s does not match the stored shape %s" % (img.shape, shape.tolist()))
+    return img, gt
+
+
+def _resize_bilinear_legacy(img, oh, ow):
+    """tf.image.resize_images(BILINEAR, align_corners=False), TF1 legacy sampling."""
+    h, w = img.shape[:2]
+    x = img.astype(np.float32)
+    ys = (np.arange(oh, dtype=np.float32) * np.float32(h / oh))
+    xs = (np.arange(ow, dtype=np.float32) * np.float32(w / ow))
+    y0 = np.floor(ys).astype(np.int64)
+    x0 = np.floor(xs).astype(np.int64)
+    y1 = np.minimum(np.ceil(ys).astype(np.int64), h - 1)
+    x1 = np.minimum(np.ceil(xs).astype(np.int64), w - 1)
+    wy = (ys - y0).astype(np.float32).reshape(-1, 1, 1)
+    wx = (xs - x0).astype(np.float32).reshape(1, -1, 1)
+    top = x[y0][:, x0] * (1 - wx) + x[y0][:, x1] * wx
+    bot = x[y1][:, x0] * (1 - wx) + x[y1][:, x1] * wx
+    return (top * (1 - wy) + bot * wy).astype(np.float32)
+
+
+def preprocess(img, gt, config, rng=None):
+    """Deterministic core of image_augmentor for keep_aspect_ratios=False (see module doc)."""
+    oh, ow = config["output_shape"]
+    for k in ("zoom_size", "color_jitter_prob", "rotate"):
+        if config.get(k) is not None and not preprocess._warned.get(k):
+            preprocess._warned[k] = True
+            sys.stderr.write("[odt_b200] image_augmentor option %r is a random training augmentation that is "
+                             "not restated; the deterministic resize path is used\n" % k)
+    h, w = img.shape[:2]
+    out = _resize_bilinear_legacy(img, oh, ow)
+    ymin, ymax, xmin, xmax = [gt[:, i] * (oh / h if i < 2 else ow / w) for i in range(4)]
+    flip = config.get("flip_prob")
+    if flip is not None and rng is not None and rng.random() < flip[1]:
+        out = out[:, ::-1]
+        xmin, xmax = ow - xmax, ow - xmin
+    box = np.stack([(ymin + ymax) / 2, (xmin + xmax) / 2, ymax - ymin, xmax - xmin, gt[:, 4]], -1).astype(np.float32)
+    pad = config.get("pad_truth_to")
+    if pad:
+        full = np.full((int(pad), 5), -1.0, np.float32)
+        n = min(len(box), int(pad))
+        full[:n] = box[:n]
+        box = full
+    if config.get("data_format") == "channels_first":
+        out = np.transpose(out, (2, 0, 1))
+    return np.ascontiguousarray(out, np.float32), box
+
+
+preprocess._warned = {}
+
+
+class BatchIterator:
+    """`iterator.get_next()` of `get_generator` (utils/tfrecord_voc_utils.py:115-120): endless batches
+    (images float32 [B,...], ground_truth float32 [B,pad,5]); drop_remainder, shuffle buffer, repeat."""
+
+    def __init__(self, tfrecords, batch_size, buffer_size, config, seed=0):
+        self.files = [tfrecords] if isinstance(tfrecords, str) else list(tfrecords)
+        self.batch_size, self.buffer_size, self.config = int(batch_size), max(int(buffer_size), 1), dict(config)
+        self.rng = np.random.default_rng(seed)
+        self._it = None
+
+    def initialize(self):
+        self._it = self._batches()
+
+    def _examples(self):
+        while True:  # .repeat()
+            n = 0
+            for path in self.files:
+                for rec in read_records(path):
+                    n += 1
+                    yield preprocess(*decode_voc_example(rec), self.config, self.rng)
+            if n == 0:
+                raise RecordError("no records in %r" % (self.files,))
+
+    def _shuffled(self):
+        buf = []
+        for ex in self._examples():
+            buf.append(ex)
+            if len(buf) >= self.buffer_size:
+                yield buf.pop(int(self.rng.integers(len(buf))))
+
+    def _batches(self):
+        src = self._shuffled()
+        while True:
+            items = [next(src) for _ in range(self.batch_size)]
+            yield np.stack([i[0] for i in items]), np.stack([i[1] for i in items])
+
+    def get_next(self):
+        if self._it is None:
+            self.initialize()
+        return next(self._it)

@@ -1,0 +1,92 @@
+"""TFRecord / tf.train.Example / VOC record schema, CPU only.  PARITY UNPINNED (no
+TensorFlow, no TF-written file): framing and protobuf layout are checked on hand-assembled bytes and
+round trips."""
+import struct
+
+import numpy as np
+import pytest
+
+
+@pytest.fixture()
+def tr():
+    from odt_b200 import tfrecord
+    return tfrecord
+
+
+def _varint(v):
+    out = bytearray()
+    while v >= 0x80:
+        out.append((v & 0x7F) | 0x80)
+        v >>= 7
+    out.append(v)
+    return bytes(out)
+
+
+def test_framing_bytes_and_corruption(tr, tmp_path):
+    from odt_b200.tf_checkpoint import crc32c, mask_crc
+    p = str(tmp_path / "a.tfrecord")
+    tr.write_records(p, [b"hello", b"", b"x" * 1000])
+    raw = open(p, "rb").read()
+    # first record by hand: u64 5 | masked crc of those 8 bytes | payload | masked crc of payload
+    head = struct.pack("<Q", 5)
+    assert raw[:8] == head and raw[8:12] == struct.pack("<I", mask_crc(crc32c(head)))
+    assert raw[12:17] == b"hello" and raw[17:21] == struct.pack("<I", mask_crc(crc32c(b"hello")))
+    assert list(tr.read_records(p)) == [b"hello", b"", b"x" * 1000]
+    bad = bytearray(raw)
+    bad[14] ^= 1
+    open(p, "wb").write(bytes(bad))
+    with pytest.raises(tr.RecordError, match="payload checksum"):
+        list(tr.read_records(p))
+
+
+def test_example_protobuf_layout_by_hand(tr):
+    """Example{features{feature{key:'k' value{bytes_list{value:'ab'}}}}} assembled byte by byte."""
+    bytes_list = b"\x0a\x02ab"                       # field 1, len 2
+    feature = b"\x0a" + _varint(len(bytes_list)) + bytes_list   # Feature.bytes_list = field 1
+    entry = b"\x0a\x01k" + b"\x12" + _varint(len(feature)) + feature
+    features = b"\x0a" + _varint(len(entry)) + entry
+    example = b"\x0a" + _varint(len(features)) + features
+    assert tr.parse_example(example) == {"k": [b"ab"]}
+    assert tr.encode_example({"k": b"ab"}) == example
+    # float_list (packed) and int64_list (packed varints, negative value)
+    ex = tr.parse_example(tr.encode_example({"f": np.asarray([1.5, -2.0], np.float32), "i": np.asarray([3, -1])}))
+    np.testing.assert_array_equal(ex["f"], np.asarray([1.5, -2.0], np.float32))
+    np.testing.assert_array_equal(ex["i"], np.asarray([3, -1], np.int64))
+
+
+def test_voc_records_through_get_generator(tr, tmp_path):
+    import cv2
+    from utils import tfrecord_voc_utils as voc_utils
+    rng = np.random.default_rng(0)
+    recs = []
+    for i in range(5):
+        h, w = 40 + 4 * i, 60
+        img = np.zeros((h, w, 3), np.uint8)
+        img[:, : w // 2] = (200, 30, 30)             # left half red (RGB), smooth -> JPEG-stable
+        ok, enc = cv2.imencode(".jpg", cv2.cvtColor(img, cv2.COLOR_RGB2BGR))
+        assert ok
+        gt = np.asarray([[4, 24, 6, 36, i % 20], [10, 30, 20, 50, (i + 1) % 20]], np.float32)
+        recs.append(tr.encode_voc_example(enc.tobytes(), [h, w, 3], gt))
+    path = str(tmp_path / "voc_00001-of-00001.tfrecord")
+    tr.write_records(path, recs)
+    img0, gt0 = tr.decode_voc_example(next(tr.read_records(path)))
+    assert img0.shape == (40, 60, 3) and img0[5, 5, 0] > 150 and img0[5, 55, 0] < 40   # RGB order kept
+    cfg = {"data_format": "channels_last", "output_shape": [20, 30], "zoom_size": None, "crop_method": None,
+           "flip_prob": None, "fill_mode": "BILINEAR", "keep_aspect_ratios": False, "constant_values": 0.,
+           "color_jitter_prob": None, "rotate": None, "pad_truth_to": 6}
+    init_op, it = voc_utils.get_generator([path], 2, 3, cfg)
+    init_op()
+    images, truth = it.get_next()
+    assert images.shape == (2, 20, 30, 3) and images.dtype == np.float32
+    assert truth.shape == (2, 6, 5) and np.all(truth[:, 2:] == -1)
+    # the 40x60 record at half scale: box (ymin 4, ymax 24, xmin 6, xmax 36) -> centre (7, 10.5), size (10, 15)
+    seen = False
+    for _ in range(6):
+        for t in truth.reshape(-1, 5):
+            if t[4] == 0 and abs(t[2] - 10) < 1e-4:
+                np.testing.assert_allclose(t[:4], [7.0, 10.5, 10.0, 15.0], atol=1e-4)
+                seen = True
+        images, truth = it.get_next()
+    assert seen
+    for _ in range(4):   # repeat(): the stream never ends
+        it.get_next()
