@@ -169,6 +169,12 @@ int odt_groupnorm_stats(const void* in, float* stats, int dtype, int B, long lon
 int odt_groupnorm_apply(const void* in, void* out, const float* stats, int dtype, int B,
                         long long hw, int C, int ld, int groups, const float* gamma,
                         const float* beta, int act, void* stream);
+/* GroupNorm + activation in two launches (power-of-two C and groups, 16-byte aligned tensors):
+ * `acc_zeroed` = B*groups*2 doubles the CALLER has zeroed (e.g. one memset of an arena per forward);
+ * returns ODT_ERR_UNSUPPORTED (nothing launched) for other shapes -- use stats + apply then. */
+int odt_groupnorm_act(const void* in, void* out, double* acc_zeroed, int dtype, int B, long long hw, int C,
+                      int ld, int groups, float eps, const float* gamma, const float* beta, int act,
+                      void* stream);
 
 /* ------------------------------------------------- decode + NMS tail ----- */
 #define ODT_DECODE_SSD 0    /* SSD300/SSD512/RetinaNet: softmax+argmax+bg filter */

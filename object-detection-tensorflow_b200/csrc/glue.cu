@@ -387,6 +387,47 @@ __global__ void groupnorm_apply_kernel(const T* __restrict__ in, T* __restrict__
   }
 }
 
+// apply with the finalisation folded in: every block first turns the (sum, sum of squares)
+// accumulators of all (image, group) pairs into (mean, rstd) in shared memory
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+    groupnorm_apply_acc_kernel(const T* __restrict__ in, T* __restrict__ out, const double* __restrict__ acc,
+                               int B, long long hw, int C, int ld, int groups, double n, float eps,
+                               const float* __restrict__ gamma, const float* __restrict__ beta, int act) {
+  pdl_launch_dependents();
+  extern __shared__ float s_stat[];  // [B*groups][2]
+  for (int i = threadIdx.x; i < B * groups; i += blockDim.x) {
+    const double mean = acc[2 * i] / n;
+    double var = acc[2 * i + 1] / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_stat[2 * i] = (float)mean;
+    s_stat[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  const int cv = C / V;
+  const int cpg = C / groups;
+  const long long total = (long long)B * hw * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * V;
+    const long long pix = i / cv;
+    const int b = (int)(pix / hw);
+    float v[V];
+    VecIO<T, V>::ld(in + pix * ld + c, v);
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+      const int g = (c + q) / cpg;
+      const float mean = s_stat[(b * groups + g) * 2], rstd = s_stat[(b * groups + g) * 2 + 1];
+      const float gm = gamma ? __ldg(gamma + c + q) : 1.f;
+      const float bt = beta ? __ldg(beta + c + q) : 0.f;
+      const float gain = __fmul_rn(rstd, gm);
+      const float off = __fadd_rn(__fmul_rn(-mean, gain), bt);
+      v[q] = apply_act(__fadd_rn(__fmul_rn(v[q], gain), off), act);
+    }
+    VecIO<T, V>::st(out + pix * ld + c, v);
+  }
+}
+
 }  // namespace odt
 
 using namespace odt;
@@ -584,4 +625,44 @@ extern "C" int odt_groupnorm_apply(const void* in, void* out, const float* stats
   })
   ODT_LAUNCH_OK();
   return ODT_OK;
+}
+
+// GroupNorm + activation in two launches: parallel (sum, sum^2) accumulation into the caller's
+// PRE-ZEROED fp64 workspace, then normalise with the finalisation done per block.
+extern "C" int odt_groupnorm_act(const void* in, void* out, double* acc_zeroed, int dtype, int B, long long hw,
+                                 int C, int ld, int groups, float eps, const float* gamma, const float* beta,
+                                 int act, void* stream) {
+  ODT_CHECK_ARG(in && out && acc_zeroed && B > 0 && hw > 0 && C > 0 && ld >= C && groups > 0 && C % groups == 0,
+                "args");
+  ODT_CHECK_ARG(((uintptr_t)acc_zeroed & 7) == 0, "workspace must be 8-byte aligned");
+  ODT_CHECK_ARG((long long)B * groups * 2 * 4 <= 48 * 1024, "B * groups too large for the in-kernel finalisation");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int cpg = C / groups;
+  const bool pow2 = (C & (C - 1)) == 0 && (groups & (groups - 1)) == 0;
+  int rc = ODT_ERR_UNSUPPORTED;
+  DISPATCH_DTYPE(dtype, {
+    constexpr int V = FullVec<T>::V;
+    const int cv = C / V;
+    const bool fast = pow2 && C % V == 0 && cv <= 256 && groups <= 64 && ld % V == 0 &&
+                      ((uintptr_t)in % 16) == 0 && ((uintptr_t)out % 16) == 0 &&
+                      (cpg >= V ? cpg % V == 0 : V % cpg == 0) && (cpg >= V || V / cpg <= 8);
+    if (fast) {
+      long long blocks = (long long)kNumSMs * 4 / B;
+      if (blocks < 1) blocks = 1;
+      long long ppb = (hw + blocks - 1) / blocks;
+      const long long min_ppb = 256 / cv * 8;
+      if (ppb < min_ppb) ppb = min_ppb;
+      blocks = (hw + ppb - 1) / ppb;
+      groupnorm_partial_kernel<T, V><<<dim3((unsigned)blocks, B), 256, 0, st>>>((const T*)in, acc_zeroed, hw, C, ld,
+                                                                             groups, ppb);
+      ODT_LAUNCH_OK();
+      const long long work = (long long)B * hw * cv;
+      groupnorm_apply_acc_kernel<T, V><<<grid_for(work, 256), 256, (size_t)B * groups * 2 * sizeof(float), st>>>(
+          (const T*)in, (T*)out, acc_zeroed, B, hw, C, ld, groups, (double)hw * cpg, eps, gamma, beta, act);
+      ODT_LAUNCH_OK();
+      rc = ODT_OK;
+    }
+  })
+  if (rc == ODT_ERR_UNSUPPORTED) set_error("odt_groupnorm_act: shape outside the two-launch path (use stats + apply)");
+  return rc;
 }
