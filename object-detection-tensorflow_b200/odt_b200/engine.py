@@ -272,16 +272,32 @@ class GroupNormActOp(Op):
     def __init__(self, x, y, gn, act, groups=8):
         self.x, self.y, self.gn, self.act, self.groups = x, y, gn, act, groups
         self.reads, self.writes = (x,), (y,)
+        self.acc = None  # slice of the net's fp64 arena (zeroed once per forward): the two-launch path
 
     def prepare(self, net):
         dev = net.device
         self.gamma = torch.from_numpy(np.asarray(net.weights[self.gn + "/gamma"], np.float32)).to(dev)
         self.beta = torch.from_numpy(np.asarray(net.weights[self.gn + "/beta"], np.float32)).to(dev)
         self.stats = torch.zeros(self.x.B * self.groups * 6, dtype=torch.float32, device=dev)
+        x = self.x
+        C_, g = x.C, self.groups
+        self.two_launch = (net.gn_arena is not None and (C_ & (C_ - 1)) == 0 and (g & (g - 1)) == 0
+                           and x.B * g * 8 <= 48 * 1024)
+        if self.two_launch:
+            self.acc = net.gn_take(x.B * g * 2)
 
     def launch(self, net, stream):
         x = self.x
         hw = x.H * x.W
+        if self.two_launch:
+            rc = net.lib.odt_groupnorm_act(x.ptr(), self.y.ptr(), self.acc, net.dt, x.B, hw, x.C, x.ld,
+                                           self.groups, GN_EPS, self.gamma.data_ptr(), self.beta.data_ptr(),
+                                           ACT[self.act], stream)
+            if rc == 0:
+                return
+            if rc != L.ERR_UNSUPPORTED:
+                L.check(rc, "gn_act")
+            self.two_launch = False  # shape outside the fused path: fall through to stats + apply
         L.check(net.lib.odt_groupnorm_stats(x.ptr(), self.stats.data_ptr(), net.dt, x.B, hw, x.C,
                                             x.ld, self.groups, GN_EPS, stream), "gn_stats")
         L.check(net.lib.odt_groupnorm_apply(x.ptr(), self.y.ptr(), self.stats.data_ptr(), net.dt,
@@ -592,15 +608,29 @@ class Net:
         self.head_buf = torch.zeros((self.batch, self.N, 25), dtype=torch.float32, device=dev)
         self.tail = tail
         tail.prepare(self)
+        # one fp64 arena for the (sum, sum^2) accumulators of every GroupNorm, zeroed once per forward
+        n_gn = sum(op.x.B * op.groups * 2 for op in self.ops if isinstance(op, GroupNormActOp))
+        use_arena = n_gn > 0 and os.environ.get("ODT_GN_FUSED", "1") != "0"
+        self.gn_arena = torch.zeros(n_gn, dtype=torch.float64, device=dev) if use_arena else None
+        self._gn_used = 0
         for op in self.ops:
             op.prepare(self)
         self.conv_flops = sum(getattr(op, "flops", 0) for op in self.ops)
         return self
 
     # ---------------------------------------------------------------- run ---
+    def gn_take(self, n):
+        ptr = self.gn_arena.data_ptr() + 8 * self._gn_used
+        self._gn_used += n
+        assert self._gn_used <= self.gn_arena.numel()
+        return ptr
+
     def forward(self, stream=None):
         """Launch backbone + heads + tail on the current torch stream."""
         st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        if self.gn_arena is not None:
+            assert stream is None, "the GroupNorm arena is zeroed on the current torch stream"
+            self.gn_arena.zero_()
         for op in self.ops:
             op.launch(self, st)
         self.tail.launch(self, st)
@@ -649,6 +679,8 @@ class Net:
         main = torch.cuda.current_stream()
         if len(tails) <= 1:
             return self.forward()
+        if self.gn_arena is not None:
+            self.gn_arena.zero_()  # on the capturing stream, ahead of every lane
         if getattr(self, "_lanes", None) is None or len(self._lanes) < len(tails):
             self._lanes = [None] + [torch.cuda.Stream(device=self.device) for _ in range(len(tails) - 1)]
         streams = [main] + self._lanes[1:len(tails)]
@@ -687,7 +719,7 @@ class Net:
     def num_launches(self):
         n = 0
         for op in self.ops:
-            n += 3 if isinstance(op, GroupNormActOp) else 1
+            n += (2 if op.two_launch else 3) if isinstance(op, GroupNormActOp) else 1
         return n + self.tail.num_launches()
 
 

@@ -15,6 +15,7 @@ ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 DECODE_SSD, DECODE_YOLO3, DECODE_FCOS = 0, 1, 2
 MAX_LEVELS, MAX_PRIORS = 8, 9
 ERR_OVERFLOW = -4
+ERR_UNSUPPORTED = -3
 
 
 class ConvParams(C.Structure):

@@ -34,6 +34,8 @@ def main():
     torch.cuda.synchronize()
     reps, rec = 3, {}
     for _ in range(reps):
+        if getattr(net, "gn_arena", None) is not None:
+            net.gn_arena.zero_()  # per-op launches bypass Net.forward, which zeroes the GroupNorm accumulators
         evs = []
         for i, op in enumerate(net.ops):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
