@@ -818,6 +818,42 @@ class RowsHarness:
         anc = self.tail.det_anchor.cpu().numpy()
         return [anc[b, :cnt[b]].copy() for b in range(self.batch)]
 
+    def loss(self, kind, ground_truth, **kw):
+        """Training-loss forward kernels on the same rows: kind in 'retina' | 'ssd' | 'fcos' | 'yolo'.
+        ground_truth [B,G,5] (y,x,h,w,id) padded with -1.  Returns float32 [B]."""
+        gt = torch.as_tensor(np.ascontiguousarray(ground_truth, dtype=np.float32)).to(self.device)
+        B, G = gt.shape[0], gt.shape[1]
+        assert B == self.batch
+        st = torch.cuda.current_stream().cuda_stream
+        out = torch.zeros(B, dtype=torch.float32, device=self.device)
+        p = C.byref(self.tail.p)
+        if kind == "retina":
+            partial = torch.zeros(self.lib.odt_retina_loss_scratch_floats(B), dtype=torch.float32, device=self.device)
+            match = torch.zeros(B * G, dtype=torch.int32, device=self.device)
+            L.check(self.lib.odt_retina_loss_fwd(self.head_buf.data_ptr(), p, B, gt.data_ptr(), G,
+                                                 float(kw.get("alpha", 0.25)), float(kw.get("gamma", 2.0)),
+                                                 partial.data_ptr(), match.data_ptr(), out.data_ptr(), st), "retina_loss")
+        elif kind == "ssd":
+            scratch = torch.zeros((self.lib.odt_ssd_loss_scratch_bytes(p, B) + 7) // 8, dtype=torch.int64,
+                                  device=self.device)
+            L.check(self.lib.odt_ssd_loss_fwd(self.head_buf.data_ptr(), p, B, gt.data_ptr(), G, scratch.data_ptr(),
+                                              out.data_ptr(), st), "ssd_loss")
+        elif kind == "fcos":
+            scratch = torch.zeros((self.lib.odt_fcos_loss_scratch_bytes(B) + 3) // 4, dtype=torch.int32,
+                                  device=self.device)
+            L.check(self.lib.odt_fcos_loss_fwd(self.head_buf.data_ptr(), p, B, gt.data_ptr(), G, scratch.data_ptr(),
+                                               out.data_ptr(), st), "fcos_loss")
+        elif kind == "yolo":
+            scratch = torch.zeros((self.lib.odt_yolo_loss_scratch_bytes(p, B) + 3) // 4, dtype=torch.int32,
+                                  device=self.device)
+            L.check(self.lib.odt_yolo_loss_fwd(self.head_buf.data_ptr(), p, B, gt.data_ptr(), G,
+                                               float(kw.get("coord_scale", 1.0)), float(kw.get("noobj_scale", 1.0)),
+                                               float(kw.get("obj_scale", 5.0)), float(kw.get("class_scale", 1.0)),
+                                               scratch.data_ptr(), out.data_ptr(), st), "yolo_loss")
+        else:
+            raise ValueError(kind)
+        return out.cpu().numpy()
+
 
 # ------------------------------------------------------------------ weights --
 def init_weights(variables, seed=1, bn_mode="tf_init", stem_scale=1.0 / 64.0):

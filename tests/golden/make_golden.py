@@ -94,7 +94,60 @@ def run_case(name, rows, image=0):
     return OT.fcos_detect(heads, c["score_thr"], c["max_boxes"], c["iou_thr"], image)
 
 
+# ---------------------------------------------------------------- losses ----
+# kind -> (tail case whose geometry / rows are re-used, image size that places the GT boxes)
+LOSS_CASES = {"loss_ssd": ("tail_ssd", 300), "loss_retina": ("tail_retina", 128), "loss_yolo": ("tail_yolo", 160),
+              "loss_fcos": ("tail_fcos", 256)}
+
+
+def make_gt(name, batch=2, seed=7, G=12):
+    _, size = LOSS_CASES[name]
+    rng = np.random.default_rng(seed)
+    gt = np.full((batch, G, 5), -1.0, np.float32)
+    for b in range(batch):
+        n = 2 + 3 * b
+        gt[b, :n, 0:2] = rng.uniform(0.2 * size, 0.8 * size, (n, 2))
+        gt[b, :n, 2:4] = rng.uniform(0.08 * size, 0.6 * size, (n, 2))
+        gt[b, :n, 4] = rng.integers(0, 20, n)
+    return gt
+
+
+def run_loss_case(name, rows, gt, image=0):
+    """Oracle loss of one image on candidate rows [B,N,25]."""
+    from oracle import loss as OL
+    tail, _ = LOSS_CASES[name]
+    c = CASES[tail]
+    rows = np.asarray(rows, np.float32)
+    B = rows.shape[0]
+    shapes = [(h, w) for h, w, _ in c["levels"]]
+    r = rows[image]
+    if name == "loss_ssd":
+        a1, a2, ayx, ahw = OT.ssd_anchors(c["size"], shapes)
+        return OL.ssd_image_loss(r[:, :21], r[:, 21:23], r[:, 23:], a1, a2, ayx, ahw, gt[image])[0]
+    if name == "loss_retina":
+        a1, a2, ayx, ahw = OT.retina_anchors(c["data_shape"], shapes)
+        return OL.retina_image_loss(r[:, :21], r[:, 21:23], r[:, 23:], a1, a2, ayx, ahw, gt[image])[0]
+    off, lv = 0, []
+    for h, w, a in c["levels"]:
+        blk = rows[:, off:off + h * w * a]
+        if name == "loss_yolo":
+            lv.append(blk.reshape(B, h, w, a * 25))
+        else:
+            q = blk.reshape(B, h, w, 25)
+            lv.append((q[..., :20], q[..., 20:21], q[..., 21:25]))
+        off += h * w * a
+    if name == "loss_yolo":
+        return OL.yolo_image_loss(lv, YOLO_PRIORS, gt[image], image=image)
+    return OL.fcos_image_loss(lv, gt[image], image=image)
+
+
 def main():
+    for name, (tail, _) in LOSS_CASES.items():
+        rows = make_rows(tail, batch=2, seed=5)
+        gt = make_gt(name)
+        losses = np.asarray([run_loss_case(name, rows, gt, b) for b in range(2)], np.float64)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), rows=rows, gt=gt, loss=losses)
+        print(name, "rows", rows.shape, "loss", losses)
     for name in CASES:
         rows = make_rows(name)[0]
         s, bx, cid, keep = run_case(name, rows)

@@ -166,3 +166,19 @@ def test_tail_full_size_properties(built):
                         assert _iou_py(bb[i], bb[j]) <= np.float32(case["iou_thr"])
     exp = mg.run_case("tail_ssd", rows, image=63)
     _check(res[63], h.keep_indices()[63], exp)
+
+
+@pytest.mark.parametrize("name,kind", [("loss_ssd", "ssd"), ("loss_retina", "retina"), ("loss_yolo", "yolo"),
+                                       ("loss_fcos", "fcos")])
+def test_loss_kernels_match_committed_golden(built, name, kind):
+    """The four training-loss forward kernels on the committed seeded rows vs the frozen oracle values
+    (2e-5 relative: float summation order)."""
+    from golden import make_golden as mg
+    from odt_b200.engine import RowsHarness
+    d = np.load(os.path.join(GOLD, name + ".npz"))
+    tail_name = mg.LOSS_CASES[name][0]
+    case = mg.CASES[tail_name]
+    h = RowsHarness(_tail_for(tail_name, case), case["levels"], d["rows"])
+    got = h.loss(kind, d["gt"])
+    for b in range(len(got)):
+        assert abs(got[b] - d["loss"][b]) <= 2e-5 * max(abs(d["loss"][b]), 1.0), (name, b, got[b], d["loss"][b])

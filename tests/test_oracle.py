@@ -158,3 +158,13 @@ def test_oracle_reproduces_committed_golden(name):
     np.testing.assert_array_equal(out[3], d["keep"])
     np.testing.assert_allclose(out[0], d["scores"], rtol=1e-6)
     np.testing.assert_allclose(out[1], d["bbox"], rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("name", ["loss_ssd", "loss_retina", "loss_yolo", "loss_fcos"])
+def test_loss_oracle_reproduces_committed_golden(name):
+    """Frozen loss values of the four training-loss oracles on seeded rows (tests/golden/make_golden.py)."""
+    from golden import make_golden as mg
+    d = np.load(os.path.join(GOLD, name + ".npz"))
+    for b in range(d["rows"].shape[0]):
+        got = mg.run_loss_case(name, d["rows"], d["gt"], b)
+        assert abs(got - d["loss"][b]) <= 1e-9 * max(abs(d["loss"][b]), 1.0), (name, b, got, d["loss"][b])
