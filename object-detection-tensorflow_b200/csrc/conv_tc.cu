@@ -828,9 +828,9 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
     g.num_n_tiles = 1;
     g.a_bytes = TC_FLAT_A_BYTES;
     g.a_tx = (g.XB + 2) * g.RP * 128;
-    // CTA pairs (half of each tap tile per CTA) pay off once a tile is long enough to hide the
-    // cross-CTA handshakes: measured +21 % at Cin = 128 (conv2_2), -10 % at Cin <= 64 (conv2_1)
-    g.pair = (flat_pair_enabled() && g.num_m_tiles >= 2 && g.cchunks >= 2) ? 1 : 0;
+    // CTA pairs (half of each tap tile per CTA): +21 % at Cin = 128 (conv2_2), +3 % at Cin = 64 in this
+    // pooled mode (conv1_2: the light pooled epilogue leaves room for the handshakes)
+    g.pair = (flat_pair_enabled() && g.num_m_tiles >= 2) ? 1 : 0;
     g.b_bytes = 3 * (g.pair ? g.BN / 2 : g.BN) * 128;
   } else if (g.flat) {
     g.a_tx = TC_FLAT_A_BYTES;

@@ -15,4 +15,9 @@ GroupNorm eps 1e-6, legacy bilinear resize, NonMaxSuppressionV3 ...) come from
 knowledge of TF 1.13's published kernels and could not
 be checked against a running TensorFlow.  The only pins are the hand-derived
 known answers of SURVEY.md section 8(c) (anchor tables) checked in tests/test_oracle.py.
+
+oracle/loss.py restates the four per-image training losses (RetinaNet.py:357-474,
+SSD300.py:345-453, YOLOv3.py:115-318, FCOS.py:153-187,266-348) for the loss-forward kernels;
+its pins are the hand-derived tiny cases of tests/test_oracle_loss.py and the frozen values in
+tests/golden/loss_*.npz -- equally unpinned against TensorFlow itself.
 """
