@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-op CUDA-event timing of one forward (not a bench value): which launches
-own the step.  usage: python scripts/profile_ops.py [ssd300|retinanet|yolov3|fcos] [batch]"""
+own the step.  usage: python scripts/profile_ops.py [ssd300|ssd512|retinanet|yolov3|fcos] [batch]"""
 import os
 import sys
 
@@ -16,9 +16,11 @@ from helpers import model_cfg
 def main():
     kind = sys.argv[1] if len(sys.argv) > 1 else "ssd300"
     B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
-    import FCOS, RetinaNet, SSD300, YOLOv3
+    import FCOS, RetinaNet, SSD300, SSD512, YOLOv3
     if kind == "ssd300":
         m, hw = SSD300.SSD300(model_cfg("ssd"), None), (300, 300)
+    elif kind == "ssd512":
+        m, hw = SSD512.SSD512(model_cfg("ssd"), None), (512, 512)
     elif kind == "retinanet":
         m, hw = RetinaNet.RetinaNet(model_cfg("retinanet", data_shape=[800, 800, 3]), None), (800, 800)
     elif kind == "yolov3":
