@@ -3,17 +3,23 @@
 //   D[m, n] = sum_{r,s,c} X[b, p*stride - pad + r*dil, q*stride - pad + s*dil, c] * W[n, r, s, c]
 //   m = (b, p, q) linearised over B*OH*OW, fp16 operands, fp32 accumulation in TMEM.
 //
-// * A operand (activations, NHWC): one im2col-mode TMA load per (filter tap,
-//   64-channel chunk) brings a [128 pixels x 64 channels] slab -- 128 consecutive
-//   output pixels in B*OH*OW order, wrapping across rows and images, zero-filled
-//   where the tap falls into the SAME padding -- into 128B-swizzled shared memory.
-// * B operand (weights, KRSC = K-major): one tiled TMA load [BN x 64].
-// * MMA: tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN(<=256), K=16, issued by
-//   one thread; accumulators double-buffered in TMEM (2 x 256 columns) so the
-//   epilogue of tile i overlaps the MMAs of tile i+1.
-// * Epilogue: tcgen05.ld -> folded bias/BN scale+shift, activation, residual,
-//   optional second (pre-activated) output -> 128-bit global stores.
-// * Persistent: one CTA per SM, static round-robin tile schedule, warp roles:
+// * A operand (activations, NHWC), three feeding modes:
+//   - im2col-mode TMA: one load per (filter tap, 64-channel chunk) brings a [128 pixels x 64
+//     channels] slab -- 128 consecutive output pixels in B*OH*OW order, wrapping across rows and
+//     images, zero-filled where the tap falls into the SAME padding (any filter geometry);
+//   - halo-flat (3x3 / stride 1 / N <= 128, input stored with a zero halo): one [136 x 64] slab of
+//     consecutive padded positions per (filter row, chunk) feeds the three horizontal taps
+//     through row-shifted UMMA descriptors;
+//   - row-block (the same shapes + fused 2x2/2 max-pool): RP rows x 128/RP columns per tile, a 4-D
+//     tiled box with the row dimension second, the pooling window in four lanes of one warp.
+// * B operand (weights, KRSC = K-major): tiled TMA loads [BN x 64] (half of it per CTA in a pair),
+//   optionally resident in shared memory for small filter banks.
+// * MMA: tcgen05.mma kind::f16, K=16, issued by one elected lane; M=128, N=BN<=256 per CTA
+//   (cta_group::1) or M=256 across the two SMs of a TPC (cta_group::2, conv_tc_kernel<2>);
+//   accumulators in TMEM (2 x 256 or 4 x <=128 columns) so epilogues overlap the next tiles' MMAs.
+// * Epilogue: tcgen05.ld -> folded bias/BN scale+shift, activation, residual, up to two extra
+//   pre-activated outputs, fused max-pool, fp32 head scatter; 128-bit / bulk global stores.
+// * Persistent: one CTA (or CTA pair) per SM, static round-robin tile schedule, warp roles:
 //   w0 = TMA producer, w1 = TMEM allocator + MMA issuer, w2..9 = epilogue (2 warps per TMEM lane quarter).
 //
 // ref call sites: tf.nn.conv2d SSD300.py:519; tf.layers.conv2d SSD300.py:524,
