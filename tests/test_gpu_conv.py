@@ -450,6 +450,20 @@ def test_conv_direct_two_preactivation_outputs(built):
     assert np.abs(got - ref).max() <= 2e-5 * max(np.abs(ref).max(), 1.0)
 
 
+@pytest.mark.parametrize("shape,kw", [
+    ((2, 40, 40, 7, 7, 3, 1, 1), {"in_halo": 1, "out_halo": 1}),     # thin flat layer: 1 of 4 K steps issued
+    ((2, 40, 40, 28, 7, 1, 1, 1), {}),                               # thin 1x1: 2 of 4
+    ((2, 26, 26, 40, 64, 3, 2, 1), {}),                              # 3 of 4, stride 2
+    ((8, 75, 75, 100, 256, 3, 1, 1), {}),                            # second chunk holds 36 channels, CTA pairs
+    ((2, 64, 64, 16, 28, 3, 1, 1), {"in_halo": 1, "pool": 2}),       # row-block pooled mode
+])
+def test_conv_tc_thin_input_channels_skip_zero_k_steps(built, shape, kw):
+    """Cin that does not fill its 64-channel chunk: the all-zero 16-deep K steps are not issued; results
+    must equal the fp32 reference as before."""
+    got, ref, _, _ = _conv_case(*shape, mode="tc", seed=sum(shape), **kw)
+    assert np.abs(got - ref).max() <= 2e-3 * max(np.abs(ref).max(), 1.0), shape
+
+
 def test_conv_tc_flat_equals_im2col_path(built, monkeypatch):
     """Same halo input through both tensor-core paths (ODT_TC_FLAT toggles per call)."""
     shape = (2, 38, 38, 128, 128, 3, 1, 1)
