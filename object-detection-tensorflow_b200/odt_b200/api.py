@@ -109,12 +109,12 @@ class _Detector:
         path = self.config.get("pretraining_weight")
         if path and os.path.exists(path) and path.endswith(".npz"):
             self._load_npz_into(w, path)
-        elif path and tf_checkpoint.is_v2_checkpoint(path):
+        elif path and tf_checkpoint.is_checkpoint(path):
             self._load_bundle_into(w, path)
         elif path:
             # the reference throws inside NewCheckpointReader (SSD300.py:31); BASELINE config 1
             # asks for random-init VGG-16, so a missing file falls back to the seeded init
-            sys.stderr.write("[odt_b200] pretraining weight %r not found as a TF V2 bundle or .npz; "
+            sys.stderr.write("[odt_b200] pretraining weight %r not found as a TF checkpoint (V2 bundle / V1 file) or .npz; "
                              "using seeded random init\n" % (path,))
         return w
 
@@ -123,7 +123,7 @@ class _Detector:
         """Variables by their own names (checkpoints written by save_weight / the reference's
         Saver), plus the VGG-16 classification names the SSD constructors read
         (`vgg_16/convN/convN_M/{weights,biases}`, SSD300.py:195-301)."""
-        r = tf_checkpoint.CheckpointReader(prefix)
+        r = tf_checkpoint.open_checkpoint(prefix)  # V2 bundle or V1 single file (the slim vgg_16.ckpt)
         n = 0
         for k in w:
             if r.has_tensor(k):
@@ -258,7 +258,7 @@ class _Detector:
             self._load_npz_into(w, path)
         else:
             self._load_bundle_into(w, path)
-            r = tf_checkpoint.CheckpointReader(path)
+            r = tf_checkpoint.open_checkpoint(path)
             if r.has_tensor("global_step"):
                 self.global_step = int(r.get_tensor("global_step"))
         self.set_weights(w)

@@ -16,8 +16,14 @@ Format restated from the public definitions (nothing copied):
 
 PARITY UNPINNED: no TensorFlow and no TF-written checkpoint exists in this environment; the
 reader is exercised against this module's own writer plus hand-assembled blocks
-(tests/test_checkpoint.py).  V1 checkpoints (one SSTable of SavedTensorSlices protos, e.g.
-the 2016 slim `vgg_16.ckpt`) are detected and rejected with a clear message.
+(tests/test_checkpoint.py).
+
+V1 checkpoints (ONE SSTable file, usually snappy-compressed blocks, e.g. the 2016 slim `vgg_16.ckpt`
+the SSD constructors read) are supported read-only: key "" holds SavedTensorSlices{1: meta{1: tensor
+SavedSliceMeta{1: name, 2: shape, 3: type, 4: slices}}}, every other entry SavedTensorSlices{2: data
+SavedSlice{1: name, 2: slice TensorSliceProto{1: extent{1: start, 2: length}}, 3: data TensorProto{1:
+dtype, 4: tensor_content | 5: float_val | 6: double_val | 7: int_val | 10: int64_val | 11: bool_val |
+13: half_val}}}.  Slices are pasted into the full tensor by their extents.
 """
 import os
 import struct
@@ -387,10 +393,8 @@ class CheckpointReader:
                         f.seek(n - 8)
                         magic = struct.unpack("<Q", f.read(8))[0]
                 if magic == TABLE_MAGIC:
-                    raise CheckpointError(
-                        "%s is a V1 checkpoint (SavedTensorSlices table); only V2 bundles "
-                        "(<prefix>.index + .data-*) are supported -- re-save it with "
-                        "tf.train.Saver(write_version=V2)" % prefix)
+                    raise CheckpointError("%s is a V1 checkpoint (one SavedTensorSlices table): open it with "
+                                          "open_checkpoint() / CheckpointReaderV1" % prefix)
             raise CheckpointError("no checkpoint at %r (expected %s.index)" % (prefix, prefix))
         self.entries, self.num_shards = {}, 1
         for key, value in _read_table(prefix + ".index", verify_index):
@@ -431,8 +435,155 @@ class CheckpointReader:
         return np.frombuffer(raw, dtype=dt.newbyteorder("<")).astype(dt).reshape(e["shape"])
 
 
+def _parse_extents(buf):
+    """TensorSliceProto -> [(start, length or None)] per dimension."""
+    ext = []
+    for f, _, v in _pb_fields(buf):
+        if f == 1:
+            start, length = 0, None
+            for f2, _, v2 in _pb_fields(v):
+                if f2 == 1:
+                    start = _signed64(v2)
+                elif f2 == 2:
+                    length = _signed64(v2)
+            ext.append((start, length))
+    return ext
+
+
+def _parse_tensor_proto(buf):
+    """TensorProto -> (dtype enum, shape, flat numpy array)."""
+    dtype, shape, content = 0, (), None
+    packed = {5: ("<f4", []), 6: ("<f8", []), 7: ("varint", []), 10: ("varint", []), 11: ("varint", []), 13: ("varint", [])}
+    for f, wt, v in _pb_fields(buf):
+        if f == 1:
+            dtype = v
+        elif f == 2:
+            shape = _parse_shape(v)
+        elif f == 4:
+            content = v
+        elif f in packed:
+            kind, acc = packed[f]
+            if wt == 2 and kind != "varint":
+                acc.append(np.frombuffer(v, kind))
+            elif wt == 2:
+                pos, vals = 0, []
+                while pos < len(v):
+                    x, pos = _get_varint(v, pos)
+                    vals.append(_signed64(x))
+                acc.append(np.asarray(vals, np.int64))
+            elif wt == 5:
+                acc.append(np.frombuffer(struct.pack("<I", v), "<f4"))
+            elif wt == 1:
+                acc.append(np.frombuffer(struct.pack("<Q", v), "<f8"))
+            else:
+                acc.append(np.asarray([_signed64(v)], np.int64))
+    if dtype not in _DTYPES:
+        raise CheckpointError("dtype %d is not supported" % dtype)
+    dt = np.dtype(_DTYPES[dtype])
+    if content is not None:
+        flat = np.frombuffer(content, dt.newbyteorder("<")).astype(dt)
+    else:
+        field = {np.dtype(np.float32): 5, np.dtype(np.float64): 6, np.dtype(np.int64): 10, np.dtype(np.bool_): 11,
+                 np.dtype(np.float16): 13}.get(dt, 7)
+        parts = packed[field][1]
+        flat = np.concatenate(parts) if parts else np.zeros(0)
+        if field == 13:  # half_val carries the raw 16 bits in an int
+            flat = flat.astype(np.uint16).view(np.float16)
+        flat = flat.astype(dt)
+    return dtype, shape, flat
+
+
+class CheckpointReaderV1:
+    """One-file V1 checkpoint (tensorflow::checkpoint::TensorSliceReader format), read-only."""
+
+    def __init__(self, path, verify=True):
+        self.prefix = path
+        self.meta, self._values = {}, {}
+        for key, value in _read_table(path, verify):
+            for f, _, v in _pb_fields(value):
+                if key == b"" and f == 1:  # SavedTensorSliceMeta
+                    for f2, _, t in _pb_fields(v):
+                        if f2 != 1:
+                            continue
+                        name, shape, dtype = None, (), 0
+                        for f3, _, x in _pb_fields(t):
+                            if f3 == 1:
+                                name = x.decode("utf-8")
+                            elif f3 == 2:
+                                shape = _parse_shape(x)
+                            elif f3 == 3:
+                                dtype = x
+                        self.meta[name] = (shape, dtype)
+                elif key != b"" and f == 2:  # SavedSlice
+                    name, ext, tp = None, [], None
+                    for f2, _, x in _pb_fields(v):
+                        if f2 == 1:
+                            name = x.decode("utf-8")
+                        elif f2 == 2:
+                            ext = _parse_extents(x)
+                        elif f2 == 3:
+                            tp = x
+                    if name is not None and tp is not None:
+                        self._values.setdefault(name, []).append((ext, tp))
+        if not self.meta:
+            raise CheckpointError("%s: no SavedTensorSliceMeta entry (not a V1 checkpoint?)" % path)
+
+    def has_tensor(self, name):
+        return name in self.meta
+
+    def get_variable_to_shape_map(self):
+        return {k: list(v[0]) for k, v in self.meta.items()}
+
+    @property
+    def entries(self):
+        return self.meta
+
+    def get_tensor(self, name, verify=False):
+        if name not in self.meta:
+            raise CheckpointError("tensor %r not found in %s" % (name, self.prefix))
+        shape, dtype = self.meta[name]
+        if dtype not in _DTYPES:
+            raise CheckpointError("dtype %d of %r is not supported" % (dtype, name))
+        out = np.zeros(shape, _DTYPES[dtype])
+        filled = 0
+        for ext, tp in self._values.get(name, []):
+            _, _, flat = _parse_tensor_proto(tp)
+            idx, sub = [], []
+            for d, size in enumerate(shape):
+                start, length = ext[d] if d < len(ext) else (0, None)
+                length = size - start if length is None else length
+                idx.append(slice(start, start + length))
+                sub.append(length)
+            if int(np.prod(sub)) != flat.size:
+                raise CheckpointError("slice of %r does not match its extents" % name)
+            out[tuple(idx)] = flat.reshape(sub)
+            filled += flat.size
+        if filled != out.size:
+            raise CheckpointError("slices of %r do not cover the tensor" % name)
+        return out
+
+
+def open_checkpoint(path):
+    """V2 bundle prefix or V1 single file -> reader with has_tensor / get_tensor / get_variable_to_shape_map."""
+    if os.path.exists(path + ".index"):
+        return CheckpointReader(path)
+    if os.path.isfile(path):
+        return CheckpointReaderV1(path)
+    raise CheckpointError("no checkpoint at %r (expected %s.index or a V1 file)" % (path, path))
+
+
+def is_checkpoint(path):
+    if os.path.exists(path + ".index"):
+        return True
+    if os.path.isfile(path) and os.path.getsize(path) >= 48:
+        with open(path, "rb") as f:
+            f.seek(-8, os.SEEK_END)
+            return struct.unpack("<Q", f.read(8))[0] == TABLE_MAGIC
+    return False
+
+
 def read_checkpoint(prefix, verify=False):
-    r = CheckpointReader(prefix)
+    r = open_checkpoint(prefix)
     return {k: r.get_tensor(k, verify) for k in r.entries}
 
 

@@ -157,3 +157,90 @@ def test_model_save_load_and_vgg_pretraining_names(ck, tmp_path):
     np.testing.assert_array_equal(w3["feature_extractor/kernel_conv1_1"], vgg["vgg_16/conv1/conv1_1/weights"])
     np.testing.assert_array_equal(w3["feature_extractor/bias_conv_3_1"], vgg["vgg_16/conv3/conv3_1/biases"])
     np.testing.assert_array_equal(w3["feature_extractor/kernel_conv5_3"], vgg["vgg_16/conv5/conv5_3/weights"])
+
+
+# ---------------------------------------------------------------- V1 files ----
+def _pb(field, wt, payload):
+    def varint(v):
+        out = bytearray()
+        v &= (1 << 64) - 1
+        while v >= 0x80:
+            out.append((v & 0x7F) | 0x80)
+            v >>= 7
+        out.append(v)
+        return bytes(out)
+    if wt == 0:
+        return varint((field << 3) | 0) + varint(payload)
+    return varint((field << 3) | 2) + varint(len(payload)) + payload
+
+
+def _shape_pb(shape):
+    return b"".join(_pb(2, 2, _pb(1, 0, d)) for d in shape)
+
+
+def _v1_file(ck, path, tensors, split=None):
+    """Hand-assembled V1 checkpoint: {name: array}; `split` = name whose first axis is saved as two slices."""
+    meta = b""
+    entries = []
+    for name in sorted(tensors):
+        a = tensors[name]
+        dt = {np.dtype(np.float32): 1, np.dtype(np.int64): 9}[a.dtype]
+        full_slice = _pb(1, 2, b"") * a.ndim        # extent without start/length = whole dimension
+        meta += _pb(1, 2, _pb(1, 2, name.encode()) + _pb(2, 2, _shape_pb(a.shape)) + _pb(3, 0, dt) + _pb(4, 2, full_slice))
+        parts = [(0, a.shape[0])] if (a.ndim and name != split) else ([(0, 1), (1, a.shape[0] - 1)] if a.ndim else [None])
+        for i, pr in enumerate(parts):
+            if pr is None:
+                sub, ext = a, b""
+            else:
+                sub = a[pr[0]:pr[0] + pr[1]]
+                first = _pb(1, 2, (_pb(1, 0, pr[0]) if pr[0] else b"") + _pb(2, 0, pr[1])) if name == split else _pb(1, 2, b"")
+                ext = first + _pb(1, 2, b"") * (a.ndim - 1)
+            if a.dtype == np.float32 and name.endswith("weights"):
+                body = _pb(4, 2, sub.astype("<f4").tobytes())               # tensor_content
+            elif a.dtype == np.float32:
+                body = _pb(5, 2, sub.astype("<f4").tobytes())               # packed float_val
+            else:
+                body = _pb(10, 2, b"".join(_pb(1, 0, int(x))[1:] for x in sub.reshape(-1)))  # packed int64_val varints
+            tp = _pb(1, 0, dt) + _pb(2, 2, _shape_pb(sub.shape)) + body
+            saved = _pb(2, 2, _pb(1, 2, name.encode()) + _pb(2, 2, ext) + _pb(3, 2, tp))
+            entries.append((b"\x00" + name.encode() + b"\x00\x01" + bytes([i]), saved))
+    items = [(b"", _pb(1, 2, meta))] + sorted(entries)
+    ck._write_table(path, items)
+
+
+def test_v1_single_file_checkpoint(ck, tmp_path):
+    rng = np.random.default_rng(3)
+    t = {"vgg_16/conv1/conv1_1/weights": rng.standard_normal((3, 3, 3, 64)).astype(np.float32),
+         "vgg_16/conv1/conv1_1/biases": rng.standard_normal(64).astype(np.float32),
+         "vgg_16/fc8/biases": rng.standard_normal(10).astype(np.float32),
+         "global_step": np.asarray(30000, np.int64)}
+    p = str(tmp_path / "vgg_16.ckpt")
+    _v1_file(ck, p, t, split="vgg_16/fc8/biases")
+    assert ck.is_checkpoint(p) and not ck.is_v2_checkpoint(p)
+    r = ck.open_checkpoint(p)
+    assert isinstance(r, ck.CheckpointReaderV1)
+    assert r.get_variable_to_shape_map()["vgg_16/conv1/conv1_1/weights"] == [3, 3, 3, 64]
+    for k, v in t.items():
+        got = r.get_tensor(k)
+        assert got.dtype == v.dtype and got.shape == v.shape
+        np.testing.assert_array_equal(got, v)
+    assert set(ck.read_checkpoint(p)) == set(t)
+
+
+def test_v1_vgg_checkpoint_feeds_the_ssd_constructor(ck, tmp_path):
+    """The slim `vgg_16.ckpt` the reference's SSD constructors read is a V1 file (SSD300.py:31,195-301)."""
+    import SSD300
+    from odt_b200.api import VGG16_CKPT_NAMES
+    cfg = model_cfg("ssd300")
+    w = SSD300.SSD300(cfg, None).get_weights()
+    rng = np.random.default_rng(9)
+    vgg = {}
+    for ck_name, (kvar, bvar) in VGG16_CKPT_NAMES.items():
+        vgg["vgg_16/%s/weights" % ck_name] = rng.standard_normal(w[kvar].shape).astype(np.float32)
+        vgg["vgg_16/%s/biases" % ck_name] = rng.standard_normal(w[bvar].shape).astype(np.float32)
+    p = str(tmp_path / "vgg_16.ckpt")
+    _v1_file(ck, p, vgg)
+    m = SSD300.SSD300(dict(cfg, pretraining_weight=p), None)
+    w2 = m.get_weights()
+    np.testing.assert_array_equal(w2["feature_extractor/kernel_conv4_3"], vgg["vgg_16/conv4/conv4_3/weights"])
+    np.testing.assert_array_equal(w2["feature_extractor/bias_conv1_2"], vgg["vgg_16/conv1/conv1_2/biases"])
