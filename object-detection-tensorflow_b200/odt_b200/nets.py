@@ -3,7 +3,6 @@ B200 engine (engine.Net).  Each builder mirrors the reference's layer creation
 order so variables get the same TF1 names as in the reference checkpoints
 (SURVEY.md App. D); citations give the reference lines each block stands for.
 """
-import math
 
 import numpy as np
 
