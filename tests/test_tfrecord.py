@@ -90,3 +90,28 @@ def test_voc_records_through_get_generator(tr, tmp_path):
     assert seen
     for _ in range(4):   # repeat(): the stream never ends
         it.get_next()
+
+
+def test_dataset2tfrecord_from_voc_xml(tr, tmp_path):
+    import cv2
+    from utils import tfrecord_voc_utils as voc_utils
+    xml_dir, img_dir, out_dir = tmp_path / "Annotations", tmp_path / "JPEGImages", tmp_path / "out"
+    xml_dir.mkdir()
+    img_dir.mkdir()
+    for i in range(4):
+        img = np.full((30, 50, 3), 40 * i, np.uint8)
+        cv2.imwrite(str(img_dir / ("im%d.jpg" % i)), img)
+        (xml_dir / ("im%d.xml" % i)).write_text(
+            "<annotation><filename>im%d.jpg</filename><size><width>50</width><height>30</height><depth>3</depth></size>"
+            "<object><name>dog</name><bndbox><xmin>5</xmin><ymin>6</ymin><xmax>25</xmax><ymax>16</ymax></bndbox></object>"
+            "<object><name>person</name><bndbox><xmin>1</xmin><ymin>2</ymin><xmax>40</xmax><ymax>28</ymax></bndbox></object>"
+            "</annotation>" % i)
+    files = voc_utils.dataset2tfrecord(str(xml_dir), str(img_dir), str(out_dir), "voc", total_shards=2)
+    assert [f.split("/")[-1] for f in files] == ["voc_00001-of-00002.tfrecord", "voc_00002-of-00002.tfrecord"]
+    recs = [r for f in files for r in tr.read_records(f)]
+    assert len(recs) == 4
+    from utils.voc_classname_encoder import classname_to_ids
+    img, gt = tr.decode_voc_example(recs[0])
+    assert img.shape == (30, 50, 3)
+    np.testing.assert_array_equal(gt, np.asarray([[6, 16, 5, 25, classname_to_ids["dog"]],
+                                                  [2, 28, 1, 40, classname_to_ids["person"]]], np.float32))
