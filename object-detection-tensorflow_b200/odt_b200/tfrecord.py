@@ -7,11 +7,13 @@ SURVEY section 8(f) row 3; not on the accelerated hot path.
   {1: BytesList{1: bytes...}, 2: FloatList{1: packed float}, 3: Int64List{1: packed varint}}.
 * VOC schema written by `xml_to_example` (:30-62): 'image' = JPEG bytes, 'shape' = int32[3]
   (h, w, c) as bytes, 'ground_truth' = float32[n,5] rows (ymin, ymax, xmin, xmax, class id).
-* `preprocess` is the deterministic core of `image_augmentor` (utils/image_augmentor.py) for
-  keep_aspect_ratios=False: resize to `output_shape`, boxes scaled and converted to
-  (y_centre, x_centre, h, w, id), padded with -1 rows to `pad_truth_to`; optional left-right flip
-  with a seeded numpy generator.  Random zoom/crop, colour jitter and rotation are training
-  augmentations and are not restated (a warning is printed when the config asks for them).
+* `preprocess` restates `image_augmentor` (utils/image_augmentor.py:7-233) except colour jitter and
+  rotation: align_corners bilinear resize (optionally aspect-preserving + constant padding) to
+  `zoom_size`/`output_shape`, centre or random crop, top-down / left-right flips (with the reference's
+  `- 1` offsets), box clamping, the centre-inside filter, (y_centre, x_centre, h, w, id) rows padded with
+  -1 to `pad_truth_to`; randomness from a seeded numpy generator.  (The reference returns the UNaugmented
+  `image_copy` when `pad_truth_to` is set, :229 -- an upstream slip that would defeat batching; the
+  augmented image is returned here.)
 PARITY UNPINNED: no TensorFlow and no TF-written record here; JPEG decoding goes through
 OpenCV (libjpeg-turbo), TF uses libjpeg -- pixels can differ by a few levels.
 """
@@ -163,16 +165,19 @@ def decode_voc_example(data):
     return img, gt
 
 
-def _resize_bilinear_legacy(img, oh, ow):
-    """tf.image.resize_images(BILINEAR, align_corners=False), TF1 legacy sampling."""
+def _resize_bilinear_aligned(img, oh, ow):
+    """tf.image.resize_images(..., BILINEAR, align_corners=True) as image_augmentor calls it (:103-106,:124-127):
+    src = dst * (in - 1) / (out - 1)."""
     h, w = img.shape[:2]
     x = img.astype(np.float32)
-    ys = (np.arange(oh, dtype=np.float32) * np.float32(h / oh))
-    xs = (np.arange(ow, dtype=np.float32) * np.float32(w / ow))
+    sy = np.float32((h - 1) / (oh - 1)) if oh > 1 else np.float32(0)
+    sx = np.float32((w - 1) / (ow - 1)) if ow > 1 else np.float32(0)
+    ys = np.arange(oh, dtype=np.float32) * sy
+    xs = np.arange(ow, dtype=np.float32) * sx
     y0 = np.floor(ys).astype(np.int64)
     x0 = np.floor(xs).astype(np.int64)
-    y1 = np.minimum(np.ceil(ys).astype(np.int64), h - 1)
-    x1 = np.minimum(np.ceil(xs).astype(np.int64), w - 1)
+    y1 = np.minimum(y0 + 1, h - 1)
+    x1 = np.minimum(x0 + 1, w - 1)
     wy = (ys - y0).astype(np.float32).reshape(-1, 1, 1)
     wx = (xs - x0).astype(np.float32).reshape(1, -1, 1)
     top = x[y0][:, x0] * (1 - wx) + x[y0][:, x1] * wx
@@ -181,21 +186,61 @@ def _resize_bilinear_legacy(img, oh, ow):
 
 
 def preprocess(img, gt, config, rng=None):
-    """Deterministic core of image_augmentor for keep_aspect_ratios=False (see module doc)."""
+    """image_augmentor (utils/image_augmentor.py:7-233) without colour jitter and rotation: resize (or
+    aspect-preserving resize + constant padding) to `zoom_size` / `output_shape`, centre or random crop, top-down /
+    left-right flips, box clamping and the centre-inside filter, conversion to (y_c, x_c, h, w, id), `pad_truth_to`.
+    Randomness comes from the seeded numpy generator `rng` (TF's generator is not reproducible outside TF)."""
     oh, ow = config["output_shape"]
-    for k in ("zoom_size", "color_jitter_prob", "rotate"):
+    for k in ("color_jitter_prob", "rotate"):
         if config.get(k) is not None and not preprocess._warned.get(k):
             preprocess._warned[k] = True
-            sys.stderr.write("[odt_b200] image_augmentor option %r is a random training augmentation that is "
-                             "not restated; the deterministic resize path is used\n" % k)
+            sys.stderr.write("[odt_b200] image_augmentor option %r (random colour / rotation augmentation) is not "
+                             "restated and is ignored\n" % k)
+    zoom = config.get("zoom_size")
+    zh, zw = (zoom if zoom is not None else (oh, ow))
     h, w = img.shape[:2]
-    out = _resize_bilinear_legacy(img, oh, ow)
-    ymin, ymax, xmin, xmax = [gt[:, i] * (oh / h if i < 2 else ow / w) for i in range(4)]
+    ymin, ymax, xmin, xmax = [gt[:, i].astype(np.float32) for i in range(4)]
+    fill = config.get("fill_mode", "BILINEAR")
+    keep = bool(config.get("keep_aspect_ratios")) or fill == "CONSTANT"
+    if fill not in ("BILINEAR", "CONSTANT") and not preprocess._warned.get("fill"):
+        preprocess._warned["fill"] = True
+        sys.stderr.write("[odt_b200] fill_mode %r: bilinear resampling is used\n" % fill)
+    cval = np.float32(config.get("constant_values") or 0.0)
+    if keep and fill != "CONSTANT":           # :93-114
+        ratio = np.float32(min(zh / h, zw / w))
+        rh, rw = (zh, int(np.float32(w) * ratio)) if zh / h < zw / w else (int(np.float32(h) * ratio), zw)
+        out = np.full((zh, zw, img.shape[2]), cval, np.float32)
+        out[:rh, :rw] = _resize_bilinear_aligned(img, rh, rw)
+        ymin, ymax, xmin, xmax = ymin * ratio, ymax * ratio, xmin * ratio, xmax * ratio
+    elif keep:                                # CONSTANT: pad only (:115-119)
+        out = np.full((zh, zw, img.shape[2]), cval, np.float32)
+        out[:min(h, zh), :min(w, zw)] = img[:zh, :zw]
+    else:                                     # :121-131
+        out = _resize_bilinear_aligned(img, zh, zw)
+        ry, rx = np.float32(zh / h), np.float32(zw / w)
+        ymin, ymax, xmin, xmax = ymin * ry, ymax * ry, xmin * rx, xmax * rx
+    if zoom is not None:                      # :133-147
+        if config.get("crop_method") == "random" and rng is not None:
+            ch = int(rng.integers(0, zh - oh)) if zh > oh else 0
+            cw = int(rng.integers(0, zw - ow)) if zw > ow else 0
+        else:
+            ch, cw = (zh - oh) // 2, (zw - ow) // 2
+        out = out[ch:ch + oh, cw:cw + ow]
+        ymin, ymax, xmin, xmax = ymin - ch, ymax - ch, xmin - cw, xmax - cw
     flip = config.get("flip_prob")
-    if flip is not None and rng is not None and rng.random() < flip[1]:
-        out = out[:, ::-1]
-        xmin, xmax = ow - xmax, ow - xmin
-    box = np.stack([(ymin + ymax) / 2, (xmin + xmax) / 2, ymax - ymin, xmax - xmin, gt[:, 4]], -1).astype(np.float32)
+    if flip is not None and rng is not None:  # :149-173 (note the reference's "- 1." offsets)
+        if rng.random() < flip[0]:
+            out = out[::-1]
+            ymax, ymin = oh - ymin - 1.0, oh - ymax - 1.0
+        if rng.random() < flip[1]:
+            out = out[:, ::-1]
+            xmax, xmin = ow - xmin - 1.0, ow - xmax - 1.0
+    lim_y, lim_x = np.float32(oh - 1), np.float32(ow - 1)   # :199-218
+    ymin, ymax = np.clip(ymin, 0, lim_y), np.clip(ymax, 0, lim_y)
+    xmin, xmax = np.clip(xmin, 0, lim_x), np.clip(xmax, 0, lim_x)
+    yc, xc = (ymin + ymax) / 2, (xmin + xmax) / 2
+    m = (yc > 0) & (yc < lim_y) & (xc > 0) & (xc < lim_x)
+    box = np.stack([yc[m], xc[m], (ymax - ymin)[m], (xmax - xmin)[m], gt[:, 4][m]], -1).astype(np.float32)
     pad = config.get("pad_truth_to")
     if pad:
         full = np.full((int(pad), 5), -1.0, np.float32)

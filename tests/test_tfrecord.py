@@ -115,3 +115,30 @@ def test_dataset2tfrecord_from_voc_xml(tr, tmp_path):
     assert img.shape == (30, 50, 3)
     np.testing.assert_array_equal(gt, np.asarray([[6, 16, 5, 25, classname_to_ids["dog"]],
                                                   [2, 28, 1, 40, classname_to_ids["person"]]], np.float32))
+
+
+def test_preprocess_zoom_crop_flip_clamp_by_hand(tr):
+    """image_augmentor arithmetic on a 10x10 image: resize to zoom 8x8 (ratio .8), centre crop to 6x6 (offset 1),
+    left-right flip (prob 1) with the reference's `- 1` offsets, clamping to [0, 5], centre filter, centre form."""
+    img = np.arange(300, dtype=np.float32).reshape(10, 10, 3) % 251
+    gt = np.asarray([[2, 6, 0, 10, 3],      # -> (1.6, 4.8, 0, 8) -> crop (.6, 3.8, -1, 7) -> flip x (-2, 6) -> clamp (0, 5)
+                     [0, 1, 0, 1, 5]], np.float32)   # -> ends up with its centre on the border: dropped
+    cfg = {"data_format": "channels_last", "output_shape": [6, 6], "zoom_size": [8, 8], "crop_method": "center",
+           "flip_prob": [0.0, 1.0], "fill_mode": "BILINEAR", "keep_aspect_ratios": False, "constant_values": 0.,
+           "color_jitter_prob": None, "rotate": None, "pad_truth_to": 3}
+    out, box = tr.preprocess(img, gt, cfg, np.random.default_rng(0))
+    assert out.shape == (6, 6, 3)
+    np.testing.assert_allclose(box[0], [2.2, 2.5, 3.2, 5.0, 3.0], atol=1e-5)
+    assert np.all(box[1:] == -1)
+    # the image itself: aligned resize 10 -> 8 then rows/cols 1..6, then mirrored
+    full = tr._resize_bilinear_aligned(img, 8, 8)
+    np.testing.assert_allclose(out, full[1:7, 1:7][:, ::-1], atol=1e-5)
+    # align_corners: the corners of the resized image are the corners of the source
+    np.testing.assert_allclose(full[0, 0], img[0, 0])
+    np.testing.assert_allclose(full[7, 7], img[9, 9])
+    # aspect-preserving path: 10x20 image into an 8x8 canvas -> 4x8 content + constant padding
+    wide = np.ones((10, 20, 3), np.float32) * 7
+    cfg2 = dict(cfg, zoom_size=None, output_shape=[8, 8], keep_aspect_ratios=True, constant_values=0.5, flip_prob=None)
+    o2, b2 = tr.preprocess(wide, np.asarray([[2, 8, 4, 16, 1]], np.float32), cfg2)
+    assert np.all(o2[:4] == 7) and np.all(o2[4:] == 0.5)
+    np.testing.assert_allclose(b2[0], [2.0, 4.0, 2.4, 4.8, 1.0], atol=1e-5)

@@ -3,8 +3,8 @@
 `get_generator(tfrecords, batch_size, buffer_size, image_preprocess_config)` returns the reference's
 `(init_op, iterator)` pair (:115-120): `init_op()` (re)starts the stream, `iterator.get_next()` yields
 `(images float32 [B,H,W,3] or [B,3,H,W], ground_truth float32 [B,pad_truth_to,5])` batches read from the
-TFRecord files with odt_b200.tfrecord (TFRecord framing, tf.train.Example, OpenCV JPEG decoding, the
-deterministic resize path of image_augmentor).  Nothing is opened until the first `get_next()`, so the
+TFRecord files with odt_b200.tfrecord (TFRecord framing, tf.train.Example, OpenCV JPEG decoding,
+image_augmentor's resize / zoom / crop / flip / box arithmetic).  Nothing is opened until the first `get_next()`, so the
 drivers' construction order (`get_generator` before the model, testSSD300.py:48-60) works even when the
 data directory is empty.  `dataset2tfrecord` / `xml_to_example` (:30-92) convert a VOC annotation
 directory into the same sharded records with the standard-library XML parser.
