@@ -244,3 +244,82 @@ def test_v1_vgg_checkpoint_feeds_the_ssd_constructor(ck, tmp_path):
     w2 = m.get_weights()
     np.testing.assert_array_equal(w2["feature_extractor/kernel_conv4_3"], vgg["vgg_16/conv4/conv4_3/weights"])
     np.testing.assert_array_equal(w2["feature_extractor/bias_conv1_2"], vgg["vgg_16/conv1/conv1_2/biases"])
+
+
+# ------------------------------------------------------------ property tests ----
+def _snappy_compress_simple(data):
+    """Tiny greedy snappy encoder (test-only): literals + 2-byte-offset copies of 4..64 bytes."""
+    def varint(v):
+        out = bytearray()
+        while v >= 0x80:
+            out.append((v & 0x7F) | 0x80)
+            v >>= 7
+        out.append(v)
+        return bytes(out)
+
+    out = bytearray(varint(len(data)))
+    lit = bytearray()
+
+    def flush():
+        nonlocal lit
+        i = 0
+        while i < len(lit):
+            chunk = lit[i:i + 60]
+            out.append((len(chunk) - 1) << 2)
+            out.extend(chunk)
+            i += 60
+        lit = bytearray()
+
+    table, i, n = {}, 0, len(data)
+    while i < n:
+        key = bytes(data[i:i + 4])
+        j = table.get(key)
+        if len(key) == 4 and j is not None and 0 < i - j < 65536:
+            ln = 4
+            while ln < 64 and i + ln < n and data[j + ln] == data[i + ln]:
+                ln += 1
+            flush()
+            out.append(((ln - 1) << 2) | 2)
+            out.extend(struct.pack("<H", i - j))
+            for k in range(i, i + ln):
+                table[bytes(data[k:k + 4])] = k
+            i += ln
+        else:
+            table[key] = i
+            lit.append(data[i])
+            i += 1
+    flush()
+    return bytes(out)
+
+
+def test_snappy_decoder_against_a_test_encoder(ck):
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.binary(max_size=600), st.integers(1, 6))
+    def run(seed_bytes, rep):
+        data = (seed_bytes * rep)[:3000]            # repetition creates back-references, incl. overlapping runs
+        assert ck._snappy_decompress(_snappy_compress_simple(data)) == data
+    run()
+    assert ck._snappy_decompress(_snappy_compress_simple(b"a" * 500)) == b"a" * 500
+
+
+def test_bundle_round_trip_property(ck, tmp_path):
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+    names = st.text(alphabet="abcdefgh/_0123456789", min_size=1, max_size=24)
+    shapes = st.lists(st.integers(0, 5), min_size=0, max_size=3)
+
+    @settings(max_examples=25, deadline=None)
+    @given(st.dictionaries(names, shapes, min_size=1, max_size=12), st.integers(0, 2 ** 31 - 1))
+    def run(spec, seed):
+        rng = np.random.default_rng(seed)
+        t = {k: rng.standard_normal(s).astype(np.float32) for k, s in spec.items()}
+        prefix = str(tmp_path / ("p%d" % seed))
+        ck.write_checkpoint(prefix, t)
+        got = ck.read_checkpoint(prefix, verify=True)
+        assert set(got) == set(t)
+        for k in t:
+            np.testing.assert_array_equal(got[k], t[k])
+    run()

@@ -252,3 +252,38 @@ def test_sharded_gather_world2_gloo():
             assert k == g % 6
             if k:
                 assert s0 == g + 0.5 and c0 == g
+
+
+def test_lane_plan_on_random_dags():
+    """plan_lanes on synthetic op graphs: dependencies are honoured for any lane budget."""
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+    from odt_b200 import engine as E
+
+    class _T:
+        pass
+
+    class _Op:
+        def __init__(self, reads, writes):
+            self.reads, self.writes = tuple(reads), tuple(writes)
+
+    @settings(max_examples=80, deadline=None)
+    @given(st.lists(st.lists(st.integers(0, 10 ** 6), max_size=3), min_size=1, max_size=40), st.integers(1, 6))
+    def run(spec, lanes):
+        tensors, ops = [], []
+        for picks in spec:
+            reads = [tensors[p % len(tensors)] for p in picks] if tensors else []
+            out = _T()
+            tensors.append(out)
+            ops.append(_Op(reads, [out]))
+        net = E.Net.__new__(E.Net)
+        net.ops = ops
+        lane_of, waits, tails = E.Net.plan_lanes(net, lanes)
+        assert len(lane_of) == len(ops) and max(lane_of) < lanes and len(tails) <= lanes
+        producer = {}
+        for i, op in enumerate(ops):
+            for t in op.reads:
+                p = producer[id(t)]
+                assert p < i and (lane_of[p] == lane_of[i] or p in waits[i])
+            producer[id(op.writes[0])] = i
+    run()
