@@ -81,6 +81,25 @@ constexpr int TC_HEAD_STAGE = TC_EPI_WARPS * 32 * 33 * 4;  // per-warp [32][33] 
 constexpr int TC_FLAT_ROWS = 136;                    // 128 + 2 neighbours, padded to 1024 B
 constexpr int TC_FLAT_A_BYTES = TC_FLAT_ROWS * 128;  // 17408
 
+// Optional per-role timeline of CTA 0 (compile with -DODT_TC_TIMELINE; off in the product build): lane 0 of
+// each role stamps clock64 at its hand-over points so that a tile's latency chain (TMA -> MMA -> commit ->
+// epilogue -> accumulator hand-back) can be read off directly.  Entries: (clock, role << 56 | event << 48 | tile).
+#ifdef ODT_TC_TIMELINE
+__device__ unsigned long long* g_tl_buf = nullptr;
+__device__ unsigned int g_tl_cap = 0, g_tl_len = 0;
+__device__ __forceinline__ void tl_stamp(int role, int event, int tile) {
+  if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && g_tl_buf) {
+    const unsigned int i = atomicAdd(&g_tl_len, 1u);
+    if (i < g_tl_cap) {
+      g_tl_buf[2 * i] = (unsigned long long)clock64();
+      g_tl_buf[2 * i + 1] = ((unsigned long long)role << 56) | ((unsigned long long)event << 48) | (unsigned)tile;
+    }
+  }
+}
+#else
+#define tl_stamp(role, event, tile) ((void)0)
+#endif
+
 // --------------------------------------------------------------- kernel ----
 // CG = 1: one CTA per tile.  CG = 2 (im2col mode only): the two CTAs of a cluster (one TPC)
 // share every MMA -- tcgen05.mma.cta_group::2, M = 256 = two M tiles, each CTA stages its own
@@ -193,6 +212,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       if (CG == 2 && m_tile >= g.num_m_tiles) m_tile = g.num_m_tiles - 1;  // phantom half of the last pair: valid loads, no stores
       const long long m0 = (long long)m_tile * TC_BM;
       const int n0 = n_tile * g.BN;
+      tl_stamp(0, 0, tile);  // producer starts the tile's loads
       if (g.flat) {
         // one slab of 136 consecutive padded-linear rows per (filter row, chunk): rows
         // m0 + (r-1)*PW - 1 ...; negative / past-the-end rows are TMA zero fill
@@ -302,6 +322,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const uint32_t use = (uint32_t)(local_tile / g.nacc);
       mbar_wait(tempty_bar(acc), (use & 1u) ^ 1u);
       tc_fence_after();
+      tl_stamp(1, 0, tile);  // accumulator stage free
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * g.BN);
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(full_bar(stage), phase);
@@ -351,6 +372,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           }
         }
         __syncwarp();
+        if (kb == 0) tl_stamp(1, 1, tile);            // first stage of the tile issued
+        if (kb == kblocks - 1) tl_stamp(1, 2, tile);  // last stage issued + committed
         if (++stage == stages) {
           stage = 0;
           phase ^= 1u;
@@ -456,6 +479,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
       mbar_wait(tfull_bar(acc), use & 1u);
       tc_fence_after();
+      if (quarter == 0) tl_stamp(2 + group, 0, tile);  // accumulator complete (MMAs retired)
       const uint32_t taddr0 = tmem_base + (uint32_t)(acc * g.BN) + ((uint32_t)(quarter * 32) << 16);
       for (int j = split ? 0 : group; j < g.BN / 32; j += split ? 1 : 2) {
         const int nb = n0 + j * 32;
@@ -640,6 +664,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         else
           mbar_arrive(tempty_bar(acc));
       }
+      if (quarter == 0) tl_stamp(2 + group, 1, tile);  // accumulator handed back
       if (g.bulk_store) {
         // the warp staged its 32 x BN block, contiguous in out0 (rows = consecutive pixels)
         fence_proxy_async_smem();
@@ -1003,4 +1028,21 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
   }
   ODT_LAUNCH_OK();
   return ODT_OK;
+}
+
+// Debug only (see tl_stamp): hands CTA 0's timeline buffer to the kernels; `entries` pairs of u64.
+extern "C" int odt_debug_tc_timeline(void* buf, int entries) {
+#ifdef ODT_TC_TIMELINE
+  unsigned long long* b = static_cast<unsigned long long*>(buf);
+  unsigned int cap = (unsigned int)entries, zero = 0;
+  ODT_CUDA_OK(cudaMemcpyToSymbol(g_tl_buf, &b, sizeof(b)));
+  ODT_CUDA_OK(cudaMemcpyToSymbol(g_tl_cap, &cap, sizeof(cap)));
+  ODT_CUDA_OK(cudaMemcpyToSymbol(g_tl_len, &zero, sizeof(zero)));
+  return ODT_OK;
+#else
+  (void)buf;
+  (void)entries;
+  set_error("built without -DODT_TC_TIMELINE");
+  return ODT_ERR_UNSUPPORTED;
+#endif
 }
