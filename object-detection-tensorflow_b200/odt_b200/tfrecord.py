@@ -7,13 +7,15 @@ SURVEY section 8(f) row 3; not on the accelerated hot path.
   {1: BytesList{1: bytes...}, 2: FloatList{1: packed float}, 3: Int64List{1: packed varint}}.
 * VOC schema written by `xml_to_example` (:30-62): 'image' = JPEG bytes, 'shape' = int32[3]
   (h, w, c) as bytes, 'ground_truth' = float32[n,5] rows (ymin, ymax, xmin, xmax, class id).
-* `preprocess` restates `image_augmentor` (utils/image_augmentor.py:7-233) except colour jitter and
-  rotation: align_corners bilinear resize (optionally aspect-preserving + constant padding) to
-  `zoom_size`/`output_shape`, centre or random crop, top-down / left-right flips (with the reference's
-  `- 1` offsets), box clamping, the centre-inside filter, (y_centre, x_centre, h, w, id) rows padded with
-  -1 to `pad_truth_to`; randomness from a seeded numpy generator.  (The reference returns the UNaugmented
-  `image_copy` when `pad_truth_to` is set, :229 -- an upstream slip that would defeat batching; the
-  augmented image is returned here.)
+* `preprocess` restates `image_augmentor` (utils/image_augmentor.py:7-264): align_corners bilinear /
+  nearest resize (optionally aspect-preserving + constant padding) to `zoom_size`/`output_shape`, centre or
+  random crop, top-down / left-right flips (with the reference's `- 1` offsets), colour jitter (brightness,
+  contrast, hue as TF's adjust_* ops define them), small-angle rotation with the box re-fit of
+  `rotate_helper`, box clamping, the centre-inside filter, the "no box left" fallback of
+  `gt_checker_helper`, (y_centre, x_centre, h, w, id) rows padded with -1 to `pad_truth_to`; randomness
+  from a seeded numpy generator.  BICUBIC resampling is not restated (bilinear is used, with a warning).
+  (The reference returns the UNaugmented `image_copy` when `pad_truth_to` is set, :229 -- an upstream slip
+  that would defeat batching; the augmented image is returned here.)
 PARITY UNPINNED: no TensorFlow and no TF-written record here; JPEG decoding goes through
 OpenCV (libjpeg-turbo), TF uses libjpeg -- pixels can differ by a few levels.
 """
@@ -185,38 +187,149 @@ def _resize_bilinear_aligned(img, oh, ow):
     return (top * (1 - wy) + bot * wy).astype(np.float32)
 
 
+def _resize_nearest_aligned(img, oh, ow):
+    """ResizeNearestNeighbor with align_corners=True (TF 1.13): src = min(round(dst * (in-1)/(out-1)), in-1)."""
+    h, w = img.shape[:2]
+    sy = np.float32((h - 1) / (oh - 1)) if oh > 1 else np.float32(0)
+    sx = np.float32((w - 1) / (ow - 1)) if ow > 1 else np.float32(0)
+    ys = np.minimum(np.floor(np.arange(oh, dtype=np.float32) * sy + np.float32(0.5)).astype(np.int64), h - 1)
+    xs = np.minimum(np.floor(np.arange(ow, dtype=np.float32) * sx + np.float32(0.5)).astype(np.int64), w - 1)
+    return img[ys][:, xs].astype(np.float32)
+
+
+def _resize_bilinear_legacy(img, oh, ow):
+    """tf.image.resize(image, size) of gt_checker_helper (:260): TF1 bilinear, align_corners=False, no
+    half-pixel centres: src = dst * in/out, hi = min(lo + 1, in - 1)."""
+    h, w = img.shape[:2]
+    x = img.astype(np.float32)
+    ys = np.arange(oh, dtype=np.float32) * np.float32(h / oh)
+    xs = np.arange(ow, dtype=np.float32) * np.float32(w / ow)
+    y0 = np.minimum(np.floor(ys).astype(np.int64), h - 1)
+    x0 = np.minimum(np.floor(xs).astype(np.int64), w - 1)
+    y1 = np.minimum(y0 + 1, h - 1)
+    x1 = np.minimum(x0 + 1, w - 1)
+    wy = (ys - y0).astype(np.float32).reshape(-1, 1, 1)
+    wx = (xs - x0).astype(np.float32).reshape(1, -1, 1)
+    top = x[y0][:, x0] * (1 - wx) + x[y0][:, x1] * wx
+    bot = x[y1][:, x0] * (1 - wx) + x[y1][:, x1] * wx
+    return (top * (1 - wy) + bot * wy).astype(np.float32)
+
+
+def adjust_brightness(img, delta):
+    """tf.image.adjust_brightness on a float image: image + delta (no rescale, no clipping)."""
+    return (img + np.float32(delta)).astype(np.float32)
+
+
+def adjust_contrast(img, factor):
+    """tf.image.adjust_contrast: (x - mean) * factor + mean with the mean of each channel over H, W."""
+    mean = img.mean(axis=(0, 1), keepdims=True, dtype=np.float32)
+    return ((img - mean) * np.float32(factor) + mean).astype(np.float32)
+
+
+def adjust_hue(img, delta):
+    """tf.image.adjust_hue (AdjustHue kernel): RGB -> (hue in [0,6), min, max), hue += 6*delta (wrapped),
+    back to RGB.  The (min, max) pair is kept, so the result is independent of the value range."""
+    x = img.astype(np.float32)
+    r, g, b = x[..., 0], x[..., 1], x[..., 2]
+    vmax = np.maximum(np.maximum(r, g), b)
+    vmin = np.minimum(np.minimum(r, g), b)
+    rng_ = vmax - vmin
+    safe = np.where(rng_ > 0, rng_, np.float32(1))
+    # sector of the hue hexagon and the position inside it (all six orderings of r, g, b; ties as the kernel)
+    cat = np.select([(r < g) & (b < r), (r < g) & (b > g), (r < g), (b < g), (b > r)], [1, 3, 2, 0, 4], 5)
+    vmid = r + g + b - vmax - vmin
+    ratio = (vmid - vmin) / safe
+    inc = (cat % 2) == 0
+    h = np.where(rng_ > 0, cat + np.where(inc, ratio, 1 - ratio), np.float32(0)).astype(np.float32)
+    h = np.mod(h + np.float32(delta) * np.float32(6), np.float32(6)).astype(np.float32)
+    cat2 = np.minimum(h.astype(np.int64), 5)
+    frac = h - cat2
+    frac = np.where((cat2 % 2) == 0, frac, 1 - frac)
+    mid = vmin + frac * rng_
+    r2 = np.select([cat2 == 0, cat2 == 1, cat2 == 2, cat2 == 3, cat2 == 4], [vmax, mid, vmin, vmin, mid], vmax)
+    g2 = np.select([cat2 == 0, cat2 == 1, cat2 == 2, cat2 == 3, cat2 == 4], [mid, vmax, vmax, mid, vmin], vmin)
+    b2 = np.select([cat2 == 0, cat2 == 1, cat2 == 2, cat2 == 3, cat2 == 4], [vmin, vmin, mid, vmax, vmax], mid)
+    return np.stack([r2, g2, b2], -1).astype(np.float32)
+
+
+def rotate_bilinear(img, angle):
+    """tf.contrib.image.rotate(img, angle, 'BILINEAR'): counter-clockwise by `angle` (radians) about the
+    image centre; output pixel (x, y) samples input (cos*x - sin*y + x_off, sin*x + cos*y + y_off) with the
+    offsets of angles_to_projective_transforms; neighbours outside the image read 0."""
+    h, w = img.shape[:2]
+    c, s = np.float32(np.cos(angle)), np.float32(np.sin(angle))
+    x_off = np.float32(((w - 1) - (c * (w - 1) - s * (h - 1))) / 2.0)
+    y_off = np.float32(((h - 1) - (s * (w - 1) + c * (h - 1))) / 2.0)
+    xs, ys = np.meshgrid(np.arange(w, dtype=np.float32), np.arange(h, dtype=np.float32))
+    sx = c * xs - s * ys + x_off
+    sy = s * xs + c * ys + y_off
+    x0, y0 = np.floor(sx), np.floor(sy)
+    wx, wy = (sx - x0)[..., None], (sy - y0)[..., None]
+    x0, y0 = x0.astype(np.int64), y0.astype(np.int64)
+    src = img.astype(np.float32)
+
+    def read(yy, xx):
+        ok = (yy >= 0) & (yy < h) & (xx >= 0) & (xx < w)
+        return np.where(ok[..., None], src[np.clip(yy, 0, h - 1), np.clip(xx, 0, w - 1)], np.float32(0))
+
+    top = read(y0, x0) * (1 - wx) + read(y0, x0 + 1) * wx
+    bot = read(y0 + 1, x0) * (1 - wx) + read(y0 + 1, x0 + 1) * wx
+    return (top * (1 - wy) + bot * wy).astype(np.float32)
+
+
+def rotate_boxes(angle, ymin, xmin, ymax, xmax, oh, ow):
+    """Box re-fit of rotate_helper (:236-256): the four corners rotated by -angle about
+    ((ow-1)/2, (oh-1)/2), then their axis-aligned hull."""
+    a = np.float32(-angle)
+    c, s = np.float32(np.cos(a)), np.float32(np.sin(a))
+    cx, cy = np.float32((ow - 1.0) / 2.0), np.float32((oh - 1.0) / 2.0)
+    off_x = cx * (1 - c) + cy * s
+    off_y = cy * (1 - c) - cx * s
+    px = [x * c - y * s + off_x for x, y in ((xmin, ymin), (xmax, ymax), (xmin, ymax), (xmax, ymin))]
+    py = [x * s + y * c + off_y for x, y in ((xmin, ymin), (xmax, ymax), (xmin, ymax), (xmax, ymin))]
+    return (np.minimum.reduce(py).astype(np.float32), np.minimum.reduce(px).astype(np.float32),
+            np.maximum.reduce(py).astype(np.float32), np.maximum.reduce(px).astype(np.float32))
+
+
 def preprocess(img, gt, config, rng=None):
-    """image_augmentor (utils/image_augmentor.py:7-233) without colour jitter and rotation: resize (or
-    aspect-preserving resize + constant padding) to `zoom_size` / `output_shape`, centre or random crop, top-down /
-    left-right flips, box clamping and the centre-inside filter, conversion to (y_c, x_c, h, w, id), `pad_truth_to`.
-    Randomness comes from the seeded numpy generator `rng` (TF's generator is not reproducible outside TF)."""
+    """image_augmentor (utils/image_augmentor.py:7-233): resize (or aspect-preserving resize + constant padding) to
+    `zoom_size` / `output_shape`, centre or random crop, top-down / left-right flips, colour jitter, rotation, box
+    clamping and the centre-inside filter, conversion to (y_c, x_c, h, w, id), `pad_truth_to`.  Randomness comes
+    from the seeded numpy generator `rng` (TF's generator is not reproducible outside TF); without one the
+    random steps are skipped."""
     oh, ow = config["output_shape"]
-    for k in ("color_jitter_prob", "rotate"):
-        if config.get(k) is not None and not preprocess._warned.get(k):
-            preprocess._warned[k] = True
-            sys.stderr.write("[odt_b200] image_augmentor option %r (random colour / rotation augmentation) is not "
-                             "restated and is ignored\n" % k)
+    rot = config.get("rotate")
+    if rot is not None:                       # argument checks of :50-59
+        if len(rot) != 3:
+            raise ValueError('please provide "rotate" parameter as [rotate_prob, min_angle, max_angle]!')
+        if not 0.0 <= rot[0] <= 1.0 or not rot[1] <= rot[2]:
+            raise ValueError("rotate: prob must be in [0, 1] and min_angle <= max_angle")
+    cj = config.get("color_jitter_prob")
+    if cj is not None and not 0.0 <= cj <= 1.0:
+        raise ValueError("color_jitter_prob can't be less than 0.0 or greater than 1.0")
+    img_copy, gt_copy = img, gt
     zoom = config.get("zoom_size")
     zh, zw = (zoom if zoom is not None else (oh, ow))
     h, w = img.shape[:2]
     ymin, ymax, xmin, xmax = [gt[:, i].astype(np.float32) for i in range(4)]
     fill = config.get("fill_mode", "BILINEAR")
     keep = bool(config.get("keep_aspect_ratios")) or fill == "CONSTANT"
-    if fill not in ("BILINEAR", "CONSTANT") and not preprocess._warned.get("fill"):
+    resize = _resize_nearest_aligned if fill == "NEAREST_NEIGHBOR" else _resize_bilinear_aligned
+    if fill == "BICUBIC" and not preprocess._warned.get("fill"):
         preprocess._warned["fill"] = True
-        sys.stderr.write("[odt_b200] fill_mode %r: bilinear resampling is used\n" % fill)
+        sys.stderr.write("[odt_b200] fill_mode 'BICUBIC' is not restated: bilinear resampling is used\n")
     cval = np.float32(config.get("constant_values") or 0.0)
     if keep and fill != "CONSTANT":           # :93-114
         ratio = np.float32(min(zh / h, zw / w))
         rh, rw = (zh, int(np.float32(w) * ratio)) if zh / h < zw / w else (int(np.float32(h) * ratio), zw)
         out = np.full((zh, zw, img.shape[2]), cval, np.float32)
-        out[:rh, :rw] = _resize_bilinear_aligned(img, rh, rw)
+        out[:rh, :rw] = resize(img, rh, rw)
         ymin, ymax, xmin, xmax = ymin * ratio, ymax * ratio, xmin * ratio, xmax * ratio
     elif keep:                                # CONSTANT: pad only (:115-119)
         out = np.full((zh, zw, img.shape[2]), cval, np.float32)
         out[:min(h, zh), :min(w, zw)] = img[:zh, :zw]
     else:                                     # :121-131
-        out = _resize_bilinear_aligned(img, zh, zw)
+        out = resize(img, zh, zw)
         ry, rx = np.float32(zh / h), np.float32(zw / w)
         ymin, ymax, xmin, xmax = ymin * ry, ymax * ry, xmin * rx, xmax * rx
     if zoom is not None:                      # :133-147
@@ -235,12 +348,31 @@ def preprocess(img, gt, config, rng=None):
         if rng.random() < flip[1]:
             out = out[:, ::-1]
             xmax, xmin = ow - xmin - 1.0, ow - xmax - 1.0
+    if cj is not None and rng is not None:    # :174-187 (deltas drawn only when the step fires, like tf.cond)
+        bcs = rng.random(3)
+        if bcs[0] < cj:
+            out = adjust_brightness(out, rng.uniform(0.0, 0.3))
+        if bcs[1] < cj:
+            out = adjust_contrast(out, rng.uniform(0.8, 1.2))
+        if bcs[2] < cj:
+            out = adjust_hue(out, rng.uniform(-0.1, 0.1))
+    if rot is not None and rng is not None:   # :189-196
+        if rng.random() < rot[0]:
+            ang = np.float32(rng.uniform(rot[1], rot[2]) * 3.1415926 / 180.0)
+            out = rotate_bilinear(out, ang)
+            ymin, xmin, ymax, xmax = rotate_boxes(ang, ymin, xmin, ymax, xmax, float(oh), float(ow))
     lim_y, lim_x = np.float32(oh - 1), np.float32(ow - 1)   # :199-218
     ymin, ymax = np.clip(ymin, 0, lim_y), np.clip(ymax, 0, lim_y)
     xmin, xmax = np.clip(xmin, 0, lim_x), np.clip(xmax, 0, lim_x)
     yc, xc = (ymin + ymax) / 2, (xmin + xmax) / 2
     m = (yc > 0) & (yc < lim_y) & (xc > 0) & (xc < lim_x)
     box = np.stack([yc[m], xc[m], (ymax - ymin)[m], (xmax - xmin)[m], gt[:, 4][m]], -1).astype(np.float32)
+    if len(box) == 0 and len(gt_copy):        # gt_checker_helper (:220-225,:259-264): plain resize of the original
+        out = _resize_bilinear_legacy(img_copy, oh, ow)
+        fy, fx = np.float32(oh) / np.float32(h), np.float32(ow) / np.float32(w)
+        g = gt_copy.astype(np.float32)
+        box = np.stack([(g[:, 0] / 2 + g[:, 1] / 2) * fy, (g[:, 2] / 2 + g[:, 3] / 2) * fx,
+                        (g[:, 1] - g[:, 0]) * fy, (g[:, 3] - g[:, 2]) * fx, g[:, 4]], -1).astype(np.float32)
     pad = config.get("pad_truth_to")
     if pad:
         full = np.full((int(pad), 5), -1.0, np.float32)

@@ -142,3 +142,83 @@ def test_preprocess_zoom_crop_flip_clamp_by_hand(tr):
     o2, b2 = tr.preprocess(wide, np.asarray([[2, 8, 4, 16, 1]], np.float32), cfg2)
     assert np.all(o2[:4] == 7) and np.all(o2[4:] == 0.5)
     np.testing.assert_allclose(b2[0], [2.0, 4.0, 2.4, 4.8, 1.0], atol=1e-5)
+
+
+def test_colour_adjustments_match_their_definitions(tr):
+    import colorsys
+    rng = np.random.default_rng(5)
+    img = rng.uniform(0, 255, (6, 7, 3)).astype(np.float32)
+    np.testing.assert_allclose(tr.adjust_brightness(img, 0.25), img + 0.25, rtol=0, atol=1e-5)
+    mean = img.reshape(-1, 3).mean(0)
+    np.testing.assert_allclose(tr.adjust_contrast(img, 1.15), (img - mean) * 1.15 + mean, rtol=1e-5, atol=1e-3)
+    # hue rotation == HSV round trip with h shifted (value and saturation kept)
+    for delta in (0.07, -0.1, 0.0):
+        got = tr.adjust_hue(img, delta)
+        for (y, x) in ((0, 0), (3, 4), (5, 6), (2, 1)):
+            hh, ss, vv = colorsys.rgb_to_hsv(*(img[y, x].astype(np.float64) / 255.0))
+            want = np.asarray(colorsys.hsv_to_rgb((hh + delta) % 1.0, ss, vv)) * 255.0
+            np.testing.assert_allclose(got[y, x], want, rtol=0, atol=2e-3)
+    # grey pixels have no hue: unchanged; min / max of every pixel are preserved
+    grey = np.full((2, 2, 3), 77.0, np.float32)
+    np.testing.assert_array_equal(tr.adjust_hue(grey, 0.05), grey)
+    got = tr.adjust_hue(img, 0.09)
+    np.testing.assert_allclose(got.max(-1), img.max(-1), rtol=0, atol=1e-4)
+    np.testing.assert_allclose(got.min(-1), img.min(-1), rtol=0, atol=1e-4)
+
+
+def test_rotation_image_and_boxes_agree(tr):
+    rng = np.random.default_rng(6)
+    img = rng.uniform(0, 255, (9, 9, 3)).astype(np.float32)
+    np.testing.assert_allclose(tr.rotate_bilinear(img, 0.0), img, rtol=0, atol=1e-4)
+    # a quarter turn is exact and counter-clockwise (tf.contrib.image.rotate's convention)
+    np.testing.assert_allclose(tr.rotate_bilinear(img, np.pi / 2), np.rot90(img), rtol=0, atol=2e-3)
+    # the box re-fit follows the pixels: pixel (r, c) lands on (n-1-c, r) under the quarter turn
+    n = 9
+    ymin, xmin, ymax, xmax = [np.asarray([v], np.float32) for v in (1.0, 2.0, 3.0, 6.0)]
+    y0, x0, y1, x1 = tr.rotate_boxes(np.pi / 2, ymin, xmin, ymax, xmax, float(n), float(n))
+    np.testing.assert_allclose([y0[0], x0[0], y1[0], x1[0]], [n - 1 - 6.0, 1.0, n - 1 - 2.0, 3.0], atol=1e-4)
+    # small angle: a bright blob stays inside the re-fitted box of the box that framed it
+    big = np.zeros((41, 61, 3), np.float32)
+    big[10:15, 40:47] = 255.0
+    ang = np.float32(4.0 * np.pi / 180)
+    out = tr.rotate_bilinear(big, ang)
+    yy, xx = np.nonzero(out[..., 0] > 128)
+    b = tr.rotate_boxes(ang, *[np.asarray([v], np.float32) for v in (10.0, 40.0, 14.0, 46.0)], 41.0, 61.0)
+    assert b[0][0] - 0.5 <= yy.min() and yy.max() <= b[2][0] + 0.5
+    assert b[1][0] - 0.5 <= xx.min() and xx.max() <= b[3][0] + 0.5
+    # pixels rotated in from outside read 0
+    assert out[0, 0, 0] == 0.0 or out[-1, -1, 0] == 0.0
+
+
+def test_preprocess_jitter_rotate_and_fallback(tr):
+    rng = np.random.default_rng(7)
+    img = rng.integers(0, 256, (50, 80, 3)).astype(np.uint8)
+    gt = np.asarray([[10, 30, 20, 60, 3], [5, 45, 5, 75, 7]], np.float32)   # ymin ymax xmin xmax id
+    base = dict(data_format="channels_last", output_shape=[40, 40], pad_truth_to=4)
+    plain, box0 = tr.preprocess(img, gt, base, np.random.default_rng(0))
+    cfg = dict(base, color_jitter_prob=1.0, rotate=[1.0, -5.0, 5.0])
+    out, box = tr.preprocess(img, gt, cfg, np.random.default_rng(0))
+    assert out.shape == (40, 40, 3) and box.shape == (4, 5) and out.dtype == np.float32
+    assert np.abs(out - plain).max() > 1.0                       # the image really changed
+    assert (box[:2, 4] == [3, 7]).all() and (box[2:] == -1).all()
+    assert np.abs(box[:2, :4] - box0[:2, :4]).max() < 8.0        # a <=5 degree turn moves boxes a little
+    assert (box[:2, 2:4] >= box0[:2, 2:4] - 1e-3).all()          # and the hull never shrinks
+    # same seed -> same result; probabilities 0 -> identical to the plain path
+    out2, box2 = tr.preprocess(img, gt, cfg, np.random.default_rng(0))
+    np.testing.assert_array_equal(out, out2)
+    np.testing.assert_array_equal(box, box2)
+    off, boxo = tr.preprocess(img, gt, dict(base, color_jitter_prob=0.0, rotate=[0.0, -5.0, 5.0]), np.random.default_rng(0))
+    np.testing.assert_array_equal(off, plain)
+    np.testing.assert_array_equal(boxo, box0)
+    with pytest.raises(ValueError):
+        tr.preprocess(img, gt, dict(base, rotate=[0.5, 3.0, -3.0]), np.random.default_rng(0))
+    # nearest-neighbour resampling picks source pixels only
+    nn, _ = tr.preprocess(img, gt, dict(base, fill_mode="NEAREST_NEIGHBOR"), None)
+    assert set(np.unique(nn)).issubset(set(np.unique(img).astype(np.float32)))
+    assert nn[0, 0, 0] == img[0, 0, 0] and nn[-1, -1, 2] == img[-1, -1, 2]
+    # no box keeps its centre inside after a crop -> the un-augmented, plainly resized example is returned
+    far = np.asarray([[0, 4, 0, 6, 2]], np.float32)
+    z, bz = tr.preprocess(img, far, dict(base, zoom_size=[100, 160], crop_method="center"), None)
+    np.testing.assert_allclose(z, tr._resize_bilinear_legacy(img, 40, 40))
+    np.testing.assert_allclose(bz[0], [2 * 0.8, 3 * 0.5, 4 * 0.8, 6 * 0.5, 2], rtol=1e-6)
+    assert (bz[1:] == -1).all()
