@@ -34,8 +34,8 @@ extern "C" {
 #define ODT_ERR_INVALID (-1)   /* bad argument                                 */
 #define ODT_ERR_CUDA (-2)      /* a CUDA runtime / driver call failed          */
 #define ODT_ERR_UNSUPPORTED (-3)
-#define ODT_ERR_OVERFLOW (-4)  /* candidate list capacity exceeded (reported by
-                                  odt_nms_status)                              */
+#define ODT_ERR_OVERFLOW (-4)  /* candidate list capacity exceeded (reported in
+                                  the status word of odt_nms_per_class)        */
 
 #define ODT_F16 0
 #define ODT_F32 1

@@ -37,6 +37,10 @@ bool flat_pair_enabled() {
   const char* e = getenv("ODT_TC_FLAT_PAIR");
   return pair_enabled() && !(e && e[0] == '0');
 }
+bool kskip_enabled() {
+  const char* e = getenv("ODT_TC_KSKIP");  // opt-in (default off): see TcGeom::klast
+  return e && e[0] == '1';
+}
 bool wres_enabled() {
   const char* e = getenv("ODT_TC_WRES");
   return !(e && e[0] == '0');

@@ -73,6 +73,7 @@ bool bulk_enabled();  // ODT_TC_BULK=0 disables the smem-staged bulk-store epilo
 bool flat_enabled();  // ODT_TC_FLAT=0 disables the halo-flat 3x3 path (A/B measurements)
 bool pair_enabled();  // ODT_TC_PAIR=0 disables the CTA-pair (cta_group::2) launch of large im2col-mode convs
 bool flat_pair_enabled();  // ODT_TC_FLAT_PAIR=0: no CTA pairs in the halo-flat modes
+bool kskip_enabled();  // ODT_TC_KSKIP=1: do not issue the all-zero 16-deep K steps of thin layers (Cin padded to 64)
 bool wres_enabled();  // ODT_TC_WRES=0 disables shared-memory-resident filter banks in the flat path
 
 }  // namespace odt

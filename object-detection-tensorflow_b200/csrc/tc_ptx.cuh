@@ -81,13 +81,16 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
                : "memory");
 }
 __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
-                                           uint32_t idesc, uint32_t accumulate) {
+                                           uint32_t idesc, uint32_t accumulate, uint32_t issue = 1u) {
+  // `issue` predicates the instruction itself (straight-line code: a branch around the MMA would break
+  // the uniform-datapath issue sequence, see conv_tc.cu)
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred p, q;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       :
-      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(issue)
       : "memory");
 }
 // ---- CTA-pair (cta_group::2) variants: one MMA spans the two SMs of a TPC --------------
@@ -147,13 +150,14 @@ __device__ __forceinline__ void tc_commit_cg2(uint32_t bar, uint16_t mask) {
       : "memory");
 }
 __device__ __forceinline__ void tc_mma_f16_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
-                                               uint32_t idesc, uint32_t accumulate) {
+                                               uint32_t idesc, uint32_t accumulate, uint32_t issue = 1u) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred p, q;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       :
-      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(issue)
       : "memory");
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {

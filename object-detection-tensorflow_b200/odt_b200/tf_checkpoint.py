@@ -43,6 +43,24 @@ class CheckpointError(RuntimeError):
     pass
 
 
+class _malformed:
+    """Context manager: whatever a parser trips over in corrupt input (a scalar where bytes were expected, a
+    bad UTF-8 name, an extent outside its tensor, a missing shard ...) surfaces as CheckpointError."""
+
+    def __init__(self, what):
+        self.what = what
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, et, ev, tb):
+        if et is not None and not issubclass(et, CheckpointError) and issubclass(
+                et, (ValueError, TypeError, AttributeError, IndexError, KeyError, OverflowError, struct.error, OSError,
+                     MemoryError)):
+            raise CheckpointError("%s: malformed or unreadable (%s: %s)" % (self.what, et.__name__, ev)) from None
+        return False
+
+
 # ------------------------------------------------------------------ crc32c ---
 _crc_table = None
 _crc_native = None
@@ -106,23 +124,28 @@ def _get_varint(buf, pos):
 
 # ---------------------------------------------------------------- protobuf ---
 def _pb_fields(buf):
-    """Yield (field number, wire type, value) of one message; value = int or bytes."""
+    """Yield (field number, wire type, value) of one message; value = int or bytes.  Malformed input
+    (truncated field, length past the end, group wire types) raises CheckpointError."""
+    if not isinstance(buf, (bytes, bytearray, memoryview)):
+        raise CheckpointError("protobuf: a length-delimited field was expected, got a scalar")
     pos, n = 0, len(buf)
     while pos < n:
         tag, pos = _get_varint(buf, pos)
         f, wt = tag >> 3, tag & 7
         if wt == 0:
             v, pos = _get_varint(buf, pos)
-        elif wt == 1:
-            v = struct.unpack_from("<Q", buf, pos)[0]
-            pos += 8
+        elif wt == 1 or wt == 5:
+            size = 8 if wt == 1 else 4
+            if pos + size > n:
+                raise CheckpointError("protobuf: truncated fixed%d field" % (8 * size))
+            v = struct.unpack_from("<Q" if wt == 1 else "<I", buf, pos)[0]
+            pos += size
         elif wt == 2:
             ln, pos = _get_varint(buf, pos)
+            if pos + ln > n:
+                raise CheckpointError("protobuf: field of %d bytes runs past the end of its message" % ln)
             v = bytes(buf[pos:pos + ln])
             pos += ln
-        elif wt == 5:
-            v = struct.unpack_from("<I", buf, pos)[0]
-            pos += 4
         else:
             raise CheckpointError("unsupported protobuf wire type %d" % wt)
         yield f, wt, v
@@ -157,7 +180,10 @@ def _parse_shape(buf):
 
 def _parse_entry(buf):
     e = {"dtype": 0, "shape": (), "shard_id": 0, "offset": 0, "size": 0, "crc32c": None, "sliced": False}
-    for f, _, v in _pb_fields(buf):
+    wire = {1: 0, 2: 2, 3: 0, 4: 0, 5: 0, 6: 5, 7: 2}
+    for f, wt, v in _pb_fields(buf):
+        if f in wire and wt != wire[f]:
+            raise CheckpointError("BundleEntryProto field %d has wire type %d" % (f, wt))
         if f == 1:
             e["dtype"] = v
         elif f == 2:
@@ -207,6 +233,11 @@ def _encode_header(num_shards):
 # ------------------------------------------------------------------ snappy ---
 def _snappy_decompress(buf):
     """Raw snappy block format (index blocks written with compression enabled)."""
+    with _malformed("snappy block"):
+        return _snappy_body(buf)
+
+
+def _snappy_body(buf):
     n, pos = _get_varint(buf, 0)
     out = bytearray()
     while pos < len(buf):
@@ -220,6 +251,8 @@ def _snappy_decompress(buf):
                 ln = int.from_bytes(buf[pos:pos + nb], "little")
                 pos += nb
             ln += 1
+            if pos + ln > len(buf) or len(out) + ln > n:
+                raise CheckpointError("corrupt snappy block")
             out.extend(buf[pos:pos + ln])
             pos += ln
             continue
@@ -235,7 +268,7 @@ def _snappy_decompress(buf):
             ln = (tag >> 2) + 1
             off = int.from_bytes(buf[pos:pos + 4], "little")
             pos += 4
-        if off == 0 or off > len(out):
+        if off == 0 or off > len(out) or len(out) + ln > n:
             raise CheckpointError("corrupt snappy block")
         for _ in range(ln):  # may overlap
             out.append(out[-off])
@@ -273,6 +306,8 @@ def _block_entries(block):
         shared, pos = _get_varint(block, pos)
         non_shared, pos = _get_varint(block, pos)
         vlen, pos = _get_varint(block, pos)
+        if shared > len(key) or pos + non_shared + vlen > limit:
+            raise CheckpointError("bad table block entry")
         key = key[:shared] + bytes(block[pos:pos + non_shared])
         pos += non_shared
         yield key, bytes(block[pos:pos + vlen])
@@ -397,15 +432,16 @@ class CheckpointReader:
                                           "open_checkpoint() / CheckpointReaderV1" % prefix)
             raise CheckpointError("no checkpoint at %r (expected %s.index)" % (prefix, prefix))
         self.entries, self.num_shards = {}, 1
-        for key, value in _read_table(prefix + ".index", verify_index):
-            if key == b"":
-                for f, _, v in _pb_fields(value):
-                    if f == 1:
-                        self.num_shards = v
-                    elif f == 2 and v != 0:
-                        raise CheckpointError("big-endian bundles are not supported")
-            else:
-                self.entries[key.decode("utf-8")] = _parse_entry(value)
+        with _malformed(prefix + ".index"):
+            for key, value in _read_table(prefix + ".index", verify_index):
+                if key == b"":
+                    for f, _, v in _pb_fields(value):
+                        if f == 1:
+                            self.num_shards = int(v)
+                        elif f == 2 and v != 0:
+                            raise CheckpointError("big-endian bundles are not supported")
+                else:
+                    self.entries[key.decode("utf-8")] = _parse_entry(value)
 
     def has_tensor(self, name):
         return name in self.entries
@@ -422,17 +458,25 @@ class CheckpointReader:
         if e["dtype"] not in _DTYPES:
             raise CheckpointError("dtype %d of %r is not supported" % (e["dtype"], name))
         dt = np.dtype(_DTYPES[e["dtype"]])
-        count = int(np.prod(e["shape"])) if e["shape"] else 1
-        if count * dt.itemsize != e["size"]:
-            raise CheckpointError("size of %r does not match its shape" % name)
-        with open(_shard_path(self.prefix, e["shard_id"], self.num_shards), "rb") as f:
-            f.seek(e["offset"])
-            raw = f.read(e["size"])
-        if len(raw) != e["size"]:
-            raise CheckpointError("truncated data shard for %r" % name)
-        if verify and e["crc32c"] is not None and mask_crc(crc32c(raw)) != e["crc32c"]:
-            raise CheckpointError("payload checksum mismatch for %r" % name)
-        return np.frombuffer(raw, dtype=dt.newbyteorder("<")).astype(dt).reshape(e["shape"])
+        with _malformed("tensor %r of %s" % (name, self.prefix)):
+            count = 1
+            for d in e["shape"]:
+                if d < 0:
+                    raise CheckpointError("negative dimension in the shape of %r" % name)
+                count *= int(d)
+            if count * dt.itemsize != e["size"]:
+                raise CheckpointError("size of %r does not match its shape" % name)
+            shard = _shard_path(self.prefix, e["shard_id"], self.num_shards)
+            if e["offset"] + e["size"] > os.path.getsize(shard):
+                raise CheckpointError("truncated data shard for %r" % name)
+            with open(shard, "rb") as f:
+                f.seek(e["offset"])
+                raw = f.read(e["size"])
+            if len(raw) != e["size"]:
+                raise CheckpointError("truncated data shard for %r" % name)
+            if verify and e["crc32c"] is not None and mask_crc(crc32c(raw)) != e["crc32c"]:
+                raise CheckpointError("payload checksum mismatch for %r" % name)
+            return np.frombuffer(raw, dtype=dt.newbyteorder("<")).astype(dt).reshape(e["shape"])
 
 
 def _parse_extents(buf):
@@ -499,6 +543,12 @@ class CheckpointReaderV1:
     def __init__(self, path, verify=True):
         self.prefix = path
         self.meta, self._values = {}, {}
+        with _malformed(path):
+            self._load(path, verify)
+        if not self.meta:
+            raise CheckpointError("%s: no SavedTensorSliceMeta entry (not a V1 checkpoint?)" % path)
+
+    def _load(self, path, verify):
         for key, value in _read_table(path, verify):
             for f, _, v in _pb_fields(value):
                 if key == b"" and f == 1:  # SavedTensorSliceMeta
@@ -525,8 +575,6 @@ class CheckpointReaderV1:
                             tp = x
                     if name is not None and tp is not None:
                         self._values.setdefault(name, []).append((ext, tp))
-        if not self.meta:
-            raise CheckpointError("%s: no SavedTensorSliceMeta entry (not a V1 checkpoint?)" % path)
 
     def has_tensor(self, name):
         return name in self.meta
@@ -544,6 +592,12 @@ class CheckpointReaderV1:
         shape, dtype = self.meta[name]
         if dtype not in _DTYPES:
             raise CheckpointError("dtype %d of %r is not supported" % (dtype, name))
+        with _malformed("tensor %r of %s" % (name, self.prefix)):
+            return self._assemble(name, shape, dtype)
+
+    def _assemble(self, name, shape, dtype):
+        if any(d < 0 for d in shape) or int(np.prod(shape, dtype=np.float64)) > (1 << 34):
+            raise CheckpointError("implausible shape %s for %r" % (list(shape), name))
         out = np.zeros(shape, _DTYPES[dtype])
         filled = 0
         for ext, tp in self._values.get(name, []):
@@ -552,6 +606,8 @@ class CheckpointReaderV1:
             for d, size in enumerate(shape):
                 start, length = ext[d] if d < len(ext) else (0, None)
                 length = size - start if length is None else length
+                if start < 0 or length < 0 or start + length > size:
+                    raise CheckpointError("slice of %r lies outside the tensor" % name)
                 idx.append(slice(start, start + length))
                 sub.append(length)
             if int(np.prod(sub)) != flat.size:

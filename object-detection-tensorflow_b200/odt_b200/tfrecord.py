@@ -44,6 +44,8 @@ def write_records(path, payloads):
 
 
 def read_records(path, verify=True):
+    import os
+    size = os.path.getsize(path)
     with open(path, "rb") as f:
         while True:
             head = f.read(8)
@@ -52,9 +54,13 @@ def read_records(path, verify=True):
             if len(head) != 8:
                 raise RecordError("%s: truncated record header" % path)
             (n,) = struct.unpack("<Q", head)
-            (hc,) = struct.unpack("<I", f.read(4))
-            if verify and mask_crc(crc32c(head)) != hc:
+            hc = f.read(4)
+            if len(hc) != 4:
+                raise RecordError("%s: truncated record header" % path)
+            if verify and mask_crc(crc32c(head)) != struct.unpack("<I", hc)[0]:
                 raise RecordError("%s: record length checksum mismatch" % path)
+            if n > size - f.tell():      # also keeps a corrupt length from turning into a huge allocation
+                raise RecordError("%s: truncated record" % path)
             data = f.read(n)
             tail = f.read(4)
             if len(data) != n or len(tail) != 4:
@@ -109,21 +115,37 @@ def parse_example(data):
             if f2 != 1:
                 continue
             key, feat = None, b""
-            for f3, _, v in _pb_fields(entry):
+            for f3, wt3, v in _pb_fields(entry):
+                if wt3 != 2:
+                    raise RecordError("Example: map entry field %d is not length-delimited" % f3)
                 if f3 == 1:
-                    key = v.decode("utf-8")
+                    try:
+                        key = v.decode("utf-8")
+                    except UnicodeDecodeError:
+                        raise RecordError("Example: feature name is not UTF-8") from None
                 elif f3 == 2:
                     feat = v
             val = []
-            for kind, _, lst in _pb_fields(feat):
+            for kind, wtk, lst in _pb_fields(feat):
+                if wtk != 2:
+                    raise RecordError("Example: Feature field %d is not length-delimited" % kind)
                 if kind == 1:
-                    val = [v for f4, _, v in _pb_fields(lst) if f4 == 1]
+                    val = []
+                    for f4, wt, v in _pb_fields(lst):
+                        if f4 == 1:
+                            if wt != 2:
+                                raise RecordError("Example: BytesList value is not length-delimited")
+                            val.append(v)
                 elif kind == 2:
                     parts = []
                     for f4, wt, v in _pb_fields(lst):
                         if f4 == 1:
-                            parts.append(np.frombuffer(v, "<f4") if wt == 2 else
-                                         np.frombuffer(struct.pack("<I", v), "<f4"))
+                            if wt == 2 and len(v) % 4 == 0:
+                                parts.append(np.frombuffer(v, "<f4"))
+                            elif wt == 5:
+                                parts.append(np.frombuffer(struct.pack("<I", v), "<f4"))
+                            else:
+                                raise RecordError("Example: malformed FloatList")
                     val = np.concatenate(parts).astype(np.float32) if parts else np.zeros(0, np.float32)
                 elif kind == 3:
                     ints = []
@@ -135,8 +157,10 @@ def parse_example(data):
                             while pos < len(v):
                                 x, pos = _get_varint(v, pos)
                                 ints.append(x - (1 << 64) if x >= (1 << 63) else x)
-                        else:
+                        elif wt == 0:
                             ints.append(v - (1 << 64) if v >= (1 << 63) else v)
+                        else:
+                            raise RecordError("Example: malformed Int64List")
                     val = np.asarray(ints, np.int64)
             if key is not None:
                 out[key] = val
@@ -154,8 +178,13 @@ def decode_voc_example(data):
     import cv2
     ex = parse_example(data)
     for k in ("image", "shape", "ground_truth"):
-        if k not in ex or not ex[k]:
+        if k not in ex or len(ex[k]) == 0:
             raise RecordError("record lacks the %r feature" % k)
+    for k in ("image", "shape", "ground_truth"):
+        if not isinstance(ex[k], list):
+            raise RecordError("feature %r is not a bytes list" % k)
+    if len(ex["shape"][0]) != 12 or len(ex["ground_truth"][0]) % 20:
+        raise RecordError("'shape' must hold 3 int32 and 'ground_truth' rows of 5 float32")
     shape = np.frombuffer(ex["shape"][0], "<i4")
     gt = np.frombuffer(ex["ground_truth"][0], "<f4").reshape(-1, 5).astype(np.float32)
     img = cv2.imdecode(np.frombuffer(ex["image"][0], np.uint8), cv2.IMREAD_COLOR)

@@ -323,3 +323,35 @@ def test_bundle_round_trip_property(ck, tmp_path):
         for k in t:
             np.testing.assert_array_equal(got[k], t[k])
     run()
+
+
+def test_corrupt_files_raise_checkpoint_error_only(ck, tmp_path):
+    """Byte flips / truncations of the index (checks off), of a V1 file and of snappy blocks must surface as
+    CheckpointError, never as a raw IndexError / struct.error / UnicodeDecodeError."""
+    rng = np.random.default_rng(11)
+    t = {"a/kernel": rng.standard_normal((3, 3, 3, 8)).astype(np.float32), "global_step": np.asarray(7, np.int64)}
+    pre = str(tmp_path / "m-7")
+    ck.write_checkpoint(pre, t)
+    good = open(pre + ".index", "rb").read()
+    p1 = str(tmp_path / "v1.ckpt")
+    _v1_file(ck, p1, {"x/w": rng.standard_normal((4, 6)).astype(np.float32)}, split="x/w")
+    good1 = open(p1, "rb").read()
+
+    def mutate(raw):
+        b = bytearray(raw)
+        for _ in range(int(rng.integers(1, 4))):
+            b[int(rng.integers(len(b)))] = int(rng.integers(256))
+        return bytes(b[:int(rng.integers(len(b)))] if rng.random() < 0.2 else b)
+
+    for _ in range(300):
+        open(pre + ".index", "wb").write(mutate(good))
+        open(p1, "wb").write(mutate(good1))
+        for fn in (lambda: [r.get_tensor(n, verify=True) for r in [ck.CheckpointReader(pre, verify_index=False)]
+                            for n in r.get_variable_to_shape_map()],
+                   lambda: [r.get_tensor(n) for r in [ck.CheckpointReaderV1(p1, verify=False)]
+                            for n in r.get_variable_to_shape_map()],
+                   lambda: ck._snappy_decompress(bytes(rng.integers(0, 256, int(rng.integers(1, 40))).astype(np.uint8)))):
+            try:
+                fn()
+            except ck.CheckpointError:
+                pass

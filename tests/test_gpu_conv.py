@@ -457,9 +457,11 @@ def test_conv_direct_two_preactivation_outputs(built):
     ((8, 75, 75, 100, 256, 3, 1, 1), {}),                            # second chunk holds 36 channels, CTA pairs
     ((2, 64, 64, 16, 28, 3, 1, 1), {"in_halo": 1, "pool": 2}),       # row-block pooled mode
 ])
-def test_conv_tc_thin_input_channels(built, shape, kw):
+@pytest.mark.parametrize("kskip", ["0", "1"])
+def test_conv_tc_thin_input_channels(built, monkeypatch, shape, kw, kskip):
     """Cin that does not fill its 64-channel chunk (RetinaNet's 7*2^i widths, zero-padded operands) in every
-    tensor-core mode."""
+    tensor-core mode; with ODT_TC_KSKIP=1 the all-zero 16-deep K steps are not issued (opt-in, read per call)."""
+    monkeypatch.setenv("ODT_TC_KSKIP", kskip)
     got, ref, _, _ = _conv_case(*shape, mode="tc", seed=sum(shape), **kw)
     assert np.abs(got - ref).max() <= 2e-3 * max(np.abs(ref).max(), 1.0), shape
 

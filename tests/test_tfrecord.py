@@ -222,3 +222,27 @@ def test_preprocess_jitter_rotate_and_fallback(tr):
     np.testing.assert_allclose(z, tr._resize_bilinear_legacy(img, 40, 40))
     np.testing.assert_allclose(bz[0], [2 * 0.8, 3 * 0.5, 4 * 0.8, 6 * 0.5, 2], rtol=1e-6)
     assert (bz[1:] == -1).all()
+
+
+def test_corrupt_records_raise_record_error_only(tr, tmp_path):
+    rng = np.random.default_rng(12)
+    good = tr.encode_voc_example(b"\xff\xd8abc", np.asarray([3, 4, 3], np.int32), np.zeros((2, 5), np.float32))
+    p = str(tmp_path / "a.tfrecord")
+    tr.write_records(p, [b"hello", b"x" * 100])
+    raw = open(p, "rb").read()
+
+    def mutate(src):
+        b = bytearray(src)
+        for _ in range(int(rng.integers(1, 4))):
+            b[int(rng.integers(len(b)))] = int(rng.integers(256))
+        return bytes(b[:int(rng.integers(len(b)))] if rng.random() < 0.3 else b)
+
+    for _ in range(400):
+        ex = mutate(good)
+        open(p, "wb").write(mutate(raw))
+        for fn in (lambda: tr.parse_example(ex), lambda: tr.decode_voc_example(ex),
+                   lambda: list(tr.read_records(p)), lambda: list(tr.read_records(p, verify=False))):
+            try:
+                fn()
+            except tr.RecordError.__mro__[1]:      # CheckpointError (RecordError derives from it)
+                pass
