@@ -41,6 +41,10 @@ bool kskip_enabled() {
   const char* e = getenv("ODT_TC_KSKIP");  // opt-in (default off): see TcGeom::klast
   return e && e[0] == '1';
 }
+bool tapn_enabled() {
+  const char* e = getenv("ODT_TC_TAPN");  // opt-in (default off): conv_tapn.cu
+  return e && e[0] == '1';
+}
 bool wres_enabled() {
   const char* e = getenv("ODT_TC_WRES");
   return !(e && e[0] == '0');

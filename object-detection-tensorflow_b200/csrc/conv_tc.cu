@@ -744,6 +744,24 @@ static int resolve_driver() {
   return ODT_OK;
 }
 
+int tc_encode_tiled(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                    const cuuint32_t* box, bool l2_promote_256) {
+  int rc = resolve_driver();
+  if (rc) return rc;
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult cr = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
+                               strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               l2_promote_256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(rank %d) failed (%d)", rank, (int)cr);
+    return ODT_ERR_CUDA;
+  }
+  return ODT_OK;
+}
+
+int conv_tapn_try(const void* in, const void* weights, const odt_conv_params* p, void* stream);  // conv_tapn.cu
+
 int check_conv_params(const odt_conv_params* p) {
   ODT_CHECK_ARG(p != nullptr, "params null");
   ODT_CHECK_ARG(p->B > 0 && p->H > 0 && p->W > 0 && p->Cin > 0 && p->in_ld >= p->Cin,
@@ -817,6 +835,10 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
   const int ih = p->in_halo ? 1 : 0;  // input stored as [B][H+2][W+2][ld] with zero borders
   ODT_CHECK_ARG(p->in_halo == 0 || p->in_halo == 1, "in_halo must be 0 or 1");
   ODT_CHECK_ARG(p->out0_halo == 0 || p->out0_halo == 1, "out0_halo must be 0 or 1");
+  if (tapn_enabled()) {  // opt-in: narrow 3x3 layers with the horizontal taps folded into N (conv_tapn.cu)
+    const int rt = conv_tapn_try(in, weights, p, stream);
+    if (rt != ODT_ERR_UNSUPPORTED) return rt;
+  }
   TcGeom g;
   memset(&g, 0, sizeof(g));
   g.M = (long long)p->B * p->OH * p->OW;

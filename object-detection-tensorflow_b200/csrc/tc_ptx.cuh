@@ -208,4 +208,9 @@ __device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// host: cuTensorMapEncodeTiled for an fp16 tensor with the 128-byte swizzle and zero fill (conv_tc.cu);
+// 0 or an ODT_ERR_* code with the message set
+int tc_encode_tiled(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                    const cuuint32_t* box, bool l2_promote_256);
+
 }  // namespace odt

@@ -4,6 +4,7 @@ Tolerances: fp16 tensor-core path -- fp16 operands are exact in both, fp32
 accumulation, fp16-rounded output => |err| <= 2e-3 * max|ref|; fp32 CUDA-core
 path => 2e-5 * max|ref| (accumulation order only)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -505,3 +506,29 @@ def test_maxpool_halo_layouts(built):
         np.testing.assert_array_equal(got, ref)
         if oh:
             assert float(yd[:, 0].abs().max()) == 0 and float(yd[:, :, -1].abs().max()) == 0
+
+
+# Opt-in: the "taps as N" kernel (csrc/conv_tapn.cu, ODT_TC_TAPN=1) was written after the last GPU minute of
+# round 1; its tests run only with ODT_TEST_EXPERIMENTAL=1 until it has been validated on a B200.
+_experimental = pytest.mark.skipif(os.environ.get("ODT_TEST_EXPERIMENTAL") != "1",
+                                   reason="experimental kernel: set ODT_TEST_EXPERIMENTAL=1")
+
+
+@_experimental
+@pytest.mark.parametrize("shape,kw", [
+    ((2, 40, 40, 64, 64, 3, 1, 1), {"in_halo": 1, "out_halo": 1}),
+    ((2, 37, 61, 64, 64, 3, 1, 1), {"in_halo": 1}),                              # ragged rows / columns
+    ((2, 40, 40, 7, 7, 3, 1, 1), {"in_halo": 1, "out_halo": 1}),                 # thin: N = 96, one K step
+    ((2, 40, 40, 28, 28, 3, 1, 1), {"in_halo": 1, "residual": True, "pre": True, "pre2": True}),
+    ((2, 26, 26, 128, 64, 3, 1, 1), {"in_halo": 1, "act": "leaky"}),             # two channel chunks
+    ((2, 64, 64, 64, 64, 3, 1, 1), {"in_halo": 1, "pool": 2}),
+    ((1, 8, 300, 64, 64, 3, 1, 1), {"in_halo": 1, "out_halo": 1, "pool": 2}),    # ten full column blocks
+    ((2, 30, 46, 16, 28, 3, 1, 1), {"in_halo": 1, "pool": 2}),
+])
+def test_conv_tapn_matches_reference(built, monkeypatch, shape, kw):
+    monkeypatch.setenv("ODT_TC_TAPN", "1")
+    got, ref, g1, r1 = _conv_case(*shape, mode="tc", seed=sum(shape), **kw)
+    tol = 2e-3 * max(np.abs(ref).max(), 1.0)
+    assert np.abs(got - ref).max() <= tol, shape
+    if g1 is not None:
+        assert np.abs(g1 - r1).max() <= 3 * tol
