@@ -22,8 +22,9 @@
 // channel chunk), w1 MMA issuer, w2..9 two epilogue groups draining alternate tiles from two TMEM stages;
 // the 9*cchunks weight tiles stay resident in shared memory.
 //
-// OPT-IN (ODT_TC_TAPN=1) until it has been validated and A/B-timed on a B200: written at the end of round 1
-// without GPU time left.  ref call sites: tf.nn.conv2d SSD300.py:519 (conv1_2), tf.layers.conv2d
+// OPT-IN (ODT_TC_TAPN=1) until it has been A/B-timed on a B200: written at the end of round 1; its eight parity
+// cases (tests/test_gpu_conv.py::test_conv_tapn_matches_reference) passed on a B200 with the last GPU seconds of
+// the round, no timing yet.  ref call sites: tf.nn.conv2d SSD300.py:519 (conv1_2), tf.layers.conv2d
 // RetinaNet.py:599-609, YOLOv3.py:495, FCOS.py:469-479.
 #include <string.h>
 
@@ -366,6 +367,8 @@ __global__ void __launch_bounds__(TN_THREADS, 1)
   }
 }
 
+static int g_tapn_launches = 0;  // debug: lets a test assert that the layer really took this path
+
 // ODT_ERR_UNSUPPORTED when the layer does not qualify (the caller then takes the regular paths).
 int conv_tapn_try(const void* in, const void* weights, const odt_conv_params* p, void* stream) {
   const bool shape_ok = p->in_halo == 1 && p->R == 3 && p->S == 3 && p->stride == 1 && p->dil == 1 && p->pad_t == 1 &&
@@ -452,7 +455,11 @@ int conv_tapn_try(const void* in, const void* weights, const odt_conv_params* p,
   else
     ODT_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tapn_kernel<0>, tmA, tmB, g, e));
   ODT_LAUNCH_OK();
+  ++g_tapn_launches;
   return ODT_OK;
 }
 
 }  // namespace odt
+
+// Debug only: number of convolutions launched through conv_tapn_kernel by this process.
+extern "C" int odt_debug_tapn_launches(void) { return odt::g_tapn_launches; }

@@ -508,8 +508,9 @@ def test_maxpool_halo_layouts(built):
             assert float(yd[:, 0].abs().max()) == 0 and float(yd[:, :, -1].abs().max()) == 0
 
 
-# Opt-in: the "taps as N" kernel (csrc/conv_tapn.cu, ODT_TC_TAPN=1) was written after the last GPU minute of
-# round 1; its tests run only with ODT_TEST_EXPERIMENTAL=1 until it has been validated on a B200.
+# Opt-in: the "taps as N" kernel (csrc/conv_tapn.cu, ODT_TC_TAPN=1) was written at the very end of round 1 (these
+# eight cases passed on a B200 once, untimed); its tests run only with ODT_TEST_EXPERIMENTAL=1 until it is the
+# default path.
 _experimental = pytest.mark.skipif(os.environ.get("ODT_TEST_EXPERIMENTAL") != "1",
                                    reason="experimental kernel: set ODT_TEST_EXPERIMENTAL=1")
 
@@ -526,8 +527,11 @@ _experimental = pytest.mark.skipif(os.environ.get("ODT_TEST_EXPERIMENTAL") != "1
     ((2, 30, 46, 16, 28, 3, 1, 1), {"in_halo": 1, "pool": 2}),
 ])
 def test_conv_tapn_matches_reference(built, monkeypatch, shape, kw):
+    from odt_b200 import lib as L
     monkeypatch.setenv("ODT_TC_TAPN", "1")
+    before = L.load().odt_debug_tapn_launches()
     got, ref, g1, r1 = _conv_case(*shape, mode="tc", seed=sum(shape), **kw)
+    assert L.load().odt_debug_tapn_launches() == before + 1, "the layer did not take the taps-as-N path"
     tol = 2e-3 * max(np.abs(ref).max(), 1.0)
     assert np.abs(got - ref).max() <= tol, shape
     if g1 is not None:
