@@ -320,7 +320,10 @@ def main():
             tj = json.load(f)
         if tj.get("launches_per_step") == len(tc_ops):
             traffic, traffic_src = tj["dram_bytes_per_launch_avg"], "profiles/r01_conv_traffic.json (ncu dram__bytes_read+write)"
-    roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM)",
+    kname = "conv_tc_kernel (tcgen05 implicit GEMM)"
+    if os.environ.get("ODT_TC_TAPN") == "1":
+        kname += " + conv_tapn_kernel for Cout_pad <= 64 (ODT_TC_TAPN=1)"
+    roofline = {"bound": "tensor", "kernel": kname,
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved_tf / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_src + " cuBLAS bf16 sustained (kernel timed inside a long step)",
