@@ -172,11 +172,13 @@ class _Detector:
         net.run()
         return net.tail.results()
 
-    def detect_stream(self, batches, precision=None):
+    def detect_stream(self, batches, precision=None, finish=None):
         """Pipelined inference over an iterable of host batches [B,H,W,3]: the
         host->device copy of batch i+1 runs on a copy stream while the kernels of
         batch i execute; every batch's detections are read back (D2H) before it is
-        yielded.  Sources in pinned memory make the H2D copies truly asynchronous."""
+        yielded.  Sources in pinned memory make the H2D copies truly asynchronous.
+        `finish(net)` replaces the read-back of the local detections (used by
+        detect_stream_sharded: all-gather of every rank's records)."""
         it = iter(batches)
         try:
             cur = _as_host_tensor(next(it))
@@ -213,7 +215,7 @@ class _Detector:
             except StopIteration:
                 nxt = None
             net.run()
-            yield net.tail.results()
+            yield finish(net) if finish is not None else net.tail.results()
             cur = nxt
             i += 1
 
@@ -229,6 +231,12 @@ class _Detector:
         one NCCL all-gather of the fixed-size detection records follows."""
         from . import dist
         return dist.detect_sharded(self, images_local)
+
+    def detect_stream_sharded(self, batches_local, precision=None):
+        """detect_stream over this rank's image shards: the H2D copy of shard i+1 overlaps the kernels,
+        the all-gather and the read-back of shard i; yields every rank's detections per step."""
+        from . import dist
+        return self.detect_stream(batches_local, precision, finish=dist.finish_sharded)
 
     # ---- training / checkpoints (API surface; SURVEY 8f) --------------------
     def train_one_epoch(self, lr):

@@ -72,6 +72,12 @@ def broadcast_weights(weights, src=0):
     return out
 
 
+def finish_sharded(net):
+    """After net.run(): pack this rank's detections, all-gather, read back, unpack."""
+    rec = pack_records(net.tail.dets, net.tail.det_count)
+    return unpack_records(gather_records(rec))
+
+
 def detect_sharded(model, images_local):
     """Run this rank's image shard and all-gather everybody's detections."""
     from .api import _as_host_tensor
@@ -79,5 +85,4 @@ def detect_sharded(model, images_local):
     net = model.engine(images_local.shape[0])
     net.image_buf.copy_(images_local, non_blocking=True)
     net.run()
-    rec = pack_records(net.tail.dets, net.tail.det_count)
-    return unpack_records(gather_records(rec))
+    return finish_sharded(net)
