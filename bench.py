@@ -273,7 +273,10 @@ def main():
     def run_e2e(n):
         # public API: pipelined stream of host batches (H2D of batch i+1 overlaps batch i),
         # every step copies its inputs from pinned host memory and reads its detections back
-        if world > 1 and e2e_mode["v"] == "stream":
+        if os.environ.get("ODT_BENCH_DEFERRED") == "1":  # experimental: read-back one step behind the launches
+            for _ in model.detect_stream_deferred((images for _ in range(n)), sharded=world > 1):
+                pass
+        elif world > 1 and e2e_mode["v"] == "stream":
             for _ in model.detect_stream_sharded(images for _ in range(n)):
                 pass
         elif world > 1:
@@ -354,7 +357,8 @@ def main():
                            (BATCH * CONV_GFLOP_PER_IMG * 1e9 / (ms_step * 1e-3)) / (peak_tf * 1e12)},
             "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K,
-                    "mode": "detect_stream" if world == 1 else
+                    "mode": "detect_stream_deferred" if os.environ.get("ODT_BENCH_DEFERRED") == "1" else
+                            "detect_stream" if world == 1 else
                             ("detect_stream_sharded" if e2e_mode["v"] == "stream" else "detect_batch_sharded")},
             "gpu_launches": net.num_launches() * K,
             "roofline": roofline, "clocks": clocks}

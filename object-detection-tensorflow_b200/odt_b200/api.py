@@ -232,6 +232,76 @@ class _Detector:
         from . import dist
         return dist.detect_sharded(self, images_local)
 
+    def detect_stream_deferred(self, batches, precision=None, sharded=False):
+        """detect_stream with the read-back one step behind: after the kernels of batch i are queued, its
+        records go to a pinned host buffer asynchronously (after the all-gather when `sharded`), batch i+1 is
+        launched, and only then are batch i's records unpacked on the host -- the Python work and the D2H
+        latency overlap the next batch instead of idling the GPU.  Yields results in order, one step late.
+        EXPERIMENTAL (written without GPU time left in round 1; tests/test_gpu_models.py opt-in case)."""
+        from . import dist
+        it = iter(batches)
+        try:
+            cur = _as_host_tensor(next(it))
+        except StopIteration:
+            return
+        net = self.engine(cur.shape[0], precision)
+        if not hasattr(net, "_stage"):
+            net._stage = [torch.empty_like(net.image_buf) for _ in range(2)]
+            net._copy_stream = torch.cuda.Stream()
+            net._h2d = [torch.cuda.Event() for _ in range(2)]
+            net._used = [torch.cuda.Event() for _ in range(2)]
+        world = dist.dist.get_world_size() if (sharded and dist.dist.is_initialized()) else 1
+        rec_shape = (world * cur.shape[0], net.tail.dets.shape[1] * 6 + 1)
+        if getattr(net, "_rec_host", None) is None or tuple(net._rec_host[0].shape) != rec_shape:
+            net._rec_host = [torch.empty(rec_shape, dtype=torch.float32).pin_memory() for _ in range(2)]
+            net._status_host = [torch.empty(1, dtype=torch.int32).pin_memory() for _ in range(2)]
+            net._rec_done = [torch.cuda.Event() for _ in range(2)]
+        main = torch.cuda.current_stream()
+        cs = net._copy_stream
+
+        def prefetch(t, slot):
+            cs.wait_event(net._used[slot])
+            with torch.cuda.stream(cs):
+                net._stage[slot].copy_(t, non_blocking=True)
+                net._h2d[slot].record(cs)
+
+        def complete(slot):
+            net._rec_done[slot].synchronize()
+            if int(net._status_host[slot][0]) != 0:
+                raise RuntimeError("NMS candidate list overflowed its capacity (cap=%d)" % net.tail.p.cap)
+            return dist.unpack_records(net._rec_host[slot])
+
+        for ev in net._used:
+            ev.record(main)
+        prefetch(cur, 0)
+        i, pending = 0, None
+        while cur is not None:
+            slot = i & 1
+            main.wait_event(net._h2d[slot])
+            net.image_buf.copy_(net._stage[slot], non_blocking=True)  # device-to-device
+            net._used[slot].record(main)
+            try:
+                nxt = _as_host_tensor(next(it))
+                assert nxt.shape == cur.shape, "all batches of a stream must share a shape"
+                prefetch(nxt, slot ^ 1)
+            except StopIteration:
+                nxt = None
+            net.run()
+            # snapshot of this batch's records, ordered before the next batch's kernels on the main stream
+            rec = dist.pack_records(net.tail.dets, net.tail.det_count)
+            if sharded:
+                rec = dist.gather_records(rec)
+            net._rec_host[slot].copy_(rec, non_blocking=True)
+            net._status_host[slot].copy_(net.tail.status.reshape(1), non_blocking=True)
+            net._rec_done[slot].record(main)
+            if pending is not None:
+                yield complete(pending)  # host work of batch i-1 while batch i runs
+            pending = slot
+            cur = nxt
+            i += 1
+        if pending is not None:
+            yield complete(pending)
+
     def detect_stream_sharded(self, batches_local, precision=None):
         """detect_stream over this rank's image shards: the H2D copy of shard i+1 overlaps the kernels,
         the all-gather and the read-back of shard i; yields every rank's detections per step."""

@@ -6,6 +6,8 @@ against the CPU oracle on identical inputs and weights.
   * fp16 tcgen05 path: head rows within 3e-2 * max|ref| (fp16 storage of 20-130
     layers; SURVEY.md "hard part" 1 -- graded stage-wise, never by loosening the
     tail tolerance: the tail is always exact on the rows the GPU produced)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -276,6 +278,23 @@ def test_detect_stream_matches_detect_batch(built):
     pinned = [torch.from_numpy(b).pin_memory() for b in batches]
     got = list(m.detect_stream(pinned))
     assert len(got) == 3
+    for g, r in zip(got, ref):
+        for gi, ri in zip(g, r):
+            for a, b in zip(gi, ri):
+                np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.skipif(os.environ.get("ODT_TEST_EXPERIMENTAL") != "1",
+                    reason="experimental path: set ODT_TEST_EXPERIMENTAL=1")
+def test_detect_stream_deferred_matches_detect_batch(built):
+    """Read-back one step behind the launches (results still in order) == synchronous API."""
+    import torch
+    m = _model("ssd300", precision="fp16", nms_score_threshold=0.3)
+    batches = [_img(2, 300, 300, seed=s) for s in (21, 22, 23, 24)]
+    ref = [m.detect_batch(b) for b in batches]
+    pinned = [torch.from_numpy(b).pin_memory() for b in batches]
+    got = list(m.detect_stream_deferred(pinned))
+    assert len(got) == 4
     for g, r in zip(got, ref):
         for gi, ri in zip(g, r):
             for a, b in zip(gi, ri):
