@@ -41,9 +41,9 @@ bool kskip_enabled() {
   const char* e = getenv("ODT_TC_KSKIP");  // opt-in (default off): see TcGeom::klast
   return e && e[0] == '1';
 }
-bool tapn_enabled() {
-  const char* e = getenv("ODT_TC_TAPN");  // opt-in (default off): conv_tapn.cu
-  return e && e[0] == '1';
+int tapn_mode() {
+  const char* e = getenv("ODT_TC_TAPN");  // opt-in (default 0 = off): conv_tapn.cu
+  return (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
 }
 bool wres_enabled() {
   const char* e = getenv("ODT_TC_WRES");

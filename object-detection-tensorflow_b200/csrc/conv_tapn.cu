@@ -407,6 +407,25 @@ int conv_tapn_try(const void* in, const void* weights, const odt_conv_params* p,
   if (tiles >= (1ll << 31)) return ODT_ERR_UNSUPPORTED;
   g.num_tiles = (int)tiles;
   g.out_halo = p->out0_halo;
+  if (tapn_mode() == 1) {
+    // same operand-fetch model as pick_tiling (conv_tc.cu): rounds of the slowest SM x MMAs per tile x clk per MMA
+    // (2*(32 + N/4), A and half of B with the CTA pairs the regular flat modes use), + a fixed cost per tile.
+    // Small maps lose here: a 13-wide row still occupies a 32-lane tile row.
+    const long long mm = 4ll * g.cchunks;
+    const long long c_tapn = (long long)ceil_div(tiles, kNumSMs) * (3 * mm * (64 + 3 * g.BN / 2) + 1200);
+    long long t_reg;  // tiles of the regular path
+    bool pairs;
+    if (pool) {
+      const long long t2 = (long long)((p->H + 1) / 2) * ((p->W + 63) / 64), t4 = (long long)((p->H + 3) / 4) * ((p->W + 31) / 32);
+      t_reg = (long long)p->B * (t4 < t2 ? t4 : t2);
+      pairs = true;
+    } else {
+      t_reg = ((long long)p->B * (p->H + 2) * (p->W + 2) + 127) / 128;
+      pairs = g.cchunks >= 2;
+    }
+    const long long c_reg = (long long)ceil_div(t_reg, kNumSMs) * (9 * mm * (64 + (pairs ? g.BN / 4 : g.BN / 2)) + 1200);
+    if (c_tapn >= c_reg) return ODT_ERR_UNSUPPORTED;
+  }
   const int wbytes = 9 * g.cchunks * g.BN * 128;
   const int fixed = wbytes + 256 + TN_PAR_FLOATS * 4 + (pool ? TN_XCH_BYTES : 0) + 1024;
   int stages = (TN_SMEM_LIMIT - fixed) / TN_A_BYTES;

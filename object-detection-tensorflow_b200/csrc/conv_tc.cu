@@ -835,7 +835,7 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
   const int ih = p->in_halo ? 1 : 0;  // input stored as [B][H+2][W+2][ld] with zero borders
   ODT_CHECK_ARG(p->in_halo == 0 || p->in_halo == 1, "in_halo must be 0 or 1");
   ODT_CHECK_ARG(p->out0_halo == 0 || p->out0_halo == 1, "out0_halo must be 0 or 1");
-  if (tapn_enabled()) {  // opt-in: narrow 3x3 layers with the horizontal taps folded into N (conv_tapn.cu)
+  if (tapn_mode()) {  // opt-in: narrow 3x3 layers with the horizontal taps folded into N (conv_tapn.cu)
     const int rt = conv_tapn_try(in, weights, p, stream);
     if (rt != ODT_ERR_UNSUPPORTED) return rt;
   }

@@ -14,11 +14,13 @@ echo "tapn/thin tests exit $?"; tail -n 2 gpurun_out/r2_tapn_tests.log
     for rep in 1 2 3; do
       ODT_TC_TAPN=0 ODT_TC_KSKIP=0 python scripts/conv_micro.py $shape 50 | sed 's/^/base   /'
       ODT_TC_TAPN=0 ODT_TC_KSKIP=1 python scripts/conv_micro.py $shape 50 | sed 's/^/kskip  /'
-      ODT_TC_TAPN=1 python scripts/conv_micro.py $shape 50 | sed 's/^/tapn   /'
+      ODT_TC_TAPN=2 python scripts/conv_micro.py $shape 50 | sed 's/^/tapn   /'
     done
   done
 } > gpurun_out/r2_ab_micro.txt 2>&1
 tail -n 60 gpurun_out/r2_ab_micro.txt
+ODT_TC_TAPN=1 ODT_TC_KSKIP=1 timeout 1500 python -m pytest tests -q -m gpu --timeout 300 > gpurun_out/r2_gpu_tests_tapn.log 2>&1
+echo "pytest -m gpu with TAPN=KSKIP=1 exit $?"; tail -n 3 gpurun_out/r2_gpu_tests_tapn.log
 for t in 0 1; do
   for m in "ssd300 64" "retinanet 16"; do
     n=$(echo $m | tr ' ' '_')

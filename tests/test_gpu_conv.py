@@ -528,7 +528,7 @@ _experimental = pytest.mark.skipif(os.environ.get("ODT_TEST_EXPERIMENTAL") != "1
 ])
 def test_conv_tapn_matches_reference(built, monkeypatch, shape, kw):
     from odt_b200 import lib as L
-    monkeypatch.setenv("ODT_TC_TAPN", "1")
+    monkeypatch.setenv("ODT_TC_TAPN", "2")   # 2 = wherever the layer qualifies (1 also asks the cost model)
     before = L.load().odt_debug_tapn_launches()
     got, ref, g1, r1 = _conv_case(*shape, mode="tc", seed=sum(shape), **kw)
     assert L.load().odt_debug_tapn_launches() == before + 1, "the layer did not take the taps-as-N path"
