@@ -13,8 +13,11 @@ SSD300.py / SSD512.py do not even parse (empty `else:` at line 41-43).  The
 TF-op semantics restated in oracle/tfops.py (SAME padding, BN eps 1e-3,
 GroupNorm eps 1e-6, legacy bilinear resize, NonMaxSuppressionV3 ...) come from
 knowledge of TF 1.13's published kernels and could not
-be checked against a running TensorFlow.  The only pins are the hand-derived
-known answers of SURVEY.md section 8(c) (anchor tables) checked in tests/test_oracle.py.
+be checked against a running TensorFlow.  The pins are the hand-derived known
+answers of SURVEY.md section 8(c) (anchor tables) and, for the ops whose definition
+does not depend on TensorFlow, independent implementations (torchvision.ops.nms for
+the greedy strict-> suppression on tie-free boxes, torch.nn.functional for group
+norm / softmax / l2-normalise / max-pool / nearest resize) -- tests/test_oracle.py.
 
 oracle/loss.py restates the four per-image training losses (RetinaNet.py:357-474,
 SSD300.py:345-453, YOLOv3.py:115-318, FCOS.py:153-187,266-348) for the loss-forward kernels;

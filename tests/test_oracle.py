@@ -168,3 +168,47 @@ def test_loss_oracle_reproduces_committed_golden(name):
     for b in range(d["rows"].shape[0]):
         got = mg.run_loss_case(name, d["rows"], d["gt"], b)
         assert abs(got - d["loss"][b]) <= 1e-9 * max(abs(d["loss"][b]), 1.0), (name, b, got, d["loss"][b])
+
+
+# ---- independent implementations (not TensorFlow, but not ours either) ------------------------------------
+def test_nms_agrees_with_torchvision_on_tie_free_boxes():
+    """Greedy IoU suppression (strict >) is what torchvision.ops.nms implements too; on tie-free random boxes the
+    first max_out survivors must coincide with the TF-semantics oracle (C and pure-python statements)."""
+    import torch
+    tv = pytest.importorskip("torchvision")
+    rng = np.random.default_rng(42)
+    for n, thr, max_out in ((50, 0.5, 20), (400, 0.45, 10), (1500, 0.3, 200), (7, 0.5, 20)):
+        yx = rng.uniform(0, 250, (n, 2))
+        hw = rng.uniform(8, 90, (n, 2))
+        boxes = np.concatenate([yx, yx + hw], 1).astype(np.float32)          # (y1, x1, y2, x2)
+        scores = rng.permutation(n).astype(np.float32) / n + rng.uniform(0, 1e-4, n).astype(np.float32)
+        assert len(np.unique(scores)) == n
+        keep = tv.ops.nms(torch.from_numpy(boxes[:, [1, 0, 3, 2]].copy()), torch.from_numpy(scores), thr).numpy()
+        np.testing.assert_array_equal(OT.nms_c(boxes, scores, max_out, thr), keep[:max_out])
+        np.testing.assert_array_equal(OT.nms_py(boxes, scores, max_out, thr), keep[:max_out])
+
+
+def test_tfops_agree_with_torch_functional():
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(43)
+    x = rng.standard_normal((2, 6, 9, 16)).astype(np.float32)
+    g, b = rng.uniform(.5, 1.5, 16).astype(np.float32), rng.standard_normal(16).astype(np.float32)
+    xt = torch.from_numpy(x).permute(0, 3, 1, 2)
+    ref = F.group_norm(xt, 8, torch.from_numpy(g), torch.from_numpy(b), eps=1e-6).permute(0, 2, 3, 1).numpy()
+    np.testing.assert_allclose(T.group_norm(x, g, b), ref, atol=2e-5)
+    np.testing.assert_allclose(T.softmax_lastdim(x), F.softmax(torch.from_numpy(x), -1).numpy(), atol=1e-6)
+    np.testing.assert_allclose(T.sigmoid(x), torch.sigmoid(torch.from_numpy(x)).numpy(), atol=1e-6)
+    np.testing.assert_allclose(T.leaky_relu(x), F.leaky_relu(torch.from_numpy(x), 0.1).numpy(), atol=0)
+    np.testing.assert_allclose(T.l2_normalize_channels(x), F.normalize(torch.from_numpy(x), dim=-1, eps=1e-6).numpy(),
+                               atol=1e-6)
+    # even sizes, window 2 stride 2: SAME needs no padding, so it must equal the plain max-pool
+    ref = F.max_pool2d(torch.from_numpy(x[:, :, :8]).permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).numpy()
+    np.testing.assert_array_equal(T.max_pool_same(x[:, :, :8], 2, 2), ref)
+    # nearest x2 (YOLOv3's top-down path) has one definition
+    ref = F.interpolate(xt, scale_factor=2, mode="nearest").permute(0, 2, 3, 1).numpy()
+    np.testing.assert_array_equal(T.resize_nearest_legacy(x, 12, 18), ref)
+    # TF1's legacy bilinear (no half-pixel centres) at integer x2 == align_corners=False of neither torch mode;
+    # it does agree with torch where both sample grid points exactly: the even output positions are the inputs
+    up = T.resize_bilinear_legacy(x, 12, 18)
+    np.testing.assert_allclose(up[:, ::2, ::2], x, atol=1e-6)
