@@ -10,7 +10,8 @@ echo "tapn/thin tests exit $?"; tail -n 2 gpurun_out/r2_tapn_tests.log
   # conv1_2 of SSD300 (pooled), conv1_2 of SSD512, a thin RetinaNet layer (7->7 and 28->28 at 200x200, B=16),
   # YOLOv3's 32->64 and FCOS's 64->64; each line: default path, then taps-as-N, three interleaved repeats
   for shape in "64 300 300 64 64 3 1 2 1 1" "32 512 512 64 64 3 1 2 1 1" "16 200 200 7 7 3 1 0 1 1" \
-               "16 200 200 28 28 3 1 0 1 1" "32 208 208 32 64 3 1 0 1 1" "4 256 256 64 64 3 1 0 1 1"; do
+               "16 200 200 28 28 3 1 0 1 1" "32 208 208 32 64 3 1 0 1 1" "4 256 256 64 64 3 1 0 1 1" \
+               "32 416 416 32 64 3 2 0 0 0"; do   # the last one: YOLOv3 block1 (stride 2, im2col mode): K-skip only
     for rep in 1 2 3; do
       ODT_TC_TAPN=0 ODT_TC_KSKIP=0 python scripts/conv_micro.py $shape 50 | sed 's/^/base   /'
       ODT_TC_TAPN=0 ODT_TC_KSKIP=1 python scripts/conv_micro.py $shape 50 | sed 's/^/kskip  /'
