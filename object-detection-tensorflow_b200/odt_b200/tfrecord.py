@@ -15,7 +15,9 @@ SURVEY section 8(f) row 3; not on the accelerated hot path.
   `gt_checker_helper`, (y_centre, x_centre, h, w, id) rows padded with -1 to `pad_truth_to`; randomness
   from a seeded numpy generator.  BICUBIC resampling is not restated (bilinear is used, with a warning).
   (The reference returns the UNaugmented `image_copy` when `pad_truth_to` is set, :229 -- an upstream slip
-  that would defeat batching; the augmented image is returned here.)
+  that would defeat batching; the augmented image is returned here.  It also concatenates the UNfiltered box
+  centres with the filtered sizes / ids (:211-220), a shape error whenever a box is dropped; the filtered
+  centres are used here.)
 PARITY UNPINNED: no TensorFlow and no TF-written record here; JPEG decoding goes through
 OpenCV (libjpeg-turbo), TF uses libjpeg -- pixels can differ by a few levels.
 """
