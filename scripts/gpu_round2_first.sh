@@ -38,3 +38,4 @@ ODT_TC_KSKIP=1 timeout 300 python scripts/tc_timeline.py 16 200 200 7 7 3 1 0 1 
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_tapn_kernel -s 3 -c 1 -o gpurun_out/r2_prof_tapn_c12 -f env ODT_TC_TAPN=1 python scripts/conv_micro.py 64 300 300 64 64 3 1 2 1 1 3 > gpurun_out/r2_ncu_tapn.log 2>&1; echo "ncu tapn exit $?"
 ODT_BENCH_DEFERRED=1 timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_deferred.json 2> gpurun_out/r2_bench_deferred.err; echo "bench deferred e2e: $(python -c "import json; d=json.loads(open(\"gpurun_out/r2_bench_deferred.json\").read().strip().splitlines()[-1]); print(d[\"value\"], d[\"e2e\"])")"
 ODT_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_models.py -q -k deferred 2>&1 | tail -n 2
+ODT_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_conv.py -q -k full_size 2>&1 | tail -n 3

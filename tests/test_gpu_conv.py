@@ -536,3 +536,58 @@ def test_conv_tapn_matches_reference(built, monkeypatch, shape, kw):
     assert np.abs(got - ref).max() <= tol, shape
     if g1 is not None:
         assert np.abs(g1 - r1).max() <= 3 * tol
+
+
+def _tc_raw(x, w, pool=0, in_halo=1, out_halo=1):
+    """x [B,H,W,Cin] fp16 device tensor (unpadded), w [Cout,3,3,Cin] fp16 -> raw kernel output (no CPU reference):
+    3x3 / stride 1 / SAME, zero shift, ReLU.  For size-independent properties at BASELINE sizes."""
+    from odt_b200 import lib as L
+    lib = L.load()
+    B, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    ld, old, cpad = (Cin + 63) // 64 * 64, (Cout + 63) // 64 * 64, (Cout + 31) // 32 * 32
+    ih, oh = in_halo, out_halo
+    xd = torch.zeros((B, H + 2 * ih, W + 2 * ih, ld), dtype=torch.float16, device="cuda")
+    xd[:, ih:ih + H, ih:ih + W, :Cin] = x
+    wd = torch.zeros((cpad, 3, 3, ld), dtype=torch.float16, device="cuda")
+    wd[:Cout, :, :, :Cin] = w
+    yh, yw = (H // 2, W // 2) if pool else (H, W)
+    y = torch.zeros((B, yh + 2 * oh, yw + 2 * oh, old), dtype=torch.float16, device="cuda")
+    shift = torch.zeros(Cout, device="cuda")
+    p = L.ConvParams()
+    p.B, p.H, p.W, p.Cin, p.in_ld = B, H, W, Cin, ld
+    p.OH, p.OW, p.Cout = H, W, Cout
+    p.R, p.S, p.stride, p.dil, p.pad_t, p.pad_l = 3, 3, 1, 1, 1, 1
+    p.w_ld, p.Cout_pad = ld, cpad
+    p.shift, p.act = shift.data_ptr(), 1
+    p.out0, p.out0_dtype = y.data_ptr(), L.ODT_F16
+    p.out0_img_stride, p.out0_pix_stride = (yh + 2 * oh) * (yw + 2 * oh) * old, old
+    p.in_halo, p.out0_halo, p.out0_pool = ih, oh, pool
+    L.check(lib.odt_conv2d_f16_tc(xd.data_ptr(), wd.data_ptr(), C.byref(p), torch.cuda.current_stream().cuda_stream),
+            "conv")
+    torch.cuda.synchronize()
+    return y[:, oh:oh + yh, oh:oh + yw, :Cout]
+
+
+@_experimental
+@pytest.mark.parametrize("tapn", ["0", "2"])
+def test_conv1_2_full_size_properties(built, monkeypatch, tapn):
+    """SSD300's conv1_2 + fused pool at the BASELINE batch (64 x 300 x 300 x 64 -> 64): properties that need no
+    oracle.  (a) scaling the input by 2 scales the output by 2 bit for bit (powers of two commute with every
+    rounding of a normal number, with ReLU and with max); (b) an image computed alone equals its slice of the batch (tiles never mix images);
+    (c) two runs agree bit for bit."""
+    monkeypatch.setenv("ODT_TC_TAPN", tapn)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = (torch.randn((64, 300, 300, 64), generator=g, device="cuda") * 0.5).half()
+    w = (torch.randn((64, 3, 3, 64), generator=g, device="cuda") * (2.0 / 576) ** 0.5).half()
+    y = _tc_raw(x, w, pool=2)
+    assert y.shape == (64, 150, 150, 64) and float(y.float().abs().max()) > 0.1
+    assert torch.equal(_tc_raw(x, w, pool=2), y)
+    d = (_tc_raw(x * 2, w, pool=2).float() - 2 * y.float()).abs()
+    assert float(d[y >= 1e-3].max()) == 0.0          # exact wherever the fp16 result is a normal number
+    assert float(d.max()) <= 2.0 ** -22               # fp16 subnormals: the fixed 2^-24 grid breaks the commutation
+    for b in (0, 37, 63):
+        assert torch.equal(_tc_raw(x[b:b + 1], w, pool=2)[0], y[b])
+    # pooling really happened: the un-pooled result, max-reduced on the device, is the same tensor
+    full = _tc_raw(x[:2], w, pool=0)
+    assert torch.equal(full.reshape(2, 150, 2, 150, 2, 64).amax(dim=(2, 4)), y[:2])
