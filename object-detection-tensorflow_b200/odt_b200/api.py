@@ -119,13 +119,21 @@ class _Detector:
         return w
 
     @staticmethod
-    def _load_bundle_into(w, prefix):
+    def _load_bundle_into(w, prefix, require=None):
         """Variables by their own names (checkpoints written by save_weight / the reference's
         Saver), plus the VGG-16 classification names the SSD constructors read
-        (`vgg_16/convN/convN_M/{weights,biases}`, SSD300.py:195-301)."""
+        (`vgg_16/convN/convN_M/{weights,biases}`, SSD300.py:195-301).  `require`: names that must be
+        in the file -- `Saver.restore` fails with NotFoundError on the first variable of its list
+        that the checkpoint lacks; here every missing name is reported at once."""
         r = tf_checkpoint.open_checkpoint(prefix)  # V2 bundle or V1 single file (the slim vgg_16.ckpt)
+        if require is not None:
+            missing = [k for k in require if not r.has_tensor(k)]
+            if missing:
+                raise tf_checkpoint.CheckpointError(
+                    "%s lacks %d of the %d variables to restore (first: %s)" % (prefix, len(missing), len(require),
+                                                                             ", ".join(missing[:3])))
         n = 0
-        for k in w:
+        for k in (w if require is None else require):
             if r.has_tensor(k):
                 t = r.get_tensor(k)
                 assert tuple(t.shape) == tuple(w[k].shape), (k, t.shape, w[k].shape)
@@ -330,20 +338,39 @@ class _Detector:
         return out
 
     def load_weight(self, path):
-        """`saver.restore(sess, path)` (SSD300.py:503): a TF V2 bundle prefix (or an .npz)."""
+        """`saver.restore(sess, path)` with `tf.train.Saver()` over every variable (SSD300.py:464-466,503):
+        a TF checkpoint that holds ALL of this model's variables (or an .npz of any subset)."""
         w = dict(self.get_weights())
         if path.endswith(".npz"):
             self._load_npz_into(w, path)
         else:
-            self._load_bundle_into(w, path)
+            self._load_bundle_into(w, path, require=list(w))
             r = tf_checkpoint.open_checkpoint(path)
             if r.has_tensor("global_step"):
                 self.global_step = int(r.get_tensor("global_step"))
         self.set_weights(w)
         print("load weight", path, "successfully")
 
+    # scope whose TRAINABLE variables the backbone saver covers (YOLOv3.py:376-378 and FCOS.py:390-392:
+    # 'backone'; RetinaNet.py:553-557: 'feature_extractor')
+    backbone_scope = "feature_extractor"
+
+    def pretraining_variables(self):
+        """`tf.trainable_variables(scope)`: kernels, biases, gamma / beta of the backbone -- the moving
+        statistics of batch normalisation are not trainable and are NOT in that saver."""
+        return [k for k in self.get_weights()
+                if k.startswith(self.backbone_scope + "/") and not k.endswith(("moving_mean", "moving_variance"))]
+
     def load_pretraining_weight(self, path):
-        self.load_weight(path)
+        """`pretraining_weight_saver.restore` (YOLOv3.py:481-483, RetinaNet.py:537-539, FCOS.py:434-436):
+        only the backbone's trainable variables, all of which must be in the checkpoint."""
+        w = dict(self.get_weights())
+        names = self.pretraining_variables()
+        if path.endswith(".npz"):
+            self._load_npz_into(w, path)
+        else:
+            self._load_bundle_into(w, path, require=names)
+        self.set_weights(w)
         print("load pretraining weight", path, "successfully")
 
     load_pretrained_weight = load_pretraining_weight  # FCOS spelling (FCOS.py:434)
@@ -439,6 +466,7 @@ class RetinaNet(_Detector):
 
 class YOLOv3(_Detector):
     name = "YOLOv3"
+    backbone_scope = "backone"  # sic: the reference's scope name (YOLOv3.py:377)
 
     def __init__(self, config, data_provider):
         assert len(config["data_shape"]) == 3
@@ -480,6 +508,7 @@ class YOLOv3(_Detector):
 
 class FCOS(_Detector):
     name = "FCOS"
+    backbone_scope = "backone"  # sic (FCOS.py:391)
 
     def __init__(self, config, data_provider):
         self._common_init(config, data_provider)

@@ -355,3 +355,45 @@ def test_corrupt_files_raise_checkpoint_error_only(ck, tmp_path):
                 fn()
             except ck.CheckpointError:
                 pass
+
+
+def test_saver_semantics_of_load_weight_and_pretraining_loader(ck, tmp_path):
+    """`load_weight` = Saver() over ALL variables: a file lacking one is an error (NotFoundError in TF).
+    `load_pretraining_weight` = Saver(trainable backbone variables): restores kernels / biases / gamma / beta of
+    the backbone only -- not the heads, not the BN moving statistics (YOLOv3.py:376-378,481-483)."""
+    import YOLOv3
+    cfg = dict(mode="test", data_format="channels_last", num_classes=20, weight_decay=1e-4, keep_prob=0.5,
+               batch_size=1, nms_score_threshold=0.5, nms_max_boxes=10, nms_iou_threshold=0.45,
+               data_shape=[416, 416, 3], coord_scale=1, noobj_scale=1, obj_scale=5., class_scale=1., num_priors=3,
+               priors=[[[10, 13], [16, 30], [33, 23]], [[30, 61], [62, 45], [59, 119]], [[116, 90], [156, 198], [373, 326]]])
+    m = YOLOv3.YOLOv3(cfg, None)
+    w0 = {k: v.copy() for k, v in m.get_weights().items()}
+    names = m.pretraining_variables()
+    assert names and all(n.startswith("backone/") for n in names)
+    assert not any(n.endswith(("moving_mean", "moving_variance")) for n in names)
+    assert "backone/batch_normalization/gamma" in names and "backone/conv2d/kernel" in names
+    rng = np.random.default_rng(3)
+    donor = {k: rng.standard_normal(v.shape).astype(np.float32) for k, v in w0.items()}
+    full = str(tmp_path / "full")
+    ck.write_checkpoint(full, donor)
+    m.load_pretraining_weight(full)
+    w1 = m.get_weights()
+    for k in w0:
+        want = donor[k] if k in names else w0[k]                    # heads and moving statistics untouched
+        np.testing.assert_array_equal(w1[k], want, err_msg=k)
+    # a backbone-only file is fine for the pretraining loader, an error for load_weight
+    part = str(tmp_path / "backbone")
+    ck.write_checkpoint(part, {k: donor[k] for k in names})
+    m.load_pretraining_weight(part)
+    with pytest.raises(ck.CheckpointError, match="lacks"):
+        m.load_weight(part)
+    missing_one = dict(donor)
+    missing_one.pop(names[5])
+    p2 = str(tmp_path / "holed")
+    ck.write_checkpoint(p2, missing_one)
+    with pytest.raises(ck.CheckpointError, match=names[5].replace("/", "/")):
+        m.load_pretraining_weight(p2)
+    m.load_weight(full)                                             # everything present: restores heads too
+    np.testing.assert_array_equal(m.get_weights()["head/conv2d/kernel"] if "head/conv2d/kernel" in donor
+                                  else m.get_weights()[sorted(donor)[0]],
+                                  donor["head/conv2d/kernel"] if "head/conv2d/kernel" in donor else donor[sorted(donor)[0]])
