@@ -227,6 +227,15 @@ def _gloo_worker(rank, world, port, q):
         dets[i, :k, 5] = g
     rec = od.gather_records(od.pack_records(dets, cnt))
     out = od.unpack_records(rec)
+
+    class _Net:                      # what finish_sharded reads after net.run()
+        class tail:
+            pass
+    _Net.tail.dets, _Net.tail.det_count = dets, cnt
+    again = od.finish_sharded(_Net)  # the per-step finish of detect_stream_sharded
+    assert len(again) == len(out)
+    for a, b in zip(again, out):
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
     w = od.broadcast_weights({"a": np.full((3,), rank + 1.0, np.float32)})
     q.put((rank, [(len(s), float(s[0]) if len(s) else -1.0, int(c[0]) if len(c) else -1)
                   for s, _, c in out], float(w["a"][0])))
