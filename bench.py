@@ -301,8 +301,11 @@ def main():
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     e2e_value = world * BATCH * K / (ms_e2e / 1e3)
-    h2d = int(images.numel() * 4)
-    d2h = int(net.tail.dets.numel() * 4 + net.tail.det_count.numel() * 4 + 4) * world
+    # whole-job bytes per step: every rank uploads its own shard; at N > 1 every rank reads back the
+    # all-gathered records of all N shards ([N*B, D*6+1] floats), at N = 1 its records, counts and status word
+    h2d = int(images.numel() * 4) * world
+    rec_floats = net.tail.dets.numel() + net.tail.det_count.numel()
+    d2h = int(rec_floats * 4 + 4) if world == 1 else int(rec_floats * 4 * world) * world
 
     # ---------------- roofline of the dominant kernel (tcgen05 conv) -----------
     from odt_b200.engine import ConvOp
