@@ -41,6 +41,10 @@ bool kskip_enabled() {
   const char* e = getenv("ODT_TC_KSKIP");  // opt-in (default off): see TcGeom::klast
   return e && e[0] == '1';
 }
+int thin_mode() {
+  const char* e = getenv("ODT_TC_THIN");  // opt-in (default 0 = off): conv_thin.cu
+  return (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
+}
 int tapn_mode() {
   const char* e = getenv("ODT_TC_TAPN");  // opt-in (default 0 = off): conv_tapn.cu
   return (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;

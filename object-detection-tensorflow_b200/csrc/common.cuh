@@ -74,6 +74,8 @@ bool flat_enabled();  // ODT_TC_FLAT=0 disables the halo-flat 3x3 path (A/B meas
 bool pair_enabled();  // ODT_TC_PAIR=0 disables the CTA-pair (cta_group::2) launch of large im2col-mode convs
 bool flat_pair_enabled();  // ODT_TC_FLAT_PAIR=0: no CTA pairs in the halo-flat modes
 bool kskip_enabled();  // ODT_TC_KSKIP=1: do not issue the all-zero 16-deep K steps of thin layers (Cin padded to 64)
+int thin_mode();       // ODT_TC_THIN: 1 = very thin layers (Cin, Cout <= 32, few multiply-adds per pixel) go through the
+                       // CUDA-core kernel of conv_thin.cu, 2 = wherever the layer qualifies, 0 / unset = never
 int tapn_mode();       // ODT_TC_TAPN: 1 = narrow 3x3 halo layers go through conv_tapn.cu (taps folded into N) where its
                        // cost model predicts a gain, 2 = wherever the layer qualifies, 0 / unset = never
 bool wres_enabled();  // ODT_TC_WRES=0 disables shared-memory-resident filter banks in the flat path

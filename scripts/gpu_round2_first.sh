@@ -11,21 +11,23 @@ echo "tapn/thin tests exit $?"; tail -n 2 gpurun_out/r2_tapn_tests.log
   # YOLOv3's 32->64 and FCOS's 64->64; each line: default path, then taps-as-N, three interleaved repeats
   for shape in "64 300 300 64 64 3 1 2 1 1" "32 512 512 64 64 3 1 2 1 1" "16 200 200 7 7 3 1 0 1 1" \
                "16 200 200 28 28 3 1 0 1 1" "32 208 208 32 64 3 1 0 1 1" "4 256 256 64 64 3 1 0 1 1" \
-               "32 416 416 32 64 3 2 0 0 0"; do   # the last one: YOLOv3 block1 (stride 2, im2col mode): K-skip only
+               "32 416 416 32 64 3 2 0 0 0" "16 200 200 16 7 1 1 0 0 0" "16 200 200 7 28 1 1 0 0 0" \
+               "16 100 100 14 14 3 1 0 1 1"; do   # the last one: YOLOv3 block1 (stride 2, im2col mode): K-skip only
     for rep in 1 2 3; do
       ODT_TC_TAPN=0 ODT_TC_KSKIP=0 python scripts/conv_micro.py $shape 50 | sed 's/^/base   /'
       ODT_TC_TAPN=0 ODT_TC_KSKIP=1 python scripts/conv_micro.py $shape 50 | sed 's/^/kskip  /'
       ODT_TC_TAPN=2 python scripts/conv_micro.py $shape 50 | sed 's/^/tapn   /'
+      ODT_TC_THIN=2 python scripts/conv_micro.py $shape 50 | sed 's/^/thin   /'   # = base unless Cin, Cout <= 16 (3x3) / 32 (1x1)
     done
   done
 } > gpurun_out/r2_ab_micro.txt 2>&1
 tail -n 60 gpurun_out/r2_ab_micro.txt
-ODT_TC_TAPN=1 ODT_TC_KSKIP=1 timeout 1500 python -m pytest tests -q -m gpu --timeout 300 > gpurun_out/r2_gpu_tests_tapn.log 2>&1
+ODT_TC_TAPN=1 ODT_TC_KSKIP=1 ODT_TC_THIN=1 timeout 1500 python -m pytest tests -q -m gpu --timeout 300 > gpurun_out/r2_gpu_tests_tapn.log 2>&1
 echo "pytest -m gpu with TAPN=KSKIP=1 exit $?"; tail -n 3 gpurun_out/r2_gpu_tests_tapn.log
 for t in 0 1; do
   for m in "ssd300 64" "retinanet 16"; do
     n=$(echo $m | tr ' ' '_')
-    ODT_TC_TAPN=$t ODT_TC_KSKIP=$t timeout 600 python scripts/profile_ops.py $m > gpurun_out/r2_ops_${n}_tapn$t.txt 2>&1
+    ODT_TC_TAPN=$t ODT_TC_KSKIP=$t ODT_TC_THIN=$t timeout 600 python scripts/profile_ops.py $m > gpurun_out/r2_ops_${n}_tapn$t.txt 2>&1
     echo "== $m TAPN=KSKIP=$t: $(grep -E 'CUDA-graph' gpurun_out/r2_ops_${n}_tapn$t.txt)"
   done
 done

@@ -591,3 +591,28 @@ def test_conv1_2_full_size_properties(built, monkeypatch, tapn):
     # pooling really happened: the un-pooled result, max-reduced on the device, is the same tensor
     full = _tc_raw(x[:2], w, pool=0)
     assert torch.equal(full.reshape(2, 150, 2, 150, 2, 64).amax(dim=(2, 4)), y[:2])
+
+
+@_experimental
+@pytest.mark.parametrize("shape,kw", [
+    ((2, 40, 40, 7, 7, 3, 1, 1), {"in_halo": 1, "out_halo": 1}),                       # RetinaNet stage 1, 3x3
+    ((2, 37, 41, 7, 7, 3, 1, 1), {}),                                                   # no halo: border checks
+    ((2, 40, 40, 16, 7, 1, 1, 1), {"pre": True}),                                       # 1x1 reduce + consumer BN/ReLU
+    ((2, 40, 40, 7, 28, 1, 1, 1), {"residual": True, "pre": True, "pre2": True}),       # 1x1 expand, residual, 2 extras
+    ((2, 40, 40, 28, 14, 1, 1, 1), {"in_halo": 1, "act": "leaky"}),
+    ((2, 41, 39, 14, 14, 3, 2, 1), {"in_halo": 1}),                                     # stride 2, odd sizes
+    ((2, 40, 40, 14, 14, 3, 2, 1), {"out_halo": 1}),
+    ((2, 20, 20, 32, 32, 1, 1, 1), {"no_out0": True, "pre": True}),                     # widest 1x1, out1 only
+])
+def test_conv_thin_matches_reference(built, monkeypatch, shape, kw):
+    """CUDA-core kernel for very thin layers (csrc/conv_thin.cu) behind the same entry point."""
+    from odt_b200 import lib as L
+    monkeypatch.setenv("ODT_TC_THIN", "2")
+    before = L.load().odt_debug_thin_launches()
+    got, ref, g1, r1 = _conv_case(*shape, mode="tc", seed=sum(shape), **kw)
+    assert L.load().odt_debug_thin_launches() == before + 1, "the layer did not take the thin path"
+    tol = 2e-3 * max(np.abs(ref).max(), 1.0)
+    if not kw.get("no_out0"):
+        assert np.abs(got - ref).max() <= tol, shape
+    if g1 is not None:
+        assert np.abs(g1 - r1).max() <= 3 * tol
