@@ -225,8 +225,11 @@ class PoolOp(Op):
 
     def launch(self, net, stream):
         x = self.x
-        # pooled over the padded channel range so pad lanes stay zero
-        L.check(net.lib.odt_maxpool(x.ptr(), self.y.ptr(), net.dt, x.B, x.H, x.W, x.ld, x.ld,
+        # Only the 16-byte sectors that hold real channels are pooled: every activation owns a zero-initialised
+        # buffer (Net.allocate), so the padding lanes of y that are never written stay zero, and the ones inside
+        # the last sector are maxima of zeros.  (RetinaNet's 16-channel stem output is stored 64 wide.)
+        c = min(x.ld, _round_up(x.C, 8))
+        L.check(net.lib.odt_maxpool(x.ptr(), self.y.ptr(), net.dt, x.B, x.H, x.W, c, x.ld,
                                     self.k, self.stride, x.halo, self.y.halo, stream), "maxpool")
 
 
