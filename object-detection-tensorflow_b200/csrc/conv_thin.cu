@@ -12,13 +12,30 @@
 //
 // Epilogue semantics = epilogue.cuh (scale/shift/act, residual, fp16 rounding, up to two extra pre-activated
 // outputs).  OPT-IN (ODT_TC_THIN=1: where the per-pixel work is small enough; =2: wherever the layer
-// qualifies) -- written after the last GPU minute of round 1, not yet run.
+// qualifies) -- written after the last GPU minute of round 1: the device launch has not run yet, the body has (below).
 // ref call sites: tf.layers.conv2d RetinaNet.py:579,599,609 (bottleneck 1x1 / 3x3 with 7..28 filters).
+//
+// The per-thread work lives in two __host__ __device__ functions (thin_fill / thin_pixel) so that the very same
+// source also runs on the CPU inside a TEST-ONLY harness (tests/native/thin_host.cu, built by
+// tests/test_thin_host.py): index arithmetic, rounding chain and epilogue are checked there without a GPU.
+// The product library contains no host path.
 #include <string.h>
 
 #include "epilogue.cuh"
 
+#ifdef __CUDA_ARCH__
+#define ODT_THIN_LDG(p) __ldg(p)
+#else
+#define ODT_THIN_LDG(p) (*(p))
+#endif
+
 namespace odt {
+
+__host__ __device__ __forceinline__ float thin_act(float v, int act) {  // = apply_act (common.cuh), host-callable
+  if (act == ODT_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == ODT_ACT_LEAKY) return fmaxf(v, 0.1f * v);
+  return v;
+}
 
 struct ThinGeom {
   int B, H, W, OH, OW;
@@ -30,31 +47,30 @@ struct ThinGeom {
 
 constexpr int THIN_THREADS = 256;
 
-// KS: filter size (1 or 3); CI8 / CO8: input / output channels in units of 8
+// KS: filter size (1 or 3); CI8 / CO8: input / output channels in units of 8.
+// ws: fp32 filter bank [tap][cin][cout]; par: [scale | shift | scale2 | shift2 | scale3 | shift3][cout].
 template <int KS, int CI8, int CO8>
-__global__ void __launch_bounds__(THIN_THREADS)
-    conv_thin_kernel(const __half* __restrict__ in, const __half* __restrict__ wgt, const __grid_constant__ ThinGeom g,
-                     const __grid_constant__ Epi e) {
-  pdl_launch_dependents();
+__host__ __device__ __forceinline__ void thin_fill(int tid, float* ws, float* par, const __half* wgt, const ThinGeom& g,
+                                                   const Epi& e) {
   constexpr int CI = CI8 * 8, CO = CO8 * 8, TAPS = KS * KS;
-  __shared__ __align__(16) float ws[TAPS][CI][CO];
-  __shared__ __align__(16) float par[6][CO];  // scale | shift | scale2 | shift2 | scale3 | shift3
-  for (int i = threadIdx.x; i < TAPS * CI * CO; i += THIN_THREADS) {
+  for (int i = tid; i < TAPS * CI * CO; i += THIN_THREADS) {
     const int n = i % CO, c = (i / CO) % CI, tap = i / (CO * CI);
     float v = 0.f;
     if (n < g.Cout && c < g.Cin) v = __half2float(wgt[((long long)n * TAPS + tap) * g.w_ld + c]);
-    ws[tap][c][n] = v;
+    ws[i] = v;
   }
-  for (int i = threadIdx.x; i < 6 * CO; i += THIN_THREADS) {
+  for (int i = tid; i < 6 * CO; i += THIN_THREADS) {
     const int which = i / CO, n = i % CO;
     const float* src = which == 0 ? e.scale : which == 1 ? e.shift : which == 2 ? e.scale2 : which == 3 ? e.shift2
                        : which == 4 ? e.scale3 : e.shift3;
-    par[which][n] = (n < g.Cout && src) ? __ldg(src + n) : ((which & 1) ? 0.f : 1.f);
+    par[i] = (n < g.Cout && src) ? ODT_THIN_LDG(src + n) : ((which & 1) ? 0.f : 1.f);
   }
-  __syncthreads();
+}
 
-  const long long m = (long long)blockIdx.x * THIN_THREADS + threadIdx.x;
-  if (m >= g.M) return;
+template <int KS, int CI8, int CO8>
+__host__ __device__ __forceinline__ void thin_pixel(long long m, const float* ws, const float* par, const __half* in,
+                                                    const ThinGeom& g, const Epi& e) {
+  constexpr int CI = CI8 * 8, CO = CO8 * 8;
   const int ohw = g.OH * g.OW;
   const int b = (int)(m / ohw);
   const int pix = (int)(m - (long long)b * ohw);
@@ -79,7 +95,7 @@ __global__ void __launch_bounds__(THIN_THREADS)
 #pragma unroll
       for (int c8 = 0; c8 < CI8; ++c8) {
         uint4 raw = make_uint4(0u, 0u, 0u, 0u);
-        if (inside) raw = __ldg(reinterpret_cast<const uint4*>(src) + c8);
+        if (inside) raw = ODT_THIN_LDG(reinterpret_cast<const uint4*>(src) + c8);
         const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
         float x[8];
 #pragma unroll
@@ -90,7 +106,7 @@ __global__ void __launch_bounds__(THIN_THREADS)
         }
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          const float4* wrow = reinterpret_cast<const float4*>(&ws[r * KS + s][c8 * 8 + c][0]);
+          const float4* wrow = reinterpret_cast<const float4*>(ws + ((r * KS + s) * CI + c8 * 8 + c) * CO);
 #pragma unroll
           for (int n4 = 0; n4 < CO / 4; ++n4) {
             const float4 w = wrow[n4];
@@ -110,13 +126,16 @@ __global__ void __launch_bounds__(THIN_THREADS)
                            (oh ? (long long)((oy + 1) * (g.OW + 2) + ox + 1) : (long long)pix) * e.out0_pix_stride;
   const long long o1_row = (long long)b * e.out1_img_stride + (long long)pix * e.out1_pix_stride;
   const long long o2_row = (long long)b * e.out2_img_stride + (long long)pix * e.out2_pix_stride;
+  const float* sc1 = par, *sh1 = par + CO, *sc2 = par + 2 * CO, *sh2 = par + 3 * CO, *sc3 = par + 4 * CO,
+             *sh3 = par + 5 * CO;
 #pragma unroll
   for (int n8 = 0; n8 < CO8; ++n8) {
     float v[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = apply_act(fmaf(acc[8 * n8 + i], par[0][8 * n8 + i], par[1][8 * n8 + i]), e.act);
+    for (int i = 0; i < 8; ++i) v[i] = thin_act(fmaf(acc[8 * n8 + i], sc1[8 * n8 + i], sh1[8 * n8 + i]), e.act);
     if (e.residual) {
-      const uint4 t = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(e.residual) + o0_row) + n8);
+      const uint4 t =
+          ODT_THIN_LDG(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(e.residual) + o0_row) + n8);
       const __half2* h = reinterpret_cast<const __half2*>(&t);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -136,9 +155,8 @@ __global__ void __launch_bounds__(THIN_THREADS)
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float2 f = __half22float2(ph[i]);  // the consumer sees the rounded value
-        q[i] = __floats2half2_rn(
-            apply_act(fmaf(f.x, par[2][8 * n8 + 2 * i], par[3][8 * n8 + 2 * i]), e.act2),
-            apply_act(fmaf(f.y, par[2][8 * n8 + 2 * i + 1], par[3][8 * n8 + 2 * i + 1]), e.act2));
+        q[i] = __floats2half2_rn(thin_act(fmaf(f.x, sc2[8 * n8 + 2 * i], sh2[8 * n8 + 2 * i]), e.act2),
+                                 thin_act(fmaf(f.y, sc2[8 * n8 + 2 * i + 1], sh2[8 * n8 + 2 * i + 1]), e.act2));
       }
       reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out1) + o1_row)[n8] = p1;
     }
@@ -148,13 +166,26 @@ __global__ void __launch_bounds__(THIN_THREADS)
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float2 f = __half22float2(ph[i]);
-        q[i] = __floats2half2_rn(
-            apply_act(fmaf(f.x, par[4][8 * n8 + 2 * i], par[5][8 * n8 + 2 * i]), e.act3),
-            apply_act(fmaf(f.y, par[4][8 * n8 + 2 * i + 1], par[5][8 * n8 + 2 * i + 1]), e.act3));
+        q[i] = __floats2half2_rn(thin_act(fmaf(f.x, sc3[8 * n8 + 2 * i], sh3[8 * n8 + 2 * i]), e.act3),
+                                 thin_act(fmaf(f.y, sc3[8 * n8 + 2 * i + 1], sh3[8 * n8 + 2 * i + 1]), e.act3));
       }
       reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out2) + o2_row)[n8] = p2;
     }
   }
+}
+
+template <int KS, int CI8, int CO8>
+__global__ void __launch_bounds__(THIN_THREADS)
+    conv_thin_kernel(const __half* __restrict__ in, const __half* __restrict__ wgt, const __grid_constant__ ThinGeom g,
+                     const __grid_constant__ Epi e) {
+  pdl_launch_dependents();
+  constexpr int CI = CI8 * 8, CO = CO8 * 8, TAPS = KS * KS;
+  __shared__ __align__(16) float ws[TAPS * CI * CO];
+  __shared__ __align__(16) float par[6 * CO];
+  thin_fill<KS, CI8, CO8>(threadIdx.x, ws, par, wgt, g, e);
+  __syncthreads();
+  const long long m = (long long)blockIdx.x * THIN_THREADS + threadIdx.x;
+  if (m < g.M) thin_pixel<KS, CI8, CO8>(m, ws, par, in, g, e);
 }
 
 static int g_thin_launches = 0;  // debug: lets a test assert that the layer really took this path
@@ -169,8 +200,9 @@ static int launch_thin(const void* in, const void* weights, const ThinGeom& g, c
   return ODT_OK;
 }
 
-// ODT_ERR_UNSUPPORTED when the layer does not qualify (the caller then takes the tensor-core paths).
-int conv_thin_try(const void* in, const void* weights, const odt_conv_params* p, void* stream) {
+// Eligibility + geometry; ODT_ERR_UNSUPPORTED when the layer does not qualify.  `force`: ignore the work-per-pixel gate.
+static int thin_plan(const void* in, const odt_conv_params* p, bool force, ThinGeom* gout, int* ks_out, int* ci_out,
+                     int* co_out) {
   const int ks = p->R;
   const bool shape_ok = (ks == 1 || ks == 3) && p->S == ks && p->dil == 1 && (p->stride == 1 || p->stride == 2) &&
                         p->out0_pool == 0 && p->out0_group == 0 && (p->in_halo == 0 || p->in_halo == 1) &&
@@ -190,8 +222,7 @@ int conv_thin_try(const void* in, const void* weights, const odt_conv_params* p,
   if (!io_ok) return ODT_ERR_UNSUPPORTED;
   const long long M = (long long)p->B * p->OH * p->OW;
   if (M >= (1ll << 31) * THIN_THREADS) return ODT_ERR_UNSUPPORTED;
-  if (thin_mode() == 1 && ks * ks * ci8r * 8 * co8r * 8 > 1200) return ODT_ERR_UNSUPPORTED;  // multiply-adds per pixel
-
+  if (!force && ks * ks * ci8r * 8 * co8r * 8 > 1200) return ODT_ERR_UNSUPPORTED;  // multiply-adds per pixel
   ThinGeom g;
   memset(&g, 0, sizeof(g));
   g.B = p->B;
@@ -209,23 +240,29 @@ int conv_thin_try(const void* in, const void* weights, const odt_conv_params* p,
   g.in_halo = p->in_halo;
   g.out_halo = p->out0_halo;
   g.M = M;
+  *gout = g;
+  *ks_out = ks;
+  *ci_out = ci8r;
+  *co_out = co8r;
+  return ODT_OK;
+}
+
+// every (filter size, channel width) instantiation, for the device launch and for the test-only host harness
+#define ODT_THIN_DISPATCH(CALL)                                                                               \
+  CALL(3, 1, 1) CALL(3, 1, 2) CALL(3, 2, 1) CALL(3, 2, 2) CALL(1, 1, 1) CALL(1, 1, 2) CALL(1, 1, 4) CALL(1, 2, 1) \
+  CALL(1, 2, 2) CALL(1, 2, 4) CALL(1, 4, 1) CALL(1, 4, 2) CALL(1, 4, 4)
+
+// ODT_ERR_UNSUPPORTED when the layer does not qualify (the caller then takes the tensor-core paths).
+int conv_thin_try(const void* in, const void* weights, const odt_conv_params* p, void* stream) {
+  ThinGeom g;
+  int ks, ci8r, co8r;
+  const int rc = thin_plan(in, p, thin_mode() == 2, &g, &ks, &ci8r, &co8r);
+  if (rc) return rc;
   const Epi e = make_epi(*p);
   cudaStream_t st = (cudaStream_t)stream;
 #define ODT_THIN_CASE(KS_, CI_, CO_) \
-  if (ks == KS_ && ci8r == CI_ && co8r == CO_) return launch_thin<KS_, CI_, CO_>(in, weights, g, e, st)
-  ODT_THIN_CASE(3, 1, 1);
-  ODT_THIN_CASE(3, 1, 2);
-  ODT_THIN_CASE(3, 2, 1);
-  ODT_THIN_CASE(3, 2, 2);
-  ODT_THIN_CASE(1, 1, 1);
-  ODT_THIN_CASE(1, 1, 2);
-  ODT_THIN_CASE(1, 1, 4);
-  ODT_THIN_CASE(1, 2, 1);
-  ODT_THIN_CASE(1, 2, 2);
-  ODT_THIN_CASE(1, 2, 4);
-  ODT_THIN_CASE(1, 4, 1);
-  ODT_THIN_CASE(1, 4, 2);
-  ODT_THIN_CASE(1, 4, 4);
+  if (ks == KS_ && ci8r == CI_ && co8r == CO_) return launch_thin<KS_, CI_, CO_>(in, weights, g, e, st);
+  ODT_THIN_DISPATCH(ODT_THIN_CASE)
 #undef ODT_THIN_CASE
   return ODT_ERR_UNSUPPORTED;
 }
