@@ -4,6 +4,8 @@
 #   gpurun --timeout 1500 -- 'bash scripts/gpu_round2_first.sh'
 mkdir -p gpurun_out
 python __graft_entry__.py > gpurun_out/build.log 2>&1 || { echo BUILD FAILED; tail -20 gpurun_out/build.log; }
+timeout 1500 python -m pytest tests -q -m gpu --timeout 300 > gpurun_out/r2_gpu_tests_default.log 2>&1
+echo "pytest -m gpu (defaults) exit $?"; tail -n 3 gpurun_out/r2_gpu_tests_default.log
 ODT_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_conv.py -q -k "tapn or thin" > gpurun_out/r2_tapn_tests.log 2>&1
 echo "tapn/thin tests exit $?"; tail -n 2 gpurun_out/r2_tapn_tests.log
 {
