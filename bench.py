@@ -33,6 +33,24 @@ CFG = {"mode": "test", "data_format": "channels_last", "num_classes": 20, "weigh
        "nms_iou_threshold": 0.5, "pretraining_weight": None, "precision": "fp16"}
 WORKLOAD = "SSD300 VGG-16 fp16 inference, batch 64/GPU, 300x300 synthetic VOC (BASELINE configs[1])"
 CONV_GFLOP_PER_IMG = 62.773  # SURVEY.md App. B, real (unpadded) channels
+# second workload of BASELINE.json's metric ("SSD300 & RetinaNet"): configs[2], RetinaNet FPN fp16, batch 16, 800x800
+# (reference driver defaults testretinanet.py:17-41: bottleneck [3,4,6,3], 16 stem filters, max 10 boxes, IoU 0.45)
+RETINA_BATCH = 16
+RETINA_CFG = {"mode": "test", "data_format": "channels_last", "num_classes": 20, "weight_decay": 1e-4,
+              "keep_prob": 0.5, "batch_size": RETINA_BATCH, "data_shape": [800, 800, 3], "is_bottleneck": True,
+              "residual_block_list": [3, 4, 6, 3], "init_conv_filters": 16, "is_pretraining": False,
+              "gamma": 2.0, "alpha": 0.25, "nms_score_threshold": 0.8, "nms_max_boxes": 10,
+              "nms_iou_threshold": 0.45, "pretraining_weight": None, "precision": "fp16"}
+RETINA_WORKLOAD = "RetinaNet FPN fp16 inference, batch 16/GPU, 800x800 synthetic (BASELINE configs[2]), dense-threshold NMS"
+DENSE_FRACTION = 0.02  # candidates per class = 2 % of N (SURVEY 8d asks for the 1-5 % regime)
+
+
+def bench_config(world):
+    """`config` of the JSON line -- the same dict in both arms (ours and --impl reference)."""
+    return {"workload": WORKLOAD, "global_batch": BATCH * world, "per_gpu_batch": BATCH,
+            "parallelism": "dp%d (image shards, 1 all-gather of detections)" % world,
+            "l2": "per-step activation working set ~2 GB >> 126 MB L2 (no reuse between steps)",
+            "cuda_graph": True, "conv_gflop_per_img": CONV_GFLOP_PER_IMG}
 
 
 def synthetic_images(b, seed=0):
@@ -175,12 +193,123 @@ def run_reference(args, rank, world):
             "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
             "ms_per_step": 1e3 * sample / v, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": BATCH * args.gpus},
+            "config": bench_config(args.gpus),
             "cpu_baseline": {"value": v, "unit": "images/sec", "cores": threads, "kind": "port",
                              "sample": "%d images per step, batch-1 graph semantics, torch-CPU fp32 "
                                        "convs + C NMS" % sample},
             "e2e": {"value": v, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
+
+
+def dense_threshold(net, fraction=DENSE_FRACTION):
+    """Bench SETUP (untimed, plain torch on the rows the GPU produced): the softmax-family score threshold at
+    which `fraction` * N candidates per class and image pass, so that decode compaction and NMS do real work
+    with random-init weights (report candidate load; SURVEY 8d: dense regime)."""
+    import torch
+    rows = net.head_buf
+    probs = torch.softmax(rows[..., :21], dim=-1)
+    fg = probs[..., :20][probs.argmax(dim=-1) < 20]          # rows whose arg-max is not background
+    want = int(fraction * net.N * 20 * net.batch)
+    flat = fg.reshape(-1)
+    if flat.numel() == 0:
+        return None
+    k = min(max(want, 1), flat.numel())
+    return float(torch.topk(flat, k, sorted=True).values[-1].item()) if k < 50_000_000 else float(flat.min().item())
+
+
+def timed_ops(net, pick, reps=3):
+    """Eager per-launch CUDA-event timing inside whole forwards (realistic cache state): returns the mean
+    per-forward milliseconds of the ops `pick(op)` selects, of the decode launch and of the NMS launch."""
+    import torch
+    st = torch.cuda.current_stream().cuda_stream
+    t = net.tail
+    evs, dec, nms = [], [], []
+    torch.cuda.synchronize()
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    for _ in range(reps):
+        if getattr(net, "gn_arena", None) is not None:
+            net.gn_arena.zero_()
+        for op in net.ops:
+            if pick(op):
+                a, b = ev(), ev()
+                a.record()
+                op.launch(net, st)
+                b.record()
+                evs.append((a, b))
+            else:
+                op.launch(net, st)
+        e = [ev() for _ in range(3)]
+        e[0].record()
+        t.launch_decode(net, st)
+        e[1].record()
+        t.launch_nms(net, st)
+        e[2].record()
+        dec.append((e[0], e[1]))
+        nms.append((e[1], e[2]))
+    torch.cuda.synchronize()
+    f = lambda prs: sum(a.elapsed_time(b) for a, b in prs) / reps
+    return f(evs), f(dec), f(nms)
+
+
+def tail_launch_floor_us():
+    """The same two tail launches (memset + decode, memsets + NMS) on a 32-row input: the launch-bound floor."""
+    import numpy as np
+    import torch
+    from odt_b200 import nets
+    from odt_b200.engine import RowsHarness
+    cfg = dict(CFG)
+    rows = np.zeros((1, 38 * 38 * 4, 25), np.float32)
+    h = RowsHarness(nets.ssd_tail(300, cfg), [(38, 38, 4)], rows)
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(3):
+        h.tail.launch(h, st)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(20):
+        h.tail.launch(h, st)
+    b.record()
+    torch.cuda.synchronize()
+    return 1e3 * a.elapsed_time(b) / 20
+
+
+def tail_roofline(net, dec_ms, nms_ms, peaks, floor_us):
+    t = net.tail
+    rd = net.head_buf.numel() * 4                      # N*25*4 B per image (SURVEY 8d)
+    wr = net.batch * t.D * 24                          # D_max*24 B per image
+    us = 1e3 * (dec_ms + nms_ms)
+    gbs = (rd + wr) / (us * 1e-6) / 1e9
+    cc = t.cand_count.cpu().numpy()
+    return {"bytes_per_step": int(rd + wr), "decode_us": 1e3 * dec_ms, "nms_us": 1e3 * nms_ms, "gbs": gbs,
+            "decode_gbs": rd / (dec_ms * 1e-3) / 1e9,
+            "frac_of_hbm": gbs / float(peaks["hbm_gbs"]), "decode_frac_of_hbm": rd / (dec_ms * 1e-3) / 1e9 / float(peaks["hbm_gbs"]),
+            "hbm_peak_gbs": float(peaks["hbm_gbs"]), "launch_floor_us": floor_us,
+            "score_threshold": float(t.p.score_thr),
+            "candidates_per_class_mean": float(cc.mean()), "candidates_per_class_max": int(cc.max()),
+            "dets_per_image_mean": float(t.det_count.float().mean().item()),
+            "timing": "CUDA events around the two launches inside eager whole forwards (rows just written by the head "
+                      "convs, i.e. the cache state of the real step), mean of 3"}
+
+
+def conv_roofline(net, tc_ms, ms_step, peaks, peak_src, kname):
+    from odt_b200.engine import ConvOp
+    tc_ops = [op for op in net.ops if isinstance(op, ConvOp) and getattr(op, "use_tc", False)]
+    tc_flops = sum(op.flops for op in tc_ops)
+    sus = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+    burst = float(peaks.get("bf16_tflops", sus))
+    achieved = tc_flops / (tc_ms * 1e-3) / 1e12
+    whole = net.conv_flops / (ms_step * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": sus, "unit": "TFLOP/s",
+            "frac": achieved / sus, "frac_sustained": achieved / sus, "frac_burst": achieved / burst,
+            "peak_burst": burst,
+            "peak_source": peak_src + " cuBLAS bf16: `peak`/`frac` use the sustained figure (the kernels are timed inside "
+                                      "back-to-back whole steps), frac_burst the best-of-10 burst figure",
+            "launches_per_step": len(tc_ops), "tc_ms_per_step": tc_ms,
+            "algorithmic_gflop_per_step": tc_flops / 1e9, "share_of_step": tc_ms / ms_step,
+            "whole_step_tflops": whole, "whole_step_frac_sustained": whole / sus, "whole_step_frac_burst": whole / burst}
 
 
 def main():
@@ -190,6 +319,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-retinanet", action="store_true", help="skip the second workload (RetinaNet-800 B=16)")
     args = ap.parse_args()
     assert args.warmup >= 0 and args.steps >= 1
 
@@ -222,18 +352,7 @@ def main():
     assert world == args.gpus, "launch with torchrun --nproc-per-node %d" % args.gpus
     W = max(args.warmup, 3)
     K = args.steps
-
-    import SSD300
-    model = SSD300.SSD300(dict(CFG), None)
-    net = model.engine(BATCH)  # builds, uploads seeded weights (identical on every rank), captures the graph
-    images = torch.from_numpy(synthetic_images(BATCH, seed=rank)).pin_memory()
-    net.image_buf.copy_(images)
-    torch.cuda.synchronize()
-
-    def step_resident():
-        net.run()
-        if world > 1:
-            od.gather_records(od.pack_records(net.tail.dets, net.tail.det_count))
+    peaks, peak_src = measured_peaks()
 
     def barrier():
         if world > 1:
@@ -247,124 +366,138 @@ def main():
         tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---------------- device-resident throughput (value) ----------------------
+    def time_resident(net, gathered, sampler=None):
+        """W warm-up + K timed device-resident steps (graph replay + the records' all-gather at N > 1)."""
+        def step():
+            net.run()
+            if world > 1:
+                od.gather_records(net.tail.rec, out=gathered)
+        for _ in range(W):
+            step()
+        if sampler is not None:
+            t_spin = time.perf_counter()
+            while len(sampler.lines) < 1 and time.perf_counter() - t_spin < 3.0:
+                step()  # keep the GPU under the same load until nvidia-smi has sampled once
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            step()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    def time_e2e(model, images):
+        """Public API, host buffers: pinned H2D of every step's images + D2H of every step's records inside
+        the timed region (detect_stream; sharded with rank 0 as the consumer of the gathered records)."""
+        def run(n):
+            for res in model.detect_stream((images for _ in range(n)), sharded=world > 1, consumer=0):
+                assert len(res) in (images.shape[0], images.shape[0] * world)
+        run(W)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run(K)
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    def e2e_bytes(net, images):
+        # whole job, per step: every rank uploads its shard and reads back its own records; at N > 1 the
+        # consumer rank reads back the gathered records of all N shards instead
+        rec = net.tail.rec.numel() * 4
+        return int(images.numel() * 4) * world, int(rec if world == 1 else rec * world + rec * (world - 1))
+
+    # ======================= workload 1 (headline): SSD300 B=64 ====================================
+    import SSD300
+    model = SSD300.SSD300(dict(CFG), None)
+    net = model.engine(BATCH)  # builds, uploads seeded weights (identical on every rank), captures the graph
+    images = torch.from_numpy(synthetic_images(BATCH, seed=rank)).pin_memory()
+    net.image_buf.copy_(images)
+    gathered = (torch.empty((world * BATCH, net.tail.rec.shape[1]), dtype=torch.float32, device="cuda")
+                if world > 1 else None)
+    torch.cuda.synchronize()
     sampler = ClockSampler(local)
     sampler.start()  # started before the warm-up so that samples exist for short timed regions
-    for _ in range(W):
-        step_resident()
-    t_spin = time.perf_counter()
-    while len(sampler.lines) < 1 and time.perf_counter() - t_spin < 3.0:
-        step_resident()  # keep the GPU under the same load until nvidia-smi has sampled once
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(K):
-        step_resident()
-    e1.record()
-    barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_total = time_resident(net, gathered, sampler)
     clocks = sampler.stop()
     ms_step = ms_total / K
     value = world * BATCH * K / (ms_total / 1e3)
-
-    # ---------------- end to end through the public API ------------------------
-    e2e_mode = {"v": "stream"}
-
-    def run_e2e(n):
-        # public API: pipelined stream of host batches (H2D of batch i+1 overlaps batch i),
-        # every step copies its inputs from pinned host memory and reads its detections back
-        if os.environ.get("ODT_BENCH_DEFERRED") == "1":  # experimental: read-back one step behind the launches
-            for _ in model.detect_stream_deferred((images for _ in range(n)), sharded=world > 1):
-                pass
-        elif world > 1 and e2e_mode["v"] == "stream":
-            for _ in model.detect_stream_sharded(images for _ in range(n)):
-                pass
-        elif world > 1:
-            for _ in range(n):
-                model.detect_batch_sharded(images)
-        else:
-            for _ in model.detect_stream(images for _ in range(n)):
-                pass
-
-    try:
-        run_e2e(W)
-    except Exception as ex:  # the streamed sharded path is new: fall back to one synchronous call per step
-        if world == 1:
-            raise
-        sys.stderr.write("[bench] streamed sharded e2e failed (%r); using per-batch calls\n" % (ex,))
-        e2e_mode["v"] = "per-batch"
-        run_e2e(W)
-    barrier()
-    e0.record()
-    run_e2e(K)
-    e1.record()
-    barrier()
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    ms_e2e = time_e2e(model, images)
     e2e_value = world * BATCH * K / (ms_e2e / 1e3)
-    # whole-job bytes per step: every rank uploads its own shard; at N > 1 every rank reads back the
-    # all-gathered records of all N shards ([N*B, D*6+1] floats), at N = 1 its records, counts and status word
-    h2d = int(images.numel() * 4) * world
-    rec_floats = net.tail.dets.numel() + net.tail.det_count.numel()
-    d2h = int(rec_floats * 4 + 4) if world == 1 else int(rec_floats * 4 * world) * world
+    h2d, d2h = e2e_bytes(net, images)
 
-    # ---------------- roofline of the dominant kernel (tcgen05 conv) -----------
     from odt_b200.engine import ConvOp
-    st = torch.cuda.current_stream().cuda_stream
-    tc_ops = [op for op in net.ops if isinstance(op, ConvOp) and getattr(op, "use_tc", False)]
-    evs = []
-    torch.cuda.synchronize()
-    reps = 3
-    for _ in range(reps):
-        for op in net.ops:
-            if op in tc_ops:
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                op.launch(net, st)
-                b.record()
-                evs.append((op, a, b))
-            else:
-                op.launch(net, st)
-        net.tail.launch(net, st)
-    torch.cuda.synchronize()
-    tc_ms = sum(a.elapsed_time(b) for _, a, b in evs) / reps
-    tc_flops = sum(op.flops for op in tc_ops)
-    peaks, peak_src = measured_peaks()
-    peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
-    achieved_tf = tc_flops / (tc_ms * 1e-3) / 1e12
+    is_tc = lambda op: isinstance(op, ConvOp) and getattr(op, "use_tc", False)
+    tc_ms, dec_ms, nms_ms = timed_ops(net, is_tc)
+    roofline = conv_roofline(net, tc_ms, ms_step, peaks, peak_src,
+                             "tcgen05 implicit-GEMM convolutions (conv_tc_kernel<1|2>, conv_tapn_kernel where planned)")
     traffic, traffic_src = None, None
-    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_conv_traffic.json")
-    if os.path.exists(tpath):  # committed ncu measurement of the same command (scripts/conv_traffic.py)
-        with open(tpath) as f:
-            tj = json.load(f)
-        if tj.get("launches_per_step") == len(tc_ops):
-            traffic, traffic_src = tj["dram_bytes_per_launch_avg"], "profiles/r01_conv_traffic.json (ncu dram__bytes_read+write)"
-    kname = "conv_tc_kernel (tcgen05 implicit GEMM)"
-    if os.environ.get("ODT_TC_TAPN") == "1":
-        kname += " + conv_tapn_kernel for Cout_pad <= 64 (ODT_TC_TAPN=1)"
-    roofline = {"bound": "tensor", "kernel": kname,
-                "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
-                "peak_source": peak_src + " cuBLAS bf16 sustained (kernel timed inside a long step)",
-                "launches_per_step": len(tc_ops), "tc_ms_per_step": tc_ms,
-                "algorithmic_gflop_per_step": tc_flops / 1e9,
-                "share_of_step": tc_ms / ms_step}
+    for cand in ("r02_conv_traffic.json", "r01_conv_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", cand)
+        if os.path.exists(tpath):  # committed ncu measurement of the same command (scripts/conv_traffic.py)
+            with open(tpath) as f:
+                tj = json.load(f)
+            if tj.get("launches_per_step") == roofline["launches_per_step"]:
+                traffic, traffic_src = tj["dram_bytes_per_launch_avg"], "profiles/%s (ncu dram__bytes_read+write)" % cand
+                break
+    roofline["traffic"], roofline["traffic_source"] = traffic, traffic_src
+    floor_us = tail_launch_floor_us()
+    ssd_tail_rf = tail_roofline(net, dec_ms, nms_ms, peaks, floor_us)
 
+    cfg_line = bench_config(world)
+    cfg_line["conv_roofline_frac_whole_step"] = roofline["whole_step_frac_sustained"]
     line = {"metric": "images/sec", "value": value, "unit": "images/sec", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "per_gpu_batch": BATCH,
-                       "parallelism": "dp%d (image shards, 1 all-gather of detections)" % world,
-                       "l2": "per-step activation working set ~2 GB >> 126 MB L2 (no reuse between steps)",
-                       "cuda_graph": True, "conv_gflop_per_img": CONV_GFLOP_PER_IMG,
-                       "conv_roofline_frac_whole_step":
-                           (BATCH * CONV_GFLOP_PER_IMG * 1e9 / (ms_step * 1e-3)) / (peak_tf * 1e12)},
+            "config": cfg_line,
             "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K,
-                    "mode": "detect_stream_deferred" if os.environ.get("ODT_BENCH_DEFERRED") == "1" else
-                            "detect_stream" if world == 1 else
-                            ("detect_stream_sharded" if e2e_mode["v"] == "stream" else "detect_batch_sharded")},
+                    "mode": "detect_stream (read-back one step behind)" if world == 1 else
+                            "detect_stream sharded, consumer rank 0 reads the all-gathered records"},
             "gpu_launches": net.num_launches() * K,
-            "roofline": roofline, "clocks": clocks}
+            "roofline": roofline, "clocks": clocks,
+            "tail_roofline_ssd300": ssd_tail_rf}
+
+    # ======================= workload 2: RetinaNet-800 B=16, dense-threshold NMS =====================
+    if not args.no_retinanet:
+        del gathered
+        model._engines.clear()
+        del net, model
+        torch.cuda.empty_cache()
+        import RetinaNet
+        rmodel = RetinaNet.RetinaNet(dict(RETINA_CFG), None)
+        rnet = rmodel.engine(RETINA_BATCH, graph=False)
+        rimg = torch.from_numpy(np.random.default_rng(100 + rank).integers(
+            0, 256, (RETINA_BATCH, 800, 800, 3)).astype(np.float32)).pin_memory()
+        rnet.image_buf.copy_(rimg)
+        rnet.forward()
+        torch.cuda.synchronize()
+        thr = dense_threshold(rnet)
+        if world > 1:  # one threshold for the job: rank 0's
+            tt = torch.tensor([thr if thr is not None else -1.0], dtype=torch.float64, device="cuda")
+            tdist.broadcast(tt, 0)
+            thr = float(tt.item()) if tt.item() >= 0 else None
+        if thr is not None:
+            rnet.tail.p.score_thr = thr
+            rmodel.nms_score_threshold = thr
+        rnet.capture()
+        rg = (torch.empty((world * RETINA_BATCH, rnet.tail.rec.shape[1]), dtype=torch.float32, device="cuda")
+              if world > 1 else None)
+        r_ms_total = time_resident(rnet, rg)
+        r_ms_step = r_ms_total / K
+        r_e2e_ms = time_e2e(rmodel, rimg)
+        r_tc_ms, r_dec_ms, r_nms_ms = timed_ops(rnet, is_tc)
+        rh2d, rd2h = e2e_bytes(rnet, rimg)
+        rr = conv_roofline(rnet, r_tc_ms, r_ms_step, peaks, peak_src, "tcgen05 implicit-GEMM convolutions")
+        line["workloads"] = {"retinanet800_b16": {
+            "workload": RETINA_WORKLOAD, "value": world * RETINA_BATCH * K / (r_ms_total / 1e3), "unit": "images/sec",
+            "ms_per_step": r_ms_step, "per_gpu_batch": RETINA_BATCH, "gpu_launches": rnet.num_launches() * K,
+            "e2e": {"value": world * RETINA_BATCH * K / (r_e2e_ms / 1e3), "unit": "images/sec",
+                    "ms_per_step": r_e2e_ms / K, "h2d_bytes_per_step": rh2d, "d2h_bytes_per_step": rd2h},
+            "roofline": rr}}
+        line["tail_roofline"] = tail_roofline(rnet, r_dec_ms, r_nms_ms, peaks, floor_us)
+        line["tail_roofline"]["workload"] = "retinanet800_b16"
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, threads = cpu_oracle_images_per_sec(64)

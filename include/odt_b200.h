@@ -215,8 +215,11 @@ int odt_decode_candidates(const float* head, const odt_tail_params* p, int B,
 /* per-(image,class) exact TF NonMaxSuppressionV3 + class-major compaction.
  * dets: f32 [B, nms_classes*max_boxes, 6] rows (score,y1,x1,y2,x2,class);
  * det_anchor: i32 same rows (candidate row index = the keep index);
- * det_count: i32 [B]; status: i32 [1] (0 ok, ODT_ERR_OVERFLOW if any list
- * overflowed `cap`).  work: i32 [round_up(B,2) + 2] zero-initialised, 8-byte aligned scratch
+ * det_count: i32 [B]; status: i32 [1] (zeroed by this call, then 0 ok / ODT_ERR_OVERFLOW if any
+ * list overflowed `cap`).  dets_img_stride: floats between the images of `dets` (0 = dense,
+ * D*6 with D = nms_classes*max_boxes); with a stride >= D*6+2 the two floats behind an image's D
+ * rows receive (float) det_count and its overflow flag (0 / 1): `dets` is then the packed
+ * fixed-size record [B, D*6+2] that one all-gather / one device->host copy ships.  work: i32 [round_up(B,2) + 2] zero-initialised, 8-byte aligned scratch
  * (per-image completion counters reset by the kernel, then the 64-bit bump pointer
  * of the box pool).  box_pool: optional f32 [box_pool_entries][4]
  * scratch where lists longer than the 4096-entry shared-memory window cache their
@@ -225,7 +228,8 @@ int odt_decode_candidates(const float* head, const odt_tail_params* p, int B,
 int odt_nms_per_class(const float* head, const odt_tail_params* p, int B,
                       unsigned long long* cand_keys, const int* cand_count, float* dets,
                       int* det_anchor, int* det_count, int* sel_scratch, int* work, int* status,
-                      float* box_pool, long long box_pool_entries, void* stream);
+                      float* box_pool, long long box_pool_entries, long long dets_img_stride,
+                      void* stream);
 /* bytes of sel_scratch needed by odt_nms_per_class */
 long long odt_nms_scratch_bytes(const odt_tail_params* p, int B);
 

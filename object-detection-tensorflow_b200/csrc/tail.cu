@@ -196,6 +196,7 @@ struct NmsSmem {
 // list processed (correct, slower).
 constexpr int kNmsPrefilter = kNmsSmemKeys;  // longer lists: prefilter first
 constexpr int kNmsSelectMin = 384;
+constexpr int kNselOverflowBit = 1 << 30;  // per-(image, class) "list was truncated at cap" flag in nsel_all
 
 __global__ void __launch_bounds__(kNmsThreads)
     nms_per_class_kernel(const float* __restrict__ head, const __grid_constant__ TailP tp, int B,
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(kNmsThreads)
                          int* __restrict__ det_anchor, int* __restrict__ det_count,
                          int* __restrict__ scratch, int* __restrict__ work,
                          int* __restrict__ status, float4* __restrict__ box_pool,
-                         long long box_pool_entries) {
+                         long long box_pool_entries, long long det_img_stride) {
   pdl_launch_dependents();
   const odt_tail_params& p = tp.p;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -225,7 +226,8 @@ __global__ void __launch_bounds__(kNmsThreads)
   const long long bc = (long long)b * C + c;
 
   int cnt = cand_count[b * p.num_fg + c];
-  if (cnt > p.cap) {
+  const bool overflow = cnt > p.cap;
+  if (overflow) {
     if (tid == 0) atomicExch(status, ODT_ERR_OVERFLOW);
     cnt = p.cap;
   }
@@ -409,7 +411,7 @@ __global__ void __launch_bounds__(kNmsThreads)
   // the subset ran dry before nms_max_boxes boxes were kept: redo on the full list
   if (!(subset && nsel < MB && cnt < cnt_all)) break;
   }  // attempt
-  if (tid == 0) nsel_all[bc] = nsel;
+  if (tid == 0) nsel_all[bc] = nsel | (overflow ? kNselOverflowBit : 0);
 
   // class-major compaction by the last block of this image
   __threadfence();
@@ -422,27 +424,36 @@ __global__ void __launch_bounds__(kNmsThreads)
   if (!s_last) return;
   __threadfence();
   __shared__ int s_off[33];
+  const long long D = (long long)C * MB;
+  float* img_dets = dets + (long long)b * det_img_stride;
   if (tid == 0) {
-    int acc = 0;
+    int acc = 0, ovf = 0;
     for (int i = 0; i < C; ++i) {
       s_off[i] = acc;
-      acc += ((volatile int*)nsel_all)[(long long)b * C + i];
+      const int v = ((volatile int*)nsel_all)[(long long)b * C + i];
+      acc += v & ~kNselOverflowBit;
+      ovf |= v & kNselOverflowBit;
     }
     s_off[C] = acc;
     det_count[b] = acc;
     work[b] = 0;
+    // packed record (the unit the multi-GPU all-gather and the host read-back ship): the two floats
+    // behind an image's D rows carry its detection count and its overflow flag
+    if (det_img_stride >= D * 6 + 2) {
+      img_dets[D * 6] = (float)acc;
+      img_dets[D * 6 + 1] = ovf ? 1.f : 0.f;
+    }
   }
   __syncthreads();
-  const long long D = (long long)C * MB;
   for (int i = tid; i < C * MB; i += blockDim.x) {
     int ci = i / MB, k = i % MB;
     int ns = s_off[ci + 1] - s_off[ci];
     if (k < ns) {
-      long long dst = (long long)b * D + s_off[ci] + k;
+      long long dst = s_off[ci] + k;
       const float* s = st_det + (((long long)b * C + ci) * MB + k) * 6;
 #pragma unroll
-      for (int q = 0; q < 6; ++q) dets[dst * 6 + q] = __ldcg(s + q);
-      det_anchor[dst] = __ldcg(st_anchor + ((long long)b * C + ci) * MB + k);
+      for (int q = 0; q < 6; ++q) img_dets[dst * 6 + q] = __ldcg(s + q);
+      det_anchor[(long long)b * D + dst] = __ldcg(st_anchor + ((long long)b * C + ci) * MB + k);
     }
   }
 }
@@ -498,7 +509,7 @@ extern "C" int odt_nms_per_class(const float* head, const odt_tail_params* p, in
                                  unsigned long long* cand_keys, const int* cand_count, float* dets,
                                  int* det_anchor, int* det_count, int* sel_scratch, int* work,
                                  int* status, float* box_pool, long long box_pool_entries,
-                                 void* stream) {
+                                 long long dets_img_stride, void* stream) {
   int rc = check_tail(p);
   if (rc) return rc;
   ODT_CHECK_ARG(head && cand_keys && cand_count && dets && det_anchor && det_count &&
@@ -519,9 +530,13 @@ extern "C" int odt_nms_per_class(const float* head, const odt_tail_params* p, in
   ODT_CHECK_ARG(((uintptr_t)pool_ctr & 7) == 0 || !box_pool, "work must be 8-byte aligned");
   ODT_CHECK_ARG(((uintptr_t)box_pool & 15) == 0, "box_pool must be 16-byte aligned");
   if (box_pool) ODT_CUDA_OK(cudaMemsetAsync(pool_ctr, 0, 8, st));  // pool bump pointer
+  ODT_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int), st));        // the status word describes THIS launch
+  const long long dense = (long long)p->nms_classes * p->max_boxes * 6;
+  if (dets_img_stride == 0) dets_img_stride = dense;
+  ODT_CHECK_ARG(dets_img_stride >= dense, "dets_img_stride smaller than nms_classes*max_boxes*6");
   nms_per_class_kernel<<<grid, kNmsThreads, sizeof(NmsSmem), st>>>(
       head, tp, B, cand_keys, cand_count, dets, det_anchor, det_count, sel_scratch, work, status,
-      reinterpret_cast<float4*>(box_pool), box_pool ? box_pool_entries : 0);
+      reinterpret_cast<float4*>(box_pool), box_pool ? box_pool_entries : 0, dets_img_stride);
   ODT_LAUNCH_OK();
   return ODT_OK;
 }

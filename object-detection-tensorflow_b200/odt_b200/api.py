@@ -112,10 +112,16 @@ class _Detector:
         elif path and tf_checkpoint.is_checkpoint(path):
             self._load_bundle_into(w, path)
         elif path:
-            # the reference throws inside NewCheckpointReader (SSD300.py:31); BASELINE config 1
-            # asks for random-init VGG-16, so a missing file falls back to the seeded init
-            sys.stderr.write("[odt_b200] pretraining weight %r not found as a TF checkpoint (V2 bundle / V1 file) or .npz; "
-                             "using seeded random init\n" % (path,))
+            # the reference throws inside NewCheckpointReader (SSD300.py:31).  BASELINE config 0 runs the driver's
+            # own config (pretraining_weight './vgg_16.ckpt') with random-init VGG-16: that needs the explicit
+            # opt-in config['allow_random_init'] = True or ODT_ALLOW_RANDOM_INIT=1.
+            if not (self.config.get("allow_random_init") or os.environ.get("ODT_ALLOW_RANDOM_INIT") == "1"):
+                raise FileNotFoundError(
+                    "pretraining_weight %r is neither a TF checkpoint (V2 bundle / V1 file) nor an .npz; set "
+                    "config['allow_random_init'] = True (or ODT_ALLOW_RANDOM_INIT=1) to run on the seeded random "
+                    "initialisation instead" % (path,))
+            sys.stderr.write("[odt_b200] pretraining weight %r not found; using the seeded random init (opt-in)\n"
+                             % (path,))
         return w
 
     @staticmethod
@@ -170,7 +176,7 @@ class _Detector:
 
     # ---- inference -----------------------------------------------------------
     def detect_batch(self, images, precision=None):
-        """images: array-like [B,H,W,3] float (RGB, 0..255).  Returns a list of
+        """images: array-like [B,H,W,3] float (RGB, 0..255).  Returns a sequence of
         [scores, bbox(y1,x1,y2,x2), class_id] per image."""
         images = _as_host_tensor(images)
         assert images.dim() == 4 and images.shape[3] == 3, "expected [B,H,W,3]"
@@ -180,90 +186,44 @@ class _Detector:
         net.run()
         return net.tail.results()
 
-    def detect_stream(self, batches, precision=None, finish=None):
-        """Pipelined inference over an iterable of host batches [B,H,W,3]: the
-        host->device copy of batch i+1 runs on a copy stream while the kernels of
-        batch i execute; every batch's detections are read back (D2H) before it is
-        yielded.  Sources in pinned memory make the H2D copies truly asynchronous.
-        `finish(net)` replaces the read-back of the local detections (used by
-        detect_stream_sharded: all-gather of every rank's records)."""
+    def detect_stream(self, batches, precision=None, sharded=False, consumer=None):
+        """Pipelined inference over an iterable of host batches [B,H,W,3].  Per step, on the GPU's main
+        stream: device copy of the staged images -> the captured forward graph (convs, decode, NMS; the NMS
+        kernel writes the packed per-image records) -> (sharded: ONE all-gather of the records) -> ONE
+        asynchronous D2H of the records into pinned host memory.  The H2D copy of batch i+1 runs on a copy
+        stream under the kernels of batch i, and the host only waits for / unpacks batch i AFTER batch i+1
+        has been queued, so neither the D2H latency nor the Python work idles the GPU.  Results are yielded
+        in order (the generator simply runs one batch ahead of what it yields); pinned sources make the
+        H2D copies truly asynchronous.
+        sharded: `batches` are this rank's image shards (one process per GPU, torch.distributed);
+        consumer=None: every rank reads back and yields all ranks' detections; consumer=r: only rank r
+        reads back the gathered records (the others yield their own shard's) -- the D2H volume of the job
+        then grows with N, not N^2."""
+        from . import dist
+        from .engine import unpack_records
         it = iter(batches)
         try:
             cur = _as_host_tensor(next(it))
         except StopIteration:
             return
         net = self.engine(cur.shape[0], precision)
-        if not hasattr(net, "_stage"):
-            net._stage = [torch.empty_like(net.image_buf) for _ in range(2)]
-            net._copy_stream = torch.cuda.Stream()
-            net._h2d = [torch.cuda.Event() for _ in range(2)]
-            net._used = [torch.cuda.Event() for _ in range(2)]
-        main = torch.cuda.current_stream()
-        cs = net._copy_stream
-
-        def prefetch(t, slot):
-            cs.wait_event(net._used[slot])
-            with torch.cuda.stream(cs):
-                net._stage[slot].copy_(t, non_blocking=True)
-                net._h2d[slot].record(cs)
-
-        for ev in net._used:
-            ev.record(main)
-        prefetch(cur, 0)
-        i = 0
-        while cur is not None:
-            slot = i & 1
-            main.wait_event(net._h2d[slot])
-            net.image_buf.copy_(net._stage[slot], non_blocking=True)  # device-to-device
-            net._used[slot].record(main)
-            try:
-                nxt = _as_host_tensor(next(it))
-                assert nxt.shape == cur.shape, "all batches of a stream must share a shape"
-                prefetch(nxt, slot ^ 1)  # overlaps the launches below
-            except StopIteration:
-                nxt = None
-            net.run()
-            yield finish(net) if finish is not None else net.tail.results()
-            cur = nxt
-            i += 1
-
-    def test_one_image(self, images):
-        """ref SSD300.py:486-488: returns [scores, bbox, class_id]."""
-        if self.data_format == "channels_first":
-            images = np.transpose(np.asarray(images), (0, 2, 3, 1))
-        res = self.detect_batch(images)
-        return res[0] if len(res) == 1 else res
-
-    def detect_batch_sharded(self, images_local):
-        """Batch-parallel multi-GPU inference: each rank runs its image shard,
-        one NCCL all-gather of the fixed-size detection records follows."""
-        from . import dist
-        return dist.detect_sharded(self, images_local)
-
-    def detect_stream_deferred(self, batches, precision=None, sharded=False):
-        """detect_stream with the read-back one step behind: after the kernels of batch i are queued, its
-        records go to a pinned host buffer asynchronously (after the all-gather when `sharded`), batch i+1 is
-        launched, and only then are batch i's records unpacked on the host -- the Python work and the D2H
-        latency overlap the next batch instead of idling the GPU.  Yields results in order, one step late.
-        EXPERIMENTAL (written without GPU time left in round 1; tests/test_gpu_models.py opt-in case)."""
-        from . import dist
-        it = iter(batches)
-        try:
-            cur = _as_host_tensor(next(it))
-        except StopIteration:
-            return
-        net = self.engine(cur.shape[0], precision)
+        assert tuple(cur.shape[1:]) == tuple(net.image_buf.shape[1:]), (cur.shape, net.image_buf.shape)
         if not hasattr(net, "_stage"):
             net._stage = [torch.empty_like(net.image_buf) for _ in range(2)]
             net._copy_stream = torch.cuda.Stream()
             net._h2d = [torch.cuda.Event() for _ in range(2)]
             net._used = [torch.cuda.Event() for _ in range(2)]
         world = dist.dist.get_world_size() if (sharded and dist.dist.is_initialized()) else 1
-        rec_shape = (world * cur.shape[0], net.tail.dets.shape[1] * 6 + 1)
+        rank = dist.dist.get_rank() if world > 1 else 0
+        read_all = world > 1 and (consumer is None or consumer == rank)
+        tail = net.tail
+        rec_shape = ((world if read_all else 1) * cur.shape[0], tail.rec.shape[1])
         if getattr(net, "_rec_host", None) is None or tuple(net._rec_host[0].shape) != rec_shape:
             net._rec_host = [torch.empty(rec_shape, dtype=torch.float32).pin_memory() for _ in range(2)]
-            net._status_host = [torch.empty(1, dtype=torch.int32).pin_memory() for _ in range(2)]
             net._rec_done = [torch.cuda.Event() for _ in range(2)]
+        if world > 1 and (getattr(net, "_gathered", None) is None or net._gathered.shape[0] != world * cur.shape[0]):
+            net._gathered = torch.empty((world * cur.shape[0], tail.rec.shape[1]), dtype=torch.float32,
+                                        device=tail.rec.device)
         main = torch.cuda.current_stream()
         cs = net._copy_stream
 
@@ -275,9 +235,7 @@ class _Detector:
 
         def complete(slot):
             net._rec_done[slot].synchronize()
-            if int(net._status_host[slot][0]) != 0:
-                raise RuntimeError("NMS candidate list overflowed its capacity (cap=%d)" % net.tail.p.cap)
-            return dist.unpack_records(net._rec_host[slot])
+            return unpack_records(net._rec_host[slot].numpy().copy(), tail.p.cap)
 
         for ev in net._used:
             ev.record(main)
@@ -291,16 +249,16 @@ class _Detector:
             try:
                 nxt = _as_host_tensor(next(it))
                 assert nxt.shape == cur.shape, "all batches of a stream must share a shape"
-                prefetch(nxt, slot ^ 1)
+                prefetch(nxt, slot ^ 1)  # overlaps the launches below
             except StopIteration:
                 nxt = None
             net.run()
-            # snapshot of this batch's records, ordered before the next batch's kernels on the main stream
-            rec = dist.pack_records(net.tail.dets, net.tail.det_count)
-            if sharded:
-                rec = dist.gather_records(rec)
-            net._rec_host[slot].copy_(rec, non_blocking=True)
-            net._status_host[slot].copy_(net.tail.status.reshape(1), non_blocking=True)
+            src = tail.rec
+            if world > 1:
+                dist.gather_records(tail.rec, out=net._gathered)
+                if read_all:
+                    src = net._gathered
+            net._rec_host[slot].copy_(src, non_blocking=True)  # ordered before the next batch's kernels
             net._rec_done[slot].record(main)
             if pending is not None:
                 yield complete(pending)  # host work of batch i-1 while batch i runs
@@ -310,11 +268,24 @@ class _Detector:
         if pending is not None:
             yield complete(pending)
 
-    def detect_stream_sharded(self, batches_local, precision=None):
-        """detect_stream over this rank's image shards: the H2D copy of shard i+1 overlaps the kernels,
-        the all-gather and the read-back of shard i; yields every rank's detections per step."""
+    detect_stream_deferred = detect_stream  # round-1 name of the deferred read-back variant
+
+    def test_one_image(self, images):
+        """ref SSD300.py:486-488: returns [scores, bbox, class_id]."""
+        if self.data_format == "channels_first":
+            images = np.transpose(np.asarray(images), (0, 2, 3, 1))
+        res = self.detect_batch(images)
+        return res[0] if len(res) == 1 else list(res)
+
+    def detect_batch_sharded(self, images_local, consumer=None):
+        """Batch-parallel multi-GPU inference: each rank runs its image shard,
+        one NCCL all-gather of the fixed-size detection records follows."""
         from . import dist
-        return self.detect_stream(batches_local, precision, finish=dist.finish_sharded)
+        return dist.detect_sharded(self, images_local, consumer)
+
+    def detect_stream_sharded(self, batches_local, precision=None, consumer=None):
+        """detect_stream over this rank's image shards (see detect_stream)."""
+        return self.detect_stream(batches_local, precision, sharded=True, consumer=consumer)
 
     # ---- training / checkpoints (API surface; SURVEY 8f) --------------------
     def train_one_epoch(self, lr):
@@ -332,7 +303,9 @@ class _Detector:
         # `saver.save(sess, path, global_step=...)` (SSD300.py:499): a V2 bundle `<path>-<step>`
         out = "%s-%d" % (path, self.global_step)
         tensors = dict(self.get_weights())
-        tensors["global_step"] = np.asarray(self.global_step, np.int64)
+        # int32 like the reference's variable (tf.get_variable('global_step', initializer=tf.constant(0)),
+        # SSD300.py:43): Saver.restore does not cast, an int64 entry would fail its dtype check
+        tensors["global_step"] = np.asarray(self.global_step, np.int32)
         tf_checkpoint.write_checkpoint(out, tensors)
         print("save", mode, "model in", out, "successfully")
         return out
@@ -381,6 +354,7 @@ class SSD300(_Detector):
 
     def __init__(self, config, data_provider):
         self._common_init(config, data_provider)
+        nets.check_num_classes(config)
         self.num_classes = config["num_classes"] + 1
         s = self.input_size
         self.data_shape = [s, s, 3] if config["data_format"] == "channels_last" else [3, s, s]
@@ -433,6 +407,7 @@ class RetinaNet(_Detector):
         self.is_bottleneck = config["is_bottleneck"]
         self.block_list = config["residual_block_list"]
         self.data_shape = config["data_shape"]
+        nets.check_num_classes(config)
         self.num_classes = config["num_classes"] + 1
         self.gamma, self.alpha = config["gamma"], config["alpha"]
 

@@ -32,30 +32,15 @@ def shard_range(total, rank, world):
     return rank * per, (rank + 1) * per
 
 
-def pack_records(dets, det_count):
-    """[B,D,6] f32 + [B] i32 -> one [B, D*6+1] f32 record (count rides as a float)."""
-    B = dets.shape[0]
-    return torch.cat([dets.reshape(B, -1), det_count.reshape(B, 1).to(torch.float32)], dim=1).contiguous()
-
-
-def gather_records(rec, group=None):
-    """ONE all-gather of the packed records; returns [world*B, D*6+1] on every rank."""
+def gather_records(rec, group=None, out=None):
+    """ONE all-gather of the packed per-image records [B, D*6+2] (written by the NMS kernel itself, see
+    engine.Tail); returns [world*B, D*6+2] on every rank (`out`: preallocated destination)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         return rec
-    out = torch.empty((world * rec.shape[0], rec.shape[1]), dtype=rec.dtype, device=rec.device)
+    if out is None:
+        out = torch.empty((world * rec.shape[0], rec.shape[1]), dtype=rec.dtype, device=rec.device)
     dist.all_gather_into_tensor(out, rec, group=group)
-    return out
-
-
-def unpack_records(rec):
-    rec = rec.cpu().numpy()
-    D = (rec.shape[1] - 1) // 6
-    out = []
-    for b in range(rec.shape[0]):
-        k = int(rec[b, -1])
-        d = rec[b, :D * 6].reshape(D, 6)[:k]
-        out.append([d[:, 0].copy(), d[:, 1:5].copy(), d[:, 5].astype(np.int32)])
     return out
 
 
@@ -72,17 +57,18 @@ def broadcast_weights(weights, src=0):
     return out
 
 
-def finish_sharded(net):
-    """After net.run(): pack this rank's detections, all-gather, read back, unpack."""
-    rec = pack_records(net.tail.dets, net.tail.det_count)
-    return unpack_records(gather_records(rec))
-
-
-def detect_sharded(model, images_local):
-    """Run this rank's image shard and all-gather everybody's detections."""
+def detect_sharded(model, images_local, consumer=None):
+    """Run this rank's image shard and all-gather everybody's detection records.  consumer=None: every
+    rank reads back and returns all ranks' detections; consumer=r: only rank r does (the others return
+    their own shard's detections)."""
     from .api import _as_host_tensor
+    from .engine import unpack_records
     images_local = _as_host_tensor(images_local)
     net = model.engine(images_local.shape[0])
     net.image_buf.copy_(images_local, non_blocking=True)
     net.run()
-    return finish_sharded(net)
+    rec = gather_records(net.tail.rec)
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    if world > 1 and consumer is not None and dist.get_rank() != consumer:
+        rec = net.tail.rec
+    return unpack_records(rec.cpu().numpy(), net.tail.p.cap)

@@ -754,7 +754,11 @@ class Tail:
         self.cand_count = torch.zeros((B, self.num_fg), dtype=torch.int32, device=dev)
         D = self.nms_classes * self.max_boxes
         self.D = D
-        self.dets = torch.zeros((B, D, 6), dtype=torch.float32, device=dev)
+        # ONE packed fixed-size record per image: D rows (score, y1, x1, y2, x2, class) followed by
+        # (count, overflow flag) -- written by the NMS kernel itself; the unit the host read-back and the
+        # multi-GPU all-gather ship (no pack kernels).  `dets` is the [B, D, 6] view of the same memory.
+        self.rec = torch.zeros((B, D * 6 + 2), dtype=torch.float32, device=dev)
+        self.dets = self.rec[:, :D * 6].view(B, D, 6)
         self.det_anchor = torch.zeros((B, D), dtype=torch.int32, device=dev)
         self.det_count = torch.zeros((B,), dtype=torch.int32, device=dev)
         nbytes = net.lib.odt_nms_scratch_bytes(C.byref(p), B)
@@ -767,35 +771,74 @@ class Tail:
         self.box_pool = (torch.empty((self.pool_entries, 4), dtype=torch.float32, device=dev)
                          if self.pool_entries else None)
 
-    def launch(self, net, stream):
-        lib = net.lib
-        L.check(lib.odt_decode_candidates(net.head_buf.data_ptr(), C.byref(self.p), net.batch,
+    def launch_decode(self, net, stream):
+        L.check(net.lib.odt_decode_candidates(net.head_buf.data_ptr(), C.byref(self.p), net.batch,
+                                              self.cand_keys.data_ptr(), self.cand_count.data_ptr(),
+                                              stream), "decode_candidates")
+
+    def launch_nms(self, net, stream):
+        L.check(net.lib.odt_nms_per_class(net.head_buf.data_ptr(), C.byref(self.p), net.batch,
                                           self.cand_keys.data_ptr(), self.cand_count.data_ptr(),
-                                          stream), "decode_candidates")
-        L.check(lib.odt_nms_per_class(net.head_buf.data_ptr(), C.byref(self.p), net.batch,
-                                      self.cand_keys.data_ptr(), self.cand_count.data_ptr(),
-                                      self.dets.data_ptr(), self.det_anchor.data_ptr(),
-                                      self.det_count.data_ptr(), self.scratch.data_ptr(),
-                                      self.work.data_ptr(), self.status.data_ptr(),
-                                      self.box_pool.data_ptr() if self.box_pool is not None else None,
-                                      self.pool_entries, stream),
+                                          self.dets.data_ptr(), self.det_anchor.data_ptr(),
+                                          self.det_count.data_ptr(), self.scratch.data_ptr(),
+                                          self.work.data_ptr(), self.status.data_ptr(),
+                                          self.box_pool.data_ptr() if self.box_pool is not None else None,
+                                          self.pool_entries, self.rec.shape[1], stream),
                 "nms_per_class")
+
+    def launch(self, net, stream):
+        self.launch_decode(net, stream)
+        self.launch_nms(net, stream)
 
     def num_launches(self):
         return 2  # decode + nms kernels (plus 1-2 memset nodes)
 
     def results(self):
-        """D2H read of the fixed-size detection records -> per-image python lists
-        [scores f32[K], bbox f32[K,4] (y1,x1,y2,x2), class_id i32[K]] (ref SSD300.py:190)."""
-        cnt = self.det_count.cpu().numpy()
-        dets = self.dets.cpu().numpy()
-        if int(self.status.item()) != 0:
-            raise L.OdtError("NMS candidate list overflowed its capacity (cap=%d)" % self.p.cap)
-        out = []
-        for b in range(dets.shape[0]):
-            d = dets[b, :cnt[b]]
-            out.append([d[:, 0].copy(), d[:, 1:5].copy(), d[:, 5].astype(np.int32)])
-        return out
+        """ONE D2H read of the packed records -> per-image [scores f32[K], bbox f32[K,4] (y1,x1,y2,x2),
+        class_id i32[K]] (ref SSD300.py:190)."""
+        return unpack_records(self.rec.cpu().numpy(), self.p.cap)
+
+
+class Detections:
+    """Sequence view over packed detection records [M, D*6+2] (host memory): item b is the reference's
+    per-image result `[scores f32[K], bbox f32[K,4] (y1,x1,y2,x2), class_id i32[K]]` (SSD300.py:190).
+    Built with three vectorised passes over the whole record block; indexing slices views."""
+
+    def __init__(self, rec):
+        rec = np.asarray(rec)
+        M, D = rec.shape[0], (rec.shape[1] - 2) // 6
+        rows = rec[:, :D * 6].reshape(M, D, 6)
+        self.count = rec[:, D * 6].astype(np.int64)
+        self.scores = np.ascontiguousarray(rows[:, :, 0])
+        self.boxes = np.ascontiguousarray(rows[:, :, 1:5])
+        self.class_id = rows[:, :, 5].astype(np.int32)
+
+    def __len__(self):
+        return self.count.shape[0]
+
+    def __getitem__(self, b):
+        if isinstance(b, slice):
+            return [self[i] for i in range(*b.indices(len(self)))]
+        if b < 0:
+            b += len(self)
+        if not 0 <= b < len(self):
+            raise IndexError(b)
+        k = self.count[b]
+        return [self.scores[b, :k], self.boxes[b, :k], self.class_id[b, :k]]
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+def unpack_records(rec, cap=None):
+    """Packed records (numpy [M, D*6+2]) -> Detections; raises if any image's overflow flag is set
+    (a candidate list was truncated at its capacity: the result would silently lack boxes)."""
+    rec = np.asarray(rec)
+    if rec.shape[0] and float(rec[:, -1].max()) != 0.0:
+        bad = np.nonzero(rec[:, -1])[0]
+        raise L.OdtError("NMS candidate list overflowed its capacity%s in image(s) %s"
+                         % ("" if cap is None else " (cap=%d)" % cap, bad[:8].tolist()))
+    return Detections(rec)
 
 
 class RowsHarness:

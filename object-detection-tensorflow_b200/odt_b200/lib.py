@@ -1,8 +1,7 @@
 """ctypes binding of libodt_b200.so (the C ABI declared in include/odt_b200.h).
 
 The product path has no CPU fallback: if the CUDA extension is missing the
-import fails loudly (build it with `python __graft_entry__.py` or
-`make -C object-detection-tensorflow_b200/csrc`).
+import fails loudly (build it with `python __graft_entry__.py`).
 """
 import ctypes as C
 import os
@@ -16,6 +15,7 @@ DECODE_SSD, DECODE_YOLO3, DECODE_FCOS = 0, 1, 2
 MAX_LEVELS, MAX_PRIORS = 8, 9
 ERR_OVERFLOW = -4
 ERR_UNSUPPORTED = -3
+ABI_VERSION = 3  # odt_abi_version(): bumped whenever a signature in include/odt_b200.h changes
 
 
 class ConvParams(C.Structure):
@@ -78,7 +78,7 @@ SYMBOLS = {
     "odt_groupnorm_apply": (_I, [_P, _P, _P, _I, _I, _L, _I, _I, _I, _P, _P, _I, _P]),
     "odt_groupnorm_act": (_I, [_P, _P, _P, _I, _I, _L, _I, _I, _I, _F, _P, _P, _I, _P]),
     "odt_decode_candidates": (_I, [_P, C.POINTER(TailParams), _I, _P, _P, _P]),
-    "odt_nms_per_class": (_I, [_P, C.POINTER(TailParams), _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
+    "odt_nms_per_class": (_I, [_P, C.POINTER(TailParams), _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _P]),
     "odt_nms_scratch_bytes": (_L, [C.POINTER(TailParams), _I]),
     "odt_retina_loss_fwd": (_I, [_P, C.POINTER(TailParams), _I, _P, _I, _F, _F, _P, _P, _P, _P]),
     "odt_retina_loss_scratch_floats": (_L, [_I]),
@@ -113,6 +113,9 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
+    if lib.odt_abi_version() != ABI_VERSION:
+        raise OdtError("%s has ABI version %d, this binding expects %d: rebuild it (python __graft_entry__.py)"
+                       % (LIB_PATH, lib.odt_abi_version(), ABI_VERSION))
     _lib = lib
     return lib
 

@@ -23,6 +23,15 @@ _VGG = [("conv1_1", "kernel_conv1_1", "bias_conv1_1", 64), ("conv1_2", "kernel_c
         ("conv5_3", "kernel_conv5_3", "bias_conv5_3", 512)]
 
 
+def check_num_classes(cfg):
+    """The candidate-row layout of the whole path is 25 floats (20 class scores + 5): head
+    scatter, decode kernel, NMS and the loss kernels hard-code it, so only the VOC class count of every BASELINE
+    config is supported.  Any other value would make the head convolutions write overlapping / out-of-bounds rows."""
+    if cfg["num_classes"] != 20:
+        raise ValueError("num_classes = %r: this path stores 25-float candidate rows and supports exactly 20 "
+                         "foreground classes (VOC)" % (cfg["num_classes"],))
+
+
 # ------------------------------------------------------------------- SSD ----
 def ssd_scales(size):
     """ref SSD300.py:112-113, SSD512.py:116-118 (Python doubles like the reference)."""
@@ -40,6 +49,7 @@ def ssd_ratios(size):
 
 def build_ssd(size, batch, cfg, precision="fp16", device="cuda", allow_tc=True):
     """ref SSD300.py:71-90,192-314 (+SSD512.py:320-322)."""
+    check_num_classes(cfg)
     nc = cfg["num_classes"] + 1
     net = Net(batch, size, size, precision, device, allow_tc)
     with net.scope("feature_extractor"):
@@ -147,6 +157,7 @@ def _pyramid(net, feat, top, norm):
 
 def build_retinanet(batch, cfg, precision="fp16", device="cuda", allow_tc=True):
     """ref RetinaNet.py:137-155,258-301."""
+    check_num_classes(cfg)
     H, W, _ = cfg["data_shape"]
     nc = cfg["num_classes"] + 1
     blocks = cfg["residual_block_list"]

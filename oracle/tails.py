@@ -172,21 +172,26 @@ def _per_class_nms(conf, boxes, anchor_idx, n_classes, score_thr, max_boxes, iou
             np.concatenate(out_c), np.concatenate(out_k).astype(np.int32))
 
 
+def softmax_scores_boxes(pconf, pyx, phw, ayx, ahw, num_fg):
+    """Per-row quantities of SSD300.py:157-171 / RetinaNet.py:224-238 for ONE image, before any filtering:
+    softmax probabilities [N,num_fg+1], boxes [N,4] (y1,x1,y2,x2) and the background filter (arg-max is a
+    foreground class; background is the LAST class, first maximum wins)."""
+    prob = T.softmax_lastdim(pconf)
+    valid = np.argmax(prob, axis=-1) < num_fg
+    dyx = (pyx * ahw).astype(F32)
+    dyx = (dyx + ayx).astype(F32)
+    dhw = (ahw * np.exp(phw.astype(F32)).astype(F32)).astype(F32)
+    y1x1 = (dyx - dhw / F32(2.0)).astype(F32)
+    y2x2 = (dyx + dhw / F32(2.0)).astype(F32)
+    return prob, np.concatenate([y1x1, y2x2], axis=-1), valid
+
+
 def softmax_tail(pconf, pyx, phw, ayx, ahw, num_fg, score_thr, max_boxes, iou_thr):
     """SSD300.py:157-190 / RetinaNet.py:224-256 for ONE image.
     pconf [N,21], pyx/phw [N,2], anchors [N,2]."""
-    conf = T.softmax_lastdim(pconf)
-    cid = np.argmax(conf, axis=-1)  # first maximum
-    keep = cid < num_fg  # background is the LAST class
+    prob, boxes, keep = softmax_scores_boxes(pconf, pyx, phw, ayx, ahw, num_fg)
     idx = np.nonzero(keep)[0].astype(np.int32)
-    conf = conf[keep][:, :num_fg]
-    dyx = (pyx[keep] * ahw[keep]).astype(F32)
-    dyx = (dyx + ayx[keep]).astype(F32)
-    dhw = (ahw[keep] * np.exp(phw[keep].astype(F32)).astype(F32)).astype(F32)
-    y1x1 = (dyx - dhw / F32(2.0)).astype(F32)
-    y2x2 = (dyx + dhw / F32(2.0)).astype(F32)
-    boxes = np.concatenate([y1x1, y2x2], axis=-1)
-    return _per_class_nms(conf, boxes, idx, num_fg, score_thr, max_boxes, iou_thr)
+    return _per_class_nms(prob[keep][:, :num_fg], boxes[keep], idx, num_fg, score_thr, max_boxes, iou_thr)
 
 
 def ssd_rows(preds, num_classes=21):
@@ -226,10 +231,10 @@ def yolo_rows(preds, num_classes=20, num_priors=3):
     return np.concatenate([p.reshape(b, -1, num_classes + 5) for p in preds], axis=1)
 
 
-def yolo_detect(preds, priors, score_thr, max_boxes, iou_thr, image=0, num_classes=20):
-    """YOLOv3.py:320-368 for one image.  priors: config['priors'] (3x3x2 nested list).
-    Level k uses priors[k]/stride[k] with stride=[8,16,32] in *config order*
-    (YOLOv3.py:38-41) and output multipliers 32,32,16 (:346-348)."""
+def yolo_scores_boxes(preds, priors, image=0, num_classes=20):
+    """Per-row confidences [N,20] and boxes [N,4] of YOLOv3.py:320-351 for one image (no filtering).
+    priors: config['priors'] (3x3x2 nested list).  Level k uses priors[k]/stride[k] with stride=[8,16,32] in
+    *config order* (YOLOv3.py:38-41) and output multipliers 32,32,16 (:346-348)."""
     stride = [8.0, 16.0, 32.0]
     mult = [stride[-1], stride[-1], stride[-2]]
     confs, boxes = [], []
@@ -249,8 +254,12 @@ def yolo_detect(preds, priors, score_thr, max_boxes, iou_thr, image=0, num_class
         box = np.concatenate([byx - bhw / F32(2.0), byx + bhw / F32(2.0)], axis=-1).astype(F32)
         boxes.append((box * F32(mult[k])).astype(F32).reshape(-1, 4))
         confs.append((cls * obj).astype(F32).reshape(-1, num_classes))
-    conf = np.concatenate(confs, axis=0)
-    box = np.concatenate(boxes, axis=0)
+    return np.concatenate(confs, axis=0), np.concatenate(boxes, axis=0)
+
+
+def yolo_detect(preds, priors, score_thr, max_boxes, iou_thr, image=0, num_classes=20):
+    """YOLOv3.py:320-368 for one image."""
+    conf, box = yolo_scores_boxes(preds, priors, image, num_classes)
     idx = np.arange(conf.shape[0], dtype=np.int32)
     return _per_class_nms(conf, box, idx, num_classes, score_thr, max_boxes, iou_thr)
 
@@ -263,8 +272,8 @@ def fcos_rows(heads):
                         axis=2) for c, ct, rg in heads], axis=1)
 
 
-def fcos_detect(heads, score_thr, max_boxes, iou_thr, image=0, num_classes=20):
-    """FCOS.py:130-150,197-264 for one image.  NMS visits num_classes-1 classes (:252)."""
+def fcos_scores_boxes(heads, image=0, num_classes=20):
+    """Per-row confidences [N,20] and boxes [N,4] of FCOS.py:130-150,197-248 for one image (no filtering)."""
     strides = [8, 16, 32, 64, 128]
     confs, boxes = [], []
     for (cls, ctr, reg), s in zip(heads, strides):
@@ -280,7 +289,27 @@ def fcos_detect(heads, score_thr, max_boxes, iou_thr, image=0, num_classes=20):
         box = (np.concatenate([y1, x1, y2, x2], axis=-1).astype(F32).reshape(-1, 4) * F32(s)).astype(F32)
         confs.append(conf)
         boxes.append(box)
-    conf = np.concatenate(confs, axis=0)
-    box = np.concatenate(boxes, axis=0)
+    return np.concatenate(confs, axis=0), np.concatenate(boxes, axis=0)
+
+
+def fcos_detect(heads, score_thr, max_boxes, iou_thr, image=0, num_classes=20):
+    """FCOS.py:130-150,197-264 for one image.  NMS visits num_classes-1 classes (:252)."""
+    conf, box = fcos_scores_boxes(heads, image, num_classes)
     idx = np.arange(conf.shape[0], dtype=np.int32)
     return _per_class_nms(conf, box, idx, num_classes - 1, score_thr, max_boxes, iou_thr)
+
+
+def rows_to_levels(rows, levels, kind):
+    """Inverse of *_rows: candidate rows [B,N,25] -> the per-level tensors the *_detect functions take
+    (`levels`: [(H,W,A)] in candidate order).  kind: 'yolo' -> preds [B,H,W,A*25]; 'fcos' -> (cls, ctr, reg)."""
+    b, off, out = rows.shape[0], 0, []
+    for h, w, a in levels:
+        r = rows[:, off:off + h * w * a]
+        if kind == "yolo":
+            out.append(r.reshape(b, h, w, a * 25))
+        else:
+            r = r.reshape(b, h, w, 25)
+            out.append((r[..., :20], r[..., 20:21], r[..., 21:25]))
+        off += h * w * a
+    assert off == rows.shape[1]
+    return out

@@ -4,8 +4,17 @@ import ctypes as C, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "object-detection-tensorflow_b200"))
 import numpy as np, torch
-from odt_b200 import lib as L
-lib = C.CDLL(L.LIB_PATH)
+import subprocess
+# the probe kernel is test-only code: built on demand next to the other native test harnesses, never linked into
+# the product library
+SRC = os.path.join(ROOT, "tests", "native", "tc_probe.cu")
+OUT = os.path.join(ROOT, "tests", "native", "_build", "libodt_probe.so")
+os.makedirs(os.path.dirname(OUT), exist_ok=True)
+if not os.path.exists(OUT) or os.path.getmtime(SRC) > os.path.getmtime(OUT):
+    subprocess.check_call(["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
+                           "-I", os.path.join(ROOT, "object-detection-tensorflow_b200", "csrc"), "-shared", "-o", OUT, SRC,
+                           os.path.join(ROOT, "object-detection-tensorflow_b200", "csrc", "api.cu")])
+lib = C.CDLL(OUT)
 rng = np.random.default_rng(0)
 X = rng.standard_normal((136, 64)).astype(np.float16)
 W = rng.standard_normal((64, 64)).astype(np.float16)

@@ -79,7 +79,7 @@ def main():
                                       t.cand_count.data_ptr(), t.dets.data_ptr(), t.det_anchor.data_ptr(),
                                       t.det_count.data_ptr(), t.scratch.data_ptr(), t.work.data_ptr(),
                                       t.status.data_ptr(), t.box_pool.data_ptr() if t.box_pool is not None else None,
-                                      t.pool_entries, st))
+                                      t.pool_entries, t.rec.shape[1], st))
     ev[2].record()
     torch.cuda.synchronize()
     # whole forward as ONE CUDA graph replay (what the bench / API actually runs)

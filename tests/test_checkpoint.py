@@ -139,6 +139,8 @@ def test_model_save_load_and_vgg_pretraining_names(ck, tmp_path):
     assert out.endswith("model-0") and ck.is_v2_checkpoint(out)
     r = ck.CheckpointReader(out)
     assert r.has_tensor("global_step") and r.has_tensor("feature_extractor/kenrel_conv2_1")
+    # the reference's variable is int32 (SSD300.py:43); Saver.restore checks the dtype
+    assert r.get_tensor("global_step").dtype == np.int32
     m2 = SSD300.SSD300(dict(cfg), None)
     m2.seed = 99                                      # different random init, then restore
     m2.load_weight(out)

@@ -11,6 +11,7 @@ import os
 import numpy as np
 import pytest
 
+import margins as MG
 from helpers import assert_boxes_close, model_cfg
 
 pytestmark = pytest.mark.gpu
@@ -63,11 +64,38 @@ def _tail_oracle_on_rows(kind, rows, cfg, image=0):
     raise NotImplementedError
 
 
+def _geom(kind, net, cfg):
+    """Geometry dict of tests/margins.py from a built network."""
+    shapes = [(h, w) for h, w, _ in net.levels]
+    if kind in ("ssd300", "ssd512"):
+        return {"size": int(kind[3:]), "shapes": shapes}
+    if kind == "retinanet":
+        return {"data_shape": cfg["data_shape"], "shapes": shapes}
+    if kind == "yolov3":
+        return {"levels": list(net.levels), "priors": cfg["priors"]}
+    return {"levels": list(net.levels)}
+
+
+MKIND = {"ssd300": "ssd", "ssd512": "ssd", "retinanet": "retina", "yolov3": "yolo", "fcos": "fcos"}
+
+
+def _dense_threshold(kind, rows_ref, geom, frac):
+    """Score threshold at which about `frac` * N candidates per class pass in the ORACLE (SURVEY 8d dense regime)."""
+    tot, vals = 0, []
+    for r in rows_ref:
+        S, _, V, _ = MG.per_row(MKIND[kind], r, geom)
+        vals.append(S[V].reshape(-1))
+        tot += S.shape[0]
+    v = np.concatenate(vals)
+    k = int(min(max(frac * tot * 20, 40), v.size - 1))
+    return float(np.partition(v, v.size - k)[v.size - k])
+
+
 SHAPES = {"ssd300": (300, 300), "retinanet": (128, 128), "yolov3": (64, 64), "fcos": (128, 128)}
 
 
 @pytest.mark.parametrize("kind", ["ssd300", "retinanet", "yolov3", "fcos"])
-@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("fp16", 3e-2)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("fp16", 5e-3)])
 def test_head_rows_vs_oracle(built, kind, precision, tol):
     m = _model(kind, bn_init="trained", precision=precision)
     h, w = SHAPES[kind]
@@ -100,24 +128,18 @@ def test_ssd300_reference_plumbing_config_fp32(built):
     np.testing.assert_array_equal(res[2], exp[2])
     np.testing.assert_array_equal(net.tail.det_anchor.cpu().numpy()[0, :len(exp[3])], exp[3])
     assert_boxes_close(res[1], exp[1])
-    # (b) end to end against the oracle's own forward: identical decisions wherever the
-    #     oracle's margins exceed the measured row error
+    # (b) end to end against the oracle's own forward: identical decisions wherever the oracle's margins
+    #     exceed the measured row error, admissible ones elsewhere (tests/margins.py)
     preds = ON.ssd_heads(m.get_weights(), img, 300)
-    full = OT.ssd_detect(preds, 300, 0.3, 20, 0.5)
-    same = len(full[2]) == len(res[2]) and np.array_equal(full[2], res[2]) and np.array_equal(
-        full[3], net.tail.det_anchor.cpu().numpy()[0, :len(full[3])])
     rows_ref = OT.ssd_rows(preds)
-    print("end-to-end fp32: identical decisions =", same, " rows max|err| =",
-          float(np.abs(rows - rows_ref).max()))
-    if same:
-        d = np.abs(res[1] - full[1])
-        print("end-to-end fp32: max box |err| = %.3g px" % float(d.max()) if len(d) else "no boxes")
-        # rows differ by ~1e-6 relative (accumulation order) and t_hw goes through exp()
-        assert_boxes_close(res[1], full[1], abs_tol=5e-3, rel_tol=3e-4, what="end-to-end fp32 boxes")
-    else:
-        frac = len(set(zip(full[2].tolist(), full[3].tolist())) &
-                   set(zip(res[2].tolist(), net.tail.det_anchor.cpu().numpy()[0, :len(res[2])].tolist())))
-        assert frac >= 0.9 * max(len(full[2]), 1), "more than 10% of decisions differ"
+    keep = net.tail.det_anchor.cpu().numpy()[0, :len(res[2])]
+    rep = MG.compare_image("ssd", rows[0], rows_ref[0], _geom("ssd300", net, m.config), res[2], keep, res[1],
+                           0.3, 20, 0.5)
+    print("end-to-end fp32: %d/20 classes clean, %d identical, ds %.3g di %.3g, reasons %s, box err %.3g px"
+          % (rep["clean"], rep["identical"], rep["ds"], rep["di"], rep["reasons"], rep["box_err"]))
+    assert rep["ds"] <= 1e-5 and rep["clean"] >= 15, rep
+    # rows differ by ~1e-6 relative (accumulation order) and t_hw goes through exp()
+    assert rep["box_err"] <= 5e-3 + 3e-4 * 300, rep
 
 
 def test_ssd300_fp16_batch_and_api(built):
@@ -125,6 +147,7 @@ def test_ssd300_fp16_batch_and_api(built):
     img = _img(4, 300, 300, seed=9)
     res = m.test_one_image(img)
     assert isinstance(res, list) and len(res) == 4
+    assert len(m.detect_batch(img)[1:3]) == 2  # the batched call returns a sequence over images
     one = m.test_one_image(img[2:3])
     # batch-invariance of the kernels: image 2 alone == image 2 inside the batch
     for a, b in zip(one, res[2]):
@@ -314,3 +337,53 @@ def test_halo_layout_does_not_change_results(built, monkeypatch):
     b = m2.engine(2).head_buf.cpu().numpy()
     assert not any(t.halo for t in m2.engine(2).acts)
     assert np.abs(a - b).max() <= 2e-3 * np.abs(b).max()
+
+
+# BASELINE.json configs at their OWN input sizes: the engine makes different choices here
+# (halo layouts, CTA pairs, row-block pooling, 12 lanes) than at the 64-128 px shapes above.
+FULL = {"ssd300": ({}, 300, 300, 2), "ssd512": ({}, 512, 512, 1),
+        "retinanet": ({"data_shape": [800, 800, 3]}, 800, 800, 1),
+        "yolov3": ({"data_shape": [416, 416, 3]}, 416, 416, 2),
+        "fcos": ({"data_shape": [1024, 1024, 3]}, 1024, 1024, 1)}
+
+
+@pytest.mark.parametrize("precision,row_tol,ds_tol", [("fp32", 2e-4, 2e-5), ("fp16", 5e-3, 2e-2)])
+@pytest.mark.parametrize("kind", ["ssd300", "ssd512", "retinanet", "yolov3", "fcos"])
+def test_full_size_end_to_end_decisions(built, kind, precision, row_tol, ds_tol):
+    """Whole network at the BASELINE input size, dense score threshold (about 1 % of N candidates per class, taken
+    from an oracle quantile), against the oracle's own forward: rows within tolerance, then margin-aware identity
+    of class ids and keep indices (tests/margins.py), boxes of the common keeps reported."""
+    over, h, w, B = FULL[kind]
+    img = _img(B, h, w, seed=11)
+    probe = _model(kind, bn_init="trained", precision=precision, **over)
+    ref = _oracle_rows(kind, probe.get_weights(), img, probe.config)
+    spec = probe._build_spec()
+    geom = _geom(kind, spec, probe.config)
+    thr = _dense_threshold(kind, ref, geom, 0.01)
+    m = _model(kind, bn_init="trained", precision=precision, nms_score_threshold=thr, **over)
+    res = m.detect_batch(img)
+    net = m.engine(B)
+    rows = net.head_buf.cpu().numpy()
+    assert rows.shape == ref.shape and np.isfinite(rows).all()
+    scale, err = float(np.abs(ref).max()), float(np.abs(rows - ref).max())
+    print("%s %s %dx%d: rows max|err| %.3g of max|ref| %.3g (%.2e rel), threshold %.4f"
+          % (kind, precision, h, w, err, scale, err / scale, thr))
+    assert err <= row_tol * scale, (kind, precision, err, scale)
+    keep_all = net.tail.det_anchor.cpu().numpy()
+    ncls = 19 if kind == "fcos" else 20
+    mb, iou = m.config["nms_max_boxes"], m.config["nms_iou_threshold"]
+    reps = []
+    for b in range(B):
+        k = len(res[b][2])
+        reps.append(MG.compare_image(MKIND[kind], rows[b], ref[b], geom, res[b][2], keep_all[b, :k], res[b][1],
+                                     thr, mb, iou, ncls))
+    tot = MG.summarize(reps)
+    cc = net.tail.cand_count.cpu().numpy()
+    print("%s %s: candidates/class mean %.0f max %d; classes clean %d ambiguous %d (reasons %s) identical %d of %d; "
+          "keeps oracle %d gpu %d common %d; ds %.3g di %.3g; common-keep box err %.3g px (%.2e rel)"
+          % (kind, precision, cc.mean(), cc.max(), tot["clean"], tot["ambiguous"], tot["reasons"], tot["identical"],
+             ncls * B, tot["kept_oracle"], tot["kept_gpu"], tot["same_keeps"], tot["ds"], tot["di"], tot["box_err"],
+             tot["box_err_rel"]))
+    assert cc.mean() >= 10, "dense regime expected (NMS must have work)"
+    assert tot["ds"] <= ds_tol, tot
+    assert tot["kept_gpu"] > 0 and tot["same_keeps"] >= 0.5 * tot["kept_oracle"], tot

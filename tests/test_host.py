@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(built):
         assert hasattr(so, name), "symbol %s declared in include/odt_b200.h is not exported" % name
     assert declared == set(lib.SYMBOLS), declared ^ set(lib.SYMBOLS)
     L = lib.load()
-    assert L.odt_abi_version() == 2
+    assert L.odt_abi_version() == 3
 
 
 def test_same_pad_abi_matches_host_and_oracle(built):
@@ -142,6 +142,25 @@ print('ok')
     r = subprocess.run([sys.executable, "-c", code], cwd=str(tmp_path), env=env, capture_output=True,
                        text=True, timeout=120)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr
+    # like NewCheckpointReader (SSD300.py:31), a missing ./vgg_16.ckpt is an error when the weights are needed,
+    # unless the random-init opt-in of BASELINE config 0 is given
+    code2 = code.replace("print('ok')", "m.get_weights(); print('ok')")
+    r = subprocess.run([sys.executable, "-c", code2], cwd=str(tmp_path), env=env, capture_output=True,
+                       text=True, timeout=120)
+    assert r.returncode != 0 and "FileNotFoundError" in r.stderr
+    r = subprocess.run([sys.executable, "-c", code2], cwd=str(tmp_path), env=dict(env, ODT_ALLOW_RANDOM_INIT="1"),
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr
+
+
+def test_other_class_counts_are_rejected():
+    """25-float candidate rows: only 20 foreground classes."""
+    import RetinaNet
+    import SSD300
+    with pytest.raises(ValueError):
+        SSD300.SSD300(model_cfg("ssd", num_classes=80), None)
+    with pytest.raises(ValueError):
+        RetinaNet.RetinaNet(model_cfg("retinanet", num_classes=10), None)
 
 
 def test_init_weights_deterministic_and_layouts():
@@ -225,17 +244,23 @@ def _gloo_worker(rank, world, port, q):
         cnt[i] = k
         dets[i, :k, 0] = g + 0.5
         dets[i, :k, 5] = g
-    rec = od.gather_records(od.pack_records(dets, cnt))
-    out = od.unpack_records(rec)
-
-    class _Net:                      # what finish_sharded reads after net.run()
-        class tail:
-            pass
-    _Net.tail.dets, _Net.tail.det_count = dets, cnt
-    again = od.finish_sharded(_Net)  # the per-step finish of detect_stream_sharded
-    assert len(again) == len(out)
-    for a, b in zip(again, out):
-        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    # the packed record the NMS kernel writes: [B, D*6 + 2] = D rows, then (count, overflow flag)
+    local = torch.zeros((hi - lo, D * 6 + 2))
+    local[:, :D * 6] = dets.reshape(hi - lo, -1)
+    local[:, D * 6] = cnt.to(torch.float32)
+    rec = od.gather_records(local)
+    from odt_b200.engine import unpack_records
+    out = unpack_records(rec.numpy())
+    assert len(out) == 8 and len(out[-1]) == 3 and len(out[0:2]) == 2
+    pre = torch.empty((world * (hi - lo), D * 6 + 2))
+    assert od.gather_records(local, out=pre) is pre and torch.equal(pre, rec)
+    flagged = rec.clone()
+    flagged[3, -1] = 1.0             # an image whose candidate list overflowed must not pass silently
+    try:
+        unpack_records(flagged.numpy())
+        raise AssertionError("overflow flag ignored")
+    except RuntimeError:
+        pass
     w = od.broadcast_weights({"a": np.full((3,), rank + 1.0, np.float32)})
     q.put((rank, [(len(s), float(s[0]) if len(s) else -1.0, int(c[0]) if len(c) else -1)
                   for s, _, c in out], float(w["a"][0])))
