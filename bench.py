@@ -423,7 +423,10 @@ def main():
     clocks = sampler.stop()
     ms_step = ms_total / K
     value = world * BATCH * K / (ms_total / 1e3)
+    sampler2 = ClockSampler(local)
+    sampler2.start()
     ms_e2e = time_e2e(model, images)
+    e2e_clocks = sampler2.stop()
     e2e_value = world * BATCH * K / (ms_e2e / 1e3)
     h2d, d2h = e2e_bytes(net, images)
 
@@ -452,7 +455,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": cfg_line,
             "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K, "clocks": e2e_clocks,
                     "mode": "detect_stream (read-back one step behind)" if world == 1 else
                             "detect_stream sharded, consumer rank 0 reads the all-gathered records"},
             "gpu_launches": net.num_launches() * K,

@@ -65,6 +65,12 @@ int odt_same_pad(int in, int k, int stride, int dil, int* out, int* pad_before, 
 int odt_normalize_input(const float* images, void* out, int out_dtype, int B, int H, int W,
                         int out_ld, const float* mean3_host, void* stream);
 
+/* images - mean as fp16 RGBX: out [B][H+2*pad][W+2*pad][4] (4th channel 0), interior only -- the zero border of
+ * `pad` pixels is the caller's (zero-fill the buffer once).  Input format of odt_conv2d_stem_rgbx.
+ * ref: the same `images - mean` lines as odt_normalize_input */
+int odt_pack_input_rgbx(const float* images, void* out_f16, int B, int H, int W, int pad,
+                        const float* mean3_host, void* stream);
+
 /* ---------------------------------------------------------------- conv --- */
 typedef struct {
   /* input  [B,H,W,in_ld] (Cin real channels, in_ld >= Cin channel stride)    */
@@ -137,12 +143,26 @@ int odt_conv2d_direct(const void* in, const void* weights, int dtype, const odt_
 int odt_conv2d_stem(const float* images, const float* mean3_host, const void* weights, int dtype,
                     const odt_conv_params* p, void* stream);
 
+/* tcgen05 stem on the packed image of odt_pack_input_rgbx (p->in_ld = 4, p->in_halo = its pad: 1 for the
+ * 3x3/stride-1 stems with 64 / 32 outputs, 4 for the 7x7/stride-2 stem with 16 outputs and even W / left pad);
+ * every filter row of an output pixel is one aligned span of the image, so the im2col rows are built with
+ * wide loads and no arithmetic.  ODT_ERR_UNSUPPORTED for other shapes (use odt_conv2d_stem).
+ * ref: conv1_1 SSD300.py:193-200; YOLOv3.py:388; RetinaNet.py:260-265; FCOS.py:73-78 */
+int odt_conv2d_stem_rgbx(const void* rgbx, const void* weights, const odt_conv_params* p, void* stream);
+
 /* --------------------------------------------------------------- glue ---- */
 /* max pooling, TF SAME (pads ignored).  in_halo / out_halo: the tensor is stored with a
  * zero 1-pixel border ([B][H+2][W+2][ld], see odt_conv_params).
  * ref: SSD300.py:539-547, RetinaNet.py:645-653 */
 int odt_maxpool(const void* in, void* out, int dtype, int B, int H, int W, int C, int ld, int k,
                 int stride, int in_halo, int out_halo, void* stream);
+/* max pooling plus up to two per-channel affine + activation outputs of the pooled value:
+ *   out (optional, may be NULL) = pool(in);  outK = actK(pool(in)*scaleK[c] + shiftK[c]), dense [B][OH][OW][ld].
+ * One pass for the pooled stem of the pre-activation ResNets feeding the two BN+ReLU of block1_unit1.
+ * ref: RetinaNet.py:645-653 (pool) + :594-597 (BN, ReLU of _bn_activation_conv); FCOS.py likewise */
+int odt_maxpool_affine(const void* in, void* out, int dtype, int B, int H, int W, int C, int ld, int k, int stride,
+                       int in_halo, int out_halo, const float* scale1, const float* shift1, int act1, void* out1,
+                       const float* scale2, const float* shift2, int act2, void* out2, void* stream);
 /* x * rsqrt(max(sum_c x^2, 1e-12)) * gamma.  ref: SSD300.py:74-83 */
 int odt_l2norm_scale(const void* in, void* out, int dtype, long long pixels, int C, int ld,
                      float gamma, void* stream);

@@ -37,17 +37,20 @@ bool flat_pair_enabled() {
   const char* e = getenv("ODT_TC_FLAT_PAIR");
   return pair_enabled() && !(e && e[0] == '0');
 }
+// Defaults settled by the same-box A/B of round 2 (profiles/r02_ab_micro.md): all three on.
 bool kskip_enabled() {
-  const char* e = getenv("ODT_TC_KSKIP");  // opt-in (default off): see TcGeom::klast
-  return e && e[0] == '1';
+  const char* e = getenv("ODT_TC_KSKIP");  // default on: all-zero K steps of thin layers are not issued (TcGeom::klast)
+  return !(e && e[0] == '0');
 }
 int thin_mode() {
-  const char* e = getenv("ODT_TC_THIN");  // opt-in (default 0 = off): conv_thin.cu
-  return (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
+  // conv_thin.cu: 0 = off, 1 = where its cost rule takes the layer (default), 2 = wherever the layer qualifies
+  const char* e = getenv("ODT_TC_THIN");
+  return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
 }
 int tapn_mode() {
-  const char* e = getenv("ODT_TC_TAPN");  // opt-in (default 0 = off): conv_tapn.cu
-  return (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
+  // conv_tapn.cu: 0 = off, 1 = where its cost model predicts a gain (default), 2 = wherever the layer qualifies
+  const char* e = getenv("ODT_TC_TAPN");
+  return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
 }
 bool wres_enabled() {
   const char* e = getenv("ODT_TC_WRES");

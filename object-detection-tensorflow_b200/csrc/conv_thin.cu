@@ -222,7 +222,10 @@ static int thin_plan(const void* in, const odt_conv_params* p, bool force, ThinG
   if (!io_ok) return ODT_ERR_UNSUPPORTED;
   const long long M = (long long)p->B * p->OH * p->OW;
   if (M >= (1ll << 31) * THIN_THREADS) return ODT_ERR_UNSUPPORTED;
-  if (!force && ks * ks * ci8r * 8 * co8r * 8 > 1200) return ODT_ERR_UNSUPPORTED;  // multiply-adds per pixel
+  // default planner (mode 1): only 1x1 layers with few multiply-adds per pixel.  Same-box A/B of round 2
+  // (profiles/r02_ab_micro.md): 1x1 16->7 0.035 -> 0.027 ms, 28->7 0.052 -> 0.037 ms at 200x200x16, but every 3x3
+  // layer is faster through the taps-as-N tensor-core kernel (7->7: 0.041 vs 0.055 ms; 14->14: 0.015 vs 0.045 ms)
+  if (!force && (ks != 1 || ci8r * 8 * co8r * 8 > 1200)) return ODT_ERR_UNSUPPORTED;
   ThinGeom g;
   memset(&g, 0, sizeof(g));
   g.B = p->B;

@@ -87,6 +87,62 @@ __global__ void normalize_kernel(const float* __restrict__ img, T* __restrict__ 
   }
 }
 
+// images - mean -> fp16 RGBX with a zero border of `pad` pixels (the border is never written: the caller zero-fills
+// the buffer once).  One thread = 4 pixels: 3 x LDG.128 in, 2 x STG.128 out.
+__global__ void pack_rgbx_kernel(const float* __restrict__ img, __half* __restrict__ out, int B, int H, int W,
+                                 int pad, float m0, float m1, float m2, int vec) {
+  pdl_launch_dependents();
+  const int PW = W + 2 * pad, PH = H + 2 * pad;
+  if (vec) {
+    const int wq = W >> 2;
+    const long long total = (long long)B * H * wq;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+      const int xq = (int)(i % wq);
+      const long long row = i / wq;  // b*H + y
+      const int y = (int)(row % H), b = (int)(row / H);
+      const float4* s = reinterpret_cast<const float4*>(img + (row * W + 4 * xq) * 3);
+      const float4 a = __ldcs(s), c = __ldcs(s + 1), d = __ldcs(s + 2);
+      uint4 o0, o1;
+      __half2* h0 = reinterpret_cast<__half2*>(&o0);
+      __half2* h1 = reinterpret_cast<__half2*>(&o1);
+      h0[0] = __floats2half2_rn(__fsub_rn(a.x, m0), __fsub_rn(a.y, m1));
+      h0[1] = __floats2half2_rn(__fsub_rn(a.z, m2), 0.f);
+      h0[2] = __floats2half2_rn(__fsub_rn(a.w, m0), __fsub_rn(c.x, m1));
+      h0[3] = __floats2half2_rn(__fsub_rn(c.y, m2), 0.f);
+      h1[0] = __floats2half2_rn(__fsub_rn(c.z, m0), __fsub_rn(c.w, m1));
+      h1[1] = __floats2half2_rn(__fsub_rn(d.x, m2), 0.f);
+      h1[2] = __floats2half2_rn(__fsub_rn(d.y, m0), __fsub_rn(d.z, m1));
+      h1[3] = __floats2half2_rn(__fsub_rn(d.w, m2), 0.f);
+      __half* dst = out + (((long long)b * PH + y + pad) * PW + 4 * xq + pad) * 4;
+      if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        reinterpret_cast<uint4*>(dst)[0] = o0;
+        reinterpret_cast<uint4*>(dst)[1] = o1;
+      } else {  // odd pad: 8-byte aligned rows
+        uint2* d2 = reinterpret_cast<uint2*>(dst);
+        d2[0] = make_uint2(o0.x, o0.y);
+        d2[1] = make_uint2(o0.z, o0.w);
+        d2[2] = make_uint2(o1.x, o1.y);
+        d2[3] = make_uint2(o1.z, o1.w);
+      }
+    }
+  } else {
+    const long long total = (long long)B * H * W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+      const int x = (int)(i % W);
+      const long long row = i / W;
+      const int y = (int)(row % H), b = (int)(row / H);
+      const float* s = img + i * 3;
+      uint2 o;
+      __half2* h = reinterpret_cast<__half2*>(&o);
+      h[0] = __floats2half2_rn(__fsub_rn(s[0], m0), __fsub_rn(s[1], m1));
+      h[1] = __floats2half2_rn(__fsub_rn(s[2], m2), 0.f);
+      *reinterpret_cast<uint2*>(out + (((long long)b * PH + y + pad) * PW + x + pad) * 4) = o;
+    }
+  }
+}
+
 // ---- max pool, TF SAME (a4) -------------------------------------------------
 template <typename T, int V>
 __global__ void maxpool_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int H, int W,
@@ -120,6 +176,58 @@ __global__ void maxpool_kernel(const T* __restrict__ in, T* __restrict__ out, in
       }
     }
     VecIO<T, V>::st(out + (((long long)b * PH + oy + oh) * PW + ox + oh) * ld + c, m);
+  }
+}
+
+// max pool + up to two per-channel affine+activation outputs of the pooled value (RetinaNet / FCOS: the pooled stem
+// feeds the two pre-activation BN+ReLU of block1_unit1, RetinaNet.py:594-597,634-643): one pass instead of three.
+// `out` (the raw pooled tensor) may be NULL; out1 / out2 are dense [B][OH][OW][ld].
+template <typename T, int V>
+__global__ void maxpool_affine_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int H, int W,
+                                      int OH, int OW, int C, int ld, int k, int stride, int pt, int pl,
+                                      int ih, int oh, const float* __restrict__ s1, const float* __restrict__ h1,
+                                      int act1, T* __restrict__ out1, const float* __restrict__ s2,
+                                      const float* __restrict__ h2, int act2, T* __restrict__ out2) {
+  pdl_launch_dependents();
+  const int IW = W + 2 * ih, IH = H + 2 * ih, PW = OW + 2 * oh, PH = OH + 2 * oh;
+  const int cv = C / V;
+  const long long total = (long long)B * OH * OW * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % cv) * V;
+    long long pix = i / cv;
+    int ox = (int)(pix % OW);
+    int oy = (int)((pix / OW) % OH);
+    int b = (int)(pix / ((long long)OW * OH));
+    float m[V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) m[q] = -INFINITY;
+    for (int r = 0; r < k; ++r) {
+      int iy = oy * stride - pt + r;
+      if (iy < 0 || iy >= H) continue;
+      for (int s = 0; s < k; ++s) {
+        int ix = ox * stride - pl + s;
+        if (ix < 0 || ix >= W) continue;
+        float v[V];
+        VecIO<T, V>::ld(in + (((long long)b * IH + iy + ih) * IW + ix + ih) * ld + c, v);
+#pragma unroll
+        for (int q = 0; q < V; ++q) m[q] = fmaxf(m[q], v[q]);
+      }
+    }
+    if (out) VecIO<T, V>::st(out + (((long long)b * PH + oy + oh) * PW + ox + oh) * ld + c, m);
+    // (the maximum of stored values is itself a stored value: no rounding between the pool and the affine)
+    if (out1) {
+      float v[V];
+#pragma unroll
+      for (int q = 0; q < V; ++q) v[q] = apply_act(fmaf(m[q], s1 ? __ldg(s1 + c + q) : 1.f, h1 ? __ldg(h1 + c + q) : 0.f), act1);
+      VecIO<T, V>::st(out1 + pix * ld + c, v);
+    }
+    if (out2) {
+      float v[V];
+#pragma unroll
+      for (int q = 0; q < V; ++q) v[q] = apply_act(fmaf(m[q], s2 ? __ldg(s2 + c + q) : 1.f, h2 ? __ldg(h2 + c + q) : 0.f), act2);
+      VecIO<T, V>::st(out2 + pix * ld + c, v);
+    }
   }
 }
 
@@ -457,6 +565,19 @@ extern "C" int odt_normalize_input(const float* images, void* out, int out_dtype
   return ODT_OK;
 }
 
+extern "C" int odt_pack_input_rgbx(const float* images, void* out_f16, int B, int H, int W, int pad,
+                                   const float* mean3_host, void* stream) {
+  ODT_CHECK_ARG(images && out_f16 && mean3_host && B > 0 && H > 0 && W > 0 && pad >= 0 && pad <= 8, "args");
+  ODT_CHECK_ARG(((uintptr_t)out_f16 & 15) == 0, "out must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int vec = ((W & 3) == 0 && ((uintptr_t)images & 15) == 0) ? 1 : 0;
+  const long long work = (long long)B * H * (vec ? W / 4 : W);
+  pack_rgbx_kernel<<<grid_for(work, 256), 256, 0, st>>>(images, (__half*)out_f16, B, H, W, pad, mean3_host[0],
+                                                        mean3_host[1], mean3_host[2], vec);
+  ODT_LAUNCH_OK();
+  return ODT_OK;
+}
+
 extern "C" int odt_maxpool(const void* in, void* out, int dtype, int B, int H, int W, int C,
                            int ld, int k, int stride, int in_halo, int out_halo, void* stream) {
   ODT_CHECK_ARG(in && out && B > 0 && H > 0 && W > 0 && C > 0 && ld >= C && k > 0 && stride > 0,
@@ -476,6 +597,38 @@ extern "C" int odt_maxpool(const void* in, void* out, int dtype, int B, int H, i
       long long work = (long long)B * OH * OW * C;
       maxpool_kernel<T, 1><<<grid_for(work, 256), 256, 0, st>>>((const T*)in, (T*)out, B, H, W, OH,
                                                                OW, C, ld, k, stride, pt, pl, in_halo, out_halo);
+    }
+  })
+  ODT_LAUNCH_OK();
+  return ODT_OK;
+}
+
+extern "C" int odt_maxpool_affine(const void* in, void* out, int dtype, int B, int H, int W, int C, int ld, int k,
+                                  int stride, int in_halo, int out_halo, const float* scale1, const float* shift1,
+                                  int act1, void* out1, const float* scale2, const float* shift2, int act2,
+                                  void* out2, void* stream) {
+  ODT_CHECK_ARG(in && (out || out1 || out2) && B > 0 && H > 0 && W > 0 && C > 0 && ld >= C && k > 0 && stride > 0,
+                "args");
+  ODT_CHECK_ARG((in_halo == 0 || in_halo == 1) && (out_halo == 0 || out_halo == 1), "halo must be 0/1");
+  ODT_CHECK_ARG(act1 >= 0 && act1 <= 2 && act2 >= 0 && act2 <= 2, "activation code");
+  int OH, OW, pt, pl, pa;
+  odt_same_pad(H, k, stride, 1, &OH, &pt, &pa);
+  odt_same_pad(W, k, stride, 1, &OW, &pl, &pa);
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_DTYPE(dtype, {
+    constexpr int V = FullVec<T>::V;
+    const bool vec = can_vec(in, out ? out : in, C, ld, V, sizeof(T)) && ((uintptr_t)out1 % 16) == 0 &&
+                     ((uintptr_t)out2 % 16) == 0;
+    if (vec) {
+      long long work = (long long)B * OH * OW * (C / V);
+      maxpool_affine_kernel<T, V><<<grid_for(work, 256), 256, 0, st>>>(
+          (const T*)in, (T*)out, B, H, W, OH, OW, C, ld, k, stride, pt, pl, in_halo, out_halo, scale1, shift1, act1,
+          (T*)out1, scale2, shift2, act2, (T*)out2);
+    } else {
+      long long work = (long long)B * OH * OW * C;
+      maxpool_affine_kernel<T, 1><<<grid_for(work, 256), 256, 0, st>>>(
+          (const T*)in, (T*)out, B, H, W, OH, OW, C, ld, k, stride, pt, pl, in_halo, out_halo, scale1, shift1, act1,
+          (T*)out1, scale2, shift2, act2, (T*)out2);
     }
   })
   ODT_LAUNCH_OK();

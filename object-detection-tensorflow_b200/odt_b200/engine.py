@@ -202,10 +202,32 @@ class ConvOp(Op):
             p.out2_pix_stride = t.ld
         self.p = p
         self.flops = 2 * B * OH * OW * cout * R * S * cin
+        # stems: the tcgen05 variants read a packed fp16 RGBX copy of the image (mean subtracted, zero border of
+        # `rgbx` pixels) so that every filter row is one aligned span -- see csrc/conv_stem_tc.cu
+        self.rgbx = 0
+        if (self.is_image and f16 and net.allow_tc and self.pre is None and self.head is None
+                and os.environ.get("ODT_STEM_RGBX", "1") != "0"):
+            if (R, self.stride, cout) in ((3, 1, 64), (3, 1, 32)):
+                self.rgbx = 1
+            elif (R, self.stride, cout) == (7, 2, 16) and Wd % 2 == 0 and pl % 2 == 0 and pl <= 4 and pt <= 4:
+                self.rgbx = 4
+        if self.rgbx:
+            P = self.rgbx
+            net.image_rgbx = torch.zeros((B, H + 2 * P, Wd + 2 * P, 4), dtype=torch.float16, device=dev)
 
     def launch(self, net, stream):
         lib = net.lib
-        if self.is_image:
+        if self.is_image and self.rgbx:
+            P = self.rgbx
+            L.check(lib.odt_pack_input_rgbx(net.image_buf.data_ptr(), net.image_rgbx.data_ptr(), net.batch,
+                                            net.in_h, net.in_w, P, net.mean3, stream), "pack_input_rgbx")
+            self.p.in_ld, self.p.in_halo = 4, P
+            rc = lib.odt_conv2d_stem_rgbx(net.image_rgbx.data_ptr(), self.wdev.data_ptr(), C.byref(self.p), stream)
+            if rc == L.ERR_UNSUPPORTED:  # shape outside the packed variants: the fp32-gather stem from now on
+                self.rgbx = 0
+                self.p.in_ld, self.p.in_halo = 3, 0
+                return self.launch(net, stream)
+        elif self.is_image:
             rc = lib.odt_conv2d_stem(net.image_buf.data_ptr(), net.mean3, self.wdev.data_ptr(),
                                      L.ODT_F16 if net.precision == "fp16" else L.ODT_F32,
                                      C.byref(self.p), stream)
@@ -221,7 +243,24 @@ class ConvOp(Op):
 class PoolOp(Op):
     def __init__(self, x, y, k, stride):
         self.x, self.y, self.k, self.stride = x, y, k, stride
+        self.pre = None    # fused consumer pre-activations (bn_scope, act, Act): RetinaNet / FCOS pooled stem
+        self.pre2 = None
         self.reads, self.writes = (x,), (y,)
+
+    def prepare(self, net):
+        self.aff = []
+        for pr in (self.pre, self.pre2):
+            if pr is None:
+                self.aff.append(None)
+                continue
+            scope, act, t = pr
+            sp = np.ones(self.x.ld, np.float32)
+            hp = np.zeros(self.x.ld, np.float32)
+            if scope is not None:
+                sc, sh = net.bn_fold(scope)
+                sp[:], hp[:] = 0.0, 0.0
+                sp[:self.x.C], hp[:self.x.C] = sc, sh
+            self.aff.append((torch.from_numpy(sp).to(net.device), torch.from_numpy(hp).to(net.device), ACT[act], t))
 
     def launch(self, net, stream):
         x = self.x
@@ -229,8 +268,18 @@ class PoolOp(Op):
         # buffer (Net.allocate), so the padding lanes of y that are never written stay zero, and the ones inside
         # the last sector are maxima of zeros.  (RetinaNet's 16-channel stem output is stored 64 wide.)
         c = min(x.ld, _round_up(x.C, 8))
-        L.check(net.lib.odt_maxpool(x.ptr(), self.y.ptr(), net.dt, x.B, x.H, x.W, c, x.ld,
-                                    self.k, self.stride, x.halo, self.y.halo, stream), "maxpool")
+        if self.pre is None and self.pre2 is None:
+            L.check(net.lib.odt_maxpool(x.ptr(), self.y.ptr(), net.dt, x.B, x.H, x.W, c, x.ld,
+                                        self.k, self.stride, x.halo, self.y.halo, stream), "maxpool")
+            return
+        a1, a2 = self.aff
+        L.check(net.lib.odt_maxpool_affine(
+            x.ptr(), self.y.ptr() if self.y.needed else None, net.dt, x.B, x.H, x.W, c, x.ld, self.k, self.stride,
+            x.halo, self.y.halo,
+            a1[0].data_ptr() if a1 else None, a1[1].data_ptr() if a1 else None, a1[2] if a1 else 0,
+            a1[3].ptr() if a1 else None,
+            a2[0].data_ptr() if a2 else None, a2[1].data_ptr() if a2 else None, a2[2] if a2 else 0,
+            a2[3].ptr() if a2 else None, stream), "maxpool_affine")
 
 
 class L2NormOp(Op):
@@ -492,13 +541,14 @@ class Net:
         for op in self.ops:
             if isinstance(op, AffineActOp):
                 q = producer.get(id(op.x))
-                ok = isinstance(q, (ConvOp, UpsampleAddOp)) and q.pre is None
+                ok = isinstance(q, (ConvOp, UpsampleAddOp, PoolOp)) and q.pre is None
                 if ok and isinstance(q, ConvOp):
                     ok = q.head is None
-                # second pre-activation of the same tensor: tensor-core convs only (third epilogue output)
+                # second pre-activation of the same tensor: tensor-core convs (third epilogue output) and pools
                 second = (not ok and isinstance(q, ConvOp) and q.head is None and q.pre is not None
                           and q.pre2 is None and not q.is_image and self.precision == "fp16" and self.allow_tc
                           and q.x.ld % 64 == 0 and os.environ.get("ODT_FUSE_PRE2", "1") != "0")
+                second = second or (not ok and isinstance(q, PoolOp) and q.pre is not None and q.pre2 is None)
                 if ok or second:
                     if ok:
                         q.pre = (op.bn, op.act, op.y)
@@ -506,7 +556,7 @@ class Net:
                         q.pre2 = (op.bn, op.act, op.y)
                     producer[id(op.y)] = q
                     consumers[id(op.x)].remove(op)
-                    if not consumers[id(op.x)] and isinstance(q, ConvOp):
+                    if not consumers[id(op.x)] and isinstance(q, (ConvOp, PoolOp)):
                         op.x.needed = False
                     continue
             kept.append(op)
@@ -722,7 +772,10 @@ class Net:
     def num_launches(self):
         n = 0
         for op in self.ops:
-            n += (2 if op.two_launch else 3) if isinstance(op, GroupNormActOp) else 1
+            if isinstance(op, GroupNormActOp):
+                n += 2 if op.two_launch else 3
+            else:
+                n += 2 if getattr(op, "rgbx", 0) else 1  # packed-image stems: pack + convolution
         return n + self.tail.num_launches()
 
 

@@ -69,7 +69,10 @@ SYMBOLS = {
     "odt_conv2d_f16_tc": (_I, [_P, _P, C.POINTER(ConvParams), _P]),
     "odt_conv2d_direct": (_I, [_P, _P, _I, C.POINTER(ConvParams), _P]),
     "odt_conv2d_stem": (_I, [_P, C.POINTER(_F), _P, _I, C.POINTER(ConvParams), _P]),
+    "odt_pack_input_rgbx": (_I, [_P, _P, _I, _I, _I, _I, C.POINTER(_F), _P]),
+    "odt_conv2d_stem_rgbx": (_I, [_P, _P, C.POINTER(ConvParams), _P]),
     "odt_maxpool": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "odt_maxpool_affine": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _I, _P, _P]),
     "odt_l2norm_scale": (_I, [_P, _P, _I, _L, _I, _I, _F, _P]),
     "odt_affine_act": (_I, [_P, _P, _I, _L, _I, _I, _P, _P, _I, _P]),
     "odt_upsample_bilinear_add": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P]),

@@ -41,6 +41,26 @@ def main():
     p.out0, p.out0_dtype = y.data_ptr(), L.ODT_F16
     p.out0_img_stride, p.out0_pix_stride = (yh + 2 * oh) * (yw + 2 * oh) * old, old
     p.in_halo, p.out0_halo, p.out0_pool = ih, oh, pool
+    # ODT_MICRO_EXTRA = "r" (residual) / "1" (second output) / "2" (third output) / "n" (no out0), any combination:
+    # the epilogue variants of RetinaNet's bottleneck 1x1 convolutions
+    extra = os.environ.get("ODT_MICRO_EXTRA", "")
+    keep = []
+    if "r" in extra:
+        keep.append(torch.randn(y.shape, device="cuda").half())
+        p.residual = keep[-1].data_ptr()
+    for tag, pre in (("1", "1"), ("2", "2")):
+        if tag in extra:
+            t = torch.zeros((B, OH, OW, old), dtype=torch.float16, device="cuda")
+            sc, sh = torch.ones(Cout, device="cuda"), torch.zeros(Cout, device="cuda")
+            keep += [t, sc, sh]
+            if pre == "1":
+                p.scale2, p.shift2, p.act2 = sc.data_ptr(), sh.data_ptr(), 1
+                p.out1, p.out1_img_stride, p.out1_pix_stride = t.data_ptr(), OH * OW * old, old
+            else:
+                p.scale3, p.shift3, p.act3 = sc.data_ptr(), sh.data_ptr(), 1
+                p.out2, p.out2_img_stride, p.out2_pix_stride = t.data_ptr(), OH * OW * old, old
+    if "n" in extra:
+        p.out0 = None
     st = torch.cuda.current_stream().cuda_stream
     for _ in range(3):
         L.check(lib.odt_conv2d_f16_tc(x.data_ptr(), w.data_ptr(), C.byref(p), st), "conv")
@@ -53,8 +73,8 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     fl = 2.0 * B * OH * OW * Cout * k * k * Cin
-    print("conv %s pool=%d halo=%d/%d WRES=%s FLAT=%s: %.4f ms  %.1f TFLOP/s" % (
-        a[:7], pool, ih, oh, os.environ.get("ODT_TC_WRES", "1"), os.environ.get("ODT_TC_FLAT", "1"), ms, fl / ms / 1e9))
+    print("conv %s pool=%d halo=%d/%d extra=%r thin/tapn launches %d/%d: %.4f ms  %.1f TFLOP/s" % (
+        a[:7], pool, ih, oh, extra, lib.odt_debug_thin_launches(), lib.odt_debug_tapn_launches(), ms, fl / ms / 1e9))
 
 
 if __name__ == "__main__":

@@ -215,6 +215,30 @@ def test_glue_kernels_vs_oracle_ops(built, dtype):
         xd = _dev(x, dt)
         L.check(lib.odt_maxpool(xd.data_ptr(), y.data_ptr(), code, 2, h, h, 64, 64, k, s, 0, 0, st))
         np.testing.assert_allclose(y.float().cpu().numpy(), ref, atol=0)
+    # max-pool 3/2 + two affine/activation outputs of the pooled value, raw output optional (RetinaNet pooled stem)
+    x = rnd(2, 20, 22, 16)
+    ref = T.max_pool_same(x, 3, 2)
+    s1, h1 = rng.uniform(.5, 1.5, 64).astype(np.float32), rng.standard_normal(64).astype(np.float32)
+    s2, h2 = rng.uniform(.5, 1.5, 64).astype(np.float32), rng.standard_normal(64).astype(np.float32)
+    xd = torch.zeros((2, 20, 22, 64), dtype=dt, device="cuda")
+    xd[..., :16] = _dev(x, dt)
+    for with_raw in (True, False):
+        y = torch.zeros((2, 10, 11, 64), dtype=dt, device="cuda")
+        y1, y2 = torch.zeros_like(y), torch.zeros_like(y)
+        L.check(lib.odt_maxpool_affine(xd.data_ptr(), y.data_ptr() if with_raw else None, code, 2, 20, 22, 16, 64, 3, 2,
+                                       0, 0, _dev(s1, torch.float32).data_ptr(), _dev(h1, torch.float32).data_ptr(), 1,
+                                       y1.data_ptr(), _dev(s2, torch.float32).data_ptr(),
+                                       _dev(h2, torch.float32).data_ptr(), 2, y2.data_ptr(), st))
+        torch.cuda.synchronize()
+        if with_raw:
+            np.testing.assert_array_equal(y[..., :16].float().cpu().numpy(), ref)
+        else:
+            assert float(y.abs().max()) == 0.0
+        t2 = ref * s2[:16] + h2[:16]
+        np.testing.assert_allclose(y1[..., :16].float().cpu().numpy(), np.maximum(ref * s1[:16] + h1[:16], 0),
+                                   atol=tol * 8, rtol=tol)
+        np.testing.assert_allclose(y2[..., :16].float().cpu().numpy(), np.maximum(t2, 0.1 * t2), atol=tol * 8, rtol=tol)
+        assert float(y1[..., 16:].abs().max()) == 0.0
     # channel L2 norm x scale
     x = rnd(2, 9, 9, 512)
     ref = 20.0 * T.l2_normalize_channels(x)
@@ -257,6 +281,16 @@ def test_glue_kernels_vs_oracle_ops(built, dtype):
     L.check(lib.odt_groupnorm_apply(xd.data_ptr(), y.data_ptr(), stats.data_ptr(), code, 2, 11 * 13, 64, 64, 8,
                                     gd.data_ptr(), btd.data_ptr(), 1, st))
     np.testing.assert_allclose(y.float().cpu().numpy(), ref, atol=tol * 8, rtol=tol)
+    # a1: images - RGB mean into a padded NHWC tensor (SSD300.py:52-66); channels >= 3 are written as zero
+    img = rng.integers(0, 256, (2, 9, 11, 3)).astype(np.float32)
+    mean = (C.c_float * 3)(123.68, 116.779, 103.979)
+    y = torch.full((2, 9, 11, 8), 7.0, dtype=dt, device="cuda")
+    L.check(lib.odt_normalize_input(_dev(img, torch.float32).data_ptr(), y.data_ptr(), code, 2, 9, 11, 8, mean, st))
+    got = y.float().cpu().numpy()
+    ref = img - np.array([123.68, 116.779, 103.979], np.float32)
+    np.testing.assert_allclose(got[..., :3], ref.astype(np.float16).astype(np.float32) if dtype == "f16" else ref,
+                               atol=0)
+    assert np.all(got[..., 3:] == 0)
     torch.cuda.synchronize()
 
 
@@ -268,10 +302,11 @@ def test_glue_kernels_vs_oracle_ops(built, dtype):
     (1, 33, 47, 16, 7, 2),
     (1, 20, 20, 24, 5, 1),     # no specialised variant -> generic CUDA-core stem
 ])
-@pytest.mark.parametrize("dtype", ["f16", "f32"])
+@pytest.mark.parametrize("dtype", ["f16", "f32", "rgbx"])
 def test_stem_conv_vs_oracle(built, shape, dtype):
     """odt_conv2d_stem: fp32 image - RGB mean -> conv -> bias/BN -> ReLU.  fp16 takes the
-    tcgen05 stem (A tile built in swizzled smem), fp32 the CUDA-core stem."""
+    tcgen05 stem (A tile built in swizzled smem), fp32 the CUDA-core stem; 'rgbx' = odt_pack_input_rgbx +
+    odt_conv2d_stem_rgbx (the tcgen05 stem on the packed fp16 image, the engine's default)."""
     from odt_b200 import lib as L
     from odt_b200.engine import same_pad
     from oracle import tfops as T
@@ -280,7 +315,8 @@ def test_stem_conv_vs_oracle(built, shape, dtype):
     rng = np.random.default_rng(7)
     img = rng.integers(0, 256, (B, H, W, 3)).astype(np.float32)
     w = (rng.standard_normal((k, k, 3, Cout)) * np.sqrt(2.0 / (k * k * 3)) / 64).astype(np.float32)
-    f16 = dtype == "f16"
+    rgbx = dtype == "rgbx"
+    f16 = dtype in ("f16", "rgbx")
     if f16:
         w = w.astype(np.float16).astype(np.float32)
     scale = rng.uniform(0.5, 1.5, Cout).astype(np.float32)
@@ -289,6 +325,9 @@ def test_stem_conv_vs_oracle(built, shape, dtype):
     ld = (Cout + 63) // 64 * 64 if f16 else Cout
     OH, pt, _ = same_pad(H, k, stride)
     OW, pl, _ = same_pad(W, k, stride)
+    P = {(3, 1): 1, (7, 2): 4}.get((k, stride), 0)
+    if rgbx and (P == 0 or Cout not in (16, 32, 64) or (k == 7 and (W % 2 or pl % 2))):
+        pytest.skip("no packed-image variant for this shape (the engine falls back to odt_conv2d_stem)")
     imgd = torch.from_numpy(img).cuda()
     wd = torch.from_numpy(np.ascontiguousarray(np.transpose(w, (3, 0, 1, 2)))).cuda().to(tdt)
     sd, hd = torch.from_numpy(scale).cuda(), torch.from_numpy(shift).cuda()
@@ -304,8 +343,19 @@ def test_stem_conv_vs_oracle(built, shape, dtype):
     p.out0_img_stride, p.out0_pix_stride = (OH + 2 * oh) * (OW + 2 * oh) * ld, ld
     p.out0_halo = oh
     mean = (C.c_float * 3)(123.68, 116.779, 103.979)
-    L.check(lib.odt_conv2d_stem(imgd.data_ptr(), mean, wd.data_ptr(), L.ODT_F16 if f16 else L.ODT_F32,
-                                C.byref(p), torch.cuda.current_stream().cuda_stream), "stem")
+    st = torch.cuda.current_stream().cuda_stream
+    if rgbx:
+        packed = torch.zeros((B, H + 2 * P, W + 2 * P, 4), dtype=torch.float16, device="cuda")
+        L.check(lib.odt_pack_input_rgbx(imgd.data_ptr(), packed.data_ptr(), B, H, W, P, mean, st), "pack")
+        pk = packed.float().cpu().numpy()
+        exp = (img - np.array([123.68, 116.779, 103.979], np.float32)).astype(np.float16).astype(np.float32)
+        np.testing.assert_array_equal(pk[:, P:P + H, P:P + W, :3], exp)
+        assert np.all(pk[..., 3] == 0) and np.all(pk[:, :P] == 0) and np.all(pk[:, :, W + P:] == 0)
+        p.in_ld, p.in_halo = 4, P
+        L.check(lib.odt_conv2d_stem_rgbx(packed.data_ptr(), wd.data_ptr(), C.byref(p), st), "stem_rgbx")
+    else:
+        L.check(lib.odt_conv2d_stem(imgd.data_ptr(), mean, wd.data_ptr(), L.ODT_F16 if f16 else L.ODT_F32,
+                                    C.byref(p), st), "stem")
     torch.cuda.synchronize()
     x = img - T.RGB_MEAN.reshape(1, 1, 1, 3)
     xr = x.astype(np.float16).astype(np.float32) if f16 else x  # the fp16 stem rounds the operand
@@ -331,7 +381,9 @@ FLAT_SHAPES = [
 
 @pytest.mark.parametrize("shape", FLAT_SHAPES)
 @pytest.mark.parametrize("out_halo", [0, 1])
-def test_conv_tc_flat_halo_vs_fp32_reference(built, shape, out_halo):
+@pytest.mark.parametrize("tapn", ["0", "1"])   # 0: conv_tc's own flat modes; 1: the default planner (taps-as-N where it pays)
+def test_conv_tc_flat_halo_vs_fp32_reference(built, monkeypatch, shape, out_halo, tapn):
+    monkeypatch.setenv("ODT_TC_TAPN", tapn)
     got, ref, _, _ = _conv_case(*shape, mode="tc", in_halo=1, out_halo=out_halo, seed=sum(shape))
     assert np.abs(got - ref).max() <= 2e-3 * max(np.abs(ref).max(), 1.0), (shape, out_halo)
 
@@ -348,10 +400,12 @@ POOL_SHAPES = [
 
 @pytest.mark.parametrize("shape", POOL_SHAPES)
 @pytest.mark.parametrize("out_halo", [0, 1])
-def test_conv_tc_fused_maxpool(built, shape, out_halo):
+@pytest.mark.parametrize("tapn", ["0", "1"])
+def test_conv_tc_fused_maxpool(built, monkeypatch, shape, out_halo, tapn):
     """Pooled epilogue against max_pool(fp32 conv reference), and bit-exact against the
     same conv followed by the stand-alone pooling kernel (max commutes with fp16 rounding)."""
     from odt_b200 import lib as L
+    monkeypatch.setenv("ODT_TC_TAPN", tapn)
     got, ref, _, _ = _conv_case(*shape, mode="tc", in_halo=1, out_halo=out_halo, pool=2, seed=sum(shape))
     assert np.abs(got - ref).max() <= 2e-3 * max(np.abs(ref).max(), 1.0), (shape, out_halo)
     full, _, _, _ = _conv_case(*shape, mode="tc", in_halo=1, out_halo=0, seed=sum(shape))
@@ -508,14 +562,8 @@ def test_maxpool_halo_layouts(built):
             assert float(yd[:, 0].abs().max()) == 0 and float(yd[:, :, -1].abs().max()) == 0
 
 
-# Opt-in: the "taps as N" kernel (csrc/conv_tapn.cu, ODT_TC_TAPN=1) was written at the very end of round 1 (these
-# eight cases passed on a B200 once, untimed); its tests run only with ODT_TEST_EXPERIMENTAL=1 until it is the
-# default path.
-_experimental = pytest.mark.skipif(os.environ.get("ODT_TEST_EXPERIMENTAL") != "1",
-                                   reason="experimental kernel: set ODT_TEST_EXPERIMENTAL=1")
-
-
-@_experimental
+# The "taps as N" kernel (csrc/conv_tapn.cu) and the thin-layer kernel (csrc/conv_thin.cu) are default paths since
+# the round-2 A/B (mode 1 = where their cost rules take a layer); the tests force mode 2 (wherever a layer qualifies).
 @pytest.mark.parametrize("shape,kw", [
     ((2, 40, 40, 64, 64, 3, 1, 1), {"in_halo": 1, "out_halo": 1}),
     ((2, 37, 61, 64, 64, 3, 1, 1), {"in_halo": 1}),                              # ragged rows / columns
@@ -569,7 +617,6 @@ def _tc_raw(x, w, pool=0, in_halo=1, out_halo=1):
     return y[:, oh:oh + yh, oh:oh + yw, :Cout]
 
 
-@_experimental
 @pytest.mark.parametrize("tapn", ["0", "2"])
 def test_conv1_2_full_size_properties(built, monkeypatch, tapn):
     """SSD300's conv1_2 + fused pool at the BASELINE batch (64 x 300 x 300 x 64 -> 64): properties that need no
@@ -593,7 +640,6 @@ def test_conv1_2_full_size_properties(built, monkeypatch, tapn):
     assert torch.equal(full.reshape(2, 150, 2, 150, 2, 64).amax(dim=(2, 4)), y[:2])
 
 
-@_experimental
 @pytest.mark.parametrize("shape,kw", [
     ((2, 40, 40, 7, 7, 3, 1, 1), {"in_halo": 1, "out_halo": 1}),                       # RetinaNet stage 1, 3x3
     ((2, 37, 41, 7, 7, 3, 1, 1), {}),                                                   # no halo: border checks
