@@ -126,6 +126,11 @@ typedef struct {
    * Cout_pad <= 128) with even OH and OW, fp16 out0, no residual / out1 /
    * regrouping.  0 = off.                                                      */
   int out0_pool;
+  /* halo layout of the extra outputs (tensor-core path): 1 = out1 / out2 is stored as [B][OH+2][OW+2][pix_stride]
+   * with a zero border (outK_img_stride = (OH+2)*(OW+2)*outK_pix_stride), so that the 3x3 convolution that consumes a
+   * pre-activated tensor can run in the halo-flat / taps-as-N modes like any other 3x3 layer.                      */
+  int out1_halo;
+  int out2_halo;
 } odt_conv_params;
 
 /* tcgen05 / TMA implicit-GEMM forward convolution, fp16 in, fp32 accumulate.
@@ -157,12 +162,14 @@ int odt_conv2d_stem_rgbx(const void* rgbx, const void* weights, const odt_conv_p
 int odt_maxpool(const void* in, void* out, int dtype, int B, int H, int W, int C, int ld, int k,
                 int stride, int in_halo, int out_halo, void* stream);
 /* max pooling plus up to two per-channel affine + activation outputs of the pooled value:
- *   out (optional, may be NULL) = pool(in);  outK = actK(pool(in)*scaleK[c] + shiftK[c]), dense [B][OH][OW][ld].
+ *   out (optional, may be NULL) = pool(in);  outK = actK(pool(in)*scaleK[c] + shiftK[c]), [B][OH][OW][ld] or, with outK_halo = 1,
+ * [B][OH+2][OW+2][ld] with a zero border the kernel never writes.
  * One pass for the pooled stem of the pre-activation ResNets feeding the two BN+ReLU of block1_unit1.
  * ref: RetinaNet.py:645-653 (pool) + :594-597 (BN, ReLU of _bn_activation_conv); FCOS.py likewise */
 int odt_maxpool_affine(const void* in, void* out, int dtype, int B, int H, int W, int C, int ld, int k, int stride,
                        int in_halo, int out_halo, const float* scale1, const float* shift1, int act1, void* out1,
-                       const float* scale2, const float* shift2, int act2, void* out2, void* stream);
+                       int out1_halo, const float* scale2, const float* shift2, int act2, void* out2, int out2_halo,
+                       void* stream);
 /* x * rsqrt(max(sum_c x^2, 1e-12)) * gamma.  ref: SSD300.py:74-83 */
 int odt_l2norm_scale(const void* in, void* out, int dtype, long long pixels, int C, int ld,
                      float gamma, void* stream);
@@ -291,6 +298,24 @@ long long odt_yolo_loss_scratch_bytes(const odt_tail_params* p, int B);
 int odt_yolo_loss_fwd(const float* head, const odt_tail_params* p, int B, const float* gt, int G,
                       float coord_scale, float noobj_scale, float obj_scale, float class_scale,
                       void* scratch, float* loss_out, void* stream);
+
+/* ------------------------------------------------------- multi-GPU ------- */
+/* One process per GPU; images shard batch-parallel, weights are replicated, and the only data-path collective is
+ * ONE all-gather of the packed detection records (the `dets` buffer of odt_nms_per_class with the record stride).
+ * The context holds the NCCL communicator -- the library's only piece of cross-call state.  NCCL is loaded at run
+ * time (libnccl.so.2, or ODT_NCCL_LIB); without it these calls return ODT_ERR_UNSUPPORTED.  The reference is
+ * single-device (SSD300.py:458-462): no counterpart there.
+ *   odt_ctx_unique_id : rank 0 fills a 128-byte id; the host ships it to the other ranks out of band
+ *   odt_ctx_create    : collective over all ranks, binds the communicator to the CURRENT CUDA device
+ *   odt_allgather_dets: rec_all[r*floats_per_rank ...] = rank r's rec_local, on `stream`
+ *   odt_bcast_weights : in-place broadcast of `bytes` bytes from `root` (weight replication at start-up)          */
+typedef struct odt_ctx odt_ctx;
+int odt_ctx_unique_id(void* id128_host);
+int odt_ctx_create(odt_ctx** ctx, int rank, int world, const void* id128_host);
+int odt_ctx_destroy(odt_ctx* ctx);
+int odt_allgather_dets(odt_ctx* ctx, const float* rec_local, float* rec_all, long long floats_per_rank,
+                       void* stream);
+int odt_bcast_weights(odt_ctx* ctx, void* buf, long long bytes, int root, void* stream);
 
 #ifdef __cplusplus
 }

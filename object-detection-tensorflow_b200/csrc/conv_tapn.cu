@@ -218,8 +218,8 @@ __global__ void __launch_bounds__(TN_THREADS, 1)
         const int pix = row_ok ? y * g.W + x : 0;
         o0_row += g.out_halo ? (long long)((y + 1) * (g.W + 2) + x + 1) * e.out0_pix_stride
                              : (long long)pix * e.out0_pix_stride;
-        o1_row = (long long)img * e.out1_img_stride + (long long)pix * e.out1_pix_stride;
-        o2_row = (long long)img * e.out2_img_stride + (long long)pix * e.out2_pix_stride;
+        o1_row = aux_row(e.out1_img_stride, e.out1_pix_stride, e.out1_halo, g.W, img, pix);
+        o2_row = aux_row(e.out2_img_stride, e.out2_pix_stride, e.out2_halo, g.W, img, pix);
       }
       mbar_wait(tfull_bar(group), use & 1u);
       tc_fence_after();

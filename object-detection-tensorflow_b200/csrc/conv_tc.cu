@@ -477,10 +477,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       } else {
         o0_row += (long long)pix * e.out0_pix_stride;
       }
-      const long long o1_row =
-          (long long)img * e.out1_img_stride + (long long)pix * e.out1_pix_stride;
-      const long long o2_row =
-          (long long)img * e.out2_img_stride + (long long)pix * e.out2_pix_stride;
+      const long long o1_row = aux_row(e.out1_img_stride, e.out1_pix_stride, e.out1_halo, g.OW, img, pix);
+      const long long o2_row = aux_row(e.out2_img_stride, e.out2_pix_stride, e.out2_halo, g.OW, img, pix);
       if (g.bulk_store) {
         // this warp's previous bulk store must have drained its staging rows
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -774,6 +772,8 @@ int check_conv_params(const odt_conv_params* p) {
   ODT_CHECK_ARG(p->act >= 0 && p->act <= 2 && p->act2 >= 0 && p->act2 <= 2 && p->act3 >= 0 && p->act3 <= 2,
                 "activation code");
   ODT_CHECK_ARG(p->out0_dtype == ODT_F16 || p->out0_dtype == ODT_F32, "out0 dtype");
+  ODT_CHECK_ARG((p->out1_halo == 0 || p->out1_halo == 1) && (p->out2_halo == 0 || p->out2_halo == 1),
+                "out1_halo / out2_halo must be 0 or 1");
   return ODT_OK;
 }
 

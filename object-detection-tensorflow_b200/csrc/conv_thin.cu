@@ -124,8 +124,8 @@ __host__ __device__ __forceinline__ void thin_pixel(long long m, const float* ws
   const int oh = g.out_halo;
   const long long o0_row = (long long)b * e.out0_img_stride +
                            (oh ? (long long)((oy + 1) * (g.OW + 2) + ox + 1) : (long long)pix) * e.out0_pix_stride;
-  const long long o1_row = (long long)b * e.out1_img_stride + (long long)pix * e.out1_pix_stride;
-  const long long o2_row = (long long)b * e.out2_img_stride + (long long)pix * e.out2_pix_stride;
+  const long long o1_row = aux_row(e.out1_img_stride, e.out1_pix_stride, e.out1_halo, g.OW, b, pix);
+  const long long o2_row = aux_row(e.out2_img_stride, e.out2_pix_stride, e.out2_halo, g.OW, b, pix);
   const float* sc1 = par, *sh1 = par + CO, *sc2 = par + 2 * CO, *sh2 = par + 3 * CO, *sc3 = par + 4 * CO,
              *sh3 = par + 5 * CO;
 #pragma unroll

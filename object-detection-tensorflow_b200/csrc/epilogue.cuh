@@ -32,6 +32,7 @@ struct Epi {
   long long out2_img_stride;
   int out2_pix_stride;
   int Cout;
+  int out1_halo, out2_halo, OW;  // extra outputs stored with a zero 1-pixel border (row length OW + 2)
 };
 
 int check_conv_params(const odt_conv_params* p);
@@ -66,7 +67,20 @@ inline Epi make_epi(const odt_conv_params& p) {
   e.out2_img_stride = p.out2_img_stride;
   e.out2_pix_stride = p.out2_pix_stride;
   e.Cout = p.Cout;
+  e.out1_halo = p.out1_halo;
+  e.out2_halo = p.out2_halo;
+  e.OW = p.OW;
   return e;
+}
+
+// element offset of pixel (image b, linear pixel `pix` = oy*OW + ox) in an extra output (dense or halo layout)
+__host__ __device__ __forceinline__ long long aux_row(long long img_stride, int pix_stride, int halo, int OW, int b,
+                                                      int pix) {
+  if (halo) {
+    const int oy = pix / OW, ox = pix - oy * OW;
+    return (long long)b * img_stride + (long long)((oy + 1) * (OW + 2) + ox + 1) * pix_stride;
+  }
+  return (long long)b * img_stride + (long long)pix * pix_stride;
 }
 
 __device__ __forceinline__ int regroup(const Epi& e, int n) {
@@ -95,14 +109,14 @@ __device__ __forceinline__ void epi_store_one(const Epi& e, int b, int pix, int 
     float s2 = e.scale2 ? __ldg(e.scale2 + n) : 1.f;
     float h2 = e.shift2 ? __ldg(e.shift2 + n) : 0.f;
     float w = apply_act(fmaf(v, s2, h2), e.act2);
-    const long long o1 = (long long)b * e.out1_img_stride + (long long)pix * e.out1_pix_stride + n;
+    const long long o1 = aux_row(e.out1_img_stride, e.out1_pix_stride, e.out1_halo, e.OW, b, pix) + n;
     Elem<T>::st(reinterpret_cast<T*>(e.out1) + o1, w);
   }
   if (e.out2) {
     float s3 = e.scale3 ? __ldg(e.scale3 + n) : 1.f;
     float h3 = e.shift3 ? __ldg(e.shift3 + n) : 0.f;
     float w = apply_act(fmaf(v, s3, h3), e.act3);
-    const long long o2 = (long long)b * e.out2_img_stride + (long long)pix * e.out2_pix_stride + n;
+    const long long o2 = aux_row(e.out2_img_stride, e.out2_pix_stride, e.out2_halo, e.OW, b, pix) + n;
     Elem<T>::st(reinterpret_cast<T*>(e.out2) + o2, w);
   }
 }

@@ -186,8 +186,8 @@ template <typename T, int V>
 __global__ void maxpool_affine_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int H, int W,
                                       int OH, int OW, int C, int ld, int k, int stride, int pt, int pl,
                                       int ih, int oh, const float* __restrict__ s1, const float* __restrict__ h1,
-                                      int act1, T* __restrict__ out1, const float* __restrict__ s2,
-                                      const float* __restrict__ h2, int act2, T* __restrict__ out2) {
+                                      int act1, T* __restrict__ out1, int halo1, const float* __restrict__ s2,
+                                      const float* __restrict__ h2, int act2, T* __restrict__ out2, int halo2) {
   pdl_launch_dependents();
   const int IW = W + 2 * ih, IH = H + 2 * ih, PW = OW + 2 * oh, PH = OH + 2 * oh;
   const int cv = C / V;
@@ -220,13 +220,15 @@ __global__ void maxpool_affine_kernel(const T* __restrict__ in, T* __restrict__ 
       float v[V];
 #pragma unroll
       for (int q = 0; q < V; ++q) v[q] = apply_act(fmaf(m[q], s1 ? __ldg(s1 + c + q) : 1.f, h1 ? __ldg(h1 + c + q) : 0.f), act1);
-      VecIO<T, V>::st(out1 + pix * ld + c, v);
+      const long long o = halo1 ? ((long long)b * (OH + 2) + oy + 1) * (OW + 2) + ox + 1 : pix;
+      VecIO<T, V>::st(out1 + o * ld + c, v);
     }
     if (out2) {
       float v[V];
 #pragma unroll
       for (int q = 0; q < V; ++q) v[q] = apply_act(fmaf(m[q], s2 ? __ldg(s2 + c + q) : 1.f, h2 ? __ldg(h2 + c + q) : 0.f), act2);
-      VecIO<T, V>::st(out2 + pix * ld + c, v);
+      const long long o = halo2 ? ((long long)b * (OH + 2) + oy + 1) * (OW + 2) + ox + 1 : pix;
+      VecIO<T, V>::st(out2 + o * ld + c, v);
     }
   }
 }
@@ -605,12 +607,13 @@ extern "C" int odt_maxpool(const void* in, void* out, int dtype, int B, int H, i
 
 extern "C" int odt_maxpool_affine(const void* in, void* out, int dtype, int B, int H, int W, int C, int ld, int k,
                                   int stride, int in_halo, int out_halo, const float* scale1, const float* shift1,
-                                  int act1, void* out1, const float* scale2, const float* shift2, int act2,
-                                  void* out2, void* stream) {
+                                  int act1, void* out1, int out1_halo, const float* scale2, const float* shift2,
+                                  int act2, void* out2, int out2_halo, void* stream) {
   ODT_CHECK_ARG(in && (out || out1 || out2) && B > 0 && H > 0 && W > 0 && C > 0 && ld >= C && k > 0 && stride > 0,
                 "args");
   ODT_CHECK_ARG((in_halo == 0 || in_halo == 1) && (out_halo == 0 || out_halo == 1), "halo must be 0/1");
   ODT_CHECK_ARG(act1 >= 0 && act1 <= 2 && act2 >= 0 && act2 <= 2, "activation code");
+  ODT_CHECK_ARG((out1_halo == 0 || out1_halo == 1) && (out2_halo == 0 || out2_halo == 1), "out halo must be 0/1");
   int OH, OW, pt, pl, pa;
   odt_same_pad(H, k, stride, 1, &OH, &pt, &pa);
   odt_same_pad(W, k, stride, 1, &OW, &pl, &pa);
@@ -623,12 +626,12 @@ extern "C" int odt_maxpool_affine(const void* in, void* out, int dtype, int B, i
       long long work = (long long)B * OH * OW * (C / V);
       maxpool_affine_kernel<T, V><<<grid_for(work, 256), 256, 0, st>>>(
           (const T*)in, (T*)out, B, H, W, OH, OW, C, ld, k, stride, pt, pl, in_halo, out_halo, scale1, shift1, act1,
-          (T*)out1, scale2, shift2, act2, (T*)out2);
+          (T*)out1, out1_halo, scale2, shift2, act2, (T*)out2, out2_halo);
     } else {
       long long work = (long long)B * OH * OW * C;
       maxpool_affine_kernel<T, 1><<<grid_for(work, 256), 256, 0, st>>>(
           (const T*)in, (T*)out, B, H, W, OH, OW, C, ld, k, stride, pt, pl, in_halo, out_halo, scale1, shift1, act1,
-          (T*)out1, scale2, shift2, act2, (T*)out2);
+          (T*)out1, out1_halo, scale2, shift2, act2, (T*)out2, out2_halo);
     }
   })
   ODT_LAUNCH_OK();

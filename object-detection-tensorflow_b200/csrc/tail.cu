@@ -12,164 +12,309 @@
 #include <stdlib.h>
 
 #include "tail_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace odt {
 
 constexpr int kDecodeWarps = 8;
+constexpr int kGroupFloats = 32 * kRow;          // one warp iteration = 32 candidate rows = 3200 contiguous bytes
+constexpr int kGroupBytes = kGroupFloats * 4;
+constexpr int kDecodeStages = 2;
 
-// One warp = 32 consecutive candidate rows (3200 contiguous bytes), staged
-// through shared memory with 128-bit loads, then one lane per row.
-__global__ void __launch_bounds__(kDecodeWarps * 32)
+struct DecodeSmem {
+  float rows[kDecodeWarps][kDecodeStages][kGroupFloats];  // 51 200 B: 4 CTAs / SM
+  unsigned long long bar[kDecodeWarps][kDecodeStages];
+};
+
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// One warp = 32 consecutive candidate rows per iteration.  The 3200-byte group is fetched by ONE bulk copy (TMA,
+// cp.async.bulk) into a per-warp double buffer and signalled on an mbarrier, so no thread holds load registers or
+// issues load instructions while it computes (round 1 kept 7 float4 per lane in flight: 80 registers, 3 CTAs / SM,
+// 826 warp instructions per group; this kernel: KIND at compile time, no 64-bit divisions, the row's scores stay in
+// registers only).  Then one lane per row: score activation, background filter, threshold, per-class ballots and ONE
+// atomic per (warp, class) to reserve the candidate slots.
+template <int KIND, int OCC>
+__global__ void __launch_bounds__(kDecodeWarps * 32, OCC)
     decode_candidates_kernel(const float* __restrict__ head, const __grid_constant__ TailP tp,
                              long long total_rows, unsigned long long* __restrict__ cand_keys,
                              int* __restrict__ cand_count) {
   pdl_launch_dependents();
   const odt_tail_params& p = tp.p;
-  __shared__ __align__(16) float srow[kDecodeWarps][32 * kRow];
+  extern __shared__ __align__(128) unsigned char dsm_raw[];
+  DecodeSmem& sm = *reinterpret_cast<DecodeSmem*>(dsm_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* my = srow[warp];
-  const long long warps_total = (long long)gridDim.x * kDecodeWarps;
-  const long long groups = (total_rows + 31) / 32;
-  // Software pipeline per warp: the 128-bit loads of the NEXT 32-row group are issued into registers
-  // before the current group (already staged in shared memory) is decoded, so every warp keeps
-  // ~3 KB in flight while it computes.
-  constexpr int kVecPerLane = (32 * kRow / 4 + 31) / 32;  // 7
-  float4 pre[kVecPerLane];
-  auto fetch = [&](long long gg) {
-    const long long r0 = gg * 32;
-    const int nr = (int)min((long long)32, total_rows - r0);
-    const int nv = nr * kRow / 4;
-    const float4* s4 = reinterpret_cast<const float4*>(head + r0 * kRow);
+  const uint32_t bar0 = smem_u32(&sm.bar[warp][0]);
+  if (lane == 0) {
 #pragma unroll
-    for (int i = 0; i < kVecPerLane; ++i) {
-      const int idx = lane + 32 * i;
-      if (idx < nv) pre[i] = __ldcs(s4 + idx);
+    for (int s = 0; s < kDecodeStages; ++s) mbar_init(bar0 + 8u * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const long long groups = (total_rows + 31) / 32;
+  const long long full_groups = total_rows / 32;  // groups below this index are whole (bulk-copy eligible)
+  const int step = (int)gridDim.x * kDecodeWarps;  // groups between two iterations of one warp
+  long long g = (long long)blockIdx.x * kDecodeWarps + warp;
+  // (image, row) of the group's first row, advanced incrementally: no 64-bit division in the loop
+  const int N = p.N;
+  int b = (int)((g * 32) / N), n = (int)((g * 32) % N);
+  const int adv_b = (int)(((long long)step * 32) / N), adv_n = (int)(((long long)step * 32) % N);
+  auto issue = [&](long long gg, int slot) {  // lane 0 only
+    if (gg < full_groups) {
+      mbar_expect_tx(bar0 + 8u * slot, kGroupBytes);
+      bulk_load_1d(smem_u32(&sm.rows[warp][slot][0]), head + gg * kGroupFloats, kGroupBytes, bar0 + 8u * slot);
     }
   };
-  long long g = (long long)blockIdx.x * kDecodeWarps + warp;
-  if (g < groups) fetch(g);
-  for (; g < groups; g += warps_total) {
-    const long long row0 = g * 32;
-    const int nrows = (int)min((long long)32, total_rows - row0);
-    const float* src = head + row0 * kRow;
-    // row0*25 floats: 32-row groups start at a multiple of 800 floats = 3200 B -> 16 B aligned
-    const int nvec = nrows * kRow / 4;
-    float4* dst4 = reinterpret_cast<float4*>(my);
-#pragma unroll
-    for (int i = 0; i < kVecPerLane; ++i) {
-      const int idx = lane + 32 * i;
-      if (idx < nvec) dst4[idx] = pre[i];
+  if (lane == 0 && g < groups) issue(g, 0);
+  uint32_t phase = 0u;  // bit s = parity of stage s
+  for (int it = 0; g < groups; g += step, ++it) {
+    const int slot = it & 1;
+    const int nrows = (int)min((long long)32, total_rows - g * 32);
+    float* my = &sm.rows[warp][slot][0];
+    if (lane == 0 && g + step < groups) issue(g + step, slot ^ 1);
+    if (g < full_groups) {
+      mbar_wait(bar0 + 8u * slot, (phase >> slot) & 1u);
+      phase ^= 1u << slot;
+    } else {  // ragged last group: plain loads
+      const float* src = head + g * kGroupFloats;
+      for (int i = lane; i < nrows * kRow; i += 32) my[i] = __ldg(src + i);
+      __syncwarp();
     }
-    for (int i = nvec * 4 + lane; i < nrows * kRow; i += 32) my[i] = __ldg(src + i);
-    __syncwarp();
-    if (g + warps_total < groups) fetch(g + warps_total);
-
     const bool active = lane < nrows;
-    const long long row = row0 + lane;
-    const int b = active ? (int)(row / p.N) : 0;
-    const int n = active ? (int)(row % p.N) : 0;
+    int lb = b, ln = n + lane;
+    while (ln >= N) {
+      ln -= N;
+      ++lb;
+    }
+    const bool one_image = (n + nrows <= N);  // warp-uniform
     const float* r = my + lane * kRow;
-    float conf[20];
-    bool keep_row = active;
-    if (p.kind == ODT_DECODE_SSD) {
-      // softmax over 21 logits, TF form exp(x-max) * (1/sum); argmax first-max; drop
-      // rows whose argmax is background (last index).  ref SSD300.py:159-164
-      float m = r[0];
-#pragma unroll
-      for (int i = 1; i < 21; ++i) m = fmaxf(m, r[i]);
+    // pass_bits: bit c = class c of this row passes the score threshold.  The scores themselves are NOT kept in
+    // registers across the ballot section: score(c) recomputes the (few) passing ones from the staged row and
+    // two saved scalars, bit-identically.
+    unsigned pass_bits = 0u;
+    float k0 = 0.f, k1 = 0.f;  // SSD: (max logit, 1/sum); YOLO / FCOS: (sigmoid(obj | ctr), unused)
+    if (KIND == ODT_DECODE_SSD) {
+      // softmax over 21 logits, TF form exp(x-max) * (1/sum); rows whose arg-max (first maximum) is the
+      // background (last index) are dropped: background wins only if strictly greater than every foreground
+      // probability.  ref SSD300.py:159-164
       float e[21];
+#pragma unroll
+      for (int i = 0; i < 21; ++i) e[i] = r[i];
+      float m = e[0];
+#pragma unroll
+      for (int i = 1; i < 21; ++i) m = fmaxf(m, e[i]);
       float s = 0.f;
 #pragma unroll
       for (int i = 0; i < 21; ++i) {
-        e[i] = expf(__fsub_rn(r[i], m));
+        e[i] = exp_score(__fsub_rn(e[i], m));
         s = __fadd_rn(s, e[i]);
       }
-      float inv = __fdiv_rn(1.f, s);
-      float best = -1.f;
-      int arg = 0;
+      const float inv = __frcp_rn(s);
+      float best_fg = -1.f;
 #pragma unroll
-      for (int i = 0; i < 21; ++i) {
-        float pi = __fmul_rn(e[i], inv);
-        if (pi > best) {
-          best = pi;
-          arg = i;
-        }
-        if (i < 20) conf[i] = pi;
+      for (int i = 0; i < 20; ++i) {
+        const float pi = __fmul_rn(e[i], inv);
+        best_fg = fmaxf(best_fg, pi);
+        pass_bits |= (pi >= p.score_thr) ? (1u << i) : 0u;
       }
-      keep_row = keep_row && (arg < 20);
-    } else if (p.kind == ODT_DECODE_YOLO3) {
-      float so = sigmoid_rn(r[24]);  // ref YOLOv3.py:338-339,349
-#pragma unroll
-      for (int i = 0; i < 20; ++i) conf[i] = __fmul_rn(sigmoid_rn(r[i]), so);
+      if (!active || __fmul_rn(e[20], inv) > best_fg) pass_bits = 0u;
+      k0 = m;
+      k1 = inv;
     } else {
-      float sc = sigmoid_rn(r[20]);  // ref FCOS.py:197-201
+      k0 = sigmoid_score(r[KIND == ODT_DECODE_YOLO3 ? 24 : 20]);  // ref YOLOv3.py:338-339,349; FCOS.py:197-201
 #pragma unroll
-      for (int i = 0; i < 20; ++i) conf[i] = __fmul_rn(sigmoid_rn(r[i]), sc);
+      for (int i = 0; i < 20; ++i)
+        pass_bits |= (__fmul_rn(sigmoid_score(r[i]), k0) >= p.score_thr) ? (1u << i) : 0u;
+      if (!active) pass_bits = 0u;
     }
-    // Threshold + append.  Fast path (all rows of the warp in one image, i.e. everywhere but at image
-    // boundaries): the 20 per-class ballots are taken first, then lane c reserves the slots of class c
-    // with ONE atomic -- 20 independent atomics in flight instead of 20 dependent round trips.
-    const int b0 = __shfl_sync(0xffffffffu, b, 0);
-    const bool one_image = __all_sync(0xffffffffu, !active || b == b0);
-    if (one_image) {
-      unsigned my_mask = 0u;  // lane c keeps the ballot of class c
-      unsigned pass_bits = 0u;
-#pragma unroll
-      for (int c = 0; c < 20; ++c) {
-        const bool pass = c < p.num_fg && keep_row && (conf[c] >= p.score_thr);
-        const unsigned m = __ballot_sync(0xffffffffu, pass);
-        if (lane == c) my_mask = m;
-        pass_bits |= pass ? (1u << c) : 0u;
-      }
-      int my_base = 0;
-      if (my_mask) my_base = atomicAdd(&cand_count[b0 * p.num_fg + lane], __popc(my_mask));
-      const unsigned any = __ballot_sync(0xffffffffu, my_mask != 0u);  // classes with candidates
-#pragma unroll
-      for (int c = 0; c < 20; ++c) {
-        if (!((any >> c) & 1u)) continue;  // warp-uniform
-        const unsigned m = __shfl_sync(0xffffffffu, my_mask, c);
-        const int base = __shfl_sync(0xffffffffu, my_base, c);
-        if ((pass_bits >> c) & 1u) {
-          const int slot = base + __popc(m & ((1u << lane) - 1));
-          if (slot < p.cap)
-            cand_keys[((long long)b0 * p.num_fg + c) * p.cap + slot] =
-                ((unsigned long long)__float_as_uint(conf[c]) << 32) | (0xFFFFFFFFu - (unsigned)n);
+    if (p.num_fg < 20) pass_bits &= (1u << p.num_fg) - 1u;
+    auto score = [&](int c) -> float {
+      if (KIND == ODT_DECODE_SSD) return __fmul_rn(exp_score(__fsub_rn(r[c], k0)), k1);
+      return __fmul_rn(sigmoid_score(r[c]), k0);
+    };
+    // classes with at least one candidate in this warp: the work below is proportional to their number
+    const unsigned any = __reduce_or_sync(0xffffffffu, pass_bits);
+    if (any != 0u) {
+      if (one_image) {
+        // lane c collects the ballot of class c, then reserves the slots of its class with ONE atomic: up to 20
+        // independent atomics in flight instead of dependent round trips
+        unsigned my_mask = 0u;
+        for (unsigned rem = any; rem; rem &= rem - 1u) {
+          const int c = __ffs(rem) - 1;  // warp-uniform
+          const unsigned mk = __ballot_sync(0xffffffffu, (pass_bits >> c) & 1u);
+          if (lane == c) my_mask = mk;
         }
-      }
-    } else {
-#pragma unroll
-      for (int c = 0; c < 20; ++c) {
-        if (c >= p.num_fg) break;
-        const bool pass = keep_row && (conf[c] >= p.score_thr);
-        const unsigned mask = __ballot_sync(0xffffffffu, pass);
-        if (mask == 0) continue;
-        // rows of this warp straddle two images: aggregate the counter update per image
-        unsigned rem = mask;
-        int slot = -1;
-        while (rem) {
-          const int leader = __ffs(rem) - 1;
-          const int bl = __shfl_sync(0xffffffffu, b, leader);
-          const unsigned grp = __ballot_sync(0xffffffffu, pass && b == bl);
-          int base = 0;
-          if (lane == leader) base = atomicAdd(&cand_count[bl * p.num_fg + c], __popc(grp));
-          base = __shfl_sync(0xffffffffu, base, leader);
-          if (pass && b == bl) slot = base + __popc(grp & ((1u << lane) - 1));
-          rem &= ~grp;
+        // image index b (warp-uniform), NOT the lane's own lb: lane c only carries class c's ballot and may be an
+        // inactive lane of a ragged last group, whose row index lies past the image
+        int my_base = 0;
+        if (my_mask) my_base = atomicAdd(&cand_count[b * p.num_fg + lane], __popc(my_mask));
+        for (unsigned rem = any; rem; rem &= rem - 1u) {
+          const int c = __ffs(rem) - 1;
+          const unsigned mk = __shfl_sync(0xffffffffu, my_mask, c);
+          const int base = __shfl_sync(0xffffffffu, my_base, c);
+          if ((pass_bits >> c) & 1u) {
+            const int slot_i = base + __popc(mk & ((1u << lane) - 1));
+            if (slot_i < p.cap)
+              cand_keys[((long long)b * p.num_fg + c) * p.cap + slot_i] =
+                  ((unsigned long long)__float_as_uint(score(c)) << 32) | (0xFFFFFFFFu - (unsigned)ln);
+          }
         }
-        if (pass && slot < p.cap) {
-          const unsigned long long key =
-              ((unsigned long long)__float_as_uint(conf[c]) << 32) | (0xFFFFFFFFu - (unsigned)n);
-          cand_keys[((long long)b * p.num_fg + c) * p.cap + slot] = key;
+      } else {
+        for (unsigned rem_c = any; rem_c; rem_c &= rem_c - 1u) {
+          const int c = __ffs(rem_c) - 1;
+          const bool pass = (pass_bits >> c) & 1u;
+          const unsigned mask = __ballot_sync(0xffffffffu, pass);
+          // rows of this warp straddle images: aggregate the counter update per image
+          unsigned rem = mask;
+          int slot_i = -1;
+          while (rem) {
+            const int leader = __ffs(rem) - 1;
+            const int bl = __shfl_sync(0xffffffffu, lb, leader);
+            const unsigned grp = __ballot_sync(0xffffffffu, pass && lb == bl);
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&cand_count[bl * p.num_fg + c], __popc(grp));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (pass && lb == bl) slot_i = base + __popc(grp & ((1u << lane) - 1));
+            rem &= ~grp;
+          }
+          if (pass && slot_i < p.cap)
+            cand_keys[((long long)lb * p.num_fg + c) * p.cap + slot_i] =
+                ((unsigned long long)__float_as_uint(score(c)) << 32) | (0xFFFFFFFFu - (unsigned)ln);
         }
       }
     }
-    __syncwarp();
+    __syncwarp();  // every lane is done with this stage before lane 0 refills it (next iteration's issue)
+    n += adv_n;
+    b += adv_b;
+    if (n >= N) {
+      n -= N;
+      ++b;
+    }
   }
 }
 
 // ----------------------------------------------------------------- NMS ----
 constexpr int kNmsThreads = 256;
 constexpr int kNmsSmemKeys = 1024;  // candidates (keys + boxes, 24 KB) a CTA works on in shared memory: 8 CTAs / SM
+
+constexpr int kNmsWarpMax = 256;           // lists up to this length are run by one warp (8 keys per lane in registers)
+constexpr int kNselOverflowBit = 1 << 30;  // per-(image, class) "list was truncated at cap" flag in nsel_all
+
+// ---- short lists: one WARP per (image, class) list of up to kNmsWarpMax candidates ------------------------------
+// Keys (8 per lane) and the min/max-normalised boxes + areas of the lane's candidates live in registers; the original
+// boxes (what the record reports) in 4 KB of shared memory per warp.  A round = lane-local arg-max over 8 registers,
+// two redux.sync, one ballot; then the 8 IoU tests of a lane are independent instruction streams (no branches), and
+// the division of TF's `inter / union > thr` is only executed when |inter - thr * union| is within 1e-6 * union of
+// zero (otherwise the sign of the fused difference decides: the quotient is then more than 1e-6 away from the
+// threshold, sixteen times the rounding error of the fp32 division).  No block barriers, no block-wide scans: at the
+// SSD300 driver threshold (1280 lists of ~130 candidates, 20 kept boxes each) the block-per-list kernel below spends
+// its time in 2 __syncthreads + a 256-thread scan per kept box.
+constexpr int kShortWarps = 8;
+constexpr int kShortPerLane = kNmsWarpMax / 32;
+
+__global__ void __launch_bounds__(kShortWarps * 32)
+    nms_short_kernel(const float* __restrict__ head, const __grid_constant__ TailP tp, int B,
+                     const unsigned long long* __restrict__ cand_keys, const int* __restrict__ cand_count,
+                     int* __restrict__ scratch, int* __restrict__ status) {
+  pdl_launch_dependents();
+  const odt_tail_params& p = tp.p;
+  __shared__ float4 s_box[kShortWarps][kNmsWarpMax];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = p.nms_classes, MB = p.max_boxes;
+  const long long list = (long long)blockIdx.x * kShortWarps + warp;
+  if (list >= (long long)B * C) return;
+  const int b = (int)(list / C), c = (int)(list % C);
+  int cnt = cand_count[b * p.num_fg + c];
+  if (cnt > kNmsWarpMax) return;  // the block-per-list kernel takes it
+  const bool overflow = cnt > p.cap;
+  if (overflow) {
+    if (lane == 0) atomicExch(status, ODT_ERR_OVERFLOW);
+    cnt = p.cap;
+  }
+  int* nsel_all = scratch;
+  float* st_det = reinterpret_cast<float*>(scratch + B * C);
+  int* st_anchor = scratch + B * C + (long long)B * C * MB * 6;
+  const long long bc = (long long)b * C + c;
+  const unsigned long long* gkeys = cand_keys + ((long long)b * p.num_fg + c) * p.cap;
+  const float* hb = head + (long long)b * p.N * kRow;
+  float4* wbox = s_box[warp];
+
+  unsigned long long k[kShortPerLane];
+  float y1[kShortPerLane], x1[kShortPerLane], y2[kShortPerLane], x2[kShortPerLane], ar[kShortPerLane];
+#pragma unroll
+  for (int j = 0; j < kShortPerLane; ++j) {
+    const int i = lane + 32 * j;
+    k[j] = 0ull;
+    y1[j] = x1[j] = y2[j] = x2[j] = ar[j] = 0.f;
+    if (i < cnt) {
+      k[j] = gkeys[i];
+      const int n = (int)(0xFFFFFFFFu - (unsigned)(k[j] & 0xFFFFFFFFull));
+      Cell cell = locate(p, n);
+      const float4 bx = decode_box(p, cell, hb + (long long)n * kRow);
+      wbox[i] = bx;
+      y1[j] = fminf(bx.x, bx.z);
+      x1[j] = fminf(bx.y, bx.w);
+      y2[j] = fmaxf(bx.x, bx.z);
+      x2[j] = fmaxf(bx.y, bx.w);
+      ar[j] = __fmul_rn(__fsub_rn(y2[j], y1[j]), __fsub_rn(x2[j], x1[j]));
+    }
+  }
+  __syncwarp();
+  const float thr = p.iou_thr;
+  int nsel = 0;
+  while (nsel < MB) {
+    unsigned long long bk = 0ull;
+    int bj = 0;
+#pragma unroll
+    for (int j = 0; j < kShortPerLane; ++j)
+      if (k[j] > bk) {
+        bk = k[j];
+        bj = j;
+      }
+    const unsigned hi = (unsigned)(bk >> 32), lo = (unsigned)bk;
+    const unsigned whi = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned wlo = __reduce_max_sync(0xffffffffu, hi == whi ? lo : 0u);
+    if ((whi | wlo) == 0u) break;  // nothing alive (a live key is never 0)
+    const bool mine = hi == whi && lo == wlo;  // keys are unique: exactly one lane
+    const int owner = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
+    const int pos = __shfl_sync(0xffffffffu, lane + 32 * bj, owner);
+    const float4 cur = wbox[pos];
+    if (lane == 0) {
+      float* d = st_det + (bc * MB + nsel) * 6;
+      d[0] = __uint_as_float(whi);
+      d[1] = cur.x;
+      d[2] = cur.y;
+      d[3] = cur.z;
+      d[4] = cur.w;
+      d[5] = (float)c;
+      st_anchor[bc * MB + nsel] = (int)(0xFFFFFFFFu - wlo);
+    }
+    ++nsel;
+    if (nsel >= MB) break;
+    // the kept box in TF's normalised form (iou_tf of tail_common.cuh, same operations)
+    const float cy1 = fminf(cur.x, cur.z), cx1 = fminf(cur.y, cur.w);
+    const float cy2 = fmaxf(cur.x, cur.z), cx2 = fmaxf(cur.y, cur.w);
+    const float car = __fmul_rn(__fsub_rn(cy2, cy1), __fsub_rn(cx2, cx1));
+#pragma unroll
+    for (int j = 0; j < kShortPerLane; ++j) {
+      const float ih = fmaxf(__fsub_rn(fminf(y2[j], cy2), fmaxf(y1[j], cy1)), 0.f);
+      const float iw = fmaxf(__fsub_rn(fminf(x2[j], cx2), fmaxf(x1[j], cx1)), 0.f);
+      const float inter = __fmul_rn(ih, iw);
+      const float uni = __fsub_rn(__fadd_rn(ar[j], car), inter);
+      const float diff = __fmaf_rn(-thr, uni, inter);       // inter - thr * union, one rounding
+      bool sup;
+      if (fabsf(diff) > 1e-6f * uni) sup = diff > 0.f;       // clear margin (false for NaN: exact path below)
+      else sup = __fdiv_rn(inter, uni) > thr;                // TF's own comparison
+      sup = sup && ar[j] > 0.f && car > 0.f;                 // degenerate boxes have IoU 0
+      if (sup || (mine && j == bj)) k[j] = 0ull;
+    }
+  }
+  if (lane == 0) nsel_all[bc] = nsel | (overflow ? kNselOverflowBit : 0);
+}
 
 struct NmsSmem {
   unsigned long long keys[kNmsSmemKeys];
@@ -196,7 +341,6 @@ struct NmsSmem {
 // list processed (correct, slower).
 constexpr int kNmsPrefilter = kNmsSmemKeys;  // longer lists: prefilter first
 constexpr int kNmsSelectMin = 384;
-constexpr int kNselOverflowBit = 1 << 30;  // per-(image, class) "list was truncated at cap" flag in nsel_all
 
 __global__ void __launch_bounds__(kNmsThreads)
     nms_per_class_kernel(const float* __restrict__ head, const __grid_constant__ TailP tp, int B,
@@ -205,7 +349,7 @@ __global__ void __launch_bounds__(kNmsThreads)
                          int* __restrict__ det_anchor, int* __restrict__ det_count,
                          int* __restrict__ scratch, int* __restrict__ work,
                          int* __restrict__ status, float4* __restrict__ box_pool,
-                         long long box_pool_entries, long long det_img_stride) {
+                         long long box_pool_entries, long long det_img_stride, int short_done) {
   pdl_launch_dependents();
   const odt_tail_params& p = tp.p;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -235,6 +379,11 @@ __global__ void __launch_bounds__(kNmsThreads)
   const float* hb = head + (long long)b * p.N * kRow;
   const int cnt_all = cnt;
   int nsel = 0;
+  if (cnt_all <= kNmsWarpMax && short_done) {
+    // short list: nms_short_kernel (one warp per list) has already written its kept boxes and nsel_all[bc];
+    // this CTA only takes part in the per-image completion below
+    nsel = -1;
+  } else {
   for (int attempt = 0; attempt < 2; ++attempt) {
   // ---- attempt 0 on a long list: exact prefilter (see the kernel comment) ----
   bool subset = false;
@@ -246,9 +395,21 @@ __global__ void __launch_bounds__(kNmsThreads)
       s_hist[tid] = 0;  // kNmsThreads == 256 bins
       if (tid == 0 && shift == 24) s_ctl[2] = 0u;
       __syncthreads();
-      for (int i = tid; i < cnt_all; i += blockDim.x) {
-        const unsigned sc = (unsigned)(gkeys[i] >> 32);
-        if ((sc & prefix_mask) == prefix) atomicAdd(&s_hist[(sc >> shift) & 255u], 1);
+      // four independent loads in flight per thread (a 15 000-entry list is 15 dependent L2 round trips per pass
+      // instead of 60); only the score half of the key is read
+      const unsigned* gscore = reinterpret_cast<const unsigned*>(gkeys) + 1;
+      for (int i = tid; i < cnt_all; i += kNmsThreads * 4) {
+        unsigned sc4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int ii = i + u * kNmsThreads;
+          sc4[u] = ii < cnt_all ? gscore[2 * ii] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int ii = i + u * kNmsThreads;
+          if (ii < cnt_all && (sc4[u] & prefix_mask) == prefix) atomicAdd(&s_hist[(sc4[u] >> shift) & 255u], 1);
+        }
       }
       __syncthreads();
       if (tid == 0) {
@@ -274,14 +435,23 @@ __global__ void __launch_bounds__(kNmsThreads)
       const unsigned thr_bits = prefix;
       if (tid == 0) s_ctl[3] = 0u;
       __syncthreads();
-      for (int i = tid; i < cnt_all; i += blockDim.x) {
-        const unsigned long long k = gkeys[i];
-        if ((unsigned)(k >> 32) >= thr_bits) {
-          const unsigned slot = atomicAdd(&s_ctl[3], 1u);
-          sm.keys[slot] = k;
-          const int n = (int)(0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull));
-          Cell cell = locate(p, n);
-          sm.box[slot] = decode_box(p, cell, hb + (long long)n * kRow);
+      for (int i = tid; i < cnt_all; i += kNmsThreads * 4) {
+        unsigned long long k4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int ii = i + u * kNmsThreads;
+          k4[u] = ii < cnt_all ? gkeys[ii] : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const unsigned long long k = k4[u];
+          if (i + u * kNmsThreads < cnt_all && (unsigned)(k >> 32) >= thr_bits) {
+            const unsigned slot = atomicAdd(&s_ctl[3], 1u);
+            sm.keys[slot] = k;
+            const int n = (int)(0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull));
+            Cell cell = locate(p, n);
+            sm.box[slot] = decode_box(p, cell, hb + (long long)n * kRow);
+          }
         }
       }
       __syncthreads();
@@ -411,7 +581,8 @@ __global__ void __launch_bounds__(kNmsThreads)
   // the subset ran dry before nms_max_boxes boxes were kept: redo on the full list
   if (!(subset && nsel < MB && cnt < cnt_all)) break;
   }  // attempt
-  if (tid == 0) nsel_all[bc] = nsel | (overflow ? kNselOverflowBit : 0);
+  }  // long list
+  if (tid == 0 && nsel >= 0) nsel_all[bc] = nsel | (overflow ? kNselOverflowBit : 0);
 
   // class-major compaction by the last block of this image
   __threadfence();
@@ -489,12 +660,34 @@ extern "C" int odt_decode_candidates(const float* head, const odt_tail_params* p
   long long rows = (long long)B * p->N;
   long long groups = (rows + 31) / 32;
   int blocks = (int)((groups + kDecodeWarps - 1) / kDecodeWarps);
-  int per_sm = 8;  // measured best of 2/4/8 (80 registers: 3 blocks resident, the rest back-fills the tail)
+  int per_sm = 8;  // 4 CTAs resident per SM (51 KB of staging each), two waves
   if (const char* e = getenv("ODT_DECODE_BLOCKS_PER_SM")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;
   int maxb = kNumSMs * per_sm;
   if (blocks > maxb) blocks = maxb;
-  decode_candidates_kernel<<<blocks, kDecodeWarps * 32, 0, st>>>(head, tp, rows, cand_keys,
-                                                                 cand_count);
+  // OCC = CTAs per SM the kernel is compiled for: 3 (72 registers, no spills) or 4 (64 registers, ~20 spilled words);
+  // ODT_DECODE_OCC selects, default from the round-2 A/B (profiles/r02_tail.md)
+  int occ = 3;
+  if (const char* e = getenv("ODT_DECODE_OCC")) occ = atoi(e) == 4 ? 4 : 3;
+#define ODT_DECODE_LAUNCH(KIND_, OCC_)                                                                            \
+  do {                                                                                                            \
+    static bool attr_done = false;                                                                                \
+    if (!attr_done) {                                                                                             \
+      ODT_CUDA_OK(cudaFuncSetAttribute(decode_candidates_kernel<KIND_, OCC_>,                                     \
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeSmem)));    \
+      attr_done = true;                                                                                           \
+    }                                                                                                             \
+    decode_candidates_kernel<KIND_, OCC_><<<blocks, kDecodeWarps * 32, sizeof(DecodeSmem), st>>>(head, tp, rows,  \
+                                                                                                 cand_keys,       \
+                                                                                                 cand_count);     \
+  } while (0)
+  if (p->kind == ODT_DECODE_SSD) {
+    if (occ == 4) ODT_DECODE_LAUNCH(ODT_DECODE_SSD, 4); else ODT_DECODE_LAUNCH(ODT_DECODE_SSD, 3);
+  } else if (p->kind == ODT_DECODE_YOLO3) {
+    if (occ == 4) ODT_DECODE_LAUNCH(ODT_DECODE_YOLO3, 4); else ODT_DECODE_LAUNCH(ODT_DECODE_YOLO3, 3);
+  } else {
+    if (occ == 4) ODT_DECODE_LAUNCH(ODT_DECODE_FCOS, 4); else ODT_DECODE_LAUNCH(ODT_DECODE_FCOS, 3);
+  }
+#undef ODT_DECODE_LAUNCH
   ODT_LAUNCH_OK();
   return ODT_OK;
 }
@@ -534,9 +727,18 @@ extern "C" int odt_nms_per_class(const float* head, const odt_tail_params* p, in
   const long long dense = (long long)p->nms_classes * p->max_boxes * 6;
   if (dets_img_stride == 0) dets_img_stride = dense;
   ODT_CHECK_ARG(dets_img_stride >= dense, "dets_img_stride smaller than nms_classes*max_boxes*6");
+  // short lists first (one warp each, 8 lists per CTA), then the block-per-list kernel for the long ones, which
+  // also runs the per-image class-major compaction; ODT_NMS_SHORT=0 sends every list through the second kernel
+  int short_done = 1;
+  if (const char* e = getenv("ODT_NMS_SHORT")) short_done = e[0] == '0' ? 0 : 1;
+  if (short_done) {
+    const long long lists = (long long)B * p->nms_classes;
+    nms_short_kernel<<<(unsigned)((lists + kShortWarps - 1) / kShortWarps), kShortWarps * 32, 0, st>>>(
+        head, tp, B, cand_keys, cand_count, sel_scratch, status);
+  }
   nms_per_class_kernel<<<grid, kNmsThreads, sizeof(NmsSmem), st>>>(
       head, tp, B, cand_keys, cand_count, dets, det_anchor, det_count, sel_scratch, work, status,
-      reinterpret_cast<float4*>(box_pool), box_pool ? box_pool_entries : 0, dets_img_stride);
+      reinterpret_cast<float4*>(box_pool), box_pool ? box_pool_entries : 0, dets_img_stride, short_done);
   ODT_LAUNCH_OK();
   return ODT_OK;
 }

@@ -31,6 +31,28 @@ __device__ __forceinline__ Cell locate(const odt_tail_params& p, int n) {
   return c;
 }
 
+// exp(x) for the score activations of the decode kernel: 2^(x*log2 e) through MUFU.EX2 with the rounding error of the
+// product folded back in (hi = fl(x*L2E); r = fma(x, L2E, -hi) is its exact residual, x*L2E_LO the part of log2 e
+// beyond fp32; e^x = 2^hi * (1 + ln2*(r + x*L2E_LO))): 6 instructions and ~2 ulp over the whole range, against ~20
+// instructions (range checks, exponent re-assembly) for libdevice's expf -- 21 of them per candidate row made up more
+// than a third of the decode kernel's instruction stream.  Results below 2^-126 flush to zero (they can never reach a
+// threshold).  TF's own CPU exp (Eigen pexp) is a different polynomial again, so no choice of exp is bit-identical
+// to it; parity tests compare scores to 1e-6 relative.
+__device__ __forceinline__ float exp_score(float x) {
+  const float L2E = 1.4426950216293335f;      // fl(log2 e)
+  const float L2E_LO = 1.9259629911e-08f;     // log2 e - fl(log2 e)
+  const float hi = __fmul_rn(x, L2E);
+  const float res = __fmaf_rn(x, L2E, -hi);
+  const float corr = __fmul_rn(__fmaf_rn(x, L2E_LO, res), 0.6931471805599453f);
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(hi));
+  return __fmaf_rn(r, corr, r);
+}
+
+// score sigmoid of the decode kernel: 1/(1+exp(-x)) with exp_score and the correctly rounded reciprocal
+// (__frcp_rn(y) == __fdiv_rn(1, y) bit for bit, without the division's slow-path call)
+__device__ __forceinline__ float sigmoid_score(float x) { return __frcp_rn(__fadd_rn(1.f, exp_score(-x))); }
+
 __device__ __forceinline__ float sigmoid_rn(float x) {
   // tf.sigmoid = 1/(1+exp(-x))  
   return __fdiv_rn(1.f, __fadd_rn(1.f, expf(-x)));

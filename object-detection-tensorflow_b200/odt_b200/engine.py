@@ -187,8 +187,9 @@ class ConvOp(Op):
                 p.scale2, p.shift2 = self.scale2.data_ptr(), self.shift2.data_ptr()
             p.act2 = ACT[act2]
             p.out1 = t.ptr()
-            p.out1_img_stride = t.H * t.W * t.ld
+            p.out1_img_stride = t.img_stride
             p.out1_pix_stride = t.ld
+            p.out1_halo = t.halo
         if self.pre2 is not None:
             scope, act3, t = self.pre2
             if scope is not None:
@@ -198,8 +199,9 @@ class ConvOp(Op):
                 p.scale3, p.shift3 = self.scale3.data_ptr(), self.shift3.data_ptr()
             p.act3 = ACT[act3]
             p.out2 = t.ptr()
-            p.out2_img_stride = t.H * t.W * t.ld
+            p.out2_img_stride = t.img_stride
             p.out2_pix_stride = t.ld
+            p.out2_halo = t.halo
         self.p = p
         self.flops = 2 * B * OH * OW * cout * R * S * cin
         # stems: the tcgen05 variants read a packed fp16 RGBX copy of the image (mean subtracted, zero border of
@@ -277,9 +279,9 @@ class PoolOp(Op):
             x.ptr(), self.y.ptr() if self.y.needed else None, net.dt, x.B, x.H, x.W, c, x.ld, self.k, self.stride,
             x.halo, self.y.halo,
             a1[0].data_ptr() if a1 else None, a1[1].data_ptr() if a1 else None, a1[2] if a1 else 0,
-            a1[3].ptr() if a1 else None,
+            a1[3].ptr() if a1 else None, a1[3].halo if a1 else 0,
             a2[0].data_ptr() if a2 else None, a2[1].data_ptr() if a2 else None, a2[2] if a2 else 0,
-            a2[3].ptr() if a2 else None, stream), "maxpool_affine")
+            a2[3].ptr() if a2 else None, a2[3].halo if a2 else 0, stream), "maxpool_affine")
 
 
 class L2NormOp(Op):
@@ -579,13 +581,19 @@ class Net:
                 producer[id(t)] = op
             for pr in (getattr(op, "pre", None), getattr(op, "pre2", None)):
                 if pr is not None:
-                    producer[id(pr[2])] = None  # fused second / third outputs stay dense
+                    # fused second / third outputs: the tensor-core convolutions (conv_tc / conv_tapn / conv_thin
+                    # epilogues) and the fused pool write them in the halo layout too; other producers stay dense
+                    can = ((isinstance(op, ConvOp) and not op.is_image and op.head is None and op.x.ld % 64 == 0)
+                           or isinstance(op, PoolOp)) and os.environ.get("ODT_HALO_AUX", "1") != "0"
+                    producer[id(pr[2])] = "fused" if can else None
         for t in self.acts:
             prod = producer.get(id(t))
             cons = readers.get(id(t), [])
             if not cons or not t.needed:
                 continue
-            if isinstance(prod, ConvOp):
+            if prod == "fused":
+                pass
+            elif isinstance(prod, ConvOp):
                 if prod.head is not None or prod.residual is not None:
                     continue
                 if prod.is_image and (prod.k, prod.stride, t.C) not in self.STEM_TC_VARIANTS:
@@ -844,7 +852,7 @@ class Tail:
         self.launch_nms(net, stream)
 
     def num_launches(self):
-        return 2  # decode + nms kernels (plus 1-2 memset nodes)
+        return 3  # decode + short-list NMS + block-per-list NMS / compaction kernels (plus 3 memset nodes)
 
     def results(self):
         """ONE D2H read of the packed records -> per-image [scores f32[K], bbox f32[K,4] (y1,x1,y2,x2),

@@ -15,7 +15,7 @@ DECODE_SSD, DECODE_YOLO3, DECODE_FCOS = 0, 1, 2
 MAX_LEVELS, MAX_PRIORS = 8, 9
 ERR_OVERFLOW = -4
 ERR_UNSUPPORTED = -3
-ABI_VERSION = 3  # odt_abi_version(): bumped whenever a signature in include/odt_b200.h changes
+ABI_VERSION = 4  # odt_abi_version(): bumped whenever a signature in include/odt_b200.h changes
 
 
 class ConvParams(C.Structure):
@@ -35,6 +35,7 @@ class ConvParams(C.Structure):
         ("scale3", C.c_void_p), ("shift3", C.c_void_p), ("act3", C.c_int),
         ("out2", C.c_void_p), ("out2_img_stride", C.c_longlong), ("out2_pix_stride", C.c_int),
         ("in_halo", C.c_int), ("out0_halo", C.c_int), ("out0_pool", C.c_int),
+        ("out1_halo", C.c_int), ("out2_halo", C.c_int),
     ]
 
 
@@ -72,7 +73,7 @@ SYMBOLS = {
     "odt_pack_input_rgbx": (_I, [_P, _P, _I, _I, _I, _I, C.POINTER(_F), _P]),
     "odt_conv2d_stem_rgbx": (_I, [_P, _P, C.POINTER(ConvParams), _P]),
     "odt_maxpool": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
-    "odt_maxpool_affine": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _I, _P, _P]),
+    "odt_maxpool_affine": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P, _I, _P, _I, _P]),
     "odt_l2norm_scale": (_I, [_P, _P, _I, _L, _I, _I, _F, _P]),
     "odt_affine_act": (_I, [_P, _P, _I, _L, _I, _I, _P, _P, _I, _P]),
     "odt_upsample_bilinear_add": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P]),
@@ -92,6 +93,11 @@ SYMBOLS = {
     "odt_yolo_loss_fwd": (_I, [_P, C.POINTER(TailParams), _I, _P, _I, _F, _F, _F, _F, _P, _P, _P]),
     "odt_fcos_loss_scratch_bytes": (_L, [_I]),
     "odt_fcos_loss_fwd": (_I, [_P, C.POINTER(TailParams), _I, _P, _I, _P, _P, _P]),
+    "odt_ctx_unique_id": (_I, [_P]),
+    "odt_ctx_create": (_I, [C.POINTER(_P), _I, _I, _P]),
+    "odt_ctx_destroy": (_I, [_P]),
+    "odt_allgather_dets": (_I, [_P, _P, _P, _L, _P]),
+    "odt_bcast_weights": (_I, [_P, _P, _L, _I, _P]),
 }
 
 

@@ -13,7 +13,7 @@ SURVEY section 8(f) row 3; not on the accelerated hot path.
   contrast, hue as TF's adjust_* ops define them), small-angle rotation with the box re-fit of
   `rotate_helper`, box clamping, the centre-inside filter, the "no box left" fallback of
   `gt_checker_helper`, (y_centre, x_centre, h, w, id) rows padded with -1 to `pad_truth_to`; randomness
-  from a seeded numpy generator.  BICUBIC resampling is not restated (bilinear is used, with a warning).
+  from a seeded numpy generator.  BICUBIC resampling restates TF 1.13's table-driven ResizeBicubic kernel.
   (The reference returns the UNaugmented `image_copy` when `pad_truth_to` is set, :229 -- an upstream slip
   that would defeat batching; the augmented image is returned here.  It also concatenates the UNfiltered box
   centres with the filtered sizes / ids (:211-220), a shape error whenever a box is dropped; the filtered
@@ -218,6 +218,50 @@ def _resize_bilinear_aligned(img, oh, ow):
     return (top * (1 - wy) + bot * wy).astype(np.float32)
 
 
+_BICUBIC_TABLE = None
+
+
+def _bicubic_table():
+    """TF's ResizeBicubic weight table (resize_bicubic_op.cc, TF 1.13): 1024 + 1 entries of the Keys kernel with
+    A = -0.75, float32: [i*2] = weight of a tap at distance x = i/1024 (|x| <= 1), [i*2+1] = at distance x + 1."""
+    global _BICUBIC_TABLE
+    if _BICUBIC_TABLE is None:
+        a = np.float32(-0.75)
+        x = (np.arange(1025, dtype=np.float32) * np.float32(1.0 / 1024)).astype(np.float32)
+        t = np.empty(2 * 1025, np.float32)
+        t[0::2] = ((a + 2) * x - (a + 3)) * x * x + 1
+        x1 = x + np.float32(1.0)
+        t[1::2] = ((a * x1 - 5 * a) * x1 + 8 * a) * x1 - 4 * a
+        _BICUBIC_TABLE = t
+    return _BICUBIC_TABLE
+
+
+def _bicubic_axis(n_in, n_out):
+    """Per output coordinate: four clamped source indices and their table weights (GetWeightsAndIndices with
+    align_corners=True: src = dst * (in - 1)/(out - 1), no half-pixel centres; offset = lrintf(frac * 1024))."""
+    scale = np.float32((n_in - 1) / (n_out - 1)) if n_out > 1 else np.float32(0)
+    loc = (np.arange(n_out, dtype=np.float32) * scale).astype(np.float32)
+    fl = np.floor(loc)
+    off = np.rint((loc - fl) * np.float32(1024)).astype(np.int64)   # lrintf: round half to even, like numpy
+    base = fl.astype(np.int64)
+    t = _bicubic_table()
+    w = np.stack([t[off * 2 + 1], t[off * 2], t[(1024 - off) * 2], t[(1024 - off) * 2 + 1]], axis=1)
+    idx = np.clip(np.stack([base - 1, base, base + 1, base + 2], axis=1), 0, n_in - 1)
+    return idx, w.astype(np.float32)
+
+
+def _resize_bicubic_aligned(img, oh, ow):
+    """tf.image.resize_images(..., BICUBIC, align_corners=True) of image_augmentor (:103-106,:121-127): TF 1.13's
+    ResizeBicubic kernel -- table-driven Keys cubic (A = -0.75), taps clamped at the border, float32, interpolating
+    along x first and then along y.  [TF-sem: restated from the kernel's source, unverifiable here]"""
+    x = img.astype(np.float32)
+    h, w = x.shape[:2]
+    yi, yw = _bicubic_axis(h, oh)
+    xi, xw = _bicubic_axis(w, ow)
+    rows = sum(x[:, xi[:, k]] * xw[:, k].reshape(1, -1, 1) for k in range(4)).astype(np.float32)   # [h, ow, c]
+    return sum(rows[yi[:, k]] * yw[:, k].reshape(-1, 1, 1) for k in range(4)).astype(np.float32)
+
+
 def _resize_nearest_aligned(img, oh, ow):
     """ResizeNearestNeighbor with align_corners=True (TF 1.13): src = min(round(dst * (in-1)/(out-1)), in-1)."""
     h, w = img.shape[:2]
@@ -345,10 +389,8 @@ def preprocess(img, gt, config, rng=None):
     ymin, ymax, xmin, xmax = [gt[:, i].astype(np.float32) for i in range(4)]
     fill = config.get("fill_mode", "BILINEAR")
     keep = bool(config.get("keep_aspect_ratios")) or fill == "CONSTANT"
-    resize = _resize_nearest_aligned if fill == "NEAREST_NEIGHBOR" else _resize_bilinear_aligned
-    if fill == "BICUBIC" and not preprocess._warned.get("fill"):
-        preprocess._warned["fill"] = True
-        sys.stderr.write("[odt_b200] fill_mode 'BICUBIC' is not restated: bilinear resampling is used\n")
+    resize = {"NEAREST_NEIGHBOR": _resize_nearest_aligned, "BICUBIC": _resize_bicubic_aligned}.get(
+        fill, _resize_bilinear_aligned)
     cval = np.float32(config.get("constant_values") or 0.0)
     if keep and fill != "CONSTANT":           # :93-114
         ratio = np.float32(min(zh / h, zw / w))

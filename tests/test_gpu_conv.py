@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _conv_case(B, H, W, Cin, Cout, k, stride, dil, mode, act="relu", residual=False, pre=False,
-               bn=True, f32_out=False, seed=0, in_halo=0, out_halo=0, pool=0, pre2=False, no_out0=False):
+               bn=True, f32_out=False, seed=0, in_halo=0, out_halo=0, pool=0, pre2=False, no_out0=False, aux_halo=0):
     """mode: 'tc' (fp16 tcgen05), 'direct16', 'direct32'.  Returns (got, ref, got1, ref1)."""
     from odt_b200 import lib as L
     from odt_b200.engine import same_pad
@@ -81,17 +81,21 @@ def _conv_case(B, H, W, Cin, Cout, k, stride, dil, mode, act="relu", residual=Fa
         s2 = rng.uniform(0.5, 1.5, Cout).astype(np.float32)
         h2 = (rng.standard_normal(Cout) * 0.2).astype(np.float32)
         s2d, h2d = torch.from_numpy(s2).to(dev), torch.from_numpy(h2).to(dev)
-        y1 = torch.zeros((B, OH, OW, old), dtype=tdt, device=dev)
+        ah = aux_halo
+        y1 = torch.zeros((B, OH + 2 * ah, OW + 2 * ah, old), dtype=tdt, device=dev)
         p.scale2, p.shift2, p.act2 = s2d.data_ptr(), h2d.data_ptr(), 1
-        p.out1, p.out1_img_stride, p.out1_pix_stride = y1.data_ptr(), OH * OW * old, old
+        p.out1, p.out1_img_stride, p.out1_pix_stride = y1.data_ptr(), (OH + 2 * ah) * (OW + 2 * ah) * old, old
+        p.out1_halo = ah
     s3 = h3 = y2 = None
     if pre2:  # third epilogue output (checked in here against the rounded out0 like out1)
         s3 = rng.uniform(0.5, 1.5, Cout).astype(np.float32)
         h3 = (rng.standard_normal(Cout) * 0.2).astype(np.float32)
         s3d, h3d = torch.from_numpy(s3).to(dev), torch.from_numpy(h3).to(dev)
-        y2 = torch.zeros((B, OH, OW, old), dtype=tdt, device=dev)
+        ah = aux_halo
+        y2 = torch.zeros((B, OH + 2 * ah, OW + 2 * ah, old), dtype=tdt, device=dev)
         p.scale3, p.shift3, p.act3 = s3d.data_ptr(), h3d.data_ptr(), 2
-        p.out2, p.out2_img_stride, p.out2_pix_stride = y2.data_ptr(), OH * OW * old, old
+        p.out2, p.out2_img_stride, p.out2_pix_stride = y2.data_ptr(), (OH + 2 * ah) * (OW + 2 * ah) * old, old
+        p.out2_halo = ah
     if no_out0:
         p.out0 = None
     st = torch.cuda.current_stream().cuda_stream
@@ -121,12 +125,21 @@ def _conv_case(B, H, W, Cin, Cout, k, stride, dil, mode, act="relu", residual=Fa
     if pre:
         base = got if (f16 and not f32_out and not no_out0) else ref
         ref1 = np.maximum(base * s2 + h2, 0)
-        got1 = y1[..., :Cout].float().cpu().numpy()
+        ah = aux_halo
+        got1 = y1[:, ah:ah + OH, ah:ah + OW, :Cout].float().cpu().numpy()
+        if ah:  # the zero border of a halo output is never dirtied
+            f1 = y1.float().cpu().numpy()
+            assert np.abs(f1[:, 0]).max() == 0 and np.abs(f1[:, -1]).max() == 0
+            assert np.abs(f1[:, :, 0]).max() == 0 and np.abs(f1[:, :, -1]).max() == 0
     if pre2:
         base = got if (f16 and not f32_out and not no_out0) else ref
         t = base * s3 + h3
         ref2 = np.maximum(t, 0.1 * t)
-        got2 = y2[..., :Cout].float().cpu().numpy()
+        ah = aux_halo
+        got2 = y2[:, ah:ah + OH, ah:ah + OW, :Cout].float().cpu().numpy()
+        if ah:
+            f2 = y2.float().cpu().numpy()
+            assert np.abs(f2[:, 0]).max() == 0 and np.abs(f2[:, :, -1]).max() == 0
         tol2 = (6e-3 if f16 else 4e-5) * max(np.abs(ref2).max(), 1.0)
         assert np.abs(got2 - ref2).max() <= tol2, ("out2", float(np.abs(got2 - ref2).max()))
     if mode == "tc" and old > Cout and not f32_out:
@@ -168,6 +181,10 @@ def test_conv_tc_epilogue_variants(built):
         assert np.abs(got - ref).max() <= tol, kw
         if got1 is not None:
             assert np.abs(got1 - ref1).max() <= 4e-3 * max(np.abs(ref1).max(), 1.0), kw
+    # fp32 head scatter out of the halo-flat mode (RetinaNet regression head fed by a halo'd pre-activation)
+    for cout in (36, 20):
+        got, ref, _, _ = _conv_case(2, 24, 24, 256, cout, 3, 1, 1, mode="tc", act=None, f32_out=True, in_halo=1)
+        assert np.abs(got - ref).max() <= 2e-3 * max(np.abs(ref).max(), 1.0), ("flat head", cout)
     # head-style output: ragged Cout (100, 150), fp32, through the generic store path
     for cout in (100, 150, 75, 36, 189, 20, 4, 1):
         got, ref, _, _ = _conv_case(1, 10, 10, 256, cout, 3, 1, 1, mode="tc", act=None, f32_out=True)
@@ -222,14 +239,17 @@ def test_glue_kernels_vs_oracle_ops(built, dtype):
     s2, h2 = rng.uniform(.5, 1.5, 64).astype(np.float32), rng.standard_normal(64).astype(np.float32)
     xd = torch.zeros((2, 20, 22, 64), dtype=dt, device="cuda")
     xd[..., :16] = _dev(x, dt)
+    s1d, h1d, s2d, h2d = (_dev(a, torch.float32) for a in (s1, h1, s2, h2))   # kept alive across the launches
     for with_raw in (True, False):
         y = torch.zeros((2, 10, 11, 64), dtype=dt, device="cuda")
-        y1, y2 = torch.zeros_like(y), torch.zeros_like(y)
+        y1 = torch.zeros_like(y)
+        y2h = torch.zeros((2, 12, 13, 64), dtype=dt, device="cuda")      # out2 in the halo layout
         L.check(lib.odt_maxpool_affine(xd.data_ptr(), y.data_ptr() if with_raw else None, code, 2, 20, 22, 16, 64, 3, 2,
-                                       0, 0, _dev(s1, torch.float32).data_ptr(), _dev(h1, torch.float32).data_ptr(), 1,
-                                       y1.data_ptr(), _dev(s2, torch.float32).data_ptr(),
-                                       _dev(h2, torch.float32).data_ptr(), 2, y2.data_ptr(), st))
+                                       0, 0, s1d.data_ptr(), h1d.data_ptr(), 1, y1.data_ptr(), 0, s2d.data_ptr(),
+                                       h2d.data_ptr(), 2, y2h.data_ptr(), 1, st))
         torch.cuda.synchronize()
+        y2 = y2h[:, 1:11, 1:12]
+        assert float(y2h[:, 0].abs().max()) == 0 and float(y2h[:, :, 12].abs().max()) == 0
         if with_raw:
             np.testing.assert_array_equal(y[..., :16].float().cpu().numpy(), ref)
         else:
@@ -285,7 +305,8 @@ def test_glue_kernels_vs_oracle_ops(built, dtype):
     img = rng.integers(0, 256, (2, 9, 11, 3)).astype(np.float32)
     mean = (C.c_float * 3)(123.68, 116.779, 103.979)
     y = torch.full((2, 9, 11, 8), 7.0, dtype=dt, device="cuda")
-    L.check(lib.odt_normalize_input(_dev(img, torch.float32).data_ptr(), y.data_ptr(), code, 2, 9, 11, 8, mean, st))
+    imgd = _dev(img, torch.float32)
+    L.check(lib.odt_normalize_input(imgd.data_ptr(), y.data_ptr(), code, 2, 9, 11, 8, mean, st))
     got = y.float().cpu().numpy()
     ref = img - np.array([123.68, 116.779, 103.979], np.float32)
     np.testing.assert_allclose(got[..., :3], ref.astype(np.float16).astype(np.float32) if dtype == "f16" else ref,
@@ -497,6 +518,24 @@ def test_conv_tc_two_preactivation_outputs(built, shape, kw):
     tol = 2e-3 * max(np.abs(ref).max(), 1.0)
     if not kw.get("no_out0"):
         assert np.abs(got - ref).max() <= tol
+    assert np.abs(g1 - r1).max() <= 3 * tol
+
+
+@pytest.mark.parametrize("shape,kw,env", [
+    ((2, 40, 40, 7, 28, 1, 1, 1), {"residual": True}, {}),                        # im2col mode, 1x1 expand (RetinaNet)
+    ((2, 40, 40, 28, 28, 3, 1, 1), {"in_halo": 1}, {"ODT_TC_TAPN": "0"}),         # halo-flat mode
+    ((2, 40, 40, 28, 28, 3, 1, 1), {"in_halo": 1}, {"ODT_TC_TAPN": "2"}),         # taps-as-N
+    ((2, 40, 40, 16, 7, 1, 1, 1), {}, {"ODT_TC_THIN": "2"}),                      # thin CUDA-core kernel
+    ((2, 37, 41, 128, 256, 3, 2, 1), {"act": "leaky"}, {}),                       # stride 2, odd sizes, N = 256
+])
+def test_conv_extra_outputs_in_halo_layout(built, monkeypatch, shape, kw, env):
+    """out1 / out2 (the consumer pre-activations) written as [B][OH+2][OW+2][ld] with an untouched zero border, by
+    every kernel behind odt_conv2d_f16_tc: the 3x3 convolutions that read them then take the halo modes."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    got, ref, g1, r1 = _conv_case(*shape, mode="tc", seed=sum(shape), pre=True, pre2=True, aux_halo=1, **kw)
+    tol = 2e-3 * max(np.abs(ref).max(), 1.0)
+    assert np.abs(got - ref).max() <= tol, shape
     assert np.abs(g1 - r1).max() <= 3 * tol
 
 

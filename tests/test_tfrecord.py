@@ -246,3 +246,41 @@ def test_corrupt_records_raise_record_error_only(tr, tmp_path):
                 fn()
             except tr.RecordError.__mro__[1]:      # CheckpointError (RecordError derives from it)
                 pass
+
+
+def test_bicubic_resize_restatement():
+    """fill_mode='BICUBIC' (utils/image_augmentor.py:70-74,103-106): TF 1.13 ResizeBicubic, align_corners=True --
+    Keys kernel A=-0.75 from a 1024-step table, border taps clamped.  Pins that need no TensorFlow: weights sum to 1,
+    identity at equal size, exact hits on integer source positions, a constant stays constant, cubic accuracy on a
+    smooth ramp, separability (x then y), and the call path through preprocess()."""
+    from odt_b200 import tfrecord as R
+    t = R._bicubic_table()
+    i = np.arange(1025)
+    np.testing.assert_allclose(t[i * 2 + 1] + t[i * 2] + t[(1024 - i) * 2] + t[(1024 - i) * 2 + 1], 1.0, atol=2e-6)
+    assert t[0] == 1.0 and abs(t[1]) < 1e-7 and abs(t[2048]) < 1e-7          # distance 0 / 1 / 1
+    assert abs(t[1024] - 0.59375) < 1e-7 and abs(t[1025] + 0.09375) < 1e-7   # x = 0.5 with A = -0.75: (19/32, -3/32)
+    rng = np.random.default_rng(4)
+    img = rng.uniform(0, 255, (9, 13, 3)).astype(np.float32)
+    np.testing.assert_allclose(R._resize_bicubic_aligned(img, 9, 13), img, atol=1e-4)   # scale 1: offsets 0
+    up = R._resize_bicubic_aligned(img, 17, 25)                                          # scale exactly 1/2
+    np.testing.assert_allclose(up[::2, ::2], img, atol=1e-4)
+    mid = up[2, 1::2]                                                                    # row 1, half-way columns
+    c = np.clip(np.arange(12)[:, None] + np.array([-1, 0, 1, 2])[None], 0, 12)
+    exp = (img[1][c] * np.array([-0.09375, 0.59375, 0.59375, -0.09375], np.float32)[None, :, None]).sum(1)
+    np.testing.assert_allclose(mid, exp, atol=1e-3)
+    flat = np.full((5, 7, 3), 42.0, np.float32)
+    np.testing.assert_allclose(R._resize_bicubic_aligned(flat, 11, 4), 42.0, atol=1e-4)
+    ramp = (np.arange(20, dtype=np.float32)[:, None, None] * 3.0 + np.arange(30, dtype=np.float32)[None, :, None] * 2.0)
+    out = R._resize_bicubic_aligned(ramp, 33, 47)
+    yy = np.arange(33, dtype=np.float32) * (19 / 32)
+    xx = np.arange(47, dtype=np.float32) * (29 / 46)
+    lin = yy[:, None] * 3.0 + xx[None] * 2.0
+    # away from the clamped border taps the A = -0.75 kernel stays within ~7 % of a sample step of linear data
+    # (only A = -0.5 reproduces it exactly): slopes 3 and 2 per sample
+    np.testing.assert_allclose(out[3:-3, 3:-3, 0], lin[3:-3, 3:-3], atol=0.4)
+    cfg = {"output_shape": [24, 24], "fill_mode": "BICUBIC"}
+    gt = np.array([[2, 10, 3, 12, 5]], np.float32)
+    a, _ = R.preprocess(img, gt, dict(cfg), np.random.default_rng(0))
+    b, _ = R.preprocess(img, gt, dict(cfg, fill_mode="BILINEAR"), np.random.default_rng(0))
+    assert a.shape == (24, 24, 3) and np.abs(a - b).max() > 1e-3      # a different resampler really ran
+    np.testing.assert_allclose(a, R._resize_bicubic_aligned(img, 24, 24), atol=1e-5)
