@@ -383,7 +383,8 @@ int conv_tapn_try(const void* in, const void* weights, const odt_conv_params* p,
                 (!p->out0 || aligned(p->out0, p->out0_img_stride, p->out0_pix_stride, p->Cout_pad)) &&
                 (!p->out1 || aligned(p->out1, p->out1_img_stride, p->out1_pix_stride, p->Cout_pad)) &&
                 (!p->out2 || aligned(p->out2, p->out2_img_stride, p->out2_pix_stride, p->Cout_pad)) &&
-                (!p->residual || (((uintptr_t)p->residual & 15) == 0 && p->out0));
+                (!p->residual || (((uintptr_t)p->residual & 15) == 0 && p->out0_img_stride % 8 == 0 &&
+                                  p->out0_pix_stride % 8 == 0 && p->out0_pix_stride >= p->Cout_pad));
   if (pool)
     out_ok = out_ok && p->out0 && !p->residual && !p->out1 && !p->out2 && p->OH % 2 == 0 && p->OW % 2 == 0;
   else

@@ -218,7 +218,10 @@ static int thin_plan(const void* in, const odt_conv_params* p, bool force, ThinG
                      (!p->out0 || (p->out0_dtype == ODT_F16 && aligned(p->out0, p->out0_img_stride, p->out0_pix_stride))) &&
                      (!p->out1 || aligned(p->out1, p->out1_img_stride, p->out1_pix_stride)) &&
                      (!p->out2 || aligned(p->out2, p->out2_img_stride, p->out2_pix_stride)) &&
-                     (!p->residual || (((uintptr_t)p->residual & 15) == 0 && p->out0));
+                     // the residual shares out0's addressing (strides / halo), whether or not out0 itself is stored
+                     (!p->residual || (((uintptr_t)p->residual & 15) == 0 && p->out0_img_stride % 8 == 0 &&
+                                       p->out0_pix_stride % 8 == 0 && p->out0_pix_stride >= co8r * 8 &&
+                                       (p->out0 || p->out0_dtype == ODT_F16)));
   if (!io_ok) return ODT_ERR_UNSUPPORTED;
   const long long M = (long long)p->B * p->OH * p->OW;
   if (M >= (1ll << 31) * THIN_THREADS) return ODT_ERR_UNSUPPORTED;

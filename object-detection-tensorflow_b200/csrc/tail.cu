@@ -10,6 +10,7 @@
 // Reference call sites restated here (never copied): SSD300.py:157-190,323-343;
 // RetinaNet.py:224-256,328-355; YOLOv3.py:320-368,419-433; FCOS.py:130-150,197-264.
 #include <stdlib.h>
+#include <string.h>
 
 #include "tail_common.cuh"
 #include "tc_ptx.cuh"
@@ -19,11 +20,10 @@ namespace odt {
 constexpr int kDecodeWarps = 8;
 constexpr int kGroupFloats = 32 * kRow;          // one warp iteration = 32 candidate rows = 3200 contiguous bytes
 constexpr int kGroupBytes = kGroupFloats * 4;
-constexpr int kDecodeStages = 2;
-
+template <int STAGES>
 struct DecodeSmem {
-  float rows[kDecodeWarps][kDecodeStages][kGroupFloats];  // 51 200 B: 4 CTAs / SM
-  unsigned long long bar[kDecodeWarps][kDecodeStages];
+  float rows[kDecodeWarps][STAGES][kGroupFloats];  // 25 600 B per stage
+  unsigned long long bar[kDecodeWarps][STAGES];
 };
 
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -38,7 +38,7 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
 // 826 warp instructions per group; this kernel: KIND at compile time, no 64-bit divisions, the row's scores stay in
 // registers only).  Then one lane per row: score activation, background filter, threshold, per-class ballots and ONE
 // atomic per (warp, class) to reserve the candidate slots.
-template <int KIND, int OCC>
+template <int KIND, int OCC, int STAGES>
 __global__ void __launch_bounds__(kDecodeWarps * 32, OCC)
     decode_candidates_kernel(const float* __restrict__ head, const __grid_constant__ TailP tp,
                              long long total_rows, unsigned long long* __restrict__ cand_keys,
@@ -46,12 +46,12 @@ __global__ void __launch_bounds__(kDecodeWarps * 32, OCC)
   pdl_launch_dependents();
   const odt_tail_params& p = tp.p;
   extern __shared__ __align__(128) unsigned char dsm_raw[];
-  DecodeSmem& sm = *reinterpret_cast<DecodeSmem*>(dsm_raw);
+  DecodeSmem<STAGES>& sm = *reinterpret_cast<DecodeSmem<STAGES>*>(dsm_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(&sm.bar[warp][0]);
   if (lane == 0) {
 #pragma unroll
-    for (int s = 0; s < kDecodeStages; ++s) mbar_init(bar0 + 8u * s, 1);
+    for (int s = 0; s < STAGES; ++s) mbar_init(bar0 + 8u * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
@@ -69,13 +69,23 @@ __global__ void __launch_bounds__(kDecodeWarps * 32, OCC)
       bulk_load_1d(smem_u32(&sm.rows[warp][slot][0]), head + gg * kGroupFloats, kGroupBytes, bar0 + 8u * slot);
     }
   };
-  if (lane == 0 && g < groups) issue(g, 0);
+  // STAGES - 1 groups in flight ahead of the one being decoded
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s)
+      if (g + (long long)s * step < groups) issue(g + (long long)s * step, s);
+  }
   uint32_t phase = 0u;  // bit s = parity of stage s
-  for (int it = 0; g < groups; g += step, ++it) {
-    const int slot = it & 1;
+  int slot = 0;
+  for (; g < groups; g += step) {
     const int nrows = (int)min((long long)32, total_rows - g * 32);
     float* my = &sm.rows[warp][slot][0];
-    if (lane == 0 && g + step < groups) issue(g + step, slot ^ 1);
+    {
+      // refill the stage that was drained in the previous iteration (its readers passed the __syncwarp below)
+      const long long gn = g + (long long)(STAGES - 1) * step;
+      const int sn = slot == 0 ? STAGES - 1 : slot - 1;
+      if (lane == 0 && gn < groups) issue(gn, sn);
+    }
     if (g < full_groups) {
       mbar_wait(bar0 + 8u * slot, (phase >> slot) & 1u);
       phase ^= 1u << slot;
@@ -188,6 +198,7 @@ __global__ void __launch_bounds__(kDecodeWarps * 32, OCC)
       }
     }
     __syncwarp();  // every lane is done with this stage before lane 0 refills it (next iteration's issue)
+    if (++slot == STAGES) slot = 0;
     n += adv_n;
     b += adv_b;
     if (n >= N) {
@@ -204,6 +215,54 @@ constexpr int kNmsSmemKeys = 1024;  // candidates (keys + boxes, 24 KB) a CTA wo
 constexpr int kNmsWarpMax = 256;           // lists up to this length are run by one warp (8 keys per lane in registers)
 constexpr int kNselOverflowBit = 1 << 30;  // per-(image, class) "list was truncated at cap" flag in nsel_all
 
+// Class-major compaction of one image's per-class results into its packed record, run by whoever finishes the
+// image's LAST list (a warp of nms_short_kernel or a block of nms_per_class_kernel): `nt` cooperating threads with
+// ranks `t` (nt = 32 -> one warp, barriers are __syncwarp; nt = block size -> __syncthreads), `s_off`: C + 1 ints
+// of shared memory.  The first warp of the group computes the prefix sum (one load per lane).
+__device__ __forceinline__ void compact_image(int b, int C, int MB, int t, int nt, int* s_off, const int* nsel_all,
+                                              const float* st_det, const int* st_anchor, float* dets,
+                                              long long det_img_stride, int* det_anchor, int* det_count, int* work) {
+  const long long D = (long long)C * MB;
+  float* img_dets = dets + (long long)b * det_img_stride;
+  if (t < 32) {
+    const int lane = t;
+    const int v = lane < C ? __ldcg(nsel_all + (long long)b * C + lane) : 0;
+    const int n_l = v & ~kNselOverflowBit;
+    int incl = n_l;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += up;
+    }
+    if (lane < C) s_off[lane] = incl - n_l;
+    const int acc = __shfl_sync(0xffffffffu, incl, 31);
+    const int ovf = __any_sync(0xffffffffu, (v & kNselOverflowBit) != 0);
+    if (lane == 0) {
+      s_off[C] = acc;
+      det_count[b] = acc;
+      work[b] = 0;
+      // packed record (the unit the multi-GPU all-gather and the host read-back ship): the two floats
+      // behind an image's D rows carry its detection count and its overflow flag
+      if (det_img_stride >= D * 6 + 2) {
+        img_dets[D * 6] = (float)acc;
+        img_dets[D * 6 + 1] = ovf ? 1.f : 0.f;
+      }
+    }
+  }
+  if (nt == 32) __syncwarp(); else __syncthreads();
+  for (int i = t; i < C * MB; i += nt) {
+    const int ci = i / MB, k = i % MB;
+    const int ns = s_off[ci + 1] - s_off[ci];
+    if (k < ns) {
+      const long long dst = s_off[ci] + k;
+      const float* sp = st_det + (((long long)b * C + ci) * MB + k) * 6;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) img_dets[dst * 6 + q] = __ldcg(sp + q);
+      det_anchor[(long long)b * D + dst] = __ldcg(st_anchor + ((long long)b * C + ci) * MB + k);
+    }
+  }
+}
+
 // ---- short lists: one WARP per (image, class) list of up to kNmsWarpMax candidates ------------------------------
 // Keys (8 per lane) and the min/max-normalised boxes + areas of the lane's candidates live in registers; the original
 // boxes (what the record reports) in 4 KB of shared memory per warp.  A round = lane-local arg-max over 8 registers,
@@ -219,10 +278,13 @@ constexpr int kShortPerLane = kNmsWarpMax / 32;
 __global__ void __launch_bounds__(kShortWarps * 32)
     nms_short_kernel(const float* __restrict__ head, const __grid_constant__ TailP tp, int B,
                      const unsigned long long* __restrict__ cand_keys, const int* __restrict__ cand_count,
-                     int* __restrict__ scratch, int* __restrict__ status) {
+                     int* __restrict__ scratch, int* __restrict__ status, float* __restrict__ dets,
+                     int* __restrict__ det_anchor, int* __restrict__ det_count, int* __restrict__ work,
+                     long long det_img_stride) {
   pdl_launch_dependents();
   const odt_tail_params& p = tp.p;
   __shared__ float4 s_box[kShortWarps][kNmsWarpMax];
+  __shared__ int s_offw[kShortWarps][33];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = p.nms_classes, MB = p.max_boxes;
   const long long list = (long long)blockIdx.x * kShortWarps + warp;
@@ -299,6 +361,9 @@ __global__ void __launch_bounds__(kShortWarps * 32)
     const float cy1 = fminf(cur.x, cur.z), cx1 = fminf(cur.y, cur.w);
     const float cy2 = fmaxf(cur.x, cur.z), cx2 = fmaxf(cur.y, cur.w);
     const float car = __fmul_rn(__fsub_rn(cy2, cy1), __fsub_rn(cx2, cx1));
+    // eight independent, branch-free IoU tests per lane; the (rare) candidates whose inter - thr*union is too close
+    // to zero for the fused difference to decide are collected in a mask and re-done with TF's exact division
+    unsigned fuzzy = 0u;
 #pragma unroll
     for (int j = 0; j < kShortPerLane; ++j) {
       const float ih = fmaxf(__fsub_rn(fminf(y2[j], cy2), fmaxf(y1[j], cy1)), 0.f);
@@ -306,14 +371,37 @@ __global__ void __launch_bounds__(kShortWarps * 32)
       const float inter = __fmul_rn(ih, iw);
       const float uni = __fsub_rn(__fadd_rn(ar[j], car), inter);
       const float diff = __fmaf_rn(-thr, uni, inter);       // inter - thr * union, one rounding
-      bool sup;
-      if (fabsf(diff) > 1e-6f * uni) sup = diff > 0.f;       // clear margin (false for NaN: exact path below)
-      else sup = __fdiv_rn(inter, uni) > thr;                // TF's own comparison
-      sup = sup && ar[j] > 0.f && car > 0.f;                 // degenerate boxes have IoU 0
-      if (sup || (mine && j == bj)) k[j] = 0ull;
+      const bool live = k[j] != 0ull && ar[j] > 0.f && car > 0.f;   // degenerate boxes have IoU 0
+      const bool clear = fabsf(diff) > 1e-6f * uni;                  // false for NaN: exact path
+      fuzzy |= (live && !clear) ? (1u << j) : 0u;
+      if ((live && clear && diff > 0.f) || (mine && j == bj)) k[j] = 0ull;
+    }
+    if (__any_sync(0xffffffffu, fuzzy != 0u)) {
+#pragma unroll
+      for (int j = 0; j < kShortPerLane; ++j) {
+        if ((fuzzy >> j) & 1u) {
+          const float ih = fmaxf(__fsub_rn(fminf(y2[j], cy2), fmaxf(y1[j], cy1)), 0.f);
+          const float iw = fmaxf(__fsub_rn(fminf(x2[j], cx2), fmaxf(x1[j], cx1)), 0.f);
+          const float inter = __fmul_rn(ih, iw);
+          if (__fdiv_rn(inter, __fsub_rn(__fadd_rn(ar[j], car), inter)) > thr) k[j] = 0ull;  // TF's own comparison
+        }
+      }
     }
   }
-  if (lane == 0) nsel_all[bc] = nsel | (overflow ? kNselOverflowBit : 0);
+  // per-image completion: the list that finishes an image LAST (in this kernel or in nms_per_class_kernel, which
+  // runs after it and takes the long lists) compacts the image's record
+  int done = 0;
+  if (lane == 0) {
+    nsel_all[bc] = nsel | (overflow ? kNselOverflowBit : 0);
+    __threadfence();
+    done = atomicAdd(&work[b], 1);
+  }
+  done = __shfl_sync(0xffffffffu, done, 0);
+  if (done == C - 1) {
+    __threadfence();
+    compact_image(b, C, MB, lane, 32, s_offw[warp], nsel_all, st_det, st_anchor, dets, det_img_stride, det_anchor,
+                  det_count, work);
+  }
 }
 
 struct NmsSmem {
@@ -370,6 +458,7 @@ __global__ void __launch_bounds__(kNmsThreads)
   const long long bc = (long long)b * C + c;
 
   int cnt = cand_count[b * p.num_fg + c];
+  const int cnt_raw = cnt;  // what nms_short_kernel looked at
   const bool overflow = cnt > p.cap;
   if (overflow) {
     if (tid == 0) atomicExch(status, ODT_ERR_OVERFLOW);
@@ -379,11 +468,8 @@ __global__ void __launch_bounds__(kNmsThreads)
   const float* hb = head + (long long)b * p.N * kRow;
   const int cnt_all = cnt;
   int nsel = 0;
-  if (cnt_all <= kNmsWarpMax && short_done) {
-    // short list: nms_short_kernel (one warp per list) has already written its kept boxes and nsel_all[bc];
-    // this CTA only takes part in the per-image completion below
-    nsel = -1;
-  } else {
+  if (cnt_raw <= kNmsWarpMax && short_done) return;  // nms_short_kernel has handled (and counted) this list
+  {
   for (int attempt = 0; attempt < 2; ++attempt) {
   // ---- attempt 0 on a long list: exact prefilter (see the kernel comment) ----
   bool subset = false;
@@ -582,51 +668,19 @@ __global__ void __launch_bounds__(kNmsThreads)
   if (!(subset && nsel < MB && cnt < cnt_all)) break;
   }  // attempt
   }  // long list
-  if (tid == 0 && nsel >= 0) nsel_all[bc] = nsel | (overflow ? kNselOverflowBit : 0);
-
-  // class-major compaction by the last block of this image
-  __threadfence();
-  __syncthreads();
+  // class-major compaction by whoever finishes the image's last list
   if (tid == 0) {
-    int done = atomicAdd(&work[b], 1);
+    nsel_all[bc] = nsel | (overflow ? kNselOverflowBit : 0);
+    __threadfence();  // this thread wrote the kept boxes and the count: release them before the counter moves
+    const int done = atomicAdd(&work[b], 1);
     s_last = (done == C - 1);
   }
   __syncthreads();
   if (!s_last) return;
   __threadfence();
   __shared__ int s_off[33];
-  const long long D = (long long)C * MB;
-  float* img_dets = dets + (long long)b * det_img_stride;
-  if (tid == 0) {
-    int acc = 0, ovf = 0;
-    for (int i = 0; i < C; ++i) {
-      s_off[i] = acc;
-      const int v = ((volatile int*)nsel_all)[(long long)b * C + i];
-      acc += v & ~kNselOverflowBit;
-      ovf |= v & kNselOverflowBit;
-    }
-    s_off[C] = acc;
-    det_count[b] = acc;
-    work[b] = 0;
-    // packed record (the unit the multi-GPU all-gather and the host read-back ship): the two floats
-    // behind an image's D rows carry its detection count and its overflow flag
-    if (det_img_stride >= D * 6 + 2) {
-      img_dets[D * 6] = (float)acc;
-      img_dets[D * 6 + 1] = ovf ? 1.f : 0.f;
-    }
-  }
-  __syncthreads();
-  for (int i = tid; i < C * MB; i += blockDim.x) {
-    int ci = i / MB, k = i % MB;
-    int ns = s_off[ci + 1] - s_off[ci];
-    if (k < ns) {
-      long long dst = s_off[ci] + k;
-      const float* s = st_det + (((long long)b * C + ci) * MB + k) * 6;
-#pragma unroll
-      for (int q = 0; q < 6; ++q) img_dets[dst * 6 + q] = __ldcg(s + q);
-      det_anchor[(long long)b * D + dst] = __ldcg(st_anchor + ((long long)b * C + ci) * MB + k);
-    }
-  }
+  compact_image(b, C, MB, tid, kNmsThreads, s_off, nsel_all, st_det, st_anchor, dets, det_img_stride, det_anchor,
+                det_count, work);
 }
 
 }  // namespace odt
@@ -660,32 +714,35 @@ extern "C" int odt_decode_candidates(const float* head, const odt_tail_params* p
   long long rows = (long long)B * p->N;
   long long groups = (rows + 31) / 32;
   int blocks = (int)((groups + kDecodeWarps - 1) / kDecodeWarps);
-  int per_sm = 8;  // 4 CTAs resident per SM (51 KB of staging each), two waves
+  int per_sm = 6;  // 2-3 CTAs resident per SM: two to three waves
   if (const char* e = getenv("ODT_DECODE_BLOCKS_PER_SM")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;
   int maxb = kNumSMs * per_sm;
   if (blocks > maxb) blocks = maxb;
-  // OCC = CTAs per SM the kernel is compiled for: 3 (72 registers, no spills) or 4 (64 registers, ~20 spilled words);
-  // ODT_DECODE_OCC selects, default from the round-2 A/B (profiles/r02_tail.md)
-  int occ = 3;
-  if (const char* e = getenv("ODT_DECODE_OCC")) occ = atoi(e) == 4 ? 4 : 3;
-#define ODT_DECODE_LAUNCH(KIND_, OCC_)                                                                            \
-  do {                                                                                                            \
-    static bool attr_done = false;                                                                                \
-    if (!attr_done) {                                                                                             \
-      ODT_CUDA_OK(cudaFuncSetAttribute(decode_candidates_kernel<KIND_, OCC_>,                                     \
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeSmem)));    \
-      attr_done = true;                                                                                           \
-    }                                                                                                             \
-    decode_candidates_kernel<KIND_, OCC_><<<blocks, kDecodeWarps * 32, sizeof(DecodeSmem), st>>>(head, tp, rows,  \
-                                                                                                 cand_keys,       \
-                                                                                                 cand_count);     \
+  // Two builds per kind (A/B by ODT_DECODE_CFG, default from profiles/r02_tail.md): "3x2" = 3 CTAs / SM with 2 stages
+  // per warp (24 warps x 1 group in flight ahead), "2x4" = 2 CTAs / SM with 4 stages (16 warps x 3 groups ahead: more
+  // bytes in flight per SM, fewer warps to hide instruction latency)
+  // measured (profiles/r02_tail.md): 3x2 22.1 / 75.8 / 43.9 us against 2x4 26.0 / 79.3 / 56.7 us (SSD300 B=64 /
+  // RetinaNet-800 B=16 / YOLOv3 B=32): the kernel is bound by per-warp instruction issue, not by bytes in flight
+  int deep = 0;
+  if (const char* e = getenv("ODT_DECODE_CFG")) deep = strcmp(e, "2x4") == 0 ? 1 : 0;
+#define ODT_DECODE_LAUNCH(KIND_, OCC_, ST_)                                                                      \
+  do {                                                                                                           \
+    static bool attr_done = false;                                                                               \
+    if (!attr_done) {                                                                                            \
+      ODT_CUDA_OK(cudaFuncSetAttribute(decode_candidates_kernel<KIND_, OCC_, ST_>,                               \
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,                              \
+                                       (int)sizeof(DecodeSmem<ST_>)));                                           \
+      attr_done = true;                                                                                          \
+    }                                                                                                            \
+    decode_candidates_kernel<KIND_, OCC_, ST_><<<blocks, kDecodeWarps * 32, sizeof(DecodeSmem<ST_>), st>>>(      \
+        head, tp, rows, cand_keys, cand_count);                                                                  \
   } while (0)
   if (p->kind == ODT_DECODE_SSD) {
-    if (occ == 4) ODT_DECODE_LAUNCH(ODT_DECODE_SSD, 4); else ODT_DECODE_LAUNCH(ODT_DECODE_SSD, 3);
+    if (deep) ODT_DECODE_LAUNCH(ODT_DECODE_SSD, 2, 4); else ODT_DECODE_LAUNCH(ODT_DECODE_SSD, 3, 2);
   } else if (p->kind == ODT_DECODE_YOLO3) {
-    if (occ == 4) ODT_DECODE_LAUNCH(ODT_DECODE_YOLO3, 4); else ODT_DECODE_LAUNCH(ODT_DECODE_YOLO3, 3);
+    if (deep) ODT_DECODE_LAUNCH(ODT_DECODE_YOLO3, 2, 4); else ODT_DECODE_LAUNCH(ODT_DECODE_YOLO3, 3, 2);
   } else {
-    if (occ == 4) ODT_DECODE_LAUNCH(ODT_DECODE_FCOS, 4); else ODT_DECODE_LAUNCH(ODT_DECODE_FCOS, 3);
+    if (deep) ODT_DECODE_LAUNCH(ODT_DECODE_FCOS, 2, 4); else ODT_DECODE_LAUNCH(ODT_DECODE_FCOS, 3, 2);
   }
 #undef ODT_DECODE_LAUNCH
   ODT_LAUNCH_OK();
@@ -734,7 +791,7 @@ extern "C" int odt_nms_per_class(const float* head, const odt_tail_params* p, in
   if (short_done) {
     const long long lists = (long long)B * p->nms_classes;
     nms_short_kernel<<<(unsigned)((lists + kShortWarps - 1) / kShortWarps), kShortWarps * 32, 0, st>>>(
-        head, tp, B, cand_keys, cand_count, sel_scratch, status);
+        head, tp, B, cand_keys, cand_count, sel_scratch, status, dets, det_anchor, det_count, work, dets_img_stride);
   }
   nms_per_class_kernel<<<grid, kNmsThreads, sizeof(NmsSmem), st>>>(
       head, tp, B, cand_keys, cand_count, dets, det_anchor, det_count, sel_scratch, work, status,

@@ -290,9 +290,9 @@ class _Detector:
     # ---- training / checkpoints (API surface) --------------------
     def train_one_epoch(self, lr):
         raise NotImplementedError(
-            "%s.train_one_epoch: the training step (loss backward + momentum update) is outside "
-            "the accelerated hot path in this round (SURVEY.md 8f); inference and the RetinaNet "
-            "loss forward are available" % self.name)
+            "%s.train_one_epoch: the training step exists for SSD300 / SSD512 (odt_b200/train.py: autograd forward / "
+            "backward + Momentum, SURVEY.md 8f row 2); for this family only inference and the loss forward "
+            "(loss_forward) are available" % self.name)
 
     def save_weight(self, mode, path):
         assert mode in ["latest", "best"]
@@ -361,6 +361,36 @@ class SSD300(_Detector):
 
     def _build(self, batch, precision, allow_tc=True):
         return nets.build_ssd(self.input_size, batch, self.config, precision, self.device, allow_tc)
+
+    def trainer(self):
+        """The training state (variables as tensors, Momentum slots, BN moving statistics), created on first use."""
+        if getattr(self, "_trainer", None) is None:
+            from .train import SSDTrainer
+            self._trainer = SSDTrainer(self, self.device if torch.cuda.is_available() else "cpu")
+        return self._trainer
+
+    def train_one_epoch(self, lr):
+        """ref SSD300.py:473-484: `num_train // batch_size` steps of [train_op, loss] on the train generator; returns
+        the mean loss.  The step itself is odt_b200/train.py (training-mode forward, the reference's loss, backward,
+        Momentum 0.9 + L2); afterwards the inference engines are rebuilt from the updated variables."""
+        assert self.mode == "train", "construct the model with mode='train'"
+        tr = self.trainer()
+        self.train_initializer()
+        num_iters = self.num_train // self.batch_size
+        mean_loss = []
+        for i in range(num_iters):
+            images, gt = self.train_iterator.get_next()
+            if self.data_format == "channels_first":
+                images = np.transpose(np.asarray(images), (0, 2, 3, 1))
+            loss = tr.step(images, gt, lr)
+            sys.stdout.write("\r>> iters %d/%d loss %s" % (i, num_iters, loss))
+            sys.stdout.flush()
+            mean_loss.append(loss)
+        sys.stdout.write("\n")
+        self._weights = tr.export()
+        self._engines = {}
+        self.global_step = tr.global_step
+        return float(np.mean(mean_loss)) if mean_loss else float("nan")
 
 
     def loss_forward(self, images, ground_truth, precision=None, return_info=False):

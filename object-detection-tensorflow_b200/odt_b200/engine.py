@@ -209,7 +209,10 @@ class ConvOp(Op):
         self.rgbx = 0
         if (self.is_image and f16 and net.allow_tc and self.pre is None and self.head is None
                 and os.environ.get("ODT_STEM_RGBX", "1") != "0"):
-            if (R, self.stride, cout) in ((3, 1, 64), (3, 1, 32)):
+            # same-box A/B (profiles/r02_ab_micro.md): RetinaNet-800 stem 0.36 -> 0.205 ms, but the 3x3 / stride-1
+            # stems gain nothing (SSD300 conv1_1 0.254 -> 0.278 ms incl. the pack pass): ODT_STEM_RGBX=2 forces them
+            force3 = os.environ.get("ODT_STEM_RGBX") == "2"
+            if (R, self.stride, cout) in ((3, 1, 64), (3, 1, 32)) and force3:
                 self.rgbx = 1
             elif (R, self.stride, cout) == (7, 2, 16) and Wd % 2 == 0 and pl % 2 == 0 and pl <= 4 and pt <= 4:
                 self.rgbx = 4

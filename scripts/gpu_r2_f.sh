@@ -1,0 +1,29 @@
+#!/bin/bash
+# round 2, call F: decode staging A/B, branch-free short NMS, parallel compaction, thin residual, upsample fix
+mkdir -p gpurun_out
+python __graft_entry__.py > gpurun_out/build.log 2>&1 || { echo BUILD FAILED; tail -20 gpurun_out/build.log; }
+timeout 1500 python -m pytest tests -q -m gpu --timeout 600 > gpurun_out/r2f_gpu_tests.log 2>&1
+echo "pytest -m gpu exit $?"; grep -E "^(FAILED|ERROR)|passed|failed" gpurun_out/r2f_gpu_tests.log | tail -n 15
+for cfg in 2x4 3x2 2x4 3x2; do
+  for m in "ssd300 64" "retinanet 16" "yolov3 32"; do
+    echo "CFG=$cfg $(ODT_DECODE_CFG=$cfg timeout 300 python scripts/tail_micro.py $m 2>&1 | tail -n 1)"
+  done
+done
+for short in 0 1 0 1; do
+  for m in "ssd300 64" "retinanet 16"; do
+    echo "NMS_SHORT=$short $(ODT_NMS_SHORT=$short timeout 300 python scripts/tail_micro.py $m 2>&1 | tail -n 1)"
+  done
+done
+for m in "retinanet 16" "ssd300 64"; do
+  n=$(echo $m | tr ' ' '_')
+  timeout 600 python scripts/profile_ops.py $m > gpurun_out/r2f_ops_$n.txt 2>&1; echo "== $m: $(grep -E 'CUDA-graph' gpurun_out/r2f_ops_$n.txt)"; grep -E "^decode" gpurun_out/r2f_ops_$n.txt
+done
+grep -E "k1 s1\]|topdown" gpurun_out/r2f_ops_retinanet_16.txt | head -12 | cut -c1-100
+timeout 1200 python bench.py --steps 20 --warmup 5 > gpurun_out/r2f_bench_n1.json 2> gpurun_out/r2f_bench_n1.err; echo "bench exit $?"; tail -n 3 gpurun_out/r2f_bench_n1.err; python - <<'P'
+import json
+d=json.loads(open('gpurun_out/r2f_bench_n1.json').read().strip().splitlines()[-1])
+print('value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']['value'],d['e2e'].get('clocks'),'frac',d['roofline']['frac_sustained'],d['roofline']['whole_step_frac_sustained'],d['clocks'])
+print('ssd tail',{k:d['tail_roofline_ssd300'][k] for k in ('decode_us','nms_us','frac_of_hbm','decode_frac_of_hbm','launch_floor_us')})
+w=d['workloads']['retinanet800_b16']; print('retina',w['value'],w['ms_per_step'],w['e2e']['value'],w['roofline']['whole_step_frac_sustained'],w['clocks'],w['e2e']['clocks'])
+print('retina tail',{k:d['tail_roofline'][k] for k in ('decode_us','nms_us','frac_of_hbm','decode_frac_of_hbm')})
+P

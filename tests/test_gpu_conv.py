@@ -688,6 +688,8 @@ def test_conv1_2_full_size_properties(built, monkeypatch, tapn):
     ((2, 41, 39, 14, 14, 3, 2, 1), {"in_halo": 1}),                                     # stride 2, odd sizes
     ((2, 40, 40, 14, 14, 3, 2, 1), {"out_halo": 1}),
     ((2, 20, 20, 32, 32, 1, 1, 1), {"no_out0": True, "pre": True}),                     # widest 1x1, out1 only
+    # RetinaNet's 1x1 expand as the engine launches it: residual added, raw sum not stored, both consumers' BN+ReLU
+    ((2, 40, 40, 7, 28, 1, 1, 1), {"residual": True, "pre": True, "pre2": True, "no_out0": True, "aux_halo": 1}),
 ])
 def test_conv_thin_matches_reference(built, monkeypatch, shape, kw):
     """CUDA-core kernel for very thin layers (csrc/conv_thin.cu) behind the same entry point."""

@@ -434,3 +434,45 @@ def test_sharded_two_gpus_equals_single(built):
                         "--master-addr", "127.0.0.1", "--master-port", "29547",
                         os.path.join(root, "scripts", "check_sharded.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "OK" in r.stdout, (r.stdout[-2000:], r.stderr[-3000:])
+
+
+def test_ssd_training_step_on_gpu(built):
+    """train_one_epoch's step on the GPU (odt_b200/train.py): training-mode forward, loss, backward, Momentum.  The
+    autograd loss agrees with the hand-written CUDA loss-forward kernel (odt_ssd_loss_fwd) on the same rows, the step
+    changes every trainable variable, and the updated weights flow into the inference engines."""
+    import torch
+    from odt_b200 import nets
+    from odt_b200.engine import RowsHarness
+    import SSD300
+
+    class It:
+        def get_next(self):
+            return img, gt
+    provider = {"data_shape": [300, 300, 3], "num_train": 2, "num_val": 0, "train_generator": ((lambda: None), It()),
+                "val_generator": None}
+    m = SSD300.SSD300(model_cfg("ssd", mode="train", batch_size=2, bn_init="trained"), provider)
+    rng = np.random.default_rng(3)
+    img = _img(2, 300, 300, seed=8)
+    gt = np.full((2, 10, 5), -1.0, np.float32)
+    for b in range(2):
+        n = 3 + 2 * b
+        gt[b, :n, 0:2] = rng.uniform(60, 240, (n, 2))
+        gt[b, :n, 2:4] = rng.uniform(30, 150, (n, 2))
+        gt[b, :n, 4] = rng.integers(0, 20, n)
+    tr = m.trainer()
+    assert tr.device.type == "cuda"
+    rows = tr.forward_rows(img)
+    per = [float(tr.image_loss(rows[b], gt[b])[0]) for b in range(2)]
+    levels = [(h, w, a) for (h, w), a in zip(tr._shapes, (4, 6, 6, 6, 4, 4))]
+    hrn = RowsHarness(nets.ssd_tail(300, m.config), levels, rows.detach().cpu().numpy())
+    got = hrn.loss("ssd", gt)
+    for b in range(2):
+        print("image %d: autograd loss %.6f, CUDA loss-forward kernel %.6f" % (b, per[b], got[b]))
+        assert abs(per[b] - got[b]) <= 5e-5 * max(abs(per[b]), 1.0)
+    w0 = {k: v.detach().clone() for k, v in tr.params.items()}
+    loss = m.train_one_epoch(1e-3)
+    assert np.isfinite(loss) and m.global_step == 1
+    changed = sum(int(not torch.equal(w0[k], tr.params[k].detach())) for k in w0)
+    assert changed == len(w0), "every trainable variable receives a gradient (data term or weight decay)"
+    res = m.detect_batch(img[:1])          # inference engine rebuilt from the updated variables
+    assert len(res) == 1

@@ -144,4 +144,6 @@ def test_thin_plan_declines_what_the_kernel_cannot_do(host):
     assert _run(host, 1, 8, 8, 24, 8, 3, 1)[0] == unsupported          # 3x3 with Cin > 16
     assert _run(host, 1, 8, 8, 16, 16, 3, 1, force=0)[0] == unsupported  # 2 304 multiply-adds per pixel: mode 1 declines
     assert _run(host, 1, 8, 8, 16, 16, 3, 1, force=1)[0] == 0
-    assert _run(host, 1, 8, 8, 8, 16, 3, 1, force=0)[0] == 0            # 1 152: taken
+    assert _run(host, 1, 8, 8, 8, 16, 3, 1, force=0)[0] == unsupported  # mode 1 takes 1x1 layers only (round-2 A/B:
+    assert _run(host, 1, 8, 8, 8, 16, 3, 1, force=1)[0] == 0            # every 3x3 is faster through taps-as-N)
+    assert _run(host, 1, 8, 8, 16, 8, 1, 1, force=0)[0] == 0            # 1x1, 128 multiply-adds per pixel: taken
