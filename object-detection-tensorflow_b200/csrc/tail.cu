@@ -212,13 +212,12 @@ __global__ void __launch_bounds__(kDecodeWarps * 32, OCC)
 constexpr int kNmsThreads = 256;
 constexpr int kNmsSmemKeys = 1024;  // candidates (keys + boxes, 24 KB) a CTA works on in shared memory: 8 CTAs / SM
 
-constexpr int kNmsWarpMax = 256;           // lists up to this length are run by one warp (8 keys per lane in registers)
 constexpr int kNselOverflowBit = 1 << 30;  // per-(image, class) "list was truncated at cap" flag in nsel_all
 
 // Class-major compaction of one image's per-class results into its packed record, run by whoever finishes the
-// image's LAST list (a warp of nms_short_kernel or a block of nms_per_class_kernel): `nt` cooperating threads with
-// ranks `t` (nt = 32 -> one warp, barriers are __syncwarp; nt = block size -> __syncthreads), `s_off`: C + 1 ints
-// of shared memory.  The first warp of the group computes the prefix sum (one load per lane).
+// image's LAST list: `nt` cooperating threads with ranks `t` (nt = 32 -> one warp, barriers are __syncwarp; nt = block
+// size -> __syncthreads), `s_off`: C + 1 ints of shared memory.  The first warp of the group computes the prefix sum
+// (one load per lane: one L2 round trip instead of C dependent ones).
 __device__ __forceinline__ void compact_image(int b, int C, int MB, int t, int nt, int* s_off, const int* nsel_all,
                                               const float* st_det, const int* st_anchor, float* dets,
                                               long long det_img_stride, int* det_anchor, int* det_count, int* work) {
@@ -263,147 +262,6 @@ __device__ __forceinline__ void compact_image(int b, int C, int MB, int t, int n
   }
 }
 
-// ---- short lists: one WARP per (image, class) list of up to kNmsWarpMax candidates ------------------------------
-// Keys (8 per lane) and the min/max-normalised boxes + areas of the lane's candidates live in registers; the original
-// boxes (what the record reports) in 4 KB of shared memory per warp.  A round = lane-local arg-max over 8 registers,
-// two redux.sync, one ballot; then the 8 IoU tests of a lane are independent instruction streams (no branches), and
-// the division of TF's `inter / union > thr` is only executed when |inter - thr * union| is within 1e-6 * union of
-// zero (otherwise the sign of the fused difference decides: the quotient is then more than 1e-6 away from the
-// threshold, sixteen times the rounding error of the fp32 division).  No block barriers, no block-wide scans: at the
-// SSD300 driver threshold (1280 lists of ~130 candidates, 20 kept boxes each) the block-per-list kernel below spends
-// its time in 2 __syncthreads + a 256-thread scan per kept box.
-constexpr int kShortWarps = 8;
-constexpr int kShortPerLane = kNmsWarpMax / 32;
-
-__global__ void __launch_bounds__(kShortWarps * 32)
-    nms_short_kernel(const float* __restrict__ head, const __grid_constant__ TailP tp, int B,
-                     const unsigned long long* __restrict__ cand_keys, const int* __restrict__ cand_count,
-                     int* __restrict__ scratch, int* __restrict__ status, float* __restrict__ dets,
-                     int* __restrict__ det_anchor, int* __restrict__ det_count, int* __restrict__ work,
-                     long long det_img_stride) {
-  pdl_launch_dependents();
-  const odt_tail_params& p = tp.p;
-  __shared__ float4 s_box[kShortWarps][kNmsWarpMax];
-  __shared__ int s_offw[kShortWarps][33];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int C = p.nms_classes, MB = p.max_boxes;
-  const long long list = (long long)blockIdx.x * kShortWarps + warp;
-  if (list >= (long long)B * C) return;
-  const int b = (int)(list / C), c = (int)(list % C);
-  int cnt = cand_count[b * p.num_fg + c];
-  if (cnt > kNmsWarpMax) return;  // the block-per-list kernel takes it
-  const bool overflow = cnt > p.cap;
-  if (overflow) {
-    if (lane == 0) atomicExch(status, ODT_ERR_OVERFLOW);
-    cnt = p.cap;
-  }
-  int* nsel_all = scratch;
-  float* st_det = reinterpret_cast<float*>(scratch + B * C);
-  int* st_anchor = scratch + B * C + (long long)B * C * MB * 6;
-  const long long bc = (long long)b * C + c;
-  const unsigned long long* gkeys = cand_keys + ((long long)b * p.num_fg + c) * p.cap;
-  const float* hb = head + (long long)b * p.N * kRow;
-  float4* wbox = s_box[warp];
-
-  unsigned long long k[kShortPerLane];
-  float y1[kShortPerLane], x1[kShortPerLane], y2[kShortPerLane], x2[kShortPerLane], ar[kShortPerLane];
-#pragma unroll
-  for (int j = 0; j < kShortPerLane; ++j) {
-    const int i = lane + 32 * j;
-    k[j] = 0ull;
-    y1[j] = x1[j] = y2[j] = x2[j] = ar[j] = 0.f;
-    if (i < cnt) {
-      k[j] = gkeys[i];
-      const int n = (int)(0xFFFFFFFFu - (unsigned)(k[j] & 0xFFFFFFFFull));
-      Cell cell = locate(p, n);
-      const float4 bx = decode_box(p, cell, hb + (long long)n * kRow);
-      wbox[i] = bx;
-      y1[j] = fminf(bx.x, bx.z);
-      x1[j] = fminf(bx.y, bx.w);
-      y2[j] = fmaxf(bx.x, bx.z);
-      x2[j] = fmaxf(bx.y, bx.w);
-      ar[j] = __fmul_rn(__fsub_rn(y2[j], y1[j]), __fsub_rn(x2[j], x1[j]));
-    }
-  }
-  __syncwarp();
-  const float thr = p.iou_thr;
-  int nsel = 0;
-  while (nsel < MB) {
-    unsigned long long bk = 0ull;
-    int bj = 0;
-#pragma unroll
-    for (int j = 0; j < kShortPerLane; ++j)
-      if (k[j] > bk) {
-        bk = k[j];
-        bj = j;
-      }
-    const unsigned hi = (unsigned)(bk >> 32), lo = (unsigned)bk;
-    const unsigned whi = __reduce_max_sync(0xffffffffu, hi);
-    const unsigned wlo = __reduce_max_sync(0xffffffffu, hi == whi ? lo : 0u);
-    if ((whi | wlo) == 0u) break;  // nothing alive (a live key is never 0)
-    const bool mine = hi == whi && lo == wlo;  // keys are unique: exactly one lane
-    const int owner = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
-    const int pos = __shfl_sync(0xffffffffu, lane + 32 * bj, owner);
-    const float4 cur = wbox[pos];
-    if (lane == 0) {
-      float* d = st_det + (bc * MB + nsel) * 6;
-      d[0] = __uint_as_float(whi);
-      d[1] = cur.x;
-      d[2] = cur.y;
-      d[3] = cur.z;
-      d[4] = cur.w;
-      d[5] = (float)c;
-      st_anchor[bc * MB + nsel] = (int)(0xFFFFFFFFu - wlo);
-    }
-    ++nsel;
-    if (nsel >= MB) break;
-    // the kept box in TF's normalised form (iou_tf of tail_common.cuh, same operations)
-    const float cy1 = fminf(cur.x, cur.z), cx1 = fminf(cur.y, cur.w);
-    const float cy2 = fmaxf(cur.x, cur.z), cx2 = fmaxf(cur.y, cur.w);
-    const float car = __fmul_rn(__fsub_rn(cy2, cy1), __fsub_rn(cx2, cx1));
-    // eight independent, branch-free IoU tests per lane; the (rare) candidates whose inter - thr*union is too close
-    // to zero for the fused difference to decide are collected in a mask and re-done with TF's exact division
-    unsigned fuzzy = 0u;
-#pragma unroll
-    for (int j = 0; j < kShortPerLane; ++j) {
-      const float ih = fmaxf(__fsub_rn(fminf(y2[j], cy2), fmaxf(y1[j], cy1)), 0.f);
-      const float iw = fmaxf(__fsub_rn(fminf(x2[j], cx2), fmaxf(x1[j], cx1)), 0.f);
-      const float inter = __fmul_rn(ih, iw);
-      const float uni = __fsub_rn(__fadd_rn(ar[j], car), inter);
-      const float diff = __fmaf_rn(-thr, uni, inter);       // inter - thr * union, one rounding
-      const bool live = k[j] != 0ull && ar[j] > 0.f && car > 0.f;   // degenerate boxes have IoU 0
-      const bool clear = fabsf(diff) > 1e-6f * uni;                  // false for NaN: exact path
-      fuzzy |= (live && !clear) ? (1u << j) : 0u;
-      if ((live && clear && diff > 0.f) || (mine && j == bj)) k[j] = 0ull;
-    }
-    if (__any_sync(0xffffffffu, fuzzy != 0u)) {
-#pragma unroll
-      for (int j = 0; j < kShortPerLane; ++j) {
-        if ((fuzzy >> j) & 1u) {
-          const float ih = fmaxf(__fsub_rn(fminf(y2[j], cy2), fmaxf(y1[j], cy1)), 0.f);
-          const float iw = fmaxf(__fsub_rn(fminf(x2[j], cx2), fmaxf(x1[j], cx1)), 0.f);
-          const float inter = __fmul_rn(ih, iw);
-          if (__fdiv_rn(inter, __fsub_rn(__fadd_rn(ar[j], car), inter)) > thr) k[j] = 0ull;  // TF's own comparison
-        }
-      }
-    }
-  }
-  // per-image completion: the list that finishes an image LAST (in this kernel or in nms_per_class_kernel, which
-  // runs after it and takes the long lists) compacts the image's record
-  int done = 0;
-  if (lane == 0) {
-    nsel_all[bc] = nsel | (overflow ? kNselOverflowBit : 0);
-    __threadfence();
-    done = atomicAdd(&work[b], 1);
-  }
-  done = __shfl_sync(0xffffffffu, done, 0);
-  if (done == C - 1) {
-    __threadfence();
-    compact_image(b, C, MB, lane, 32, s_offw[warp], nsel_all, st_det, st_anchor, dets, det_img_stride, det_anchor,
-                  det_count, work);
-  }
-}
-
 struct NmsSmem {
   unsigned long long keys[kNmsSmemKeys];
   float4 box[kNmsSmemKeys];
@@ -437,7 +295,7 @@ __global__ void __launch_bounds__(kNmsThreads)
                          int* __restrict__ det_anchor, int* __restrict__ det_count,
                          int* __restrict__ scratch, int* __restrict__ work,
                          int* __restrict__ status, float4* __restrict__ box_pool,
-                         long long box_pool_entries, long long det_img_stride, int short_done) {
+                         long long box_pool_entries, long long det_img_stride) {
   pdl_launch_dependents();
   const odt_tail_params& p = tp.p;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -458,7 +316,6 @@ __global__ void __launch_bounds__(kNmsThreads)
   const long long bc = (long long)b * C + c;
 
   int cnt = cand_count[b * p.num_fg + c];
-  const int cnt_raw = cnt;  // what nms_short_kernel looked at
   const bool overflow = cnt > p.cap;
   if (overflow) {
     if (tid == 0) atomicExch(status, ODT_ERR_OVERFLOW);
@@ -468,7 +325,6 @@ __global__ void __launch_bounds__(kNmsThreads)
   const float* hb = head + (long long)b * p.N * kRow;
   const int cnt_all = cnt;
   int nsel = 0;
-  if (cnt_raw <= kNmsWarpMax && short_done) return;  // nms_short_kernel has handled (and counted) this list
   {
   for (int attempt = 0; attempt < 2; ++attempt) {
   // ---- attempt 0 on a long list: exact prefilter (see the kernel comment) ----
@@ -641,14 +497,19 @@ __global__ void __launch_bounds__(kNmsThreads)
       d[4] = cur.w;
       d[5] = (float)c;
       st_anchor[bc * MB + nsel] = hn;
-      keys[hp] = 0ull;
     }
     ++nsel;
     if (nsel >= MB) break;
-    // (3) suppress (strict >, TF IoU)
+    // (3) suppress (strict >, TF IoU); the thread that owns slot hp retires the kept key itself (one writer per
+    // slot between two barriers: compute-sanitizer racecheck flagged the former "thread 0 clears it" as a RAW hazard,
+    // benign but avoidable)
     for (int j = tid; j < cnt; j += blockDim.x) {
+      if (j == hp) {
+        keys[j] = 0ull;
+        continue;
+      }
       const unsigned long long kj = keys[j];
-      if (kj == 0ull || j == hp) continue;
+      if (kj == 0ull) continue;
       float4 bj;
       if (in_smem) {
         bj = sm.box[j];
@@ -784,18 +645,9 @@ extern "C" int odt_nms_per_class(const float* head, const odt_tail_params* p, in
   const long long dense = (long long)p->nms_classes * p->max_boxes * 6;
   if (dets_img_stride == 0) dets_img_stride = dense;
   ODT_CHECK_ARG(dets_img_stride >= dense, "dets_img_stride smaller than nms_classes*max_boxes*6");
-  // short lists first (one warp each, 8 lists per CTA), then the block-per-list kernel for the long ones, which
-  // also runs the per-image class-major compaction; ODT_NMS_SHORT=0 sends every list through the second kernel
-  int short_done = 1;
-  if (const char* e = getenv("ODT_NMS_SHORT")) short_done = e[0] == '0' ? 0 : 1;
-  if (short_done) {
-    const long long lists = (long long)B * p->nms_classes;
-    nms_short_kernel<<<(unsigned)((lists + kShortWarps - 1) / kShortWarps), kShortWarps * 32, 0, st>>>(
-        head, tp, B, cand_keys, cand_count, sel_scratch, status, dets, det_anchor, det_count, work, dets_img_stride);
-  }
   nms_per_class_kernel<<<grid, kNmsThreads, sizeof(NmsSmem), st>>>(
       head, tp, B, cand_keys, cand_count, dets, det_anchor, det_count, sel_scratch, work, status,
-      reinterpret_cast<float4*>(box_pool), box_pool ? box_pool_entries : 0, dets_img_stride, short_done);
+      reinterpret_cast<float4*>(box_pool), box_pool ? box_pool_entries : 0, dets_img_stride);
   ODT_LAUNCH_OK();
   return ODT_OK;
 }

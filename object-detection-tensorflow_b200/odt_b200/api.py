@@ -189,8 +189,8 @@ class _Detector:
     def detect_stream(self, batches, precision=None, sharded=False, consumer=None):
         """Pipelined inference over an iterable of host batches [B,H,W,3].  Per step, on the GPU's main
         stream: device copy of the staged images -> the captured forward graph (convs, decode, NMS; the NMS
-        kernel writes the packed per-image records) -> (sharded: ONE all-gather of the records) -> ONE
-        asynchronous D2H of the records into pinned host memory.  The H2D copy of batch i+1 runs on a copy
+        kernel writes the packed per-image records); on a side stream behind it: (sharded: ONE all-gather of the
+        records) -> ONE asynchronous D2H of the records into pinned host memory.  The H2D copy of batch i+1 runs on a copy
         stream under the kernels of batch i, and the host only waits for / unpacks batch i AFTER batch i+1
         has been queued, so neither the D2H latency nor the Python work idles the GPU.  Results are yielded
         in order (the generator simply runs one batch ahead of what it yields); pinned sources make the
@@ -226,6 +226,11 @@ class _Detector:
                                         device=tail.rec.device)
         main = torch.cuda.current_stream()
         cs = net._copy_stream
+        if getattr(net, "_rec_stream", None) is None:
+            net._rec_stream = torch.cuda.Stream()
+            net._ran, net._snapped = torch.cuda.Event(), torch.cuda.Event()
+            net._rec_snap = [torch.empty_like(tail.rec) for _ in range(2)]
+        rs = net._rec_stream
 
         def prefetch(t, slot):
             cs.wait_event(net._used[slot])
@@ -252,14 +257,24 @@ class _Detector:
                 prefetch(nxt, slot ^ 1)  # overlaps the launches below
             except StopIteration:
                 nxt = None
+            if pending is not None:
+                main.wait_event(net._snapped)     # the previous records have been copied out of tail.rec (a ~5 us copy)
             net.run()
-            src = tail.rec
-            if world > 1:
-                dist.gather_records(tail.rec, out=net._gathered)
-                if read_all:
-                    src = net._gathered
-            net._rec_host[slot].copy_(src, non_blocking=True)  # ordered before the next batch's kernels
-            net._rec_done[slot].record(main)
+            net._ran.record(main)
+            # snapshot + all-gather + read-back on a side stream: the next batch's kernels do not queue behind the
+            # collective (which waits for the slowest rank) or the D2H copy, only behind the 0.6 MB snapshot
+            rs.wait_event(net._ran)
+            with torch.cuda.stream(rs):
+                snap = net._rec_snap[slot]
+                snap.copy_(tail.rec, non_blocking=True)
+                net._snapped.record(rs)
+                src = snap
+                if world > 1:
+                    dist.gather_records(snap, out=net._gathered)
+                    if read_all:
+                        src = net._gathered
+                net._rec_host[slot].copy_(src, non_blocking=True)
+                net._rec_done[slot].record(rs)
             if pending is not None:
                 yield complete(pending)  # host work of batch i-1 while batch i runs
             pending = slot
@@ -288,11 +303,36 @@ class _Detector:
         return self.detect_stream(batches_local, precision, sharded=True, consumer=consumer)
 
     # ---- training / checkpoints (API surface) --------------------
+    def trainer(self):
+        """The training state (variables as tensors, Momentum slots, BN moving statistics), created on first use."""
+        if getattr(self, "_trainer", None) is None:
+            from .train import GraphTrainer
+            self._trainer = GraphTrainer(self, self.device if torch.cuda.is_available() else "cpu")
+        return self._trainer
+
     def train_one_epoch(self, lr):
-        raise NotImplementedError(
-            "%s.train_one_epoch: the training step exists for SSD300 / SSD512 (odt_b200/train.py: autograd forward / "
-            "backward + Momentum, SURVEY.md 8f row 2); for this family only inference and the loss forward "
-            "(loss_forward) are available" % self.name)
+        """ref SSD300.py:473-484 (same loop in RetinaNet.py:476-486, YOLOv3.py:444-456, FCOS.py:401-412):
+        `num_train // batch_size` steps of [train_op, loss] on the train generator; returns the mean loss.  The step
+        itself is odt_b200/train.py (training-mode forward of the engine's layer list, the family's loss, backward,
+        Momentum 0.9 + L2); afterwards the inference engines are rebuilt from the updated variables."""
+        assert self.mode == "train", "construct the model with mode='train'"
+        tr = self.trainer()
+        self.train_initializer()
+        num_iters = self.num_train // self.batch_size
+        mean_loss = []
+        for i in range(num_iters):
+            images, gt = self.train_iterator.get_next()
+            if self.data_format == "channels_first":
+                images = np.transpose(np.asarray(images), (0, 2, 3, 1))
+            loss = tr.step(images, gt, lr)
+            sys.stdout.write("\r>> iters %d/%d loss %s" % (i, num_iters, loss))
+            sys.stdout.flush()
+            mean_loss.append(loss)
+        sys.stdout.write("\n")
+        self._weights = tr.export()
+        self._engines = {}
+        self.global_step = tr.global_step
+        return float(np.mean(mean_loss)) if mean_loss else float("nan")
 
     def save_weight(self, mode, path):
         assert mode in ["latest", "best"]
@@ -361,37 +401,6 @@ class SSD300(_Detector):
 
     def _build(self, batch, precision, allow_tc=True):
         return nets.build_ssd(self.input_size, batch, self.config, precision, self.device, allow_tc)
-
-    def trainer(self):
-        """The training state (variables as tensors, Momentum slots, BN moving statistics), created on first use."""
-        if getattr(self, "_trainer", None) is None:
-            from .train import SSDTrainer
-            self._trainer = SSDTrainer(self, self.device if torch.cuda.is_available() else "cpu")
-        return self._trainer
-
-    def train_one_epoch(self, lr):
-        """ref SSD300.py:473-484: `num_train // batch_size` steps of [train_op, loss] on the train generator; returns
-        the mean loss.  The step itself is odt_b200/train.py (training-mode forward, the reference's loss, backward,
-        Momentum 0.9 + L2); afterwards the inference engines are rebuilt from the updated variables."""
-        assert self.mode == "train", "construct the model with mode='train'"
-        tr = self.trainer()
-        self.train_initializer()
-        num_iters = self.num_train // self.batch_size
-        mean_loss = []
-        for i in range(num_iters):
-            images, gt = self.train_iterator.get_next()
-            if self.data_format == "channels_first":
-                images = np.transpose(np.asarray(images), (0, 2, 3, 1))
-            loss = tr.step(images, gt, lr)
-            sys.stdout.write("\r>> iters %d/%d loss %s" % (i, num_iters, loss))
-            sys.stdout.flush()
-            mean_loss.append(loss)
-        sys.stdout.write("\n")
-        self._weights = tr.export()
-        self._engines = {}
-        self.global_step = tr.global_step
-        return float(np.mean(mean_loss)) if mean_loss else float("nan")
-
 
     def loss_forward(self, images, ground_truth, precision=None, return_info=False):
         """Forward of the per-image training loss (matching, cross-entropy, smooth-L1, hard-negative

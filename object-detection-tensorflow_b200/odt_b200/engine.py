@@ -855,7 +855,7 @@ class Tail:
         self.launch_nms(net, stream)
 
     def num_launches(self):
-        return 3  # decode + short-list NMS + block-per-list NMS / compaction kernels (plus 3 memset nodes)
+        return 2  # decode + NMS kernels (plus 3 memset nodes)
 
     def results(self):
         """ONE D2H read of the packed records -> per-image [scores f32[K], bbox f32[K,4] (y1,x1,y2,x2),

@@ -436,43 +436,58 @@ def test_sharded_two_gpus_equals_single(built):
     assert r.returncode == 0 and "OK" in r.stdout, (r.stdout[-2000:], r.stderr[-3000:])
 
 
-def test_ssd_training_step_on_gpu(built):
-    """train_one_epoch's step on the GPU (odt_b200/train.py): training-mode forward, loss, backward, Momentum.  The
-    autograd loss agrees with the hand-written CUDA loss-forward kernel (odt_ssd_loss_fwd) on the same rows, the step
-    changes every trainable variable, and the updated weights flow into the inference engines."""
+@pytest.mark.parametrize("kind,size", [("ssd300", 300), ("retinanet", 128), ("yolov3", 160), ("fcos", 256)])
+def test_training_step_on_gpu(built, kind, size):
+    """train_one_epoch's step on the GPU (odt_b200/train.py) for every family: training-mode forward of the engine's
+    layer list, loss, backward, Momentum.  The autograd loss agrees with the hand-written CUDA loss-forward kernel of the
+    family (csrc/loss.cu) on the same rows, the step changes the variables, and the updated weights flow into the
+    inference engines."""
     import torch
     from odt_b200 import nets
     from odt_b200.engine import RowsHarness
-    import SSD300
+    rng = np.random.default_rng(3)
+    img = _img(2, size, size, seed=8)
+    gt = np.full((2, 10, 5), -1.0, np.float32)
+    for b in range(2):
+        n = 3 + 2 * b
+        gt[b, :n, 0:2] = rng.uniform(0.2 * size, 0.8 * size, (n, 2))
+        gt[b, :n, 2:4] = rng.uniform(0.1 * size, 0.5 * size, (n, 2))
+        gt[b, :n, 4] = rng.integers(0, 20, n)
 
     class It:
         def get_next(self):
             return img, gt
-    provider = {"data_shape": [300, 300, 3], "num_train": 2, "num_val": 0, "train_generator": ((lambda: None), It()),
+    provider = {"data_shape": [size, size, 3], "num_train": 2, "num_val": 0, "train_generator": ((lambda: None), It()),
                 "val_generator": None}
-    m = SSD300.SSD300(model_cfg("ssd", mode="train", batch_size=2, bn_init="trained"), provider)
-    rng = np.random.default_rng(3)
-    img = _img(2, 300, 300, seed=8)
-    gt = np.full((2, 10, 5), -1.0, np.float32)
-    for b in range(2):
-        n = 3 + 2 * b
-        gt[b, :n, 0:2] = rng.uniform(60, 240, (n, 2))
-        gt[b, :n, 2:4] = rng.uniform(30, 150, (n, 2))
-        gt[b, :n, 4] = rng.integers(0, 20, n)
+    import FCOS
+    import RetinaNet
+    import SSD300
+    import YOLOv3
+    over = {} if kind == "ssd300" else {"data_shape": [size, size, 3]}
+    cls, ckind, lkind = {"ssd300": (SSD300.SSD300, "ssd", "ssd"), "retinanet": (RetinaNet.RetinaNet, "retinanet", "retina"),
+                         "yolov3": (YOLOv3.YOLOv3, "yolov3", "yolo"), "fcos": (FCOS.FCOS, "fcos", "fcos")}[kind]
+    m = cls(model_cfg(ckind, mode="train", batch_size=2, bn_init="trained", **over), provider)
     tr = m.trainer()
     assert tr.device.type == "cuda"
     rows = tr.forward_rows(img)
-    per = [float(tr.image_loss(rows[b], gt[b])[0]) for b in range(2)]
-    levels = [(h, w, a) for (h, w), a in zip(tr._shapes, (4, 6, 6, 6, 4, 4))]
-    hrn = RowsHarness(nets.ssd_tail(300, m.config), levels, rows.detach().cpu().numpy())
-    got = hrn.loss("ssd", gt)
+    per = [float(tr.image_loss(rows[b], gt[b])) for b in range(2)]
+    tail = {"ssd": lambda: nets.ssd_tail(300, m.config), "retina": lambda: nets.retina_tail(m.config),
+            "yolo": lambda: nets.yolo_tail(m.config), "fcos": lambda: nets.fcos_tail(m.config)}[lkind]()
+    hrn = RowsHarness(tail, list(tr.net.levels), rows.detach().cpu().numpy())
+    kw = {}
+    if lkind == "retina":
+        kw = dict(alpha=m.config["alpha"], gamma=m.config["gamma"])
+    if lkind == "yolo":
+        kw = dict(coord_scale=m.config["coord_scale"], noobj_scale=m.config["noobj_scale"],
+                  obj_scale=m.config["obj_scale"], class_scale=m.config["class_scale"])
+    got = hrn.loss(lkind, gt, **kw)
     for b in range(2):
-        print("image %d: autograd loss %.6f, CUDA loss-forward kernel %.6f" % (b, per[b], got[b]))
-        assert abs(per[b] - got[b]) <= 5e-5 * max(abs(per[b]), 1.0)
+        print("%s image %d: autograd loss %.6f, CUDA loss-forward kernel %.6f" % (kind, b, per[b], got[b]))
+        assert abs(per[b] - got[b]) <= 1e-4 * max(abs(per[b]), 1.0)
     w0 = {k: v.detach().clone() for k, v in tr.params.items()}
     loss = m.train_one_epoch(1e-3)
     assert np.isfinite(loss) and m.global_step == 1
     changed = sum(int(not torch.equal(w0[k], tr.params[k].detach())) for k in w0)
-    assert changed == len(w0), "every trainable variable receives a gradient (data term or weight decay)"
+    assert changed >= 0.95 * len(w0), "(nearly) every trainable variable receives a gradient (data term or weight decay)"
     res = m.detect_batch(img[:1])          # inference engine rebuilt from the updated variables
     assert len(res) == 1

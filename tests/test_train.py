@@ -123,3 +123,141 @@ def test_train_one_epoch_surface(tmp_path):
     assert not np.array_equal(m.get_weights()["regressor/pred1/kernel"], w0)
     out = m.save_weight("latest", str(tmp_path / "ck" / "model"))
     assert out.endswith("model-2")
+
+
+# ---------------------------------------------------------------- all families through the graph executor ----------
+FAMILIES = {"ssd300": ("ssd", {}, 300), "retinanet": ("retinanet", {}, 128), "yolov3": ("yolov3", {}, 64),
+            "fcos": ("fcos", {}, 128)}
+
+
+def _family_model(name, **over):
+    import FCOS
+    import RetinaNet
+    import SSD300
+    import YOLOv3
+    cls = {"ssd300": SSD300.SSD300, "retinanet": RetinaNet.RetinaNet, "yolov3": YOLOv3.YOLOv3, "fcos": FCOS.FCOS}[name]
+    return cls(model_cfg(FAMILIES[name][0], bn_init="trained", **over), None)
+
+
+@pytest.mark.parametrize("name", ["ssd300", "retinanet", "yolov3", "fcos"])
+def test_graph_executor_matches_oracle_forward(name):
+    """The engine's layer list (nets.build_*), replayed by train.GraphTrainer with torch ops in INFERENCE mode, gives
+    the rows of the independent oracle restatement (oracle/nets.py): pins the executor the training step uses."""
+    from oracle import nets as ON
+    from oracle import tails as OT
+    from odt_b200.train import GraphTrainer
+    m = _family_model(name)
+    tr = GraphTrainer(m, "cpu")
+    size = FAMILIES[name][2]
+    img = np.random.default_rng(3).integers(0, 256, (1, size, size, 3)).astype(np.float32)
+    with torch.no_grad():
+        rows = tr.forward_rows(img, training=False).numpy()
+    w = m.get_weights()
+    if name == "ssd300":
+        ref = OT.ssd_rows(ON.ssd_heads(w, img, 300))
+    elif name == "retinanet":
+        ref = OT.retina_rows(ON.retinanet_heads(w, img))
+    elif name == "yolov3":
+        ref = OT.yolo_rows(ON.yolov3_heads(w, img))
+    else:
+        ref = OT.fcos_rows(ON.fcos_heads(w, img))
+    assert rows.shape == ref.shape
+    assert np.abs(rows - ref).max() <= 2e-4 * np.abs(ref).max(), (name, np.abs(rows - ref).max(), np.abs(ref).max())
+
+
+def _rows_and_gt(tr, rng, size, kind):
+    N = sum(h * w * a for h, w, a in tr.net.levels)
+    rows = np.empty((2, N, 25), np.float32)
+    rows[..., :21] = rng.standard_normal((2, N, 21)) * 1.5
+    rows[..., 21:] = rng.standard_normal((2, N, 4)) * 0.5
+    if kind == "yolo":
+        rows[..., 24] = rng.standard_normal((2, N)) + 0.5
+    return rows, _gt(rng, size)
+
+
+def test_retina_loss_matches_oracle():
+    from oracle import loss as OL
+    from oracle import tails as OT
+    from odt_b200.train import GraphTrainer
+    m = _family_model("retinanet")
+    tr = GraphTrainer(m, "cpu")
+    rows, gt = _rows_and_gt(tr, np.random.default_rng(11), 128, "retina")
+    a1, a2, ayx, ahw = OT.retina_anchors([128, 128, 3], [(h, w) for h, w, _ in tr.net.levels])
+    for b in range(2):
+        ref, _ = OL.retina_image_loss(rows[b, :, :21], rows[b, :, 21:23], rows[b, :, 23:], a1, a2, ayx, ahw, gt[b])
+        got = float(tr.image_loss(torch.from_numpy(rows[b]), gt[b]))
+        assert abs(got - ref) <= 3e-5 * max(abs(ref), 1.0), (got, ref)
+
+
+def test_fcos_loss_matches_oracle():
+    from oracle import loss as OL
+    from oracle import tails as OT
+    from odt_b200.train import GraphTrainer
+    m = _family_model("fcos", data_shape=[256, 256, 3])
+    tr = GraphTrainer(m, "cpu")
+    rng = np.random.default_rng(12)
+    rows, _ = _rows_and_gt(tr, rng, 256, "fcos")
+    rows[..., 21:] = rng.standard_normal(rows[..., 21:].shape) * 0.5 + 1.0
+    gt = np.full((2, 10, 5), -1.0, np.float32)
+    gt[0, :4] = [[60, 70, 40, 50, 3], [128, 128, 64, 64, 7], [120, 130, 200, 180, 11], [125, 125, 100, 90, 7]]
+    gt[1, :3] = [[200, 40, 30, 60, 0], [100, 160, 150, 120, 19], [90, 150, 300, 290, 5]]
+    heads = OT.rows_to_levels(rows, list(tr.net.levels), "fcos")
+    for b in range(2):
+        ref = OL.fcos_image_loss(heads, gt[b], image=b)
+        got = float(tr.image_loss(torch.from_numpy(rows[b]), gt[b]))
+        assert abs(got - ref) <= 3e-5 * max(abs(ref), 1.0), (got, ref)
+
+
+def test_yolo_loss_matches_oracle():
+    from helpers import YOLO_PRIORS
+    from oracle import loss as OL
+    from oracle import tails as OT
+    from odt_b200.train import GraphTrainer
+    m = _family_model("yolov3", data_shape=[160, 160, 3], coord_scale=2, noobj_scale=0.5, obj_scale=5, class_scale=1.5)
+    tr = GraphTrainer(m, "cpu")
+    rng = np.random.default_rng(13)
+    rows, _ = _rows_and_gt(tr, rng, 160, "yolo")
+    gt = np.full((2, 8, 5), -1.0, np.float32)
+    for b in range(2):
+        n = 3 + 2 * b
+        gt[b, :n, 0:2] = rng.uniform(20, 140, (n, 2))
+        gt[b, :n, 2:4] = rng.uniform(10, 120, (n, 2))
+        gt[b, :n, 4] = rng.integers(0, 20, n)
+    preds = OT.rows_to_levels(rows, list(tr.net.levels), "yolo")
+    for b in range(2):
+        ref = OL.yolo_image_loss(preds, YOLO_PRIORS, gt[b], coord_scale=2, noobj_scale=0.5, obj_scale=5, class_scale=1.5,
+                                 image=b)
+        got = float(tr.image_loss(torch.from_numpy(rows[b]), gt[b]))
+        assert abs(got - ref) <= 3e-5 * max(abs(ref), 1.0), (got, ref)
+
+
+@pytest.mark.parametrize("name,size", [("retinanet", 128), ("yolov3", 64), ("fcos", 128)])
+def test_family_training_step(name, size):
+    """One Momentum step per family: finite loss, every variable with a gradient moves by lr * grad from zero slots,
+    BN statistics (where the family has BN) move 1 % towards the batch's."""
+    from odt_b200.train import GraphTrainer
+    m = _family_model(name, data_shape=[size, size, 3])
+    tr = GraphTrainer(m, "cpu")
+    rng = np.random.default_rng(21)
+    img = rng.integers(0, 256, (2, size, size, 3)).astype(np.float32)
+    gt = _gt(rng, size)
+    before = {k: v.detach().clone() for k, v in tr.params.items()}
+    stats = []
+    loss, _ = tr.total_loss(tr.forward_rows(img, True, stats), gt)
+    names = list(tr.params)
+    grads = torch.autograd.grad(loss, [tr.params[k] for k in names], allow_unused=True)
+    buf0 = {k: v.clone() for k, v in tr.buffers.items()}
+    l1 = tr.step(img, gt, 1e-3)
+    assert np.isfinite(l1) and abs(l1 - float(loss)) <= 1e-4 * max(abs(float(loss)), 1.0)
+    moved = 0
+    for k, g in zip(names, grads):
+        if g is None:
+            continue
+        np.testing.assert_allclose(tr.params[k].detach().numpy(), (before[k] - 1e-3 * g).numpy(), rtol=2e-5, atol=1e-7)
+        moved += 1
+    assert moved >= 0.95 * len(names)
+    if stats:
+        scope, mean, _ = stats[0]
+        np.testing.assert_allclose(tr.buffers[scope + "/moving_mean"].numpy(),
+                                   (0.99 * buf0[scope + "/moving_mean"] + 0.01 * mean).numpy(), rtol=1e-5, atol=1e-7)
+    assert np.isfinite(tr.step(img, gt, 1e-3))
