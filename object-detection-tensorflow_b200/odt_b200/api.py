@@ -5,10 +5,12 @@ asserts and method names as the reference model scripts, so its test*.py
 drivers run unchanged:
     SSD300.py:11-50,473-504   SSD512.py   RetinaNet.py:11-79,505-539
     YOLOv3.py:11-60,444-483   FCOS.py:11-49,401-436
-Inference (`test_one_image`) runs entirely on the GPU kernels; there is no CPU
-fallback.  Extensions: `test_one_image` accepts [B,H,W,3] (returns a list per
-image for B > 1) and `detect_batch` / `detect_batch_sharded` expose the batched,
-multi-GPU path.
+Inference (`test_one_image`) runs entirely on the hand-written GPU kernels; there is no CPU
+fallback.  `train_one_epoch` runs the training step of odt_b200/train.py (PyTorch autograd over the
+engine's layer list + the reference's losses + Momentum: the first stage of SURVEY 8f row 2; RetinaNet's
+ImageNet-pretraining mode is not built).  Extensions: `test_one_image` accepts [B,H,W,3] (returns a list per
+image for B > 1), `detect_batch` / `detect_stream` / `detect_*_sharded` expose the batched, pipelined and
+multi-GPU paths.
 """
 import os
 import sys

@@ -766,11 +766,22 @@ class Net:
 
     def capture(self):
         """Capture the whole forward in a CUDA graph (launch-bound tail + 30-130 convs)."""
+        import gc
         self.forward()  # warm-up outside capture (lazy attribute sets, driver entry points)
+        # Garbage of earlier engines (CUDA graphs, streams, events) must not be finalised while the capture is
+        # open: destroying a graph exec during a capture invalidates it (cudaErrorStreamCaptureInvalidated, seen once
+        # when a collection happened to fire on the first launch).  Collect now, keep the collector off inside.
+        gc.collect()
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self.forward_lanes()
+        gc_was_on = gc.isenabled()
+        gc.disable()
+        try:
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                self.forward_lanes()
+        finally:
+            if gc_was_on:
+                gc.enable()
         self.graph = g
         return g
 
