@@ -52,6 +52,11 @@ int tapn_mode() {
   const char* e = getenv("ODT_TC_TAPN");
   return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
 }
+int pw_mode() {
+  // conv_pw.cu (staged pointwise kernel): 0 = off, 1 = where its planner takes the layer (default), 2 = wherever it qualifies
+  const char* e = getenv("ODT_TC_PW");
+  return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
+}
 bool wres_enabled() {
   const char* e = getenv("ODT_TC_WRES");
   return !(e && e[0] == '0');

@@ -78,6 +78,8 @@ int thin_mode();       // ODT_TC_THIN: 1 = very thin layers (Cin, Cout <= 32, fe
                        // CUDA-core kernel of conv_thin.cu, 2 = wherever the layer qualifies, 0 / unset = never
 int tapn_mode();       // ODT_TC_TAPN: 1 = narrow 3x3 halo layers go through conv_tapn.cu (taps folded into N) where its
                        // cost model predicts a gain, 2 = wherever the layer qualifies, 0 / unset = never
+int pw_mode();         // ODT_TC_PW: 1 = narrow 1x1 / stride-1 layers go through the staged pointwise kernel of conv_pw.cu
+                       // (tried before conv_thin.cu), 2 = wherever the layer qualifies, 0 = never
 bool wres_enabled();  // ODT_TC_WRES=0 disables shared-memory-resident filter banks in the flat path
 
 }  // namespace odt

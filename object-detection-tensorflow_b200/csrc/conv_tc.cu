@@ -760,6 +760,7 @@ int tc_encode_tiled(CUtensorMap* map, const void* base, int rank, const cuuint64
 
 int conv_tapn_try(const void* in, const void* weights, const odt_conv_params* p, void* stream);  // conv_tapn.cu
 int conv_thin_try(const void* in, const void* weights, const odt_conv_params* p, void* stream);  // conv_thin.cu
+int conv_pw_try(const void* in, const void* weights, const odt_conv_params* p, void* stream);    // conv_pw.cu
 
 int check_conv_params(const odt_conv_params* p) {
   ODT_CHECK_ARG(p != nullptr, "params null");
@@ -836,6 +837,10 @@ extern "C" int odt_conv2d_f16_tc(const void* in, const void* weights, const odt_
   const int ih = p->in_halo ? 1 : 0;  // input stored as [B][H+2][W+2][ld] with zero borders
   ODT_CHECK_ARG(p->in_halo == 0 || p->in_halo == 1, "in_halo must be 0 or 1");
   ODT_CHECK_ARG(p->out0_halo == 0 || p->out0_halo == 1, "out0_halo must be 0 or 1");
+  if (pw_mode()) {  // narrow 1x1 layers: staged, sector-coalesced CUDA-core kernel (conv_pw.cu)
+    const int rt = conv_pw_try(in, weights, p, stream);
+    if (rt != ODT_ERR_UNSUPPORTED) return rt;
+  }
   if (thin_mode()) {  // opt-in: very thin layers on CUDA cores with sector-granular traffic (conv_thin.cu)
     const int rt = conv_thin_try(in, weights, p, stream);
     if (rt != ODT_ERR_UNSUPPORTED) return rt;

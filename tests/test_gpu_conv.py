@@ -656,6 +656,75 @@ def _tc_raw(x, w, pool=0, in_halo=1, out_halo=1):
     return y[:, oh:oh + yh, oh:oh + yw, :Cout]
 
 
+@pytest.mark.parametrize("shape,kw", [
+    ((2, 40, 40, 16, 7, 1, 1, 1), {"pre": True}),                                       # 1x1 reduce + consumer BN/ReLU
+    ((2, 37, 41, 28, 7, 1, 1, 1), {"in_halo": 1, "out_halo": 1}),                       # halo both sides, ragged block
+    ((2, 40, 40, 7, 28, 1, 1, 1), {"residual": True, "pre": True, "pre2": True, "no_out0": True, "aux_halo": 1}),
+    ((2, 40, 40, 7, 28, 1, 1, 1), {"residual": True, "pre": True, "pre2": True, "out_halo": 1}),
+    ((2, 33, 35, 14, 56, 1, 1, 1), {"residual": True, "pre": True, "pre2": True, "no_out0": True, "aux_halo": 1}),
+    ((2, 25, 25, 28, 112, 1, 1, 1), {"residual": True, "pre": True, "pre2": True, "no_out0": True, "aux_halo": 1}),
+    ((2, 13, 13, 56, 224, 1, 1, 1), {"residual": True, "pre": True, "aux_halo": 1}),
+    ((2, 25, 25, 112, 28, 1, 1, 1), {"act": "leaky", "in_halo": 1}),
+    ((2, 20, 20, 56, 14, 1, 1, 1), {"pre": True, "aux_halo": 1}),
+])
+def test_conv_pw_matches_reference(built, monkeypatch, shape, kw):
+    """Staged pointwise kernel for RetinaNet's narrow 1x1 layers (csrc/conv_pw.cu) behind the tensor-core entry point:
+    ODT_TC_PW=2 = wherever the layer qualifies (the default planner leaves 56->224 to the tensor cores)."""
+    from odt_b200 import lib as L
+    monkeypatch.setenv("ODT_TC_PW", "2")
+    before = L.load().odt_debug_pw_launches()
+    got, ref, g1, r1 = _conv_case(*shape, mode="tc", seed=sum(shape), **kw)
+    assert L.load().odt_debug_pw_launches() == before + 1, "the layer did not take the pointwise path"
+    tol = 2e-3 * max(np.abs(ref).max(), 1.0)
+    if not kw.get("no_out0"):
+        assert np.abs(got - ref).max() <= tol, shape
+    if g1 is not None:
+        assert np.abs(g1 - r1).max() <= 3 * tol
+
+
+def test_conv_pw_is_bit_identical_to_the_tensor_core_path_on_exact_inputs(built, monkeypatch):
+    """Small-integer activations and weights make every product and partial sum exact in fp16 / fp32, so the
+    CUDA-core pointwise kernel and the tcgen05 kernel must agree bit for bit (same epilogue rounding chain)."""
+    from odt_b200 import lib as L
+    lib = L.load()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    B, H, W, Cin, Cout = 4, 50, 50, 28, 112
+    ld, old = 64, 128
+    x = torch.zeros((B, H, W, ld), dtype=torch.float16, device="cuda")
+    x[..., :Cin] = torch.randint(-4, 5, (B, H, W, Cin), generator=g, device="cuda").half()
+    w = torch.zeros((128, 1, 1, ld), dtype=torch.float16, device="cuda")
+    w[:Cout, 0, 0, :Cin] = torch.randint(-3, 4, (Cout, Cin), generator=g, device="cuda").half() / 8
+    res = torch.zeros((B, H, W, old), dtype=torch.float16, device="cuda")
+    res[..., :Cout] = torch.randint(-8, 9, (B, H, W, Cout), generator=g, device="cuda").half()
+    scale = torch.full((Cout,), 0.5, device="cuda")
+    shift = torch.full((Cout,), 0.25, device="cuda")
+    outs = []
+    for mode in ("0", "2"):
+        monkeypatch.setenv("ODT_TC_PW", mode)
+        monkeypatch.setenv("ODT_TC_THIN", "0")
+        y0 = torch.zeros((B, H, W, old), dtype=torch.float16, device="cuda")
+        y1 = torch.zeros((B, H + 2, W + 2, old), dtype=torch.float16, device="cuda")
+        p = L.ConvParams()
+        p.B, p.H, p.W, p.Cin, p.in_ld = B, H, W, Cin, ld
+        p.OH, p.OW, p.Cout = H, W, Cout
+        p.R, p.S, p.stride, p.dil, p.pad_t, p.pad_l = 1, 1, 1, 1, 0, 0
+        p.w_ld, p.Cout_pad = ld, 128
+        p.scale, p.shift, p.act = scale.data_ptr(), shift.data_ptr(), 0
+        p.residual = res.data_ptr()
+        p.out0, p.out0_dtype = y0.data_ptr(), L.ODT_F16
+        p.out0_img_stride, p.out0_pix_stride = H * W * old, old
+        p.scale2, p.shift2, p.act2 = shift.data_ptr(), scale.data_ptr(), 1
+        p.out1, p.out1_img_stride, p.out1_pix_stride, p.out1_halo = y1.data_ptr(), (H + 2) * (W + 2) * old, old, 1
+        before = lib.odt_debug_pw_launches()
+        L.check(lib.odt_conv2d_f16_tc(x.data_ptr(), w.data_ptr(), C.byref(p), torch.cuda.current_stream().cuda_stream),
+                "conv")
+        torch.cuda.synchronize()
+        assert lib.odt_debug_pw_launches() == before + (mode != "0")
+        outs.append((y0, y1))
+    assert float(outs[0][0].float().abs().max()) > 1.0
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 @pytest.mark.parametrize("tapn", ["0", "2"])
 def test_conv1_2_full_size_properties(built, monkeypatch, tapn):
     """SSD300's conv1_2 + fused pool at the BASELINE batch (64 x 300 x 300 x 64 -> 64): properties that need no
@@ -695,6 +764,7 @@ def test_conv_thin_matches_reference(built, monkeypatch, shape, kw):
     """CUDA-core kernel for very thin layers (csrc/conv_thin.cu) behind the same entry point."""
     from odt_b200 import lib as L
     monkeypatch.setenv("ODT_TC_THIN", "2")
+    monkeypatch.setenv("ODT_TC_PW", "0")  # the staged pointwise kernel would take the 1x1 cases first
     before = L.load().odt_debug_thin_launches()
     got, ref, g1, r1 = _conv_case(*shape, mode="tc", seed=sum(shape), **kw)
     assert L.load().odt_debug_thin_launches() == before + 1, "the layer did not take the thin path"

@@ -16,26 +16,34 @@ from oracle import tfops as T
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.fixture(scope="module")
-def host():
+def build_host_harness(name, kernel_src, entry):
+    """nvcc-build tests/native/<name>.cu (which #includes the kernel source) and bind its entry point."""
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         pytest.skip("nvcc not available")
-    src = os.path.join(HERE, "native", "thin_host.cu")
+    src = os.path.join(HERE, "native", name + ".cu")
     out_dir = os.path.join(HERE, "native", "_build")
     os.makedirs(out_dir, exist_ok=True)
-    out = os.path.join(out_dir, "libthin_host.so")
-    dep = os.path.join(HERE, "..", "object-detection-tensorflow_b200", "csrc", "conv_thin.cu")
-    if not os.path.exists(out) or any(os.path.getmtime(f) > os.path.getmtime(out) for f in (src, dep)):
+    out = os.path.join(out_dir, "lib%s.so" % name)
+    csrc = os.path.join(HERE, "..", "object-detection-tensorflow_b200", "csrc")
+    deps = [src, os.path.join(csrc, kernel_src), os.path.join(csrc, "epilogue.cuh"), os.path.join(csrc, "common.cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(f) > os.path.getmtime(out) for f in deps):
         # -fno-strict-aliasing: the kernel reinterprets uint4 registers as __half2 (fine for nvcc's device code,
         # undefined behaviour for the host compiler's optimiser)
         subprocess.check_call([nvcc, "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler",
                                "-fPIC,-fno-strict-aliasing", "-shared", "-o", out, src])
     from odt_b200 import lib as L
     lib = C.CDLL(out)
-    lib.odt_test_thin_host.restype = C.c_int
-    lib.odt_test_thin_host.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(L.ConvParams), C.c_int]
+    fn = getattr(lib, entry)
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(L.ConvParams), C.c_int]
+    lib.run = fn
     return lib, L
+
+
+@pytest.fixture(scope="module")
+def host():
+    return build_host_harness("thin_host", "conv_thin.cu", "odt_test_thin_host")
 
 
 def _act(v, act):
@@ -43,7 +51,7 @@ def _act(v, act):
 
 
 def _run(host, B, H, W, Cin, Cout, ks, stride, act=1, residual=False, pre=False, pre2=False, in_halo=0, out_halo=0,
-         no_out0=False, force=1, seed=0):
+         no_out0=False, force=1, seed=0, aux_halo=0):
     lib, L = host
     rng = np.random.default_rng(seed)
     f16 = np.float16
@@ -54,7 +62,7 @@ def _run(host, B, H, W, Cin, Cout, ks, stride, act=1, residual=False, pre=False,
     shift = (rng.standard_normal(Cout) * 0.2).astype(np.float32)
     OH, pt, _ = T.same_pad(H, ks, stride)
     OW, pl, _ = T.same_pad(W, ks, stride)
-    ih, oh = in_halo, out_halo
+    ih, oh, ah = in_halo, out_halo, aux_halo
     xd = np.zeros((B, H + 2 * ih, W + 2 * ih, ld), f16)
     xd[:, ih:ih + H, ih:ih + W, :Cin] = x
     wd = np.zeros((cpad, ks, ks, ld), f16)
@@ -79,17 +87,19 @@ def _run(host, B, H, W, Cin, Cout, ks, stride, act=1, residual=False, pre=False,
         keep.append(rd)
     if pre:
         s2, h2 = rng.uniform(0.5, 1.5, Cout).astype(np.float32), (rng.standard_normal(Cout) * 0.2).astype(np.float32)
-        y1 = np.zeros((B, OH, OW, old), f16)
+        y1 = np.zeros((B, OH + 2 * ah, OW + 2 * ah, old), f16)
         p.scale2, p.shift2, p.act2 = s2.ctypes.data, h2.ctypes.data, 1
-        p.out1, p.out1_img_stride, p.out1_pix_stride = y1.ctypes.data, OH * OW * old, old
+        p.out1, p.out1_img_stride, p.out1_pix_stride = y1.ctypes.data, (OH + 2 * ah) * (OW + 2 * ah) * old, old
+        p.out1_halo = ah
         keep += [s2, h2, y1]
     if pre2:
         s3, h3 = rng.uniform(0.5, 1.5, Cout).astype(np.float32), (rng.standard_normal(Cout) * 0.2).astype(np.float32)
-        y2 = np.zeros((B, OH, OW, old), f16)
+        y2 = np.zeros((B, OH + 2 * ah, OW + 2 * ah, old), f16)
         p.scale3, p.shift3, p.act3 = s3.ctypes.data, h3.ctypes.data, 2
-        p.out2, p.out2_img_stride, p.out2_pix_stride = y2.ctypes.data, OH * OW * old, old
+        p.out2, p.out2_img_stride, p.out2_pix_stride = y2.ctypes.data, (OH + 2 * ah) * (OW + 2 * ah) * old, old
+        p.out2_halo = ah
         keep += [s3, h3, y2]
-    rc = lib.odt_test_thin_host(xd.ctypes.data, wd.ctypes.data, C.byref(p), force)
+    rc = lib.run(xd.ctypes.data, wd.ctypes.data, C.byref(p), force)
     if rc != 0:
         return rc, None
     ref = T.conv2d_same(x.astype(np.float32), w.astype(np.float32), None, stride) * scale + shift
@@ -109,14 +119,18 @@ def _run(host, B, H, W, Cin, Cout, ks, stride, act=1, residual=False, pre=False,
     base = ref.astype(f16).astype(np.float32) if no_out0 else got      # the consumer sees the ROUNDED out0 value
     if pre:
         want = np.maximum(base * s2 + h2, 0)
-        g1 = y1[..., :Cout].astype(np.float32)
+        g1 = y1[:, ah:ah + OH, ah:ah + OW, :Cout].astype(np.float32)
         lim = (3 * tol) if no_out0 else 1.5e-3 * max(np.abs(want).max(), 1.0)
         assert np.abs(g1 - want).max() <= lim
         assert float(np.abs(y1[..., Cout:].astype(np.float32)).max()) == 0.0
+        if ah:
+            full = y1.astype(np.float32)
+            assert max(np.abs(full[:, 0]).max(), np.abs(full[:, -1]).max(), np.abs(full[:, :, 0]).max(),
+                       np.abs(full[:, :, -1]).max()) == 0
     if pre2:
         t = base * s3 + h3
         want = np.maximum(t, 0.1 * t)
-        g2 = y2[..., :Cout].astype(np.float32)
+        g2 = y2[:, ah:ah + OH, ah:ah + OW, :Cout].astype(np.float32)
         assert np.abs(g2 - want).max() <= 1.5e-3 * max(np.abs(want).max(), 1.0)
     return 0, out
 
