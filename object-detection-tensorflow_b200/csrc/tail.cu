@@ -262,6 +262,30 @@ __device__ __forceinline__ void compact_image(int b, int C, int MB, int t, int n
   }
 }
 
+// Optional timeline of block (0, 0)'s greedy rounds (compile with -DODT_NMS_TIMELINE; off in the product build):
+// thread 0 stamps clock64 at the top of a round, after the arg-max barrier and after the suppression barrier
+// (scripts/nms_timeline.py).  Entries: (clock, event << 32 | round).
+#ifdef ODT_NMS_TIMELINE
+__device__ unsigned long long* g_nms_tl_buf = nullptr;
+__device__ unsigned int g_nms_tl_cap = 0, g_nms_tl_len = 0;
+__device__ __forceinline__ void nms_stamp(int event, int round) {
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && g_nms_tl_buf) {
+    const unsigned int i = atomicAdd(&g_nms_tl_len, 1u);
+    if (i < g_nms_tl_cap) {
+      g_nms_tl_buf[2 * i] = (unsigned long long)clock64();
+      g_nms_tl_buf[2 * i + 1] = ((unsigned long long)event << 32) | (unsigned)round;
+    }
+  }
+}
+#else
+#define nms_stamp(event, round) ((void)0)
+#endif
+
+// barrier over the first `nthr` threads of the block (a multiple of 32); id 1 (0 is __syncthreads)
+__device__ __forceinline__ void nms_round_barrier(int nthr) {
+  asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
+}
+
 struct NmsSmem {
   unsigned long long keys[kNmsSmemKeys];
   float4 box[kNmsSmemKeys];
@@ -295,7 +319,7 @@ __global__ void __launch_bounds__(kNmsThreads)
                          int* __restrict__ det_anchor, int* __restrict__ det_count,
                          int* __restrict__ scratch, int* __restrict__ work,
                          int* __restrict__ status, float4* __restrict__ box_pool,
-                         long long box_pool_entries, long long det_img_stride) {
+                         long long box_pool_entries, long long det_img_stride, int adapt) {
   pdl_launch_dependents();
   const odt_tail_params& p = tp.p;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -304,6 +328,7 @@ __global__ void __launch_bounds__(kNmsThreads)
   __shared__ unsigned long long s_wkey[kNmsThreads / 32];
   __shared__ int s_wpos[kNmsThreads / 32];
   __shared__ int s_last;
+  __shared__ int s_nsel;
   __shared__ int s_hist[256];
   __shared__ unsigned s_ctl[4];  // radix select: [0] done flag, [1] prefix / threshold, [2] count above the bin, [3] subset fill
   const int c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
@@ -440,13 +465,21 @@ __global__ void __launch_bounds__(kNmsThreads)
   }
   __syncthreads();
 
+  // Greedy rounds.  A round costs every participating warp ~150 instructions whatever the list length, and with all
+  // lists of a batch resident (SSD300 B=64: 1 280 blocks, 8 per SM) the kernel is bound by that instruction count:
+  // only as many warps as the list can feed (64 candidates each, at least 2) take part; the others wait at the
+  // block barrier after the loop.  adapt == 0 (ODT_NMS_ADAPT=0): all 8 warps, as in round 1.
+  const int nw = adapt ? min(kNmsThreads / 32, max(2, (cnt + 63) / 64)) : kNmsThreads / 32;
+  const int nthr = nw * 32;
   nsel = 0;
+  if (tid < nthr) {
   while (nsel < MB && cnt > 0) {
+    nms_stamp(0, nsel);
     // (1) arg-max over alive keys: per-thread scan, 3 redux.sync per warp, then every
-    //     thread folds the 8 warp partials itself (one barrier, no second shuffle tree)
+    //     thread folds the warp partials itself (one barrier, no second shuffle tree)
     unsigned long long bk = 0ull;
     int bp = 0x7fffffff;
-    for (int i = tid; i < cnt; i += blockDim.x) {
+    for (int i = tid; i < cnt; i += nthr) {
       const unsigned long long k = keys[i];
       if (k > bk) {
         bk = k;
@@ -463,12 +496,13 @@ __global__ void __launch_bounds__(kNmsThreads)
         s_wpos[warp] = wpos;
       }
     }
-    __syncthreads();
+    nms_round_barrier(nthr);
+    nms_stamp(1, nsel);
     unsigned long long s_best_key = 0ull;
     int s_best_pos = -1;
 #pragma unroll
     for (int w = 0; w < kNmsThreads / 32; ++w) {
-      const unsigned long long k = s_wkey[w];
+      const unsigned long long k = w < nw ? s_wkey[w] : 0ull;
       if (k > s_best_key) {
         s_best_key = k;
         s_best_pos = s_wpos[w];
@@ -503,7 +537,7 @@ __global__ void __launch_bounds__(kNmsThreads)
     // (3) suppress (strict >, TF IoU); the thread that owns slot hp retires the kept key itself (one writer per
     // slot between two barriers: compute-sanitizer racecheck flagged the former "thread 0 clears it" as a RAW hazard,
     // benign but avoidable)
-    for (int j = tid; j < cnt; j += blockDim.x) {
+    for (int j = tid; j < cnt; j += nthr) {
       if (j == hp) {
         keys[j] = 0ull;
         continue;
@@ -522,9 +556,13 @@ __global__ void __launch_bounds__(kNmsThreads)
       }
       if (iou_tf(bj, cur) > p.iou_thr) keys[j] = 0ull;
     }
-    __syncthreads();
+    nms_round_barrier(nthr);
+    nms_stamp(2, nsel);
+  }
+  if (tid == 0) s_nsel = nsel;
   }
   __syncthreads();
+  nsel = s_nsel;  // the warps that sat the rounds out learn the outcome here
   // the subset ran dry before nms_max_boxes boxes were kept: redo on the full list
   if (!(subset && nsel < MB && cnt < cnt_all)) break;
   }  // attempt
@@ -645,9 +683,22 @@ extern "C" int odt_nms_per_class(const float* head, const odt_tail_params* p, in
   const long long dense = (long long)p->nms_classes * p->max_boxes * 6;
   if (dets_img_stride == 0) dets_img_stride = dense;
   ODT_CHECK_ARG(dets_img_stride >= dense, "dets_img_stride smaller than nms_classes*max_boxes*6");
+  const char* ad = getenv("ODT_NMS_ADAPT");  // 0: every round uses all 8 warps of the block (A/B against round 1)
   nms_per_class_kernel<<<grid, kNmsThreads, sizeof(NmsSmem), st>>>(
       head, tp, B, cand_keys, cand_count, dets, det_anchor, det_count, sel_scratch, work, status,
-      reinterpret_cast<float4*>(box_pool), box_pool ? box_pool_entries : 0, dets_img_stride);
+      reinterpret_cast<float4*>(box_pool), box_pool ? box_pool_entries : 0, dets_img_stride, !(ad && ad[0] == '0'));
   ODT_LAUNCH_OK();
   return ODT_OK;
 }
+
+#ifdef ODT_NMS_TIMELINE
+// Debug build only (scripts/nms_timeline.py): device buffer of `cap` (clock, tag) pairs for block (0, 0)'s rounds.
+extern "C" int odt_debug_nms_timeline(void* buf, int cap) {
+  unsigned long long* b = reinterpret_cast<unsigned long long*>(buf);
+  unsigned int c = (unsigned int)cap, z = 0;
+  ODT_CUDA_OK(cudaMemcpyToSymbol(odt::g_nms_tl_buf, &b, sizeof(b)));
+  ODT_CUDA_OK(cudaMemcpyToSymbol(odt::g_nms_tl_cap, &c, sizeof(c)));
+  ODT_CUDA_OK(cudaMemcpyToSymbol(odt::g_nms_tl_len, &z, sizeof(z)));
+  return ODT_OK;
+}
+#endif
