@@ -601,6 +601,33 @@ def test_maxpool_halo_layouts(built):
             assert float(yd[:, 0].abs().max()) == 0 and float(yd[:, :, -1].abs().max()) == 0
 
 
+@pytest.mark.parametrize("geom", [(3, 75, 75, 256, 2, 2), (2, 38, 37, 512, 2, 2), (3, 19, 19, 512, 3, 1), (2, 10, 13, 64, 3, 1)])
+@pytest.mark.parametrize("halo", [(0, 0), (1, 1), (1, 0)])
+def test_maxpool_specialised_kernel_is_bit_identical_to_the_generic_one(built, monkeypatch, geom, halo):
+    """maxpool_h8_kernel<K,S> (compile-time window, clamped taps, loads in flight) against maxpool_kernel
+    (ODT_POOL_FAST=0) and against the oracle's TF-SAME pooling, odd sizes and halo layouts included."""
+    from odt_b200 import lib as L
+    from oracle import tfops as T
+    lib = L.load()
+    st = torch.cuda.current_stream().cuda_stream
+    B, H, W, Cc, k, s = geom
+    ih, oh = halo
+    x = np.random.default_rng(H * W + Cc).standard_normal((B, H, W, Cc)).astype(np.float16)
+    ref = T.max_pool_same(x.astype(np.float32), k, s)
+    OH, OW = ref.shape[1:3]
+    xd = torch.zeros((B, H + 2 * ih, W + 2 * ih, Cc), dtype=torch.float16, device="cuda")
+    xd[:, ih:ih + H, ih:ih + W] = torch.from_numpy(x).cuda()
+    outs = []
+    for fast in ("0", "1"):
+        monkeypatch.setenv("ODT_POOL_FAST", fast)
+        yd = torch.zeros((B, OH + 2 * oh, OW + 2 * oh, Cc), dtype=torch.float16, device="cuda")
+        L.check(lib.odt_maxpool(xd.data_ptr(), yd.data_ptr(), L.ODT_F16, B, H, W, Cc, Cc, k, s, ih, oh, st))
+        torch.cuda.synchronize()
+        outs.append(yd)
+    assert torch.equal(outs[0], outs[1])
+    np.testing.assert_array_equal(outs[1][:, oh:oh + OH, oh:oh + OW].float().cpu().numpy(), ref)
+
+
 # The "taps as N" kernel (csrc/conv_tapn.cu) and the thin-layer kernel (csrc/conv_thin.cu) are default paths since
 # the round-2 A/B (mode 1 = where their cost rules take a layer); the tests force mode 2 (wherever a layer qualifies).
 @pytest.mark.parametrize("shape,kw", [
