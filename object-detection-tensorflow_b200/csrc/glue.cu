@@ -143,6 +143,51 @@ __global__ void pack_rgbx_kernel(const float* __restrict__ img, __half* __restri
   }
 }
 
+// Flat element index -> (first channel of the vector, pixel, x, y, image).  `small` (uniform: the whole index space fits
+// 31 bits) selects 32-bit unsigned divisions: the 64-bit ones cost ~100 instructions each, and five of them per vector
+// made these kernels instruction-bound (upsample_add at the 100x100 FPN level: 0.105 ms for 246 MB of traffic).
+struct PixelIndex {
+  int c, x, y, b;
+  long long pix;
+};
+template <int V>
+__device__ __forceinline__ PixelIndex split_index(long long i, int cv, int W, int H, bool small) {
+  PixelIndex r;
+  if (small) {
+    const unsigned u = (unsigned)i, p = u / (unsigned)cv;
+    const unsigned row = p / (unsigned)W, b = row / (unsigned)H;
+    r.c = (int)(u - p * (unsigned)cv) * V;
+    r.x = (int)(p - row * (unsigned)W);
+    r.y = (int)(row - b * (unsigned)H);
+    r.b = (int)b;
+    r.pix = (long long)p;
+  } else {
+    r.c = (int)(i % cv) * V;
+    r.pix = i / cv;
+    r.x = (int)(r.pix % W);
+    r.y = (int)((r.pix / W) % H);
+    r.b = (int)(r.pix / ((long long)W * H));
+  }
+  return r;
+}
+// V per-channel parameters starting at channel c (16-byte aligned when V is a multiple of 4: checked at the launch)
+template <int V>
+__device__ __forceinline__ void ld_params(const float* __restrict__ p, int c, float dflt, float* o) {
+  if (!p) {
+#pragma unroll
+    for (int q = 0; q < V; ++q) o[q] = dflt;
+  } else if (V % 4 == 0) {
+#pragma unroll
+    for (int q = 0; q < V; q += 4) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(p + c + q));
+      o[q] = t.x, o[q + 1] = t.y, o[q + 2] = t.z, o[q + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < V; ++q) o[q] = __ldg(p + c + q);
+  }
+}
+
 // ---- max pool, TF SAME (a4) -------------------------------------------------
 template <typename T, int V>
 __global__ void maxpool_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int H, int W,
@@ -230,13 +275,12 @@ __global__ void maxpool_affine_kernel(const T* __restrict__ in, T* __restrict__ 
   const int IW = W + 2 * ih, IH = H + 2 * ih, PW = OW + 2 * oh, PH = OH + 2 * oh;
   const int cv = C / V;
   const long long total = (long long)B * OH * OW * cv;
+  const bool small = total < (1ll << 31);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % cv) * V;
-    long long pix = i / cv;
-    int ox = (int)(pix % OW);
-    int oy = (int)((pix / OW) % OH);
-    int b = (int)(pix / ((long long)OW * OH));
+    const PixelIndex ix0 = split_index<V>(i, cv, OW, OH, small);
+    const int c = ix0.c, ox = ix0.x, oy = ix0.y, b = ix0.b;
+    const long long pix = ix0.pix;
     float m[V];
 #pragma unroll
     for (int q = 0; q < V; ++q) m[q] = -INFINITY;
@@ -255,16 +299,20 @@ __global__ void maxpool_affine_kernel(const T* __restrict__ in, T* __restrict__ 
     if (out) VecIO<T, V>::st(out + (((long long)b * PH + oy + oh) * PW + ox + oh) * ld + c, m);
     // (the maximum of stored values is itself a stored value: no rounding between the pool and the affine)
     if (out1) {
-      float v[V];
+      float v[V], sc[V], sh[V];
+      ld_params<V>(s1, c, 1.f, sc);
+      ld_params<V>(h1, c, 0.f, sh);
 #pragma unroll
-      for (int q = 0; q < V; ++q) v[q] = apply_act(fmaf(m[q], s1 ? __ldg(s1 + c + q) : 1.f, h1 ? __ldg(h1 + c + q) : 0.f), act1);
+      for (int q = 0; q < V; ++q) v[q] = apply_act(fmaf(m[q], sc[q], sh[q]), act1);
       const long long o = halo1 ? ((long long)b * (OH + 2) + oy + 1) * (OW + 2) + ox + 1 : pix;
       VecIO<T, V>::st(out1 + o * ld + c, v);
     }
     if (out2) {
-      float v[V];
+      float v[V], sc[V], sh[V];
+      ld_params<V>(s2, c, 1.f, sc);
+      ld_params<V>(h2, c, 0.f, sh);
 #pragma unroll
-      for (int q = 0; q < V; ++q) v[q] = apply_act(fmaf(m[q], s2 ? __ldg(s2 + c + q) : 1.f, h2 ? __ldg(h2 + c + q) : 0.f), act2);
+      for (int q = 0; q < V; ++q) v[q] = apply_act(fmaf(m[q], sc[q], sh[q]), act2);
       const long long o = halo2 ? ((long long)b * (OH + 2) + oy + 1) * (OW + 2) + ox + 1 : pix;
       VecIO<T, V>::st(out2 + o * ld + c, v);
     }
@@ -330,13 +378,12 @@ __global__ void upsample_bilinear_add_kernel(const T* __restrict__ top, const T*
   pdl_launch_dependents();
   const int cv = C / V;
   const long long total = (long long)B * H * W * cv;
+  const bool small = total < (1ll << 31);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % cv) * V;
-    long long pix = i / cv;
-    int x = (int)(pix % W);
-    int y = (int)((pix / W) % H);
-    int b = (int)(pix / ((long long)W * H));
+    const PixelIndex ix0 = split_index<V>(i, cv, W, H, small);
+    const int c = ix0.c, x = ix0.x, y = ix0.y, b = ix0.b;
+    const long long pix = ix0.pix;
     // TF1 resize_bilinear, align_corners=False: src = dst*scale (App. A.6)
     float sy = __fmul_rn((float)y, hs), sx = __fmul_rn((float)x, ws);
     int y0 = (int)floorf(sy), x0 = (int)floorf(sx);
@@ -358,14 +405,14 @@ __global__ void upsample_bilinear_add_kernel(const T* __restrict__ top, const T*
     }
     VecIO<T, V>::st(out + pix * ld + c, o);
     if (out1) {
+      float sc[V], sh[V];
+      ld_params<V>(scale2, c, 1.f, sc);
+      ld_params<V>(shift2, c, 0.f, sh);
 #pragma unroll
       for (int q = 0; q < V; ++q) {
-        float sc = scale2 ? __ldg(scale2 + c + q) : 1.f;
-        float sh = shift2 ? __ldg(shift2 + c + q) : 0.f;
-        // the consumer sees the stored (rounded) sum: round in registers (reading the element back from `out`
-        // right after the store cost 8 dependent scalar loads per vector -- 0.105 ms for the 100x100 FPN level)
+        // the consumer sees the stored (rounded) sum: round in registers instead of reading the element back
         const float stored = sizeof(T) == 2 ? __half2float(__float2half_rn(o[q])) : o[q];
-        o[q] = apply_act(fmaf(stored, sc, sh), act2);
+        o[q] = apply_act(fmaf(stored, sc[q], sh[q]), act2);
       }
       VecIO<T, V>::st(out1 + pix * ld + c, o);
     }
@@ -381,13 +428,12 @@ __global__ void upsample_nearest_concat_kernel(const T* __restrict__ a, const T*
   pdl_launch_dependents();
   const int cv = (Ca + Cb) / V;
   const long long total = (long long)B * H * W * cv;
+  const bool small = total < (1ll << 31);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % cv) * V;
-    long long pix = i / cv;
-    int x = (int)(pix % W);
-    int y = (int)((pix / W) % H);
-    int b = (int)(pix / ((long long)W * H));
+    const PixelIndex ix0 = split_index<V>(i, cv, W, H, small);
+    const int c = ix0.c, x = ix0.x, y = ix0.y, b = ix0.b;
+    const long long pix = ix0.pix;
     float v[V];
     if (c < Ca) {
       VecIO<T, V>::ld(a + pix * lda + c, v);
@@ -677,7 +723,8 @@ extern "C" int odt_maxpool_affine(const void* in, void* out, int dtype, int B, i
   DISPATCH_DTYPE(dtype, {
     constexpr int V = FullVec<T>::V;
     const bool vec = can_vec(in, out ? out : in, C, ld, V, sizeof(T)) && ((uintptr_t)out1 % 16) == 0 &&
-                     ((uintptr_t)out2 % 16) == 0;
+                     ((uintptr_t)out2 % 16) == 0 &&
+                     (((uintptr_t)scale1 | (uintptr_t)shift1 | (uintptr_t)scale2 | (uintptr_t)shift2) & 15) == 0;
     if (vec) {
       long long work = (long long)B * OH * OW * (C / V);
       maxpool_affine_kernel<T, V><<<grid_for(work, 256), 256, 0, st>>>(
@@ -734,7 +781,8 @@ extern "C" int odt_upsample_bilinear_add(const void* top, const void* a, void* o
   float hs = (float)TH / (float)H, ws = (float)TW / (float)W;
   DISPATCH_DTYPE(dtype, {
     constexpr int V = FullVec<T>::V;
-    bool vec = can_vec(top, a, C, ld, V, sizeof(T)) && can_vec(out, out1 ? out1 : out, C, ld, V, sizeof(T));
+    bool vec = can_vec(top, a, C, ld, V, sizeof(T)) && can_vec(out, out1 ? out1 : out, C, ld, V, sizeof(T)) &&
+               (((uintptr_t)scale2 | (uintptr_t)shift2) & 15) == 0;
     if (vec) {
       long long work = (long long)B * H * W * (C / V);
       upsample_bilinear_add_kernel<T, V><<<grid_for(work, 256), 256, 0, st>>>(
