@@ -50,7 +50,10 @@ def bench_config(world):
     return {"workload": WORKLOAD, "global_batch": BATCH * world, "per_gpu_batch": BATCH,
             "parallelism": "dp%d (image shards, 1 all-gather of detections)" % world,
             "l2": "per-step activation working set ~2 GB >> 126 MB L2 (no reuse between steps)",
-            "cuda_graph": True, "conv_gflop_per_img": CONV_GFLOP_PER_IMG}
+            "cuda_graph": True, "conv_gflop_per_img": CONV_GFLOP_PER_IMG,
+            "pipeline": ("decode + NMS (+ all-gather) of step i run on a second stream under the first convolutions of step i+1; "
+                         "candidate rows / lists / records double-buffered" if os.environ.get("ODT_PIPELINE", "1") != "0"
+                         else "off: one graph per step")}
 
 
 def synthetic_images(b, seed=0):
@@ -367,8 +370,20 @@ def main():
         return float(t.item())
 
     def time_resident(net, gathered, sampler=None):
-        """W warm-up + K timed device-resident steps (graph replay + the records' all-gather at N > 1)."""
+        """W warm-up + K timed device-resident steps (graph replay + the records' all-gather at N > 1).  Default: the
+        two-stage pipeline of the engine (decode + NMS + gather of step i on a second stream under the first
+        convolutions of step i+1, everything the tail touches double-buffered); ODT_PIPELINE=0: one graph per step."""
+        pipelined = os.environ.get("ODT_PIPELINE", "1") != "0"
+        if pipelined:
+            net.capture_pipelined()
+        counter = [0]
+
         def step():
+            if pipelined:
+                net.run_pipelined(counter[0] & 1,
+                                  (lambda t: od.gather_records(t.rec, out=gathered)) if world > 1 else None)
+                counter[0] += 1
+                return
             net.run()
             if world > 1:
                 od.gather_records(net.tail.rec, out=gathered)
@@ -390,6 +405,8 @@ def main():
         e0.record()
         for _ in range(K):
             step()
+        if pipelined:
+            net.join_pipelined()  # the closing event waits for the last tails as well
         e1.record()
         barrier()
         return max_over_ranks(e0.elapsed_time(e1))
@@ -475,7 +492,7 @@ def main():
             "config": cfg_line,
             "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K, "clocks": e2e_clocks,
-                    "mode": "detect_stream (read-back one step behind)" if world == 1 else
+                    "mode": "detect_stream (two-stage pipeline, read-back one step behind)" if world == 1 else
                             "detect_stream sharded, consumer rank 0 reads the all-gathered records"},
             "gpu_launches": net.num_launches() * K,
             "roofline": roofline, "clocks": clocks,

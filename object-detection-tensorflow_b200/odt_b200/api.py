@@ -248,6 +248,42 @@ class _Detector:
             ev.record(main)
         prefetch(cur, 0)
         i, pending = 0, None
+        pipelined = net.graph is not None and os.environ.get("ODT_PIPELINE", "1") != "0"
+        if pipelined:
+            # two-stage pipeline (engine.Net.run_pipelined): decode + NMS + gather + read-back of batch i on the tail
+            # stream under the first convolutions of batch i+1; the records are double-buffered by pipeline slot, so no
+            # snapshot copy is needed and the body of batch i+2 waits for the read-back of batch i only
+            net.capture_pipelined()
+
+            def after_tail(t, slot_=None):
+                src = t.rec
+                if world > 1:
+                    dist.gather_records(t.rec, out=net._gathered)
+                    if read_all:
+                        src = net._gathered
+                net._rec_host[slot_].copy_(src, non_blocking=True)
+                net._rec_done[slot_].record(torch.cuda.current_stream())
+
+            while cur is not None:
+                slot = i & 1
+                main.wait_event(net._h2d[slot])
+                net.image_buf.copy_(net._stage[slot], non_blocking=True)  # device-to-device
+                net._used[slot].record(main)
+                try:
+                    nxt = _as_host_tensor(next(it))
+                    assert nxt.shape == cur.shape, "all batches of a stream must share a shape"
+                    prefetch(nxt, slot ^ 1)
+                except StopIteration:
+                    nxt = None
+                net.run_pipelined(slot, lambda t, s_=slot: after_tail(t, s_))
+                if pending is not None:
+                    yield complete(pending)  # host work of batch i-1 while batch i runs
+                pending = slot
+                cur = nxt
+                i += 1
+            if pending is not None:
+                yield complete(pending)
+            return
         while cur is not None:
             slot = i & 1
             main.wait_event(net._h2d[slot])

@@ -220,6 +220,11 @@ class ConvOp(Op):
             P = self.rgbx
             net.image_rgbx = torch.zeros((B, H + 2 * P, Wd + 2 * P, 4), dtype=torch.float16, device=dev)
 
+    def params(self, net):
+        """The kernel parameter block; head convolutions have a second one that scatters into the candidate-row buffer of
+        pipeline slot 1 (Net.capture_pipelined)."""
+        return self.p1 if (net.slot == 1 and self.head is not None) else self.p
+
     def launch(self, net, stream):
         lib = net.lib
         if self.is_image and self.rgbx:
@@ -237,11 +242,11 @@ class ConvOp(Op):
                                      L.ODT_F16 if net.precision == "fp16" else L.ODT_F32,
                                      C.byref(self.p), stream)
         elif self.use_tc:
-            rc = lib.odt_conv2d_f16_tc(self.x.ptr(), self.wdev.data_ptr(), C.byref(self.p), stream)
+            rc = lib.odt_conv2d_f16_tc(self.x.ptr(), self.wdev.data_ptr(), C.byref(self.params(net)), stream)
         else:
             rc = lib.odt_conv2d_direct(self.x.ptr(), self.wdev.data_ptr(),
                                        L.ODT_F16 if net.precision == "fp16" else L.ODT_F32,
-                                       C.byref(self.p), stream)
+                                       C.byref(self.params(net)), stream)
         L.check(rc, "conv %s" % self.kernel)
 
 
@@ -422,6 +427,8 @@ class Net:
         self.use_halo = os.environ.get("ODT_HALO", "1") != "0"
         self.weights = None
         self.graph = None
+        self.slot = 0            # pipeline slot the launches address (capture_pipelined)
+        self.body_graphs = None
 
     # ---------------------------------------------------------- variables ---
     def var(self, name, shape, kind):
@@ -689,15 +696,16 @@ class Net:
         assert self._gn_used <= self.gn_arena.numel()
         return ptr
 
-    def forward(self, stream=None):
-        """Launch backbone + heads + tail on the current torch stream."""
+    def forward(self, stream=None, with_tail=True):
+        """Launch backbone + heads (+ tail) on the current torch stream."""
         st = torch.cuda.current_stream().cuda_stream if stream is None else stream
         if self.gn_arena is not None:
             assert stream is None, "the GroupNorm arena is zeroed on the current torch stream"
             self.gn_arena.zero_()
         for op in self.ops:
             op.launch(self, st)
-        self.tail.launch(self, st)
+        if with_tail:
+            self.tail.launch(self, st)
 
     # Independent branches of the op list (FPN levels, the two towers, SSD/YOLO heads
     # next to the rest of the backbone) are captured on separate stream lanes so that
@@ -737,12 +745,12 @@ class Net:
             tails[lane] = i
         return lane_of, waits, tails
 
-    def forward_lanes(self):
-        """Multi-lane launch of the op list (used under graph capture)."""
+    def forward_lanes(self, with_tail=True):
+        """Multi-lane launch of the op list (used under graph capture); with_tail=False: backbone + heads only."""
         lane_of, waits, tails = self.plan_lanes()
         main = torch.cuda.current_stream()
         if len(tails) <= 1:
-            return self.forward()
+            return self.forward(with_tail=with_tail)
         if self.gn_arena is not None:
             self.gn_arena.zero_()  # on the capturing stream, ahead of every lane
         if getattr(self, "_lanes", None) is None or len(self._lanes) < len(tails):
@@ -762,7 +770,8 @@ class Net:
         for l, t in enumerate(tails):         # join every lane back before the tail
             if l != 0 and t >= 0:
                 main.wait_event(events[t])
-        self.tail.launch(self, main.cuda_stream)
+        if with_tail:
+            self.tail.launch(self, main.cuda_stream)
 
     def capture(self):
         """Capture the whole forward in a CUDA graph (launch-bound tail + 30-130 convs)."""
@@ -791,6 +800,84 @@ class Net:
         else:
             self.forward()
 
+    # ---- two-stage pipeline over a stream of batches -----------------------------------------------------------
+    # decode + NMS of batch i (latency-bound, 0.1-0.2 ms) run on a second, high-priority stream under the stem and the
+    # first convolutions of batch i+1.  Everything the tail touches exists twice (candidate rows, candidate lists,
+    # packed records: pipeline slots 0 / 1), the backbone's activations once (consecutive bodies are stream-ordered).
+    def capture_pipelined(self):
+        """Capture [body graph, tail graph] per pipeline slot (idempotent)."""
+        import copy
+        import gc
+        if self.body_graphs is not None:
+            return
+        self.head_buf1 = torch.zeros_like(self.head_buf)
+        t1 = copy.copy(self.tail)
+        t1.prepare(self, head_buf=self.head_buf1)
+        self.tails = [self.tail, t1]
+        delta = self.head_buf1.data_ptr() - self.head_buf.data_ptr()
+        for op in self.ops:
+            if isinstance(op, ConvOp) and op.head is not None:
+                p1 = L.ConvParams()
+                C.memmove(C.byref(p1), C.byref(op.p), C.sizeof(p1))
+                p1.out0 = op.p.out0 + delta
+                op.p1 = p1
+        body, tails = [], []
+        gc_was_on = gc.isenabled()
+        try:
+            for s in (0, 1):
+                self.slot = s
+                self.forward(with_tail=False)  # warm-up of this slot's launches outside capture
+                self.tails[s].launch(self, torch.cuda.current_stream().cuda_stream)
+                gc.collect()
+                torch.cuda.synchronize()
+                gc.disable()
+                gb, gt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gb, capture_error_mode="thread_local"):
+                    self.forward_lanes(with_tail=False)
+                with torch.cuda.graph(gt, capture_error_mode="thread_local"):
+                    self.tails[s].launch(self, torch.cuda.current_stream().cuda_stream)
+                if gc_was_on:
+                    gc.enable()
+                body.append(gb)
+                tails.append(gt)
+        finally:
+            self.slot = 0
+            if gc_was_on:
+                gc.enable()
+        self._tail_stream = torch.cuda.Stream(device=self.device, priority=-1)
+        self._body_done = [torch.cuda.Event() for _ in range(2)]
+        self._tail_done = [torch.cuda.Event() for _ in range(2)]
+        for ev in self._tail_done:
+            ev.record(torch.cuda.current_stream())
+        self.body_graphs, self.tail_graphs = body, tails
+
+    def run_pipelined(self, slot, after_tail=None):
+        """One step on pipeline slot `slot` (alternate 0 / 1 from batch to batch): the body on the current stream, the
+        tail (+ `after_tail(tail)`: gather / read-back of its records) on the tail stream.  Returns the slot's Tail; its
+        buffers are valid once `_tail_done[slot]` has fired (sync_pipelined waits for both)."""
+        main = torch.cuda.current_stream()
+        ts = self._tail_stream
+        main.wait_event(self._tail_done[slot])  # this slot's rows / records of two batches ago have been consumed
+        self.body_graphs[slot].replay()
+        self._body_done[slot].record(main)
+        ts.wait_event(self._body_done[slot])
+        with torch.cuda.stream(ts):
+            self.tail_graphs[slot].replay()
+            if after_tail is not None:
+                after_tail(self.tails[slot])
+            self._tail_done[slot].record(ts)
+        return self.tails[slot]
+
+    def join_pipelined(self):
+        """The current stream waits for the tails of both slots (e.g. before an event that closes a timed region)."""
+        main = torch.cuda.current_stream()
+        for ev in self._tail_done:
+            main.wait_event(ev)
+
+    def sync_pipelined(self):
+        for ev in self._tail_done:
+            ev.synchronize()
+
     def num_launches(self):
         n = 0
         for op in self.ops:
@@ -810,9 +897,10 @@ class Tail:
         self.level_fn, self.cap = level_fn, cap
         self.pool_cap = 8 << 20  # box-pool entries (16 B each) for lists beyond the shared-memory window
 
-    def prepare(self, net):
+    def prepare(self, net, head_buf=None):
         dev = net.device
         B, N = net.batch, net.N
+        self.head_buf = net.head_buf if head_buf is None else head_buf  # the candidate rows this tail reads
         p = L.TailParams()
         p.kind, p.num_levels, p.N = self.kind, len(net.levels), N
         p.num_fg, p.nms_classes = self.num_fg, self.nms_classes
@@ -847,12 +935,12 @@ class Tail:
                          if self.pool_entries else None)
 
     def launch_decode(self, net, stream):
-        L.check(net.lib.odt_decode_candidates(net.head_buf.data_ptr(), C.byref(self.p), net.batch,
+        L.check(net.lib.odt_decode_candidates(self.head_buf.data_ptr(), C.byref(self.p), net.batch,
                                               self.cand_keys.data_ptr(), self.cand_count.data_ptr(),
                                               stream), "decode_candidates")
 
     def launch_nms(self, net, stream):
-        L.check(net.lib.odt_nms_per_class(net.head_buf.data_ptr(), C.byref(self.p), net.batch,
+        L.check(net.lib.odt_nms_per_class(self.head_buf.data_ptr(), C.byref(self.p), net.batch,
                                           self.cand_keys.data_ptr(), self.cand_count.data_ptr(),
                                           self.dets.data_ptr(), self.det_anchor.data_ptr(),
                                           self.det_count.data_ptr(), self.scratch.data_ptr(),

@@ -329,6 +329,46 @@ def test_detect_stream_results_survive_later_batches(built):
     assert list(m.detect_stream([])) == []
 
 
+@pytest.mark.parametrize("kind,hw", [("ssd300", 300), ("retinanet", 256)])
+def test_pipelined_and_single_graph_streams_agree(built, monkeypatch, kind, hw):
+    """The two-stage pipeline (tail of batch i on a second stream under the body of batch i+1, candidate rows / lists /
+    records double-buffered by slot) against the one-graph-per-step stream and the synchronous call: identical
+    detections for every batch of a 6-batch stream (each slot is reused three times), for two model families; then the
+    engine-level run_pipelined() against run() on the packed records themselves."""
+    import torch
+    kw = {"nms_score_threshold": 0.3} if kind == "ssd300" else {"data_shape": [hw, hw, 3], "nms_score_threshold": 0.05}
+    m = _model(kind, precision="fp16", **kw)
+    batches = [_img(2, hw, hw, seed=s) for s in range(41, 47)]
+    ref = [m.detect_batch(b) for b in batches]
+    pinned = [torch.from_numpy(b).pin_memory() for b in batches]
+    for mode in ("1", "0"):
+        monkeypatch.setenv("ODT_PIPELINE", mode)
+        got = list(m.detect_stream(pinned))
+        assert len(got) == len(ref)
+        for g, r in zip(got, ref):
+            for gi, ri in zip(g, r):
+                for a, b in zip(gi, ri):
+                    np.testing.assert_array_equal(a, b)
+    net = m.engine(2)
+    net.capture_pipelined()
+    recs = []
+    for i, b in enumerate(batches[:4]):
+        net.image_buf.copy_(torch.from_numpy(b))
+        t = net.run_pipelined(i & 1)
+        net.sync_pipelined()
+        recs.append(t.rec.clone())
+    for b, rec in zip(batches[:4], recs):
+        net.image_buf.copy_(torch.from_numpy(b))
+        net.run()
+        torch.cuda.synchronize()
+        want, got = net.tail.rec.cpu().numpy(), rec.cpu().numpy()
+        np.testing.assert_array_equal(got[:, -2:], want[:, -2:])            # counts and overflow flags
+        for img in range(want.shape[0]):                                     # rows past the count are stale by design
+            n = int(want[img, -2]) * 6
+            assert n > 0
+            np.testing.assert_array_equal(got[img, :n], want[img, :n])
+
+
 def test_overflow_is_reported_in_the_record(built):
     """cap < candidates: the status word AND the per-image flag of the packed record report it; the next launch
     with enough capacity is clean again (the status word describes one launch)."""
