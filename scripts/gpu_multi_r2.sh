@@ -8,7 +8,7 @@ if [ "$N" = "2" ]; then
   timeout 600 python -m pytest tests/test_gpu_models.py -q -m gpu -k "sharded" -s 2>&1 | tail -n 4
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 scripts/check_sharded.py > gpurun_out/r2_sharded_n2.log 2>&1; echo "sharded check exit $?"; tail -n 3 gpurun_out/r2_sharded_n2.log
 fi
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/r2_bench_n$N.json 2> gpurun_out/r2_bench_n$N.err; echo "bench n$N exit $?"; tail -n 3 gpurun_out/r2_bench_n$N.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r2_bench_n$N.json 2> gpurun_out/r2_bench_n$N.err; echo "bench n$N exit $?"; tail -n 3 gpurun_out/r2_bench_n$N.err
 python - <<P
 import json
 d=json.loads(open('gpurun_out/r2_bench_n$N.json').read().strip().splitlines()[-1])
