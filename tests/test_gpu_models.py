@@ -417,7 +417,7 @@ FULL = {"ssd300": ({}, 300, 300, 2), "ssd512": ({}, 512, 512, 1),
         "fcos": ({"data_shape": [1024, 1024, 3]}, 1024, 1024, 1)}
 
 
-@pytest.mark.parametrize("precision,row_tol,ds_tol", [("fp32", 2e-4, 1e-4), ("fp16", 1e-2, 3e-2)])
+@pytest.mark.parametrize("precision,row_tol,ds_tol", [("fp32", 2e-4, 1e-4), ("fp16", 5e-3, 3e-2)])
 @pytest.mark.parametrize("kind", ["ssd300", "ssd512", "retinanet", "yolov3", "fcos"])
 def test_full_size_end_to_end_decisions(built, kind, precision, row_tol, ds_tol):
     """Whole network at the BASELINE input size, dense score threshold (about 1 % of N candidates per class, taken
@@ -425,7 +425,7 @@ def test_full_size_end_to_end_decisions(built, kind, precision, row_tol, ds_tol)
     of class ids and keep indices (tests/margins.py), boxes of the common keeps reported."""
     over, h, w, B = FULL[kind]
     if kind == "fcos" and precision == "fp16":
-        row_tol = 2e-2   # measured 1.04e-2: GroupNorm re-normalises fp16-stored activations in every layer (a19)
+        row_tol = 1.5e-2  # measured 1.04e-2: GroupNorm re-normalises fp16-stored activations in every layer (a19)
     img = _img(B, h, w, seed=11)
     probe = _model(kind, bn_init="trained", precision=precision, **over)
     ref = _oracle_rows(kind, probe.get_weights(), img, probe.config)
